@@ -1,0 +1,245 @@
+"""Oracle (test infrastructure): numpy/scipy restatement of the reference's intertable
+build and apply.  Citations are to /root/reference/src/pyg2p/main/interpolation/.
+
+Not imported by the product package.  See oracle/__init__.py.
+"""
+from math import radians, cos, sin
+
+import numpy as np
+import numpy.ma as ma
+from scipy.spatial import cKDTree
+
+LEAFSIZE = 30  # scipy_interpolation_lib.py:559
+
+
+# --------------------------------------------------------------------------- xyz
+def to_3d(lons, lats, radius, rotation=None):
+    """scipy_interpolation_lib.py:665-696.
+
+    Default branch: `r*cos(lon)*cos(lat)`, `r*sin(lon)*cos(lat)`, `r*sin(lat)` evaluated
+    left to right, `r` a double constant (numexpr promotes f32 operands to double when a
+    Python float is involved), result cast back to float32 when the inputs are float32
+    (:691-694).  `rotation=(lat_sp, lon_sp)` selects the `to_regular` branch (:673-678),
+    which works on the UNIT sphere (no radius factor).
+    """
+    lons = np.radians(lons)
+    lats = np.radians(lats)
+    cx = np.cos(lons)
+    sx = np.sin(lons)
+    cy = np.cos(lats)
+    sy = np.sin(lats)
+    if rotation is None:
+        r = np.float64(radius)
+        x = (r * cx) * cy
+        y = (r * sx) * cy
+        z = r * sy
+    else:
+        lat_sp, lon_sp = rotation
+        teta = -radians(90 + lat_sp)
+        fi = -radians(lon_sp)
+        ux = cx * cy
+        uy = sx * cy
+        uz = sy
+        x = (np.float64(cos(teta) * cos(fi)) * ux + np.float64(sin(fi)) * uy) + np.float64(sin(teta) * cos(fi)) * uz
+        y = (np.float64(cos(teta) * sin(fi)) * ux + np.float64(cos(fi)) * uy) - np.float64(sin(teta) * sin(fi)) * uz
+        z = np.float64(-sin(teta)) * ux + np.float64(cos(teta)) * uz
+    if lons.dtype == np.float32:
+        x = np.float32(x)
+        y = np.float32(y)
+        z = np.float32(z)
+    return x, y, z
+
+
+def stack_xyz(x, y, z):
+    """`np.vstack((x.ravel(), y.ravel(), z.ravel())).T` (:552, :625)."""
+    return np.vstack((x.ravel(), y.ravel(), z.ravel())).T
+
+
+# --------------------------------------------------------------------------- k-NN
+def build_tree(source_xyz):
+    return cKDTree(source_xyz, leafsize=LEAFSIZE)
+
+
+def min_upper_bound(tree, source_xyz, nj, workers=1):
+    """Self query k=2, `dmax + dmax*4/Nj` with dmax over BOTH columns (:568-570)."""
+    d, _ = tree.query(source_xyz, k=2, workers=workers)
+    dmax = np.max(d)
+    return dmax + dmax * 4 / nj
+
+
+def query(tree, target_xyz, k, workers=1):
+    """:626-628 - distances are cast to float32 when the target xyz are float32."""
+    d, i = tree.query(target_xyz, k=k, workers=workers)
+    if target_xyz.dtype == np.float32:
+        d = np.float32(d)
+    return d, i
+
+
+def brute_knn(source_xyz, target_xyz, k):
+    """Exhaustive k-NN in the cKDTree distance arithmetic:
+    d2 = ((dx*dx)+(dy*dy))+(dz*dz) in float64, ties broken by lower source index.
+    Independent check of cKDTree on small cases; also returns a per-row flag for exact
+    float64 ties among the best k+1 squared distances."""
+    s = np.asarray(source_xyz, dtype=np.float64)
+    t = np.asarray(target_xyz, dtype=np.float64)
+    m = t.shape[0]
+    idx = np.empty((m, k), dtype=np.int64)
+    dist = np.empty((m, k), dtype=np.float64)
+    tie = np.zeros(m, dtype=bool)
+    for j in range(m):
+        dx = t[j, 0] - s[:, 0]
+        dy = t[j, 1] - s[:, 1]
+        dz = t[j, 2] - s[:, 2]
+        d2 = ((dx * dx) + (dy * dy)) + (dz * dz)
+        order = np.lexsort((np.arange(s.shape[0]), d2))[:k + 1]
+        idx[j] = order[:k]
+        dist[j] = np.sqrt(d2[order[:k]])
+        dd = d2[order]
+        tie[j] = bool(np.any(dd[1:] == dd[:-1]))
+    return dist, idx, tie
+
+
+# --------------------------------------------------------------------------- weights
+def build_nn_loop(distances, indexes, z, mub, mv_target):
+    """`_build_nn` as the reference runs it: a per-point Python loop (:698-727).
+    Kept literal because it is what the CPU baseline times."""
+    n = z.size
+    result = ma.masked_array(data=np.empty((len(distances),)), fill_value=mv_target, copy=False)
+    idxs = np.full((len(indexes),), n, dtype=int)
+    j = 0
+    for dist, ix in zip(distances, indexes):
+        if dist <= mub:
+            wz = z[ix]
+            idxs[j] = ix
+        else:
+            wz = mv_target
+        result[j] = wz
+        j += 1
+    return result, idxs
+
+
+def build_nn(distances, indexes, z, mub, mv_target):
+    """Vectorised equivalent of `build_nn_loop` (checked equal in tests); `coeffs` of a
+    nearest table are the raw distances for every row (:634-635)."""
+    n = z.size
+    inside = distances <= mub
+    idxs = np.where(inside, indexes, n).astype(int)
+    result = np.where(inside, z[np.minimum(indexes, n - 1)], mv_target)
+    return result, idxs
+
+
+def build_weights_invdist(distances, indexes, z, mub, mv_target, nnear):
+    """`_build_weights_invdist(adw_type=None)` (:774-812, :1018-1026, :1036, :1054-1056, :1076).
+
+    A: d0 <= 1e-10 -> w = [1,0,..], idx = cKDTree row.  B: ~A & d0 <= mub -> w = 1/d**2
+    over ALL k columns, normalised by the row sum.  Else: w = NaN, idx = N.
+    Arithmetic dtype follows `distances` (float32 for float32 target maps); stored into
+    `z.dtype` weights."""
+    n = z.size
+    m = len(distances)
+    result = ma.masked_array(data=np.empty((m,), dtype=z.dtype), fill_value=mv_target, copy=False)
+    weights = np.full((m, nnear), np.nan, dtype=z.dtype)
+    idxs = np.full((m, nnear), n, dtype=int)
+    a = distances[:, 0] <= 1e-10
+    b = np.logical_and(~a, distances[:, 0] <= mub)
+    first = np.zeros(nnear)
+    first[0] = 1
+    weights[a] = first
+    idxs[a] = indexes[a]
+    result[a] = z[indexes[a][:, 0]]
+    w = np.zeros_like(distances)
+    w[b] = 1. / distances[b] ** 2
+    sums = np.sum(w[b], axis=1, keepdims=True)
+    weights[b] = w[b] / sums
+    wz = np.einsum('ij,ij->i', weights, z[indexes])
+    idxs[b] = indexes[b]
+    result[b] = wz[b]
+    return result, weights, idxs
+
+
+class BuildOracle:
+    """`ScipyInterpolation.__init__` + `interpolate` for modes nearest / invdist
+    (:523-570, :572-663) with cKDTree as the neighbour search."""
+
+    def __init__(self, longrib, latgrib, grid_details, source_values, nnear, mv_target, mv_source,
+                 parallel=False, mode='nearest', source_rotation=None, target_rotation=None):
+        self.workers = -1 if parallel else 1
+        self.nnear = nnear
+        self.mode = mode
+        self.mv_target = mv_target
+        self.z = source_values
+        self.radius = grid_details.get('radius')
+        self.target_rotation = target_rotation
+        x, y, zz = to_3d(longrib, latgrib, self.radius, rotation=source_rotation)
+        self.source_xyz = stack_xyz(x, y, zz)
+        self.tree = build_tree(self.source_xyz)
+        self.min_upper_bound = min_upper_bound(self.tree, self.source_xyz, grid_details.get('Nj'), self.workers)
+
+    def interpolate(self, lonefas, latefas, python_loop=False):
+        x, y, z = to_3d(lonefas, latefas, self.radius, rotation=self.target_rotation)
+        self.target_xyz = stack_xyz(x, y, z)
+        distances, indexes = query(self.tree, self.target_xyz, self.nnear, self.workers)
+        self.raw_distances, self.raw_indexes = distances, indexes
+        if self.mode == 'nearest' and self.nnear == 1:
+            fn = build_nn_loop if python_loop else build_nn
+            result, idxs = fn(distances, indexes, self.z, self.min_upper_bound, self.mv_target)
+            return result, distances, idxs
+        if self.mode == 'invdist':
+            return build_weights_invdist(distances, indexes, self.z, self.min_upper_bound, self.mv_target, self.nnear)
+        raise ValueError(f'oracle covers nearest/invdist only, got {self.mode}')
+
+
+# --------------------------------------------------------------------------- table record
+def to_record(indexes, weights):
+    """interpolation/__init__.py:251 - array-of-structs {int64 indexes, f8|f4 coeffs}."""
+    return np.rec.fromarrays((indexes, weights), names=('indexes', 'coeffs'))
+
+
+# --------------------------------------------------------------------------- apply
+def apply_as_reference(v, weights, indexes, nnear, mv_out):
+    """`Interpolator._interpolate_scipy_append_mv` literally (interpolation/__init__.py:142-162).
+    Note the quirk: `np.append` drops the mask, so masked inputs
+    contribute their payload and the result is a plain ndarray."""
+    v = np.append(v, mv_out)
+    orig_mask = False if not isinstance(v, ma.core.MaskedArray) else v.mask
+    if nnear == 1:
+        if isinstance(orig_mask, np.ndarray):
+            result = ma.masked_where(orig_mask[indexes], v[indexes], copy=False)
+        else:
+            result = v[indexes]
+    else:
+        result = np.einsum('ij,ij->i', weights, v[indexes])
+        if isinstance(orig_mask, np.ndarray):
+            mask = None
+            for i in range(0, indexes.shape[1]):
+                mask = orig_mask[indexes.T[i]] if mask is None else mask | orig_mask[indexes.T[i]]
+            result = ma.masked_where(mask, result, copy=False)
+    return result
+
+
+def apply_sequential(v, weights, indexes, nnear, mv_out):
+    """Same values as `apply_as_reference` but with the evaluation order pinned to
+    ((w0*v0 + w1*v1) + w2*v2) + w3*v3, separate multiply and add (this
+    is what einsum does on table views loaded from file).  Bit-exact target for the GPU."""
+    vv = np.append(np.asarray(v, dtype=np.float64), mv_out)
+    if nnear == 1:
+        return vv[indexes]
+    w = np.asarray(weights, dtype=np.float64)
+    acc = w[:, 0] * vv[indexes[:, 0]]
+    for j in range(1, indexes.shape[1]):
+        acc = acc + w[:, j] * vv[indexes[:, j]]
+    return acc
+
+
+def apply_propagate(v, weights, indexes, nnear, mv_out, src_mask):
+    """Intended mask semantics of :148-161 (what the code would do with `ma.append`): the
+    output is masked where ANY of the k source points is masked; the sentinel slot N is
+    never masked.  Returns (data, mask)."""
+    data = apply_sequential(np.asarray(ma.getdata(v)), weights, indexes, nnear, mv_out)
+    m = np.append(np.asarray(src_mask, dtype=bool), False)
+    if nnear == 1:
+        return data, m[indexes]
+    out = np.zeros(indexes.shape[0], dtype=bool)
+    for j in range(indexes.shape[1]):
+        out |= m[indexes[:, j]]
+    return data, out

@@ -1,0 +1,141 @@
+"""Pin the oracle (oracle/) against golden vectors produced by the reference's own code
+(tests/golden/make_golden.py) and against the reference's golden intertable."""
+import gzip
+import os
+
+import numpy as np
+import numpy.ma as ma
+import pytest
+
+from oracle import interp_ref as R
+from oracle import manip_ref as MR
+from pyg2p_b200 import synth
+
+BUILD_CASES = ['o24_box_f64', 'o24_laea_f32mv', 'regional_global_f64', 'o24_coincident_f64']
+
+
+def _details(g):
+    return synth.GridDetails(radius=float(g['radius']), Nj=int(g['nj']), gridType='reduced_gg')
+
+
+@pytest.mark.parametrize('case', BUILD_CASES)
+@pytest.mark.parametrize('mode,k', [('nearest', 1), ('invdist', 4)])
+def test_build_matches_reference(golden_dir, case, mode, k):
+    g = np.load(os.path.join(golden_dir, f'build_{case}.npz'))
+    o = R.BuildOracle(g['src_lon'], g['src_lat'], _details(g), g['z'], k, float(g['mv_target']),
+                      synth.GRIB_MV, mode=mode)
+    assert o.min_upper_bound == float(g[f'{mode}_mub'])
+    res, w, idx = o.interpolate(g['tgt_lon'], g['tgt_lat'])
+    assert idx.dtype == g[f'{mode}_indexes'].dtype and idx.shape == g[f'{mode}_indexes'].shape
+    np.testing.assert_array_equal(idx, g[f'{mode}_indexes'])
+    assert w.dtype == g[f'{mode}_weights'].dtype
+    np.testing.assert_array_equal(w, g[f'{mode}_weights'])          # bit-exact incl. NaN rows
+    # `result` rows beyond min_upper_bound are uninitialised memory in the reference's invdist
+    # (np.empty, :786) and the caller discards `result` anyway (interpolation/__init__.py:247)
+    ok = np.ones(len(idx), bool) if k == 1 else ~np.isnan(w[:, 0])
+    np.testing.assert_array_equal(np.asarray(ma.filled(res))[ok], g[f'{mode}_result'][ok])
+
+
+def test_build_nn_loop_equals_vectorised(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'build_regional_global_f64.npz'))
+    o = R.BuildOracle(g['src_lon'], g['src_lat'], _details(g), g['z'], 1, float(g['mv_target']), synth.GRIB_MV)
+    r1, w1, i1 = o.interpolate(g['tgt_lon'], g['tgt_lat'], python_loop=True)
+    r2, w2, i2 = o.interpolate(g['tgt_lon'], g['tgt_lat'], python_loop=False)
+    np.testing.assert_array_equal(i1, i2)
+    np.testing.assert_array_equal(np.asarray(ma.filled(r1)), np.asarray(r2))
+    assert (i1 == g['z'].size).sum() > 0 and (i1 < g['z'].size).sum() > 0
+
+
+def test_f32_targets_give_f32_coeffs(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'build_o24_laea_f32mv.npz'))
+    assert g['nearest_weights'].dtype == np.float32      # distances cast to f32 (:627-628)
+    assert g['invdist_weights'].dtype == np.float64      # stored into z.dtype weights (:787)
+    w = g['invdist_weights']
+    ok = ~np.isnan(w[:, 0])
+    assert np.all(w[ok] == w[ok].astype(np.float32))     # ... but computed in float32
+
+
+def test_cKDTree_against_brute_force(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'build_o24_box_f64.npz'))
+    o = R.BuildOracle(g['src_lon'], g['src_lat'], _details(g), g['z'], 4, 0.0, 0.0, mode='invdist')
+    o.interpolate(g['tgt_lon'], g['tgt_lat'])
+    sel = np.arange(0, o.target_xyz.shape[0], 7)
+    d, i, tie = R.brute_knn(o.source_xyz, o.target_xyz[sel], 4)
+    np.testing.assert_array_equal(d, o.raw_distances[sel])           # distances always bit-equal
+    nt = ~tie
+    np.testing.assert_array_equal(i[nt], o.raw_indexes[sel][nt])     # indexes equal on non-tie rows
+    for r in np.nonzero(tie)[0]:                                     # tie rows: same multiset of distances
+        assert sorted(d[r]) == sorted(o.raw_distances[sel][r])
+
+
+@pytest.mark.parametrize('mode,k', [('nearest', 1), ('invdist', 4)])
+def test_apply_matches_reference(golden_dir, mode, k):
+    g = np.load(os.path.join(golden_dir, 'apply_regional.npz'))
+    t = np.load(os.path.join(golden_dir, 'build_regional_global_f64.npz'))
+    rec = R.to_record(t[f'{mode}_indexes'], t[f'{mode}_weights'])
+    mv_out = float(g['mv_out'])
+    for b in range(3):
+        v, mask = g[f'v{b}'], g[f'mask{b}']
+        with np.errstate(all='ignore'):
+            lit = R.apply_as_reference(v, rec['coeffs'], rec['indexes'], k, mv_out)
+            litm = R.apply_as_reference(ma.masked_where(mask, v), rec['coeffs'], rec['indexes'], k, mv_out)
+            seq = R.apply_sequential(v, rec['coeffs'], rec['indexes'], k, mv_out)
+        np.testing.assert_array_equal(np.asarray(lit), g[f'{mode}_plain{b}'])
+        np.testing.assert_array_equal(np.asarray(ma.filled(litm)), g[f'{mode}_masked{b}'])
+        # the reference silently drops masks: masked == plain
+        np.testing.assert_array_equal(g[f'{mode}_masked{b}'], g[f'{mode}_plain{b}'])
+        # pinned sequential order == einsum on strided table views, bit for bit
+        np.testing.assert_array_equal(seq, g[f'{mode}_plain{b}'])
+
+
+def test_reference_golden_table_layout(golden_dir):
+    with gzip.GzipFile(os.path.join(golden_dir, 'ref_tbl_pf10slhf_550800_scipy_nearest.npy.gz')) as f:
+        tbl = np.load(f)
+    assert tbl.dtype == np.dtype([('indexes', '<i8'), ('coeffs', '<f8')]) and tbl.shape == (550800,)
+    n = 511 * 415
+    idx, d = tbl['indexes'], tbl['coeffs']
+    assert idx.max() == n and (idx == n).sum() == 362052          # sentinel = number of source values
+    assert idx.strides == (16,) and d.strides == (16,)            # array-of-structs
+    v = np.arange(n, dtype=np.float64)
+    out = R.apply_as_reference(v, d, idx, 1, -3.4028234663852886e38)
+    assert (out == -3.4028234663852886e38).sum() == 362052
+    np.testing.assert_array_equal(out[idx < n], idx[idx < n].astype(np.float64))
+
+
+def test_manipulation_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'manip.npz'))
+    x = g['conv_x']
+    for i, f in enumerate(['x=x*1000', 'x=x-273.15', 'x=x*(-0.0353)', 'x=-x*1000', 'x=x']):
+        y = MR.convert(x.copy(), f, synth.GRIB_MV)
+        np.testing.assert_array_equal(np.asarray(y), g[f'conv{i}'])
+        np.testing.assert_array_equal(MR.cut_off_negative(np.asarray(y)), g[f'conv{i}_cut'])
+    steps = list(g['agg_steps'])
+    cum, mask, inst = g['agg_cum'], g['agg_mask'], g['inst_fields']
+
+    def vals(stepset, src=cum, masked=False):
+        return {int(s): (ma.masked_where(mask, src[steps.index(s)], copy=True) if masked else src[steps.index(s)].copy())
+                for s in stepset}
+
+    def check(tag, out):
+        keys = sorted(out.keys(), key=lambda k: (k[1], k[0]))
+        np.testing.assert_array_equal(np.array(keys), g[f'{tag}_keys'])
+        np.testing.assert_array_equal(np.array([np.asarray(ma.getdata(out[k])) for k in keys]), g[f'{tag}_vals'])
+        np.testing.assert_array_equal(
+            np.array([np.broadcast_to(ma.getmaskarray(out[k]) if isinstance(out[k], ma.MaskedArray) else False,
+                                      x.shape) for k in keys]), g[f'{tag}_masks'])
+
+    check('acc_full', MR.accumulation(vals(steps), 0, 72, 24, 24))
+    check('acc_nozero', MR.accumulation(vals(steps[1:]), 0, 72, 24, 24))
+    check('acc_gap', MR.accumulation(vals([s for s in steps if s != 48]), 0, 72, 24, 24))
+    check('acc_masked', MR.accumulation(vals(steps, masked=True), 0, 72, 24, 24))
+    check('acc_forcezero', MR.accumulation(vals(steps), 0, 72, 24, 24, force_zero=True))
+    check('acc_step12_unit6', MR.accumulation(vals(steps), 12, 72, 12, 6))
+    check('avg_full', MR.average(vals(steps, inst), 0, 72, 24))
+    check('avg_start24', MR.average(vals(steps, inst), 24, 72, 24))
+    check('inst_full', MR.instantaneous(vals(steps, inst), 0, 72, 12, input_step=6))
+    check('inst_gap', MR.instantaneous(vals([s for s in steps if s not in (0, 36)], inst), 0, 72, 12, input_step=6))
+    out = MR.correct(g['corr_p'].copy(), g['corr_dem'], g['corr_gem'], float(g['corr_dem_mv']), float(g['corr_gem_mv']))
+    np.testing.assert_array_equal(np.asarray(ma.filled(out)), g['corr_out'])
+    out = MR.correct(g['corr_p'].copy(), g['corr_dem'], g['corr_gem'], float(g['corr_dem_mv']), float(g['corr_gem_mv']),
+                     formula='p/gem*(10**((-0.159)*dem/1000))')
+    np.testing.assert_array_equal(np.asarray(ma.filled(out)), g['corr_out_pressure'])
