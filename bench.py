@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 interpolation path (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Primary line (BASELINE.json metric, second half): intertable APPLY in algorithmic GB/s against the
+HBM roofline.  Workload = configs[3] of BASELINE.json as one GPU of the 8xB200 box sees it: the
+51-member x 60-step ENS batch (3060 messages) sharded by member -> 383 O1280 messages per GPU,
+applied to the EFAS 5 km grid through an invdist (k=4) table, with missing values (mask propagate).
+One "step" = one pass over the rank's resident batch = ONE launch of the apply kernel.
+The `build` object carries the first half of the metric: intertable BUILD target-pts/s for
+configs[2] (O1280 -> GloFAS 0.05 deg, 21.6 M targets, invdist k=4), targets sharded over ranks.
+
+`--impl reference` times the reference's CPU algorithm (oracle/ restatement: np.append + einsum per
+message; cKDTree(leafsize=30, workers=-1) + numpy weights for the build) on bounded samples of the
+same workloads on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+from pyg2p_b200 import synth  # noqa: E402
+
+K_INVDIST = 4
+MESSAGES_FULL_JOB = 51 * 60
+
+
+def peaks():
+    p = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def algorithmic_bytes_apply(b, n_touched, m, k, masks):
+    """8*B*(N_touched + M) + M*k*(4+8) [+ B*ceil(N_touched/8) mask bits]."""
+    total = 8 * b * (n_touched + m) + m * k * (4 + (8 if k > 1 else 0))
+    if masks:
+        total += b * ((n_touched + 7) // 8)
+    return total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.gpu}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw = [], [], []
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                pw.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# =============================================================================== reference arm (CPU)
+def cpu_apply_reference(n_messages, seed=0):
+    """The reference's apply (`_interpolate_scipy_append_mv`, one message per call, single thread) on a
+    bounded sample of the workload.  Returns (seconds, algorithmic bytes, sample description)."""
+    import numpy.ma as ma
+
+    from oracle import interp_ref as R
+    lat, lon, det = synth.octahedral_grid(1280)
+    tl, tlo = synth.efas_target()
+    t0 = time.perf_counter()
+    o = R.BuildOracle(lon, lat, det, np.zeros(lat.size), K_INVDIST, synth.NC_FILL_F64, synth.GRIB_MV, parallel=True,
+                      mode='invdist')
+    _, w, idx = o.interpolate(tlo, tl)
+    t_table = time.perf_counter() - t0
+    rec = R.to_record(idx, w)                      # strided views, as `_read_intertable` hands them over
+    n_touched = int(np.unique(idx[idx < lat.size]).size)
+    mask = synth.missing_mask(lat)
+    fields = [ma.masked_where(mask, np.where(mask, synth.GRIB_MV, synth.field_2t(lat, lon, member=i)), copy=False)
+              for i in range(min(4, n_messages))]
+    t0 = time.perf_counter()
+    for i in range(n_messages):
+        with np.errstate(all='ignore'):
+            R.apply_as_reference(fields[i % len(fields)], rec['coeffs'], rec['indexes'], K_INVDIST, synth.NC_FILL_F64)
+    dt = time.perf_counter() - t0
+    nbytes = algorithmic_bytes_apply(n_messages, n_touched, tl.size, K_INVDIST, True)
+    return dt, nbytes, {'messages': n_messages, 'n_touched': n_touched, 'table_build_s': round(t_table, 3),
+                        'what': f'{n_messages} of the 383 O1280 messages, np.append + einsum per message, 1 thread'}
+
+
+def cpu_build_reference(row_fraction=8):
+    """The reference's build (`ScipyInterpolation`, -X => cKDTree workers=-1) for O1280 -> 0.05 deg invdist on
+    1/row_fraction of the target rows.  Fixed costs (tree, self query) are paid in full."""
+    from oracle import interp_ref as R
+    lat, lon, det = synth.octahedral_grid(1280)
+    tl, tlo = synth.latlon_target(0.05)
+    rows = tl.shape[0] // row_fraction
+    tl, tlo = tl[:rows], tlo[:rows]
+    t0 = time.perf_counter()
+    o = R.BuildOracle(lon, lat, det, np.zeros(lat.size), K_INVDIST, synth.NC_FILL_F64, synth.GRIB_MV, parallel=True,
+                      mode='invdist')
+    t_fixed = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    o.interpolate(tlo, tl)
+    t_sample = time.perf_counter() - t0
+    m_full = 7200 * 3000
+    est_full = t_fixed + t_sample * (m_full / tl.size)
+    return {'metric': 'intertable build target-pts/s', 'value': m_full / est_full, 'unit': 'target-pts/s',
+            'kind': 'port', 'cores': os.cpu_count(),
+            'sample': f'{tl.size} of {m_full} targets (first {rows} rows); tree + self-query {t_fixed:.2f} s paid in '
+                      f'full, target part {t_sample:.2f} s scaled x{row_fraction}; cKDTree workers=-1, numpy weights',
+            'seconds_full_estimate': est_full, 'seconds_fixed': t_fixed, 'seconds_sample': t_sample}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    per_step = 8
+    for _ in range(args.warmup):
+        pass                                       # numpy needs no warm-up beyond the first call below
+    dt_w, _, _ = cpu_apply_reference(1)
+    dt, nbytes, sample = cpu_apply_reference(per_step * args.steps)
+    value = nbytes / dt / 1e9
+    build = cpu_build_reference()
+    line = {
+        'impl': 'reference', 'metric': 'intertable apply GB/s vs HBM roofline', 'value': value, 'unit': 'GB/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(per_step),
+        'cpu_baseline': {'value': value, 'unit': 'GB/s', 'cores': 1, 'kind': 'port',
+                         'sample': f"{sample['what']}; each step = {per_step} messages"},
+        'e2e': {'value': value, 'unit': 'GB/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'messages_per_s': per_step * args.steps / dt,
+        'build': build,
+        'host': {'cpu_count': os.cpu_count(), 'numpy': np.__version__, 'scipy': __import__('scipy').__version__},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(messages_per_gpu):
+    return {'workload': 'BASELINE configs[3] per-GPU slice: intertable apply batch, 51-member ENS x 60 steps '
+                        '(3060 O1280 messages) sharded by member over 8 GPUs -> EFAS 5 km (950x1000), invdist k=4, '
+                        'with missing values; `build` = configs[2] O1280 -> GloFAS 0.05 deg (7200x3000) invdist k=4',
+            'messages_per_gpu': messages_per_gpu, 'n_src': 6599680, 'm_tgt': 950000, 'k': K_INVDIST,
+            'mask_policy': 'propagate',
+            'l2': 'the resident batch read by each launch (messages_per_gpu x 52.8 MB) is far larger than the '
+                  '126 MB L2, so no flush between timed iterations',
+            'parallelism': 'messages sharded by rank, no collective (apply); targets sharded + all-gather (build)'}
+
+
+# =============================================================================== B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from pyg2p_b200 import _lib as L
+    from pyg2p_b200 import device, parallel
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    ws = int(os.environ.get('WORLD_SIZE', '1'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: pyg2p_b200 has no CPU fallback (use --impl reference '
+                         'for the CPU baseline)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if ws > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    hbm_peak, peak_src = peaks()
+    lat, lon, det = synth.octahedral_grid(1280)
+    n = lat.size
+    tl, tlo = synth.efas_target()
+    m = tl.size
+    B = args.messages
+
+    # ---- table for the apply phase, built on this GPU (O1280 -> EFAS invdist)
+    ix = device.SourceIndex(lon, lat, det['radius'])
+    mub = ix.min_upper_bound(det['Nj'])
+    out = ix.knn(tlo, tl, k=K_INVDIST, mode=L.MODE_INVDIST, mub=mub, want_flags=False)
+    table = device.DeviceTable(out['idx'], out['coef'], n)
+    touched = torch.unique(table.idx[table.idx < n])
+    n_touched = int(touched.numel())
+    del touched, out
+
+    # ---- resident batch: this rank's members' messages (synthetic 2t-like fields + GRIB bitmap masks)
+    g = torch.Generator(device=dev).manual_seed(20260101 + rank)
+    src = torch.empty((B, n), dtype=torch.float64, device=dev)
+    lat_d = torch.from_numpy(lat).to(dev)
+    base = 288.0 - 45.0 * torch.sin(torch.deg2rad(lat_d)) ** 2
+    for i in range(B):
+        src[i] = base + 3.0 * torch.randn(n, generator=g, device=dev, dtype=torch.float64)
+    mask1 = torch.from_numpy(synth.missing_mask(lat).view(np.uint8)).to(dev)
+    src_mask = mask1.unsqueeze(0).repeat(B, 1).contiguous()
+    src.masked_fill_(src_mask.bool(), synth.GRIB_MV)
+    out_t = torch.empty((B, m), dtype=torch.float64, device=dev)
+    out_m = torch.empty((B, m), dtype=torch.uint8, device=dev)
+
+    def step():
+        table.apply(src, synth.NC_FILL_F64, src_mask=src_mask, mask_policy=L.MASK_PROPAGATE, out=out_t, out_mask=out_m)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = device.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for a, b_ in ev:
+        a.record()
+        step()
+        b_.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = device.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0][0].elapsed_time(ev[-1][1])
+    kern_ms = [a.elapsed_time(b_) for a, b_ in ev]
+    total_ms = parallel.max_over_ranks(total_ms, dev)
+    bytes_launch = algorithmic_bytes_apply(B, n_touched, m, K_INVDIST, True)
+    value = bytes_launch * args.steps * ws / (total_ms * 1e-3) / 1e9
+    avg_kernel_ms = float(np.mean(kern_ms))
+    achieved = bytes_launch / (avg_kernel_ms * 1e-3) / 1e9
+
+    # parity spot check of the timed output against the torch restatement of the reference order
+    rows = torch.randint(0, m, (4096,), generator=g, device=dev)
+    ii = table.idx[:, rows].long()
+    ww = table.coef[:, rows]
+    inside = ii[0] < n
+    acc = ww[0] * src[B // 2][ii[0].clamp(max=n - 1)]
+    for j in range(1, K_INVDIST):
+        acc = acc + ww[j] * src[B // 2][ii[j].clamp(max=n - 1)]
+    got = out_t[B // 2][rows]
+    assert torch.equal(got[inside], acc[inside]), 'timed apply output differs from the reference evaluation order'
+    assert torch.isnan(got[~inside]).all()
+
+    # ---- e2e: host (pinned) messages -> host results through the host-buffer pipeline
+    Be = min(args.e2e_messages, B)
+    h_src = device.pinned_empty((Be, n))
+    h_msk = device.pinned_empty((Be, n), torch.uint8)
+    h_src.copy_(src[:Be])
+    h_msk.copy_(src_mask[:Be])
+    h_out = device.pinned_empty((Be, m))
+    h_om = device.pinned_empty((Be, m), torch.uint8)
+    pipe = device.HostApplyPipeline(table, chunk_messages=args.e2e_chunk, with_mask=True)
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        pipe.run(h_src, synth.NC_FILL_F64, src_mask=h_msk, mask_policy=L.MASK_PROPAGATE, out=h_out, out_mask=h_om)
+        torch.cuda.current_stream().synchronize()      # the caller reads the result on the host
+
+    for _ in range(2):
+        e2e_step()
+    pipe.h2d_bytes = pipe.d2h_bytes = 0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
+    e2e_bytes = algorithmic_bytes_apply(Be, n_touched, m, K_INVDIST, True)
+    e2e_value = e2e_bytes * args.steps * ws / (e2e_ms * 1e-3) / 1e9
+    assert torch.equal(h_out[:Be].to(dev), out_t[:Be]) or torch.allclose(h_out[:Be].to(dev), out_t[:Be], equal_nan=True)
+    e2e = {'value': e2e_value, 'unit': 'GB/s', 'h2d_bytes_per_step': pipe.h2d_bytes // args.steps,
+           'd2h_bytes_per_step': pipe.d2h_bytes // args.steps, 'messages_per_step': Be,
+           'messages_per_s': Be * args.steps * ws / (e2e_ms * 1e-3),
+           'api': 'pyg2p_b200.device.HostApplyPipeline.run (behind Interpolator.interpolate_batch): pinned host '
+                  'messages -> H2D -> g2p_apply -> D2H, double-buffered'}
+    del h_src, h_msk, h_out, h_om, pipe, src, src_mask, out_t, out_m
+    torch.cuda.empty_cache()
+
+    # ---- build phase: O1280 -> GloFAS 0.05 deg invdist k=4, targets sharded by whole rows
+    build = None
+    if not args.skip_build:
+        gl, glo = synth.latlon_target(0.05)
+        M = gl.size
+        lo_i, hi_i = parallel.shard_bounds(M, rank, ws, align=gl.shape[1])
+        d_lon = torch.from_numpy(lon).to(dev)
+        d_lat = torch.from_numpy(lat).to(dev)
+        d_tlo = torch.from_numpy(glo.ravel()[lo_i:hi_i].copy()).to(dev)
+        d_tla = torch.from_numpy(gl.ravel()[lo_i:hi_i].copy()).to(dev)
+
+        def build_once():
+            ixb = device.SourceIndex(d_lon, d_lat, det['radius'])
+            mubb = ixb.min_upper_bound(det['Nj'])
+            o = ixb.knn(d_tlo, d_tla, k=K_INVDIST, mode=L.MODE_INVDIST, mub=mubb, want_flags=True)
+            idx_f, coef_f = parallel.all_gather_table(o['idx'], o['coef'], M)
+            return ixb, o, idx_f, coef_f
+
+        build_once()
+        barrier()
+        reps = 3
+        l0 = device.launch_count()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(reps):
+            ixb, o, idx_f, coef_f = build_once()
+        b1.record()
+        barrier()
+        build_ms = parallel.max_over_ranks(b0.elapsed_time(b1), dev) / reps
+        n_tie = int((o['flags'] & L.FLAG_TIE).ne(0).sum().item())
+        build = {'metric': 'intertable build target-pts/s', 'value': M / (build_ms * 1e-3), 'unit': 'target-pts/s',
+                 'ms_per_build': build_ms, 'targets': M, 'targets_per_gpu': hi_i - lo_i, 'k': K_INVDIST,
+                 'mode': 'invdist', 'scaling': 'strong', 'reps': reps,
+                 'includes': 'lat/lon->xyz, cube-sphere index, self k=2 query + max (min_upper_bound), k-NN, '
+                             'invdist weights' + (', NCCL all-gather of table shards' if ws > 1 else ''),
+                 'gpu_launches_per_build': (device.launch_count() - l0) // reps,
+                 'exact_tie_rows_rank0': n_tie, 'index': ixb.info(),
+                 'workload': 'BASELINE configs[2]: O1280 (6 599 680 pts) -> GloFAS 0.05 deg (7200x3000), invdist k=4'}
+        del ixb, o, idx_f, coef_f
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and ws == 1 and not args.skip_cpu:
+        dt, nbytes, sample = cpu_apply_reference(args.cpu_messages)
+        cpu = {'value': nbytes / dt / 1e9, 'unit': 'GB/s', 'cores': 1, 'kind': 'port',
+               'sample': sample['what'].replace(f'{args.cpu_messages} of', f'{args.cpu_messages} of') +
+               f' ({dt:.1f} s); the reference apply is single-threaded numpy',
+               'messages_per_s': args.cpu_messages / dt}
+        if build is not None:
+            build['cpu_baseline'] = cpu_build_reference()
+
+    if rank == 0:
+        traffic = None
+        tp = os.path.join(REPO, 'profiles', 'apply_traffic.json')
+        if os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            if tj.get('messages') == B:
+                traffic = tj.get('dram_bytes_per_launch')
+        line = {
+            'metric': 'intertable apply GB/s vs HBM roofline', 'value': value, 'unit': 'GB/s', 'n_gpus': ws,
+            'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': total_ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': workload_config(B),
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+                         'frac': achieved / hbm_peak, 'traffic': traffic, 'kernel': 'g2p::apply_kernel<4, true>',
+                         'algorithmic_bytes_per_launch': bytes_launch, 'avg_launch_ms': avg_kernel_ms,
+                         'n_touched': n_touched, 'peak_source': peak_src},
+            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
+            'messages_per_s': B * args.steps * ws / (total_ms * 1e-3),
+            'clocks': clocks, 'wall_s_timed_region': t_wall, 'build': build,
+        }
+        print(json.dumps(line), flush=True)
+    if ws > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--messages', type=int, default=383, help='resident messages per GPU (3060 / 8)')
+    ap.add_argument('--e2e-messages', type=int, default=32)
+    ap.add_argument('--e2e-chunk', type=int, default=4)
+    ap.add_argument('--cpu-messages', type=int, default=96)
+    ap.add_argument('--skip-build', action='store_true')
+    ap.add_argument('--skip-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    ws = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.gpus != ws and ws == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
+               '--master-addr', '127.0.0.1', '--master-port', '29531', os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_b200(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,157 @@
+/*
+ * g2p.h - C ABI of libg2pgpu.so: the B200 (sm_100a) implementation of pyg2p's
+ * data-parallel interpolation path (intertable build + intertable apply).
+ *
+ * The reference (ec-jrc/pyg2p 3.2.8) is pure Python and has no FFI on this path; each
+ * entry point below names the reference code it replaces (paths relative to
+ * src/pyg2p/main/).  The Python host in pyg2p_b200/ binds these with ctypes
+ * (pyg2p_b200/_lib.py); INTEGRATION.md shows the stub a pyg2p maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void*
+ *     (NULL = legacy default stream);
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless the parameter
+ *     is documented as host; buffers are caller-owned (allocate them with torch,
+ *     cudaMalloc, ...); only `g2p_index` is library-owned;
+ *   - calls are asynchronous on `stream` unless they return a scalar to the host;
+ *   - return value: 0 = G2P_OK, negative = error, text via g2p_last_error()
+ *     (thread-local).  There is no CPU fallback: without a CUDA device every compute
+ *     entry point returns G2P_ERR_CUDA / G2P_ERR_NO_DEVICE.
+ *
+ * Device table layout ("SoA table"): indexes int32 [k][m], coeffs float64 [k][m]
+ * (neighbour-major so that a warp reads consecutive targets).  The on-disk intertable
+ * layout of the reference (array of structs {int64 indexes, float64|float32 coeffs},
+ * shape (m,) or (m,k); interpolation/__init__.py:251) is produced/consumed by
+ * g2p_table_pack_rec / g2p_table_unpack_rec.
+ */
+#ifndef G2P_H
+#define G2P_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G2P_VERSION 100
+
+enum {
+  G2P_OK = 0,
+  G2P_ERR_INVALID = -1,     /* bad argument */
+  G2P_ERR_CUDA = -2,        /* CUDA runtime error (message has the CUDA string) */
+  G2P_ERR_NOMEM = -3,
+  G2P_ERR_NO_DEVICE = -4,
+  G2P_ERR_UNSUPPORTED = -5
+};
+
+enum { G2P_F64 = 0, G2P_F32 = 1 };                 /* dtype of lat/lon maps, distances, coeffs */
+enum { G2P_MODE_RAW = 0, G2P_MODE_NEAREST = 1, G2P_MODE_INVDIST = 2 };
+enum { G2P_MASK_AS_REFERENCE = 0, G2P_MASK_PROPAGATE = 1 };
+
+/* per-target flags written by g2p_knn */
+enum {
+  G2P_FLAG_TIE = 1,        /* two of the best k+1 squared distances are exactly equal */
+  G2P_FLAG_NEAR_TIE = 2,   /* ... or differ by less than 2^-44 relative */
+  G2P_FLAG_SHORT = 4       /* fewer than k source points exist: idx = n, dist = +inf (as cKDTree) */
+};
+
+/* `to_regular` rotation of scipy_interpolation_lib.py:673-678 (unit-sphere output); NULL = default branch */
+typedef struct g2p_rotation {
+  double lat_south_pole_deg;
+  double lon_south_pole_deg;
+} g2p_rotation;
+
+typedef struct g2p_index g2p_index; /* source spatial index on one device (replaces the cKDTree, :559) */
+
+typedef struct g2p_index_info {
+  int64_t n;          /* source points */
+  int32_t cells_per_face_side; /* G: the cube-sphere grid is 6 x G x G cells */
+  int64_t n_cells;
+  double radius;      /* sphere radius of the source cloud */
+  double mean_spacing;/* estimated mean point spacing (same unit as radius) */
+  int64_t bytes;      /* device memory held by the index */
+} g2p_index_info;
+
+int g2p_version(void);
+const char* g2p_last_error(void);
+/* number of CUDA devices visible, or a negative error */
+int g2p_device_count(void);
+/* make `device` current for the calling thread (the library links the CUDA runtime statically;
+ * the host calls this with torch's current device before using the other entry points) */
+int g2p_set_device(int device);
+/* kernels launched by this library in the calling process since load (bench.py's gpu_launches) */
+int64_t g2p_launch_count(void);
+
+/* K1  lat/lon -> xyz.  Replaces ScipyInterpolation.to_3d (scipy_interpolation_lib.py:665-696).
+ * lon, lat: n values of `dtype`; xyz_out: (n,3) float64 row-major (float32-rounded values
+ * when dtype == G2P_F32, as the reference casts x,y,z to float32, :691-694). */
+int g2p_latlon_to_xyz(const void* lon, const void* lat, int64_t n, int dtype, double radius,
+                      const g2p_rotation* rot /* host, nullable */, double* xyz_out, void* stream);
+
+/* K1+K2  build the source index.  Replaces `KDTree(source_locations, leafsize=30)`
+ * (scipy_interpolation_lib.py:551-559).  lon/lat: float64[n].  Synchronises `stream`. */
+int g2p_index_create(const double* lon, const double* lat, int64_t n, double radius,
+                     const g2p_rotation* rot /* host, nullable */, g2p_index** out, void* stream);
+/* same, from given xyz (n,3) float64; the points must lie on a sphere centred at the origin */
+int g2p_index_create_xyz(const double* xyz, int64_t n, g2p_index** out, void* stream);
+int g2p_index_destroy(g2p_index* index);
+int g2p_index_get_info(const g2p_index* index, g2p_index_info* info /* host */);
+/* copy the source xyz (n,3), original order, into a caller buffer */
+int g2p_index_get_xyz(const g2p_index* index, double* xyz_out, void* stream);
+
+/* K3+K4  self query k=2 and max-reduce.  Replaces `tree.query(source_locations, k=2)` + `np.max`
+ * (scipy_interpolation_lib.py:568-570).  dmax is a HOST pointer; synchronises `stream`.
+ * min_upper_bound = dmax + dmax*4/Nj is computed by the host (Python float arithmetic). */
+int g2p_index_max_nn_dist(g2p_index* index, double* dmax /* host */, void* stream);
+
+/* K1+K3(+K5)  k nearest source points of every target.
+ * Replaces `tree.query(efas_locations, k=nnear)` (scipy_interpolation_lib.py:624-628) and,
+ * with mode NEAREST / INVDIST, also `_build_nn` (:698-727) / `_build_weights_invdist`
+ * (:774-812, :1018-1026) in the same kernel.
+ *   tlon, tlat : m target coordinates of `dtype` (degrees), or NULL when `txyz` is given
+ *   txyz       : (m,3) float64 target xyz, or NULL
+ *   radius     : `r` of to_3d for the targets (grid_details['radius']); <= 0 = the index's
+ *   k          : 1..16
+ *   mode       : RAW      idx_out = neighbour ids, coef_out = distances (float32-rounded if dtype F32)
+ *                NEAREST  idx_out = id or n_src where dist > mub; coef_out = distance (all rows)
+ *                INVDIST  idx_out/coef_out = ids / normalised 1/d^2 weights, NaN + n_src beyond mub
+ *   idx_out    : int32 [k][m];  coef_out: float64 [k][m];  flags_out: uint8 [m] (nullable)
+ *   xyz_out    : (m,3) float64 target xyz as used by the search (nullable)
+ * Distances use the cKDTree arithmetic ((dx*dx + dy*dy) + dz*dz, sqrt, float64, no FMA); ties are
+ * ordered by lower source index and flagged. */
+int g2p_knn(const g2p_index* index, const void* tlon, const void* tlat, const double* txyz,
+            int64_t m, int dtype, double radius, const g2p_rotation* rot /* host, nullable */, int k, int mode,
+            double mub, int32_t* idx_out, double* coef_out, uint8_t* flags_out, double* xyz_out,
+            void* stream);
+
+/* K5  weights from raw (idx, dist).  Same arithmetic as the fused epilogue of g2p_knn; kept as
+ * its own entry point so the stage can be checked in isolation.  In place on idx / coef. */
+int g2p_weights(int mode, int k, int64_t m, int64_t n_src, double mub, int dtype,
+                int32_t* idx_inout, double* coef_inout, void* stream);
+
+/* K6  SoA table <-> the reference's record layout.  rec: m*k records of
+ * {int64 indexes; float64 coeffs} (16 B) or, coeff_dtype F32, {int64; float32} (12 B, packed). */
+int g2p_table_pack_rec(const int32_t* idx, const double* coef, int64_t m, int k, int coeff_dtype,
+                       void* rec_out, void* stream);
+int g2p_table_unpack_rec(const void* rec, int64_t m, int k, int coeff_dtype, int32_t* idx_out,
+                         double* coef_out, void* stream);
+
+/* K7  batched intertable apply.  Replaces Interpolator._interpolate_scipy_append_mv
+ * (interpolation/__init__.py:142-162) for `b` messages in one launch.
+ *   idx, coef  : SoA table, int32 [k][m], float64 [k][m] (coef may be NULL when k == 1)
+ *   src        : float64, message i at src + i*src_stride, n values each
+ *   src_mask   : uint8 (1 = missing), message i at src_mask + i*src_stride; nullable
+ *   out        : float64, message i at out + i*out_stride, m values each
+ *   out_mask   : uint8, same striding as out; required iff mask_policy == PROPAGATE
+ *   k == 1     : out = src[idx], or mv_out where idx == n (the appended slot, :147)
+ *   k  > 1     : out = ((w0*v0 + w1*v1) + w2*v2) + ..., separate multiply and add
+ *   mask_policy: AS_REFERENCE ignores src_mask (the reference drops it);
+ *                PROPAGATE sets out_mask = OR of the k source masks */
+int g2p_apply(const int32_t* idx, const double* coef, int64_t m, int k, const double* src,
+              const uint8_t* src_mask, int64_t n, int b, int64_t src_stride, int64_t out_stride,
+              double mv_out, int mask_policy, double* out, uint8_t* out_mask, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G2P_H */

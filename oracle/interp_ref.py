@@ -9,6 +9,8 @@ import numpy as np
 import numpy.ma as ma
 from scipy.spatial import cKDTree
 
+from . import libm32
+
 LEAFSIZE = 30  # scipy_interpolation_lib.py:559
 
 
@@ -24,10 +26,11 @@ def to_3d(lons, lats, radius, rotation=None):
     """
     lons = np.radians(lons)
     lats = np.radians(lats)
-    cx = np.cos(lons)
-    sx = np.sin(lons)
-    cy = np.cos(lats)
-    sy = np.sin(lats)
+    # numexpr: float32 operands go through libm sinf/cosf, float64 through libm sin/cos (== numpy's here)
+    cx = libm32.cos(lons)
+    sx = libm32.sin(lons)
+    cy = libm32.cos(lats)
+    sy = libm32.sin(lats)
     if rotation is None:
         r = np.float64(radius)
         x = (r * cx) * cy

@@ -1,0 +1,90 @@
+"""ctypes binding of libg2pgpu.so (C ABI declared in include/g2p.h).
+
+The library is the only compute path of this package: there is no CPU fallback.  If the
+shared object is missing, `lib()` raises with the build command; if a call fails, `check`
+raises `G2PError` carrying the library's message.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libg2pgpu.so')
+
+OK = 0
+F64, F32 = 0, 1
+MODE_RAW, MODE_NEAREST, MODE_INVDIST = 0, 1, 2
+MASK_AS_REFERENCE, MASK_PROPAGATE = 0, 1
+FLAG_TIE, FLAG_NEAR_TIE, FLAG_SHORT = 1, 2, 4
+
+
+class G2PError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f'libg2pgpu error {code}: {message}')
+        self.code = code
+
+
+class Rotation(C.Structure):
+    _fields_ = [('lat_south_pole_deg', C.c_double), ('lon_south_pole_deg', C.c_double)]
+
+
+class IndexInfo(C.Structure):
+    _fields_ = [('n', C.c_int64), ('cells_per_face_side', C.c_int32), ('n_cells', C.c_int64),
+                ('radius', C.c_double), ('mean_spacing', C.c_double), ('bytes', C.c_int64)]
+
+
+_vp, _i64, _i32, _f64 = C.c_void_p, C.c_int64, C.c_int, C.c_double
+_rotp = C.POINTER(Rotation)
+
+# name -> (restype, argtypes); must list every symbol include/g2p.h declares
+PROTOTYPES = {
+    'g2p_version': (C.c_int, []),
+    'g2p_last_error': (C.c_char_p, []),
+    'g2p_device_count': (C.c_int, []),
+    'g2p_set_device': (C.c_int, [_i32]),
+    'g2p_launch_count': (C.c_int64, []),
+    'g2p_latlon_to_xyz': (C.c_int, [_vp, _vp, _i64, _i32, _f64, _rotp, _vp, _vp]),
+    'g2p_index_create': (C.c_int, [_vp, _vp, _i64, _f64, _rotp, C.POINTER(_vp), _vp]),
+    'g2p_index_create_xyz': (C.c_int, [_vp, _i64, C.POINTER(_vp), _vp]),
+    'g2p_index_destroy': (C.c_int, [_vp]),
+    'g2p_index_get_info': (C.c_int, [_vp, C.POINTER(IndexInfo)]),
+    'g2p_index_get_xyz': (C.c_int, [_vp, _vp, _vp]),
+    'g2p_index_max_nn_dist': (C.c_int, [_vp, C.POINTER(C.c_double), _vp]),
+    'g2p_knn': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f64, _rotp, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp]),
+    'g2p_weights': (C.c_int, [_i32, _i32, _i64, _i64, _f64, _i32, _vp, _vp, _vp]),
+    'g2p_table_pack_rec': (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    'g2p_table_unpack_rec': (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    'g2p_apply': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _i32, _i64, _i64, _f64, _i32, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libg2pgpu.so (once).  Raises if it has not been built - never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                f'or `make -C pyg2p_b200/csrc` (nvcc, sm_100a). pyg2p_b200 has no CPU fallback.')
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)      # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        msg = lib().g2p_last_error()
+        raise G2PError(rc, msg.decode('utf-8', 'replace') if msg else '')
+    return rc
+
+
+def rotation_arg(rotation):
+    """(lat_sp, lon_sp) or None -> ctypes pointer (or None)."""
+    if rotation is None:
+        return None
+    return C.byref(Rotation(float(rotation[0]), float(rotation[1])))

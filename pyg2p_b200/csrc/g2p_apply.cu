@@ -1,0 +1,306 @@
+// K6 (table record pack/unpack) and K7 (batched intertable apply) for sm_100a.
+//
+// K7 replaces Interpolator._interpolate_scipy_append_mv (reference
+// src/pyg2p/main/interpolation/__init__.py:142-162), which gathers / einsum's ONE message per
+// call on the CPU.  Here one launch applies the table to `b` messages:
+//   - a thread owns two adjacent targets and keeps their k indexes + k weights in registers,
+//     so every index/weight is loaded once per message chunk, not once per message;
+//   - the message loop is unrolled x4: 4*2*k independent gathers are in flight per thread;
+//   - outputs are written with 128-bit streaming stores (st.global.cs), gathers go through
+//     the read-only path so that neighbouring targets share L1/L2 sectors;
+//   - the grid is persistent (SMs x resident CTAs) and walks (target tile, message chunk)
+//     tiles, target tile fastest, so concurrent CTAs stream one contiguous slab per message.
+// Arithmetic is the reference's load-path order ((w0*v0 + w1*v1) + w2*v2) + w3*v3 with separate
+// IEEE multiply and add (no FMA contraction) -> bit-exact.
+#include "g2p_common.cuh"
+
+namespace g2p {
+
+constexpr int kApplyThreads = 256;
+constexpr int kTargetsPerThread = 2;
+constexpr int kMsgUnroll = 4;
+
+struct ApplyArgs {
+  const int32_t* idx;
+  const double* coef;
+  const double* src;
+  const uint8_t* src_mask;
+  double* out;
+  uint8_t* out_mask;
+  int64_t m, n, src_stride, out_stride;
+  int b, k;
+  int msgs_per_chunk, n_target_tiles;
+  int64_t n_tiles;
+  double mv_out;
+  int vec_store;  // out rows are 16-byte aligned for even targets
+};
+
+template <int K>
+__device__ __forceinline__ double weighted(const double (&w)[K], const double (&v)[K]) {
+  if (K == 1) return v[0];
+  double acc = __dmul_rn(w[0], v[0]);
+#pragma unroll
+  for (int kk = 1; kk < K; ++kk) acc = __dadd_rn(acc, __dmul_rn(w[kk], v[kk]));
+  return acc;
+}
+
+template <int K, bool MASK, int U>
+__device__ __forceinline__ void apply_messages(const ApplyArgs& a, int msg, int64_t j0, bool has1,
+                                               const int32_t (&i0)[K], const int32_t (&i1)[K],
+                                               const double (&w0)[K], const double (&w1)[K]) {
+  double v0[U][K], v1[U][K];
+  uint8_t mk0[U], mk1[U];
+  const uint32_t n = (uint32_t)a.n;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const double* __restrict__ s = a.src + (int64_t)(msg + u) * a.src_stride;
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk) {
+      v0[u][kk] = ((uint32_t)i0[kk] < n) ? __ldg(s + i0[kk]) : a.mv_out;
+      v1[u][kk] = ((uint32_t)i1[kk] < n) ? __ldg(s + i1[kk]) : a.mv_out;
+    }
+    if (MASK) {
+      const uint8_t* __restrict__ sm = a.src_mask + (int64_t)(msg + u) * a.src_stride;
+      uint8_t m0 = 0, m1 = 0;
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk) {
+        if ((uint32_t)i0[kk] < n) m0 |= __ldg(sm + i0[kk]);
+        if ((uint32_t)i1[kk] < n) m1 |= __ldg(sm + i1[kk]);
+      }
+      mk0[u] = m0 ? 1 : 0;
+      mk1[u] = m1 ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    double r0 = weighted<K>(w0, v0[u]);
+    double r1 = weighted<K>(w1, v1[u]);
+    double* o = a.out + (int64_t)(msg + u) * a.out_stride + j0;
+    if (a.vec_store && has1) {
+      __stcs(reinterpret_cast<double2*>(o), make_double2(r0, r1));
+    } else {
+      __stcs(o, r0);
+      if (has1) __stcs(o + 1, r1);
+    }
+    if (MASK) {
+      uint8_t* om = a.out_mask + (int64_t)(msg + u) * a.out_stride + j0;
+      om[0] = mk0[u];
+      if (has1) om[1] = mk1[u];
+    }
+  }
+}
+
+template <int K, bool MASK>
+__global__ void __launch_bounds__(kApplyThreads) apply_kernel(const ApplyArgs a) {
+  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int tt = (int)(tile % a.n_target_tiles);
+    const int mc = (int)(tile / a.n_target_tiles);
+    const int64_t j0 = ((int64_t)tt * kApplyThreads + threadIdx.x) * kTargetsPerThread;
+    if (j0 >= a.m) continue;
+    const bool has1 = (j0 + 1) < a.m;
+    int32_t i0[K], i1[K];
+    double w0[K], w1[K];
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk) {
+      const int64_t p = (int64_t)kk * a.m + j0;
+      i0[kk] = __ldg(a.idx + p);
+      i1[kk] = has1 ? __ldg(a.idx + p + 1) : (int32_t)a.n;
+      if (K > 1) {
+        w0[kk] = __ldg(a.coef + p);
+        w1[kk] = has1 ? __ldg(a.coef + p + 1) : 0.0;
+      } else {
+        w0[kk] = 1.0;
+        w1[kk] = 1.0;
+      }
+    }
+    const int msg_begin = mc * a.msgs_per_chunk;
+    const int msg_end = min(a.b, msg_begin + a.msgs_per_chunk);
+    int msg = msg_begin;
+    for (; msg + kMsgUnroll <= msg_end; msg += kMsgUnroll)
+      apply_messages<K, MASK, kMsgUnroll>(a, msg, j0, has1, i0, i1, w0, w1);
+    for (; msg < msg_end; ++msg) apply_messages<K, MASK, 1>(a, msg, j0, has1, i0, i1, w0, w1);
+  }
+}
+
+// generic k (2..16 other than 4): one target per thread, runtime loop; used for k=3/11 tables
+template <bool MASK>
+__global__ void __launch_bounds__(kApplyThreads) apply_kernel_anyk(const ApplyArgs a) {
+  const int64_t total = a.m * (int64_t)a.b;
+  const uint32_t n = (uint32_t)a.n;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int msg = (int)(t / a.m);
+    const int64_t j = t - (int64_t)msg * a.m;
+    const double* __restrict__ s = a.src + (int64_t)msg * a.src_stride;
+    double acc = 0.0;
+    uint8_t mk = 0;
+    for (int kk = 0; kk < a.k; ++kk) {
+      const int32_t i = __ldg(a.idx + (int64_t)kk * a.m + j);
+      const double w = __ldg(a.coef + (int64_t)kk * a.m + j);
+      const bool in = (uint32_t)i < n;
+      const double v = in ? __ldg(s + i) : a.mv_out;
+      const double p = __dmul_rn(w, v);
+      acc = (kk == 0) ? p : __dadd_rn(acc, p);
+      if (MASK && in) mk |= __ldg(a.src_mask + (int64_t)msg * a.src_stride + i);
+    }
+    __stcs(a.out + (int64_t)msg * a.out_stride + j, acc);
+    if (MASK) a.out_mask[(int64_t)msg * a.out_stride + j] = mk ? 1 : 0;
+  }
+}
+
+template <typename Kern>
+static int resident_ctas(Kern kern) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kApplyThreads, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 2;
+  return per_sm * num_sms();
+}
+
+template <int K, bool MASK>
+static int launch_apply(ApplyArgs a, cudaStream_t st) {
+  static int grid_cap = 0;  // per (K, MASK) instantiation
+  if (grid_cap == 0) grid_cap = resident_ctas(apply_kernel<K, MASK>);
+  a.n_target_tiles = (int)ceil_div(a.m, (int64_t)kApplyThreads * kTargetsPerThread);
+  // enough (target tile x message chunk) tiles for an even spread over the persistent grid,
+  // but chunks as long as possible so the table is re-read (from L2) rarely
+  int64_t want_chunks = ceil_div((int64_t)16 * grid_cap, a.n_target_tiles);
+  int64_t max_chunks = ceil_div(a.b, kMsgUnroll * 2);
+  int64_t n_chunks = want_chunks < 1 ? 1 : (want_chunks > max_chunks ? max_chunks : want_chunks);
+  int per = (int)ceil_div(a.b, n_chunks);
+  per = (int)(ceil_div(per, kMsgUnroll) * kMsgUnroll);
+  a.msgs_per_chunk = per;
+  n_chunks = ceil_div(a.b, per);
+  a.n_tiles = (int64_t)a.n_target_tiles * n_chunks;
+  int grid = (int)(a.n_tiles < grid_cap ? a.n_tiles : grid_cap);
+  apply_kernel<K, MASK><<<grid, kApplyThreads, 0, st>>>(a);
+  G2P_LAUNCHED();
+  return G2P_OK;
+}
+
+template <bool MASK>
+static int launch_apply_anyk(ApplyArgs a, cudaStream_t st) {
+  static int grid_cap = 0;
+  if (grid_cap == 0) grid_cap = resident_ctas(apply_kernel_anyk<MASK>);
+  int64_t blocks = ceil_div(a.m * (int64_t)a.b, kApplyThreads);
+  int grid = (int)(blocks < (int64_t)grid_cap * 4 ? blocks : (int64_t)grid_cap * 4);
+  apply_kernel_anyk<MASK><<<grid, kApplyThreads, 0, st>>>(a);
+  G2P_LAUNCHED();
+  return G2P_OK;
+}
+
+// ------------------------------------------------------------------ K6 pack / unpack
+struct Rec16 {
+  int64_t idx;
+  double coef;
+};
+
+__global__ void pack_rec_kernel(const int32_t* __restrict__ idx, const double* __restrict__ coef, int64_t m, int k,
+                                int coeff_f32, void* __restrict__ rec) {
+  const int64_t total = m * k;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = r / k;
+    const int kk = (int)(r - j * k);
+    const int64_t i = idx[(int64_t)kk * m + j];
+    const double w = coef[(int64_t)kk * m + j];
+    if (!coeff_f32) {
+      Rec16 o;
+      o.idx = i;
+      o.coef = w;
+      reinterpret_cast<Rec16*>(rec)[r] = o;
+    } else {  // packed 12-byte record {int64, float32}: three 4-byte words
+      uint32_t* o = reinterpret_cast<uint32_t*>(rec) + 3 * r;
+      o[0] = (uint32_t)(i & 0xffffffffLL);
+      o[1] = (uint32_t)((uint64_t)i >> 32);
+      o[2] = __float_as_uint((float)w);
+    }
+  }
+}
+
+__global__ void unpack_rec_kernel(const void* __restrict__ rec, int64_t m, int k, int coeff_f32,
+                                  int32_t* __restrict__ idx, double* __restrict__ coef) {
+  const int64_t total = m * k;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = r / k;
+    const int kk = (int)(r - j * k);
+    int64_t i;
+    double w;
+    if (!coeff_f32) {
+      Rec16 in = reinterpret_cast<const Rec16*>(rec)[r];
+      i = in.idx;
+      w = in.coef;
+    } else {
+      const uint32_t* in = reinterpret_cast<const uint32_t*>(rec) + 3 * r;
+      i = (int64_t)(((uint64_t)in[1] << 32) | in[0]);
+      w = (double)__uint_as_float(in[2]);
+    }
+    // indexes are < 2^31 for every GRIB grid; anything else is mapped to -1 (= "no value")
+    idx[(int64_t)kk * m + j] = (i >= 0 && i <= 0x7fffffffLL) ? (int32_t)i : -1;
+    coef[(int64_t)kk * m + j] = w;
+  }
+}
+
+}  // namespace g2p
+
+using namespace g2p;
+
+extern "C" {
+
+int g2p_apply(const int32_t* idx, const double* coef, int64_t m, int k, const double* src, const uint8_t* src_mask,
+              int64_t n, int b, int64_t src_stride, int64_t out_stride, double mv_out, int mask_policy, double* out,
+              uint8_t* out_mask, void* stream) {
+  if (!idx || !src || !out) return set_error(G2P_ERR_INVALID, "g2p_apply: null idx/src/out");
+  if (k < 1 || k > 16) return set_error(G2P_ERR_INVALID, "g2p_apply: k=%d out of range 1..16", k);
+  if (k > 1 && !coef) return set_error(G2P_ERR_INVALID, "g2p_apply: coef is required for k > 1");
+  if (m < 0 || n < 0 || n > 0x7fffffffLL || b < 0) return set_error(G2P_ERR_INVALID, "g2p_apply: bad sizes");
+  if (src_stride < n || out_stride < m) return set_error(G2P_ERR_INVALID, "g2p_apply: strides shorter than rows");
+  const bool mask = (mask_policy == G2P_MASK_PROPAGATE);
+  if (mask_policy != G2P_MASK_PROPAGATE && mask_policy != G2P_MASK_AS_REFERENCE)
+    return set_error(G2P_ERR_INVALID, "g2p_apply: unknown mask_policy %d", mask_policy);
+  if (mask && (!src_mask || !out_mask))
+    return set_error(G2P_ERR_INVALID, "g2p_apply: PROPAGATE needs src_mask and out_mask");
+  if (m == 0 || b == 0) return G2P_OK;
+  ApplyArgs a{};
+  a.idx = idx;
+  a.coef = coef;
+  a.src = src;
+  a.src_mask = src_mask;
+  a.out = out;
+  a.out_mask = out_mask;
+  a.m = m;
+  a.n = n;
+  a.src_stride = src_stride;
+  a.out_stride = out_stride;
+  a.b = b;
+  a.k = k;
+  a.mv_out = mv_out;
+  a.vec_store = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (out_stride % 2 == 0);
+  cudaStream_t st = as_stream(stream);
+  if (k == 1) return mask ? launch_apply<1, true>(a, st) : launch_apply<1, false>(a, st);
+  if (k == 4) return mask ? launch_apply<4, true>(a, st) : launch_apply<4, false>(a, st);
+  return mask ? launch_apply_anyk<true>(a, st) : launch_apply_anyk<false>(a, st);
+}
+
+int g2p_table_pack_rec(const int32_t* idx, const double* coef, int64_t m, int k, int coeff_dtype, void* rec_out,
+                       void* stream) {
+  if (!idx || !coef || !rec_out) return set_error(G2P_ERR_INVALID, "g2p_table_pack_rec: null pointer");
+  if (k < 1 || k > 16 || m < 0) return set_error(G2P_ERR_INVALID, "g2p_table_pack_rec: bad m/k");
+  if (m == 0) return G2P_OK;
+  int64_t blocks = ceil_div(m * k, 256);
+  int grid = (int)(blocks < (int64_t)num_sms() * 16 ? blocks : (int64_t)num_sms() * 16);
+  pack_rec_kernel<<<grid, 256, 0, as_stream(stream)>>>(idx, coef, m, k, coeff_dtype == G2P_F32, rec_out);
+  G2P_LAUNCHED();
+  return G2P_OK;
+}
+
+int g2p_table_unpack_rec(const void* rec, int64_t m, int k, int coeff_dtype, int32_t* idx_out, double* coef_out,
+                         void* stream) {
+  if (!rec || !idx_out || !coef_out) return set_error(G2P_ERR_INVALID, "g2p_table_unpack_rec: null pointer");
+  if (k < 1 || k > 16 || m < 0) return set_error(G2P_ERR_INVALID, "g2p_table_unpack_rec: bad m/k");
+  if (m == 0) return G2P_OK;
+  int64_t blocks = ceil_div(m * k, 256);
+  int grid = (int)(blocks < (int64_t)num_sms() * 16 ? blocks : (int64_t)num_sms() * 16);
+  unpack_rec_kernel<<<grid, 256, 0, as_stream(stream)>>>(rec, m, k, coeff_dtype == G2P_F32, idx_out, coef_out);
+  G2P_LAUNCHED();
+  return G2P_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,988 @@
+// K1-K5: lat/lon -> xyz, cube-sphere source index, k-NN search, min_upper_bound reduce and
+// nearest / invdist weights for sm_100a.
+//
+// Replaces ScipyInterpolation.__init__ / interpolate_split / to_3d / _build_nn /
+// _build_weights_invdist (reference src/pyg2p/main/interpolation/scipy_interpolation_lib.py
+// :523-570, :615-663, :665-696, :698-727, :774-812 + :1018-1026) and the scipy cKDTree they
+// call.  Design:
+//   * source points are binned into an equi-angular cube-sphere grid (6 faces x G x G cells),
+//     counting-sorted by cell key into 32-byte records {x, y, z, id} so one candidate is one
+//     32-byte sector and one row of cells is one contiguous range of records;
+//   * a query is a cap search: for a radius D the cap {p : |p-q| <= D} is bounded, on each
+//     face it can reach, by an (alpha, beta) rectangle computed from the tangent planes through
+//     the face axes; all cells of the rectangles are scanned by a group of LANES threads with
+//     a register-resident sorted top-(k+1) per lane, merged with group shuffles;
+//   * the search ends when the k-th best distance is <= D, so every point that could tie or
+//     beat it has been examined; otherwise D is set to the k-th best (or doubled);
+//   * squared distances are ((dx*dx + dy*dy) + dz*dz) in float64 with separate IEEE ops - the
+//     cKDTree arithmetic - and ordered by (d2, source id).
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "g2p_common.cuh"
+
+namespace g2p {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kQuarterPi = kPi / 4.0;
+constexpr int kMaxG = 2896;  // 6*G*G <= ~50.3M cells
+
+struct __align__(32) Pt {
+  double x, y, z;
+  int32_t id;
+  int32_t pad;
+};
+
+// one candidate record = one 32-byte sector = one 256-bit read-only load (LDG.E.256 on sm_100a)
+__device__ __forceinline__ void load_pt(const Pt* p, double& x, double& y, double& z, int& id) {
+  long long w;
+  asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=l"(w) : "l"(p));
+  id = (int)(w & 0xffffffffLL);
+}
+
+struct Rot {
+  int on;
+  double xx, xy, xz, yx, yy, yz, zx, zz;  // x = (xx*ux + xy*uy) + xz*uz ; y = (yx*ux + yy*uy) - yz*uz ; z = zx*ux + zz*uz
+};
+
+static Rot make_rot(const g2p_rotation* r) {
+  Rot o{};
+  if (!r) return o;
+  // teta = -radians(90 + latSP), fi = -radians(lonSP)  (scipy_interpolation_lib.py:674-675)
+  const double deg = kPi / 180.0;
+  double teta = -((90 + r->lat_south_pole_deg) * deg);
+  double fi = -(r->lon_south_pole_deg * deg);
+  o.on = 1;
+  o.xx = cos(teta) * cos(fi);
+  o.xy = sin(fi);
+  o.xz = sin(teta) * cos(fi);
+  o.yx = cos(teta) * sin(fi);
+  o.yy = cos(fi);
+  o.yz = sin(teta) * sin(fi);
+  o.zx = -sin(teta);
+  o.zz = cos(teta);
+  return o;
+}
+
+// ------------------------------------------------------------------ K1  lat/lon -> xyz
+// f64: radians = deg * (pi/180) in double (numpy deg2rad), libdevice sin/cos, products
+// (r*cos(lon))*cos(lat) left to right with separate multiplies.
+// f32: radians in float32, sin/cos rounded to float32 (see below), promoted to double for the products with the double
+// radius, result rounded to float32 (reference :691-694) and widened again for the search.
+template <bool F32>
+__device__ __forceinline__ void latlon_to_xyz(const void* lon, const void* lat, int64_t i, double radius,
+                                              const Rot& rot, double& x, double& y, double& z) {
+  double cx, sx, cy, sy;
+  if (F32) {
+    const float dr = 0.017453292519943295f;  // float32(pi/180): numpy's deg2radf constant
+    float lo = __fmul_rn(reinterpret_cast<const float*>(lon)[i], dr);
+    float la = __fmul_rn(reinterpret_cast<const float*>(lat)[i], dr);
+    // numexpr evaluates float32 sin/cos with libm's sinf/cosf, which are correctly rounded in ~98.7 % of
+    // the cases; rounding the float64 result reproduces that (libdevice sinf/cosf are 1-2 ulp off)
+    double s, c;
+    sincos((double)lo, &s, &c);
+    cx = (double)(float)c;
+    sx = (double)(float)s;
+    sincos((double)la, &s, &c);
+    cy = (double)(float)c;
+    sy = (double)(float)s;
+  } else {
+    const double dr = 0.017453292519943295;
+    double lo = __dmul_rn(reinterpret_cast<const double*>(lon)[i], dr);
+    double la = __dmul_rn(reinterpret_cast<const double*>(lat)[i], dr);
+    sincos(lo, &sx, &cx);
+    sincos(la, &sy, &cy);
+  }
+  if (!rot.on) {
+    x = __dmul_rn(__dmul_rn(radius, cx), cy);
+    y = __dmul_rn(__dmul_rn(radius, sx), cy);
+    z = __dmul_rn(radius, sy);
+  } else {
+    double ux, uy, uz = sy;
+    if (F32) {  // cos(lons)*cos(lats) is a float32 product in numexpr before meeting the double constants
+      ux = (double)__fmul_rn((float)cx, (float)cy);
+      uy = (double)__fmul_rn((float)sx, (float)cy);
+    } else {
+      ux = __dmul_rn(cx, cy);
+      uy = __dmul_rn(sx, cy);
+    }
+    x = __dadd_rn(__dadd_rn(__dmul_rn(rot.xx, ux), __dmul_rn(rot.xy, uy)), __dmul_rn(rot.xz, uz));
+    y = __dsub_rn(__dadd_rn(__dmul_rn(rot.yx, ux), __dmul_rn(rot.yy, uy)), __dmul_rn(rot.yz, uz));
+    z = __dadd_rn(__dmul_rn(rot.zx, ux), __dmul_rn(rot.zz, uz));
+  }
+  if (F32) {
+    x = (double)(float)x;
+    y = (double)(float)y;
+    z = (double)(float)z;
+  }
+}
+
+template <bool F32>
+__global__ void xyz_kernel(const void* __restrict__ lon, const void* __restrict__ lat, int64_t n, double radius,
+                           Rot rot, double* __restrict__ xyz) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double x, y, z;
+    latlon_to_xyz<F32>(lon, lat, i, radius, rot, x, y, z);
+    xyz[3 * i + 0] = x;
+    xyz[3 * i + 1] = y;
+    xyz[3 * i + 2] = z;
+  }
+}
+
+// ------------------------------------------------------------------ cube-sphere cells
+// face f: axis = f>>1, sign = +1 (f even) / -1 (f odd); local c = sign*p[axis] (> 0 on the face),
+// a = p[(axis+1)%3], b = p[(axis+2)%3]; alpha = atan2(a, c), beta = atan2(b, c) in [-pi/4, pi/4].
+__device__ __forceinline__ void face_local(int f, double x, double y, double z, double& a, double& b, double& c) {
+  const int ax = f >> 1;
+  const double sg = (f & 1) ? -1.0 : 1.0;
+  if (ax == 0) {
+    c = sg * x; a = y; b = z;
+  } else if (ax == 1) {
+    c = sg * y; a = z; b = x;
+  } else {
+    c = sg * z; a = x; b = y;
+  }
+}
+
+__device__ __forceinline__ int dominant_face(double x, double y, double z) {
+  const double fx = fabs(x), fy = fabs(y), fz = fabs(z);
+  if (fx >= fy && fx >= fz) return x >= 0 ? 0 : 1;
+  if (fy >= fz) return y >= 0 ? 2 : 3;
+  return z >= 0 ? 4 : 5;
+}
+
+__device__ __forceinline__ int cell_coord(double ang, int G) {
+  int i = (int)floor((ang + kQuarterPi) * ((double)G / (kPi / 2.0)));
+  return i < 0 ? 0 : (i >= G ? G - 1 : i);
+}
+
+__device__ __forceinline__ uint32_t cell_key(double x, double y, double z, int G) {
+  const int f = dominant_face(x, y, z);
+  double a, b, c;
+  face_local(f, x, y, z, a, b, c);
+  const int ia = cell_coord(atan2(a, c), G);
+  const int ib = cell_coord(atan2(b, c), G);
+  return (uint32_t)((f * G + ib) * G + ia);
+}
+
+__device__ __forceinline__ void atomic_min_pos_double(double* addr, double v) {
+  atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+__device__ __forceinline__ void atomic_max_pos_double(double* addr, double v) {
+  atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// stats[0] = min |p|, stats[1] = max |p| ; coarse occupancy flags for the density estimate
+__global__ void stats_kernel(const double* __restrict__ xyz, int64_t n, int Gc, double* __restrict__ stats,
+                             uint8_t* __restrict__ coarse) {
+  double mn = DBL_MAX, mx = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    const double r = sqrt(x * x + y * y + z * z);
+    if (r == r) {
+      mn = fmin(mn, r);
+      mx = fmax(mx, r);
+      coarse[cell_key(x, y, z, Gc)] = 1;
+    } else {
+      mx = __longlong_as_double(0x7ff0000000000000LL);  // NaN coordinates poison the stats -> rejected by the host
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomic_min_pos_double(&stats[0], mn);
+    atomic_max_pos_double(&stats[1], mx);
+  }
+}
+
+__global__ void key_hist_kernel(const double* __restrict__ xyz, int64_t n, int G, uint32_t* __restrict__ keys,
+                                uint32_t* __restrict__ counts) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t key = cell_key(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], G);
+    keys[i] = key;
+    atomicAdd(&counts[key], 1u);
+  }
+}
+
+// exclusive scan of uint32 counts, three kernels: per-block scan, scan of block sums, add-back
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanBlock = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads) scan_blocks_kernel(const uint32_t* __restrict__ in,
+                                                                   uint32_t* __restrict__ out, int64_t n,
+                                                                   uint32_t* __restrict__ block_sums) {
+  __shared__ uint32_t warp_sums[kScanThreads / 32];
+  const int64_t base = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    v[i] = (base + i < n) ? in[base + i] : 0u;
+    sum += v[i];
+  }
+  uint32_t incl = sum;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = (lane < kScanThreads / 32) ? warp_sums[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    if (lane < kScanThreads / 32) warp_sums[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  uint32_t excl = incl - sum + (warp > 0 ? warp_sums[warp - 1] : 0u);
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    if (base + i < n) out[base + i] = excl;
+    excl += v[i];
+  }
+  if (threadIdx.x == kScanThreads - 1) block_sums[blockIdx.x] = warp_sums[kScanThreads / 32 - 1];
+}
+
+__global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t* __restrict__ block_sums, int nb) {
+  // one CTA; each thread owns a contiguous slice
+  __shared__ uint32_t part[1024];
+  const int per = (nb + 1023) / 1024;
+  const int b0 = threadIdx.x * per;
+  uint32_t s = 0;
+  for (int i = b0; i < b0 + per && i < nb; ++i) s += block_sums[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int i = 0; i < 1024; ++i) {
+      uint32_t t = part[i];
+      part[i] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+  uint32_t run = part[threadIdx.x];
+  for (int i = b0; i < b0 + per && i < nb; ++i) {
+    uint32_t t = block_sums[i];
+    block_sums[i] = run;
+    run += t;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_add_kernel(uint32_t* __restrict__ out, int64_t n,
+                                                                const uint32_t* __restrict__ block_sums,
+                                                                uint32_t* __restrict__ cursor, uint32_t total) {
+  const int64_t base = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * kScanItems;
+  const uint32_t add = block_sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    if (base + i < n) {
+      const uint32_t v = out[base + i] + add;
+      out[base + i] = v;
+      cursor[base + i] = v;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = total;
+}
+
+__global__ void scatter_kernel(const double* __restrict__ xyz, const uint32_t* __restrict__ keys, int64_t n,
+                               uint32_t* __restrict__ cursor, Pt* __restrict__ pts) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t pos = atomicAdd(&cursor[keys[i]], 1u);
+    Pt p;
+    p.x = xyz[3 * i];
+    p.y = xyz[3 * i + 1];
+    p.z = xyz[3 * i + 2];
+    p.id = (int32_t)i;
+    p.pad = 0;
+    pts[pos] = p;
+  }
+}
+
+}  // namespace g2p
+
+struct g2p_index {
+  int device;
+  int64_t n;
+  int G;
+  int64_t n_cells;
+  double radius;        // mean of min/max norm
+  double user_radius;   // radius given to g2p_index_create (to_3d's `r`), 0 if built from xyz
+  double mean_spacing;  // h
+  double* xyz;          // (n,3) original order
+  g2p::Pt* pts;         // counting-sorted by cell key
+  uint32_t* cell_start; // n_cells + 1
+  int64_t bytes;
+};
+
+namespace g2p {
+
+static int grid_for(int64_t n, int threads, int waves = 8) {
+  int64_t blocks = ceil_div(n, threads);
+  int64_t cap = (int64_t)num_sms() * waves;
+  return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+static void free_index(g2p_index* ix) {
+  if (!ix) return;
+  if (ix->xyz) cudaFree(ix->xyz);
+  if (ix->pts) cudaFree(ix->pts);
+  if (ix->cell_start) cudaFree(ix->cell_start);
+  delete ix;
+}
+
+static double env_double(const char* name, double dflt) {
+  const char* s = getenv(name);
+  if (!s || !*s) return dflt;
+  char* end = nullptr;
+  double v = strtod(s, &end);
+  return (end && end != s) ? v : dflt;
+}
+
+// builds cells from ix->xyz (already on device)
+static int build_cells(g2p_index* ix, cudaStream_t st) {
+  const int64_t n = ix->n;
+  // 1. norm range + coarse occupancy (density estimate for regional sources)
+  int Gc = (int)floor(sqrt((double)n / 96.0));
+  Gc = Gc < 1 ? 1 : (Gc > 64 ? 64 : Gc);
+  const int n_coarse = 6 * Gc * Gc;
+  double* d_stats = nullptr;
+  uint8_t* d_coarse = nullptr;
+  G2P_CUDA(cudaMalloc(&d_stats, 2 * sizeof(double)));
+  G2P_CUDA(cudaMalloc(&d_coarse, n_coarse));
+  const double init[2] = {DBL_MAX, 0.0};
+  G2P_CUDA(cudaMemcpyAsync(d_stats, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  G2P_CUDA(cudaMemsetAsync(d_coarse, 0, n_coarse, st));
+  stats_kernel<<<grid_for(n, 256), 256, 0, st>>>(ix->xyz, n, Gc, d_stats, d_coarse);
+  G2P_LAUNCHED();
+  double stats[2];
+  std::vector<uint8_t> coarse(n_coarse);
+  G2P_CUDA(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
+  G2P_CUDA(cudaMemcpyAsync(coarse.data(), d_coarse, n_coarse, cudaMemcpyDeviceToHost, st));
+  G2P_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_stats);
+  cudaFree(d_coarse);
+  const double rmin = stats[0], rmax = stats[1];
+  if (!(rmax > 0.0) || !std::isfinite(rmax) || !(rmin > 0.0))
+    return set_error(G2P_ERR_INVALID, "source coordinates are not finite / not on a sphere (|p| in [%g, %g])", rmin, rmax);
+  if ((rmax - rmin) > 1e-9 * rmax)
+    return set_error(G2P_ERR_UNSUPPORTED,
+                     "source points must lie on a sphere centred at the origin (|p| in [%.17g, %.17g])", rmin, rmax);
+  ix->radius = 0.5 * (rmin + rmax);
+  int64_t n_occ = 0;
+  for (uint8_t c : coarse) n_occ += c;
+  if (n_occ < 1) n_occ = 1;
+  const double covered_sr = (double)n_occ * 4.0 * kPi / (double)n_coarse;
+  ix->mean_spacing = ix->radius * sqrt(covered_sr / (double)n);
+  // 2. grid resolution: about `occ` points per occupied cell
+  const double occ = env_double("G2P_CELL_OCC", 2.0);
+  double g = (double)Gc * sqrt((double)n / (occ * (double)n_occ));
+  int G = (int)floor(g);
+  G = G < 2 ? 2 : (G > kMaxG ? kMaxG : G);
+  ix->G = G;
+  ix->n_cells = 6LL * G * G;
+  // 3. counting sort by cell key
+  uint32_t *d_keys = nullptr, *d_counts = nullptr, *d_cursor = nullptr, *d_bsums = nullptr;
+  const int64_t nc = ix->n_cells;
+  const int nb = (int)ceil_div(nc, kScanBlock);
+  G2P_CUDA(cudaMalloc(&d_keys, (size_t)n * 4));
+  G2P_CUDA(cudaMalloc(&d_counts, (size_t)nc * 4));
+  G2P_CUDA(cudaMalloc(&d_cursor, (size_t)nc * 4));
+  G2P_CUDA(cudaMalloc(&d_bsums, (size_t)nb * 4));
+  G2P_CUDA(cudaMalloc(&ix->cell_start, (size_t)(nc + 1) * 4));
+  G2P_CUDA(cudaMalloc(&ix->pts, (size_t)n * sizeof(Pt)));
+  G2P_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nc * 4, st));
+  key_hist_kernel<<<grid_for(n, 256), 256, 0, st>>>(ix->xyz, n, G, d_keys, d_counts);
+  G2P_LAUNCHED();
+  scan_blocks_kernel<<<nb, kScanThreads, 0, st>>>(d_counts, ix->cell_start, nc, d_bsums);
+  G2P_LAUNCHED();
+  scan_sums_kernel<<<1, 1024, 0, st>>>(d_bsums, nb);
+  G2P_LAUNCHED();
+  scan_add_kernel<<<nb, kScanThreads, 0, st>>>(ix->cell_start, nc, d_bsums, d_cursor, (uint32_t)n);
+  G2P_LAUNCHED();
+  scatter_kernel<<<grid_for(n, 256), 256, 0, st>>>(ix->xyz, d_keys, n, d_cursor, ix->pts);
+  G2P_LAUNCHED();
+  G2P_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_keys);
+  cudaFree(d_counts);
+  cudaFree(d_cursor);
+  cudaFree(d_bsums);
+  ix->bytes = (int64_t)n * 24 + (int64_t)n * sizeof(Pt) + (nc + 1) * 4;
+  return G2P_OK;
+}
+
+// ------------------------------------------------------------------ K3  k-NN search
+struct IndexView {
+  const Pt* pts;
+  const uint32_t* cell_start;
+  int G;
+  int64_t n;
+  double radius, h;
+};
+
+struct KnnArgs {
+  IndexView ix;
+  const void* tlon;
+  const void* tlat;
+  const double* txyz;
+  int64_t m;
+  Rot rot;
+  double xyz_radius;  // radius used by to_3d for the targets (= grid_details['radius'])
+  int k, mode;
+  double mub;
+  int32_t* idx_out;
+  double* coef_out;
+  uint8_t* flags_out;
+  double* xyz_out;
+  double* dmax2_out;         // SELF mode: max over queries of d2[1]
+  unsigned long long* stats; // [0] extra passes, [1] candidates examined (debug counters; nullable)
+};
+
+__device__ __forceinline__ bool lex_lt(double da, int ia, double db, int ib) {
+  return (da < db) || (da == db && ia < ib);
+}
+
+template <int KK>
+struct TopK {
+  double d[KK];
+  int id[KK];
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int s = 0; s < KK; ++s) {
+      d[s] = __longlong_as_double(0x7ff0000000000000LL);
+      id[s] = INT_MAX;
+    }
+  }
+  __device__ __forceinline__ void insert(double nd, int ni) {
+    if (!lex_lt(nd, ni, d[KK - 1], id[KK - 1])) return;
+    d[KK - 1] = nd;
+    id[KK - 1] = ni;
+#pragma unroll
+    for (int s = KK - 1; s > 0; --s) {
+      if (lex_lt(d[s], id[s], d[s - 1], id[s - 1])) {
+        double td = d[s]; d[s] = d[s - 1]; d[s - 1] = td;
+        int ti = id[s]; id[s] = id[s - 1]; id[s - 1] = ti;
+      }
+    }
+  }
+  __device__ __forceinline__ void pop_front() {
+#pragma unroll
+    for (int s = 0; s < KK - 1; ++s) {
+      d[s] = d[s + 1];
+      id[s] = id[s + 1];
+    }
+    d[KK - 1] = __longlong_as_double(0x7ff0000000000000LL);
+    id[KK - 1] = INT_MAX;
+  }
+};
+
+template <int KK, int LANES>
+__device__ __forceinline__ void scan_range(const Pt* __restrict__ pts, uint32_t p0, uint32_t p1, int lane, double qx,
+                                           double qy, double qz, TopK<KK>& top, unsigned& examined) {
+  for (uint32_t p = p0 + lane; p < p1; p += LANES) {
+    double px, py, pz;
+    int id;
+    load_pt(pts + p, px, py, pz, id);
+    const double dx = __dsub_rn(qx, px), dy = __dsub_rn(qy, py), dz = __dsub_rn(qz, pz);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    top.insert(d2, id);
+    ++examined;
+  }
+}
+
+// (alpha or beta) range on one face axis of the cap with sin(gamma) = s around unit q; returns false if empty.
+// L = sqrt(a^2 + c^2) is the length of q's projection on the plane spanned by the axis pair.
+__device__ __forceinline__ bool axis_range(float a, float c, float s, int G, int& lo, int& hi) {
+  const float L = sqrtf(a * a + c * c);
+  float amin = -(float)kQuarterPi, amax = (float)kQuarterPi;
+  if (c > 0.0f && s < 0.70f * L) {
+    const float th = atanf(a / c);
+    const float de = asinf(s / L) * 1.00001f + 4e-6f;  // slack >> float error of th/de, << a cell
+    amin = fmaxf(amin, th - de);
+    amax = fminf(amax, th + de);
+    if (amin > amax) return false;
+  }
+  const double scale = (double)G / (kPi / 2.0);
+  int l = (int)floor(((double)amin + kQuarterPi) * scale);
+  int h = (int)floor(((double)amax + kQuarterPi) * scale);
+  lo = l < 0 ? 0 : (l >= G ? G - 1 : l);
+  hi = h < 0 ? 0 : (h >= G ? G - 1 : h);
+  return true;
+}
+
+// Examine every source point within Euclidean distance D of q (and possibly more).
+template <int KK, int LANES>
+__device__ __forceinline__ void scan_cap(const IndexView& ix, double qx, double qy, double qz, double qnorm, double D,
+                                         int lane, TopK<KK>& top, unsigned& examined, bool& whole) {
+  // |p-q|^2 = R^2 + rho^2 - 2 R rho cos(g)  =>  cos(g) >= c
+  const double R = ix.radius, rho = qnorm;
+  const double c = (R * R + rho * rho - D * D) / (2.0 * R * rho);
+  if (c > 1.0 + 1e-9) return;  // the sphere is farther than D from q
+  if (!(c > 0.82) || !(rho > 0.0)) {
+    // cap wider than ~35 degrees (or a degenerate query): exhaustive scan
+    scan_range<KK, LANES>(ix.pts, 0u, (uint32_t)ix.n, lane, qx, qy, qz, top, examined);
+    whole = true;
+    return;
+  }
+  const double cc = c > 1.0 ? 1.0 : c;
+  const float s = (float)(sqrt(1.0 - cc * cc) * (1.0 + 1e-6)) + 1e-7f;
+  const float gam = asinf(fminf(s, 1.0f));
+  const double inv = 1.0 / rho;
+  const double ux = qx * inv, uy = qy * inv, uz = qz * inv;
+  const int G = ix.G;
+#pragma unroll 1
+  for (int f = 0; f < 6; ++f) {
+    double a, b, cf;
+    face_local(f, ux, uy, uz, a, b, cf);
+    // the face lies within 54.74 deg of its axis: unreachable if angle(q, axis) > gamma + 54.74 deg
+    if ((float)cf < cosf(fminf(gam + 0.9554f, 3.1415926f)) - 1e-5f) continue;
+    int alo, ahi, blo, bhi;
+    if (!axis_range((float)a, (float)cf, s, G, alo, ahi)) continue;
+    if (!axis_range((float)b, (float)cf, s, G, blo, bhi)) continue;
+    for (int ib = blo; ib <= bhi; ++ib) {
+      const int64_t row = ((int64_t)f * G + ib) * G;
+      const uint32_t p0 = __ldg(ix.cell_start + row + alo);
+      const uint32_t p1 = __ldg(ix.cell_start + row + ahi + 1);
+      scan_range<KK, LANES>(ix.pts, p0, p1, lane, qx, qy, qz, top, examined);
+    }
+  }
+}
+
+template <int KK, int LANES>
+__device__ __forceinline__ void merge_group(TopK<KK>& top, unsigned gmask) {
+  if (LANES == 1) return;
+  TopK<KK> res;
+#pragma unroll
+  for (int s = 0; s < KK; ++s) {
+    double bd = top.d[0];
+    int bi = top.id[0];
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(gmask, bd, o);
+      const int oi = __shfl_xor_sync(gmask, bi, o);
+      if (lex_lt(od, oi, bd, bi)) {
+        bd = od;
+        bi = oi;
+      }
+    }
+    res.d[s] = bd;
+    res.id[s] = bi;
+    if (top.id[0] == bi && bi != INT_MAX) top.pop_front();
+  }
+  top = res;
+}
+
+// initial search radius in units of the mean spacing h, by k
+__device__ __forceinline__ double initial_radius_factor(int k) {
+  return k <= 1 ? 0.85 : (k == 2 ? 1.25 : (k <= 4 ? 1.6 : 0.62 * sqrt((double)k) + 0.5));
+}
+
+template <int KK, int LANES>
+__device__ __forceinline__ void knn_search(const IndexView& ix, int k, double qx, double qy, double qz, int lane,
+                                           unsigned gmask, TopK<KK>& top, unsigned& passes, unsigned& examined) {
+  const double qnorm = sqrt(qx * qx + qy * qy + qz * qz);
+  double D = ix.h * initial_radius_factor(k);
+  const double Dmax = 2.0 * (ix.radius + qnorm) + ix.radius;
+  passes = 0;
+  examined = 0;
+  for (;;) {
+    top.reset();
+    bool whole = false;
+    scan_cap<KK, LANES>(ix, qx, qy, qz, qnorm, D, lane, top, examined, whole);
+    merge_group<KK, LANES>(top, gmask);
+    ++passes;
+    const double dk2 = top.d[k - 1];
+    if (whole || dk2 <= D * D) return;
+    if (dk2 < __longlong_as_double(0x7ff0000000000000LL)) {
+      D = sqrt(dk2) * (1.0 + 1e-9);  // k candidates known: the cap through the k-th one is final
+    } else {
+      D *= 2.0;
+      if (D > Dmax) D = Dmax * 4.0;  // forces the exhaustive branch
+    }
+  }
+}
+
+// K5 epilogue arithmetic (also used by weights_kernel).  d[] are float64 distances.
+template <bool F32>
+__device__ __forceinline__ void invdist_weights(const double* d, int k, double mub, double* w, bool& inside) {
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  if (F32) {
+    const float d0 = (float)d[0];
+    if (d0 <= 1e-10f) {
+      for (int j = 0; j < k; ++j) w[j] = (j == 0) ? 1.0 : 0.0;
+      inside = true;
+    } else if ((double)d0 <= mub) {
+      float wf[16];
+      float sum = 0.0f;
+      for (int j = 0; j < k; ++j) {
+        const float dj = (float)d[j];
+        wf[j] = __fdiv_rn(1.0f, __fmul_rn(dj, dj));
+        sum = (j == 0) ? wf[0] : __fadd_rn(sum, wf[j]);
+      }
+      for (int j = 0; j < k; ++j) w[j] = (double)__fdiv_rn(wf[j], sum);
+      inside = true;
+    } else {
+      for (int j = 0; j < k; ++j) w[j] = nan;
+      inside = false;
+    }
+  } else {
+    if (d[0] <= 1e-10) {
+      for (int j = 0; j < k; ++j) w[j] = (j == 0) ? 1.0 : 0.0;
+      inside = true;
+    } else if (d[0] <= mub) {
+      double wd[16];
+      double sum = 0.0;
+      for (int j = 0; j < k; ++j) {
+        wd[j] = __ddiv_rn(1.0, __dmul_rn(d[j], d[j]));
+        sum = (j == 0) ? wd[0] : __dadd_rn(sum, wd[j]);
+      }
+      for (int j = 0; j < k; ++j) w[j] = __ddiv_rn(wd[j], sum);
+      inside = true;
+    } else {
+      for (int j = 0; j < k; ++j) w[j] = nan;
+      inside = false;
+    }
+  }
+}
+
+enum { QUERY_LATLON_F64 = 0, QUERY_LATLON_F32 = 1, QUERY_XYZ = 2, QUERY_SELF = 3 };
+
+template <int KK, int LANES, int QSRC>
+__global__ void __launch_bounds__(256) knn_kernel(const KnnArgs a) {
+  constexpr bool F32 = (QSRC == QUERY_LATLON_F32);
+  const int lane = threadIdx.x % LANES;
+  const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31) / LANES * LANES));
+  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / LANES;
+  const int k = a.k;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  double self_max = 0.0;
+  unsigned long long extra_passes = 0, cand = 0;
+  for (int64_t q = group; q < a.m; q += n_groups) {
+    double qx, qy, qz;
+    if (QSRC == QUERY_SELF) {
+      int self_id;
+      load_pt(a.ix.pts + q, qx, qy, qz, self_id);
+    } else if (QSRC == QUERY_XYZ) {
+      qx = a.txyz[3 * q]; qy = a.txyz[3 * q + 1]; qz = a.txyz[3 * q + 2];
+    } else {
+      latlon_to_xyz<F32>(a.tlon, a.tlat, q, a.xyz_radius, a.rot, qx, qy, qz);
+    }
+    TopK<KK> top;
+    unsigned passes, examined;
+    knn_search<KK, LANES>(a.ix, k, qx, qy, qz, lane, gmask, top, passes, examined);
+    extra_passes += passes - 1;
+    cand += examined;
+    if (QSRC == QUERY_SELF) {
+      // np.max over both columns of the k=2 self query: d[:,0] is 0 (the point itself)
+      const double d2 = top.d[1];
+      if (lane == 0 && d2 > self_max) self_max = d2;
+      continue;
+    }
+    if (lane != 0) continue;
+    if (a.xyz_out) {
+      a.xyz_out[3 * q] = qx; a.xyz_out[3 * q + 1] = qy; a.xyz_out[3 * q + 2] = qz;
+    }
+    uint8_t flag = 0;
+    double dist[KK];
+#pragma unroll
+    for (int s = 0; s < KK; ++s) {
+      if (s < k) {
+        double d = __dsqrt_rn(top.d[s]);
+        if (F32) d = (double)(float)d;
+        dist[s] = d;
+        if (top.id[s] == INT_MAX) flag |= G2P_FLAG_SHORT;
+      }
+      if (s + 1 < KK && s < k && top.d[s + 1] < inf) {
+        if (top.d[s] == top.d[s + 1]) flag |= G2P_FLAG_TIE;
+        else if (top.d[s + 1] - top.d[s] <= top.d[s + 1] * 5.7e-14) flag |= G2P_FLAG_NEAR_TIE;
+      }
+    }
+    if (a.flags_out) a.flags_out[q] = flag;
+    const int32_t nsrc = (int32_t)a.ix.n;
+    if (a.mode == G2P_MODE_RAW) {
+#pragma unroll
+      for (int s = 0; s < KK; ++s)
+        if (s < k) {
+          a.idx_out[(int64_t)s * a.m + q] = (top.id[s] == INT_MAX) ? nsrc : top.id[s];
+          a.coef_out[(int64_t)s * a.m + q] = dist[s];
+        }
+    } else if (a.mode == G2P_MODE_NEAREST) {
+      // _build_nn: idx = ix if dist <= mub else N ; coeffs = distance for every row
+      a.idx_out[q] = (dist[0] <= a.mub && top.id[0] != INT_MAX) ? top.id[0] : nsrc;
+      a.coef_out[q] = dist[0];
+    } else {
+      double w[KK];
+      bool inside;
+      invdist_weights<F32>(dist, k, a.mub, w, inside);
+#pragma unroll
+      for (int s = 0; s < KK; ++s)
+        if (s < k) {
+          a.idx_out[(int64_t)s * a.m + q] = (inside && top.id[s] != INT_MAX) ? top.id[s] : nsrc;
+          a.coef_out[(int64_t)s * a.m + q] = w[s];
+        }
+    }
+  }
+  if (QSRC == QUERY_SELF) {
+    for (int o = 16; o > 0; o >>= 1) self_max = fmax(self_max, __shfl_xor_sync(0xffffffffu, self_max, o));
+    if ((threadIdx.x & 31) == 0) atomic_max_pos_double(a.dmax2_out, self_max);
+  }
+  if (a.stats && lane == 0) {
+    atomicAdd(&a.stats[0], extra_passes);
+    atomicAdd(&a.stats[1], cand);
+  }
+}
+
+// standalone K5
+template <bool F32>
+__global__ void weights_kernel(int mode, int k, int64_t m, int32_t nsrc, double mub, int32_t* __restrict__ idx,
+                               double* __restrict__ coef) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < m; q += (int64_t)gridDim.x * blockDim.x) {
+    if (mode == G2P_MODE_NEAREST) {
+      double d = coef[q];
+      if (F32) d = (double)(float)d;
+      coef[q] = d;
+      if (!(d <= mub)) idx[q] = nsrc;
+    } else {
+      double d[16], w[16];
+      for (int j = 0; j < k; ++j) d[j] = coef[(int64_t)j * m + q];
+      bool inside;
+      invdist_weights<F32>(d, k, mub, w, inside);
+      for (int j = 0; j < k; ++j) {
+        coef[(int64_t)j * m + q] = w[j];
+        if (!inside) idx[(int64_t)j * m + q] = nsrc;
+      }
+    }
+  }
+}
+
+static int knn_lanes() {
+  static int lanes = 0;
+  if (lanes == 0) {
+    int v = (int)env_double("G2P_KNN_LANES", 8);
+    lanes = (v == 1 || v == 4 || v == 8 || v == 32) ? v : 8;
+  }
+  return lanes;
+}
+
+template <int KK, int LANES>
+static int launch_knn_q(const KnnArgs& a, int qsrc, cudaStream_t st) {
+  const int threads = 256;
+  const int64_t groups_per_block = threads / LANES;
+  int64_t blocks = ceil_div(a.m, groups_per_block);
+  int64_t cap = (int64_t)num_sms() * 32;
+  int grid = (int)(blocks < cap ? blocks : cap);
+  switch (qsrc) {
+    case QUERY_LATLON_F64: knn_kernel<KK, LANES, QUERY_LATLON_F64><<<grid, threads, 0, st>>>(a); break;
+    case QUERY_LATLON_F32: knn_kernel<KK, LANES, QUERY_LATLON_F32><<<grid, threads, 0, st>>>(a); break;
+    case QUERY_XYZ: knn_kernel<KK, LANES, QUERY_XYZ><<<grid, threads, 0, st>>>(a); break;
+    default: knn_kernel<KK, LANES, QUERY_SELF><<<grid, threads, 0, st>>>(a); break;
+  }
+  G2P_LAUNCHED();
+  return G2P_OK;
+}
+
+template <int KK>
+static int launch_knn_l(const KnnArgs& a, int qsrc, cudaStream_t st) {
+  switch (knn_lanes()) {
+    case 1: return launch_knn_q<KK, 1>(a, qsrc, st);
+    case 4: return launch_knn_q<KK, 4>(a, qsrc, st);
+    case 32: return launch_knn_q<KK, 32>(a, qsrc, st);
+    default: return launch_knn_q<KK, 8>(a, qsrc, st);
+  }
+}
+
+static int launch_knn(const KnnArgs& a, int qsrc, cudaStream_t st) {
+  const int k = a.k;
+  if (k <= 1) return launch_knn_l<2>(a, qsrc, st);
+  if (k <= 2) return launch_knn_l<3>(a, qsrc, st);
+  if (k <= 4) return launch_knn_l<5>(a, qsrc, st);
+  if (k <= 11) return launch_knn_l<12>(a, qsrc, st);
+  return launch_knn_l<17>(a, qsrc, st);
+}
+
+static IndexView view_of(const g2p_index* ix) {
+  IndexView v;
+  v.pts = ix->pts;
+  v.cell_start = ix->cell_start;
+  v.G = ix->G;
+  v.n = ix->n;
+  v.radius = ix->radius;
+  v.h = ix->mean_spacing;
+  return v;
+}
+
+}  // namespace g2p
+
+using namespace g2p;
+
+extern "C" {
+
+int g2p_latlon_to_xyz(const void* lon, const void* lat, int64_t n, int dtype, double radius, const g2p_rotation* rot,
+                      double* xyz_out, void* stream) {
+  if (!lon || !lat || !xyz_out || n < 0) return set_error(G2P_ERR_INVALID, "g2p_latlon_to_xyz: bad arguments");
+  if (dtype != G2P_F64 && dtype != G2P_F32) return set_error(G2P_ERR_INVALID, "g2p_latlon_to_xyz: bad dtype");
+  if (n == 0) return G2P_OK;
+  Rot r = make_rot(rot);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == G2P_F32)
+    xyz_kernel<true><<<grid_for(n, 256), 256, 0, st>>>(lon, lat, n, radius, r, xyz_out);
+  else
+    xyz_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(lon, lat, n, radius, r, xyz_out);
+  G2P_LAUNCHED();
+  return G2P_OK;
+}
+
+static int index_alloc(int64_t n, g2p_index** out, g2p_index** ixp) {
+  if (!out) return set_error(G2P_ERR_INVALID, "g2p_index_create: out is null");
+  *out = nullptr;
+  if (n < 1 || n > 0x7ffffff0LL) return set_error(G2P_ERR_INVALID, "g2p_index_create: n=%lld out of range", (long long)n);
+  g2p_index* ix = new g2p_index();
+  ix->n = n;
+  G2P_CUDA(cudaGetDevice(&ix->device));
+  cudaError_t e = cudaMalloc(&ix->xyz, (size_t)n * 24);
+  if (e != cudaSuccess) {
+    delete ix;
+    return cuda_fail(e, "cudaMalloc(xyz)", __FILE__, __LINE__);
+  }
+  *ixp = ix;
+  return G2P_OK;
+}
+
+int g2p_index_create(const double* lon, const double* lat, int64_t n, double radius, const g2p_rotation* rot,
+                     g2p_index** out, void* stream) {
+  if (!lon || !lat) return set_error(G2P_ERR_INVALID, "g2p_index_create: null lon/lat");
+  g2p_index* ix = nullptr;
+  int rc = index_alloc(n, out, &ix);
+  if (rc) return rc;
+  ix->user_radius = radius;
+  rc = g2p_latlon_to_xyz(lon, lat, n, G2P_F64, radius, rot, ix->xyz, stream);
+  if (rc == G2P_OK) rc = build_cells(ix, as_stream(stream));
+  if (rc != G2P_OK) {
+    free_index(ix);
+    return rc;
+  }
+  *out = ix;
+  return G2P_OK;
+}
+
+int g2p_index_create_xyz(const double* xyz, int64_t n, g2p_index** out, void* stream) {
+  if (!xyz) return set_error(G2P_ERR_INVALID, "g2p_index_create_xyz: null xyz");
+  g2p_index* ix = nullptr;
+  int rc = index_alloc(n, out, &ix);
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpyAsync(ix->xyz, xyz, (size_t)n * 24, cudaMemcpyDeviceToDevice, as_stream(stream));
+  rc = (e == cudaSuccess) ? build_cells(ix, as_stream(stream)) : cuda_fail(e, "cudaMemcpyAsync(xyz)", __FILE__, __LINE__);
+  if (rc != G2P_OK) {
+    free_index(ix);
+    return rc;
+  }
+  *out = ix;
+  return G2P_OK;
+}
+
+int g2p_index_destroy(g2p_index* index) {
+  free_index(index);
+  return G2P_OK;
+}
+
+int g2p_index_get_info(const g2p_index* ix, g2p_index_info* info) {
+  if (!ix || !info) return set_error(G2P_ERR_INVALID, "g2p_index_get_info: null argument");
+  info->n = ix->n;
+  info->cells_per_face_side = ix->G;
+  info->n_cells = ix->n_cells;
+  info->radius = ix->radius;
+  info->mean_spacing = ix->mean_spacing;
+  info->bytes = ix->bytes;
+  return G2P_OK;
+}
+
+int g2p_index_get_xyz(const g2p_index* ix, double* xyz_out, void* stream) {
+  if (!ix || !xyz_out) return set_error(G2P_ERR_INVALID, "g2p_index_get_xyz: null argument");
+  G2P_CUDA(cudaMemcpyAsync(xyz_out, ix->xyz, (size_t)ix->n * 24, cudaMemcpyDeviceToDevice, as_stream(stream)));
+  return G2P_OK;
+}
+
+int g2p_index_max_nn_dist(g2p_index* ix, double* dmax, void* stream) {
+  if (!ix || !dmax) return set_error(G2P_ERR_INVALID, "g2p_index_max_nn_dist: null argument");
+  cudaStream_t st = as_stream(stream);
+  double* d_max = nullptr;
+  G2P_CUDA(cudaMalloc(&d_max, sizeof(double)));
+  G2P_CUDA(cudaMemsetAsync(d_max, 0, sizeof(double), st));
+  KnnArgs a{};
+  a.ix = view_of(ix);
+  a.m = ix->n;
+  a.k = 2;
+  a.mode = G2P_MODE_RAW;
+  a.dmax2_out = d_max;
+  int rc = launch_knn(a, QUERY_SELF, st);
+  double d2 = 0.0;
+  if (rc == G2P_OK) {
+    cudaError_t e = cudaMemcpyAsync(&d2, d_max, sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "max_nn_dist readback", __FILE__, __LINE__);
+  }
+  cudaFree(d_max);
+  if (rc != G2P_OK) return rc;
+  *dmax = sqrt(d2);  // sqrt is monotone and correctly rounded: sqrt(max d2) == max sqrt(d2)
+  return G2P_OK;
+}
+
+int g2p_knn(const g2p_index* ix, const void* tlon, const void* tlat, const double* txyz, int64_t m, int dtype,
+            double radius, const g2p_rotation* rot, int k, int mode, double mub, int32_t* idx_out, double* coef_out,
+            uint8_t* flags_out, double* xyz_out, void* stream) {
+  if (!ix || !idx_out || !coef_out) return set_error(G2P_ERR_INVALID, "g2p_knn: null index/outputs");
+  if (!txyz && (!tlon || !tlat)) return set_error(G2P_ERR_INVALID, "g2p_knn: give tlon+tlat or txyz");
+  if (k < 1 || k > 16) return set_error(G2P_ERR_INVALID, "g2p_knn: k=%d out of range 1..16", k);
+  if (dtype != G2P_F64 && dtype != G2P_F32) return set_error(G2P_ERR_INVALID, "g2p_knn: bad dtype");
+  if (mode != G2P_MODE_RAW && mode != G2P_MODE_NEAREST && mode != G2P_MODE_INVDIST)
+    return set_error(G2P_ERR_INVALID, "g2p_knn: bad mode %d", mode);
+  if (mode == G2P_MODE_NEAREST && k != 1) return set_error(G2P_ERR_INVALID, "g2p_knn: NEAREST needs k == 1");
+  if (m < 0) return set_error(G2P_ERR_INVALID, "g2p_knn: m < 0");
+  if (m == 0) return G2P_OK;
+  KnnArgs a{};
+  a.ix = view_of(ix);
+  a.tlon = tlon;
+  a.tlat = tlat;
+  a.txyz = txyz;
+  a.m = m;
+  a.rot = make_rot(rot);
+  a.xyz_radius = radius > 0.0 ? radius : (ix->user_radius > 0.0 ? ix->user_radius : ix->radius);
+  a.k = k;
+  a.mode = mode;
+  a.mub = mub;
+  a.idx_out = idx_out;
+  a.coef_out = coef_out;
+  a.flags_out = flags_out;
+  a.xyz_out = xyz_out;
+  int qsrc = txyz ? QUERY_XYZ : (dtype == G2P_F32 ? QUERY_LATLON_F32 : QUERY_LATLON_F64);
+  return launch_knn(a, qsrc, as_stream(stream));
+}
+
+int g2p_weights(int mode, int k, int64_t m, int64_t n_src, double mub, int dtype, int32_t* idx, double* coef,
+                void* stream) {
+  if (!idx || !coef) return set_error(G2P_ERR_INVALID, "g2p_weights: null pointer");
+  if (mode != G2P_MODE_NEAREST && mode != G2P_MODE_INVDIST) return set_error(G2P_ERR_INVALID, "g2p_weights: bad mode");
+  if (k < 1 || k > 16 || (mode == G2P_MODE_NEAREST && k != 1)) return set_error(G2P_ERR_INVALID, "g2p_weights: bad k");
+  if (m <= 0) return G2P_OK;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == G2P_F32)
+    weights_kernel<true><<<grid_for(m, 256), 256, 0, st>>>(mode, k, m, (int32_t)n_src, mub, idx, coef);
+  else
+    weights_kernel<false><<<grid_for(m, 256), 256, 0, st>>>(mode, k, m, (int32_t)n_src, mub, idx, coef);
+  G2P_LAUNCHED();
+  return G2P_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,403 @@
+"""Device-side objects of the interpolation path: source index, k-NN/weights build, SoA
+intertable and batched apply.  Thin host code over the C ABI in include/g2p.h; torch is used
+for device memory, pinned staging buffers and streams only.
+
+There is no CPU fallback: every function here needs libg2pgpu.so and a CUDA device and
+raises otherwise.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+_NP_DTYPE_CODE = {np.dtype('float64'): L.F64, np.dtype('float32'): L.F32}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError('pyg2p_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    return L.lib()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _bind_device(device):
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.index is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+    L.check(L.lib().g2p_set_device(dev.index))
+    return dev
+
+
+def to_device(a, dtype=None, device=None):
+    """numpy array / tensor -> contiguous device tensor (no copy if already there)."""
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        a = np.ascontiguousarray(np.ma.getdata(a))
+        t = torch.from_numpy(a)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.to(device, non_blocking=False).contiguous()
+
+
+class SourceIndex:
+    """Cube-sphere spatial index over the source (GRIB) points on one GPU.
+
+    Replaces `KDTree(source_locations, leafsize=30)` of ScipyInterpolation.__init__
+    (reference scipy_interpolation_lib.py:551-559).
+    """
+
+    def __init__(self, lon=None, lat=None, radius=None, rotation=None, xyz=None, device=None):
+        lib = require_cuda()
+        self.device = _bind_device(device)
+        self._h = C.c_void_p()
+        self._lib = lib
+        with torch.cuda.device(self.device):
+            if xyz is not None:
+                x = to_device(xyz, torch.float64, self.device).reshape(-1, 3)
+                self.n = x.shape[0]
+                L.check(lib.g2p_index_create_xyz(_ptr(x), self.n, C.byref(self._h), _stream()))
+            else:
+                lo = to_device(np.asarray(lon).ravel() if not isinstance(lon, torch.Tensor) else lon.reshape(-1),
+                               torch.float64, self.device)
+                la = to_device(np.asarray(lat).ravel() if not isinstance(lat, torch.Tensor) else lat.reshape(-1),
+                               torch.float64, self.device)
+                if lo.numel() != la.numel():
+                    raise ValueError('lon/lat length mismatch')
+                self.n = lo.numel()
+                L.check(lib.g2p_index_create(_ptr(lo), _ptr(la), self.n, float(radius), L.rotation_arg(rotation),
+                                             C.byref(self._h), _stream()))
+        self.radius = radius
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self._lib.g2p_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        inf = L.IndexInfo()
+        L.check(self._lib.g2p_index_get_info(self._h, C.byref(inf)))
+        return {f: getattr(inf, f) for f, _ in L.IndexInfo._fields_}
+
+    def xyz(self):
+        """(n,3) float64 device tensor: source xyz in original order (to_3d output, :551-552)."""
+        _bind_device(self.device)
+        with torch.cuda.device(self.device):
+            out = torch.empty((self.n, 3), dtype=torch.float64, device=self.device)
+            L.check(self._lib.g2p_index_get_xyz(self._h, _ptr(out), _stream()))
+        return out
+
+    def max_nn_dist(self):
+        """max over sources of the distance to the nearest OTHER source (k=2 self query + np.max,
+        reference :568-570)."""
+        _bind_device(self.device)
+        d = C.c_double()
+        with torch.cuda.device(self.device):
+            L.check(self._lib.g2p_index_max_nn_dist(self._h, C.byref(d), _stream()))
+        return d.value
+
+    def min_upper_bound(self, nj):
+        """`dmax + dmax*4/Nj` in Python float arithmetic, as the reference (:570)."""
+        dmax = self.max_nn_dist()
+        return dmax + dmax * 4 / nj
+
+    def knn(self, tlon=None, tlat=None, k=1, mode=L.MODE_RAW, mub=0.0, radius=None, rotation=None, txyz=None,
+            want_flags=True, want_xyz=False):
+        """k nearest sources of every target; returns dict(idx int32 [k,m], coef f64 [k,m], flags u8 [m], xyz).
+
+        tlon/tlat: numpy arrays or device tensors, float64 or float32 (PCRaster REAL4 maps keep
+        float32: the reference then rounds xyz and distances to float32, :627-628, :691-694)."""
+        _bind_device(self.device)
+        with torch.cuda.device(self.device):
+            if txyz is not None:
+                tx = to_device(txyz, torch.float64, self.device).reshape(-1, 3)
+                m = tx.shape[0]
+                lo = la = None
+                code = L.F64
+            else:
+                lo = to_device(tlon, None, self.device).reshape(-1)
+                la = to_device(tlat, None, self.device).reshape(-1)
+                if lo.dtype != la.dtype or lo.dtype not in (torch.float64, torch.float32):
+                    lo = lo.to(torch.float64)
+                    la = la.to(torch.float64)
+                if lo.numel() != la.numel():
+                    raise ValueError('target lon/lat length mismatch')
+                m = lo.numel()
+                code = L.F32 if lo.dtype == torch.float32 else L.F64
+                tx = None
+            idx = torch.empty((k, m), dtype=torch.int32, device=self.device)
+            coef = torch.empty((k, m), dtype=torch.float64, device=self.device)
+            flags = torch.empty((m,), dtype=torch.uint8, device=self.device) if want_flags else None
+            xyz = torch.empty((m, 3), dtype=torch.float64, device=self.device) if want_xyz else None
+            r = float(radius) if radius is not None else (float(self.radius) if self.radius else 0.0)
+            L.check(self._lib.g2p_knn(self._h, _ptr(lo), _ptr(la), _ptr(tx), m, code, r, L.rotation_arg(rotation),
+                                      int(k), int(mode), float(mub), _ptr(idx), _ptr(coef), _ptr(flags), _ptr(xyz),
+                                      _stream()))
+        return {'idx': idx, 'coef': coef, 'flags': flags, 'xyz': xyz, 'coef_dtype': code}
+
+
+def weights(mode, idx, coef, n_src, mub, dtype_code=L.F64):
+    """Standalone K5 (in place on idx/coef): raw (idx, dist) -> nearest / invdist table."""
+    lib = require_cuda()
+    _bind_device(idx.device)
+    k, m = idx.shape
+    with torch.cuda.device(idx.device):
+        L.check(lib.g2p_weights(int(mode), int(k), int(m), int(n_src), float(mub), int(dtype_code), _ptr(idx),
+                                _ptr(coef), _stream()))
+    return idx, coef
+
+
+def latlon_to_xyz(lon, lat, radius, rotation=None, device=None):
+    """K1: `to_3d` (reference scipy_interpolation_lib.py:665-696) on the device; (n,3) float64."""
+    lib = require_cuda()
+    dev = _bind_device(device)
+    with torch.cuda.device(dev):
+        lo = to_device(lon, None, dev).reshape(-1)
+        la = to_device(lat, None, dev).reshape(-1)
+        code = L.F32 if lo.dtype == torch.float32 else L.F64
+        if code == L.F64:
+            lo, la = lo.to(torch.float64), la.to(torch.float64)
+        out = torch.empty((lo.numel(), 3), dtype=torch.float64, device=dev)
+        L.check(lib.g2p_latlon_to_xyz(_ptr(lo), _ptr(la), lo.numel(), code, float(radius), L.rotation_arg(rotation),
+                                      _ptr(out), _stream()))
+    return out
+
+
+REC_F8 = np.dtype([('indexes', '<i8'), ('coeffs', '<f8')])
+REC_F4 = np.dtype([('indexes', '<i8'), ('coeffs', '<f4')])
+
+
+class DeviceTable:
+    """Intertable resident in HBM as SoA: idx int32 [k][m], coef float64 [k][m].
+
+    On disk / at the Python boundary the reference layout is kept: structured array
+    {int64 indexes, f8|f4 coeffs}, shape (m,) for k=1 and (m,k) otherwise
+    (reference interpolation/__init__.py:251)."""
+
+    def __init__(self, idx, coef, n_src, coef_f32=False, shape_1d=None):
+        self.idx = idx
+        self.coef = coef
+        self.k, self.m = idx.shape
+        self.n_src = int(n_src)
+        self.coef_f32 = bool(coef_f32)
+        self.shape_1d = (self.k == 1) if shape_1d is None else shape_1d
+        self.device = idx.device
+
+    # ---- record layout
+    @classmethod
+    def from_record(cls, rec, n_src, device=None):
+        """structured array as loaded from an intertable file -> device SoA (K6 unpack)."""
+        lib = require_cuda()
+        dev = _bind_device(device)
+        rec = np.asarray(rec)
+        if rec.dtype.names != ('indexes', 'coeffs'):
+            raise ValueError(f'not an intertable record dtype: {rec.dtype}')
+        f32 = rec.dtype['coeffs'] == np.dtype('<f4')
+        want = REC_F4 if f32 else REC_F8
+        if rec.dtype != want:
+            rec = rec.astype(want)
+        rec = np.ascontiguousarray(rec)
+        one_d = rec.ndim == 1
+        m = rec.shape[0]
+        k = 1 if one_d else rec.shape[1]
+        with torch.cuda.device(dev):
+            raw = torch.from_numpy(rec.view(np.uint8).reshape(-1)).to(dev)
+            idx = torch.empty((k, m), dtype=torch.int32, device=dev)
+            coef = torch.empty((k, m), dtype=torch.float64, device=dev)
+            L.check(lib.g2p_table_unpack_rec(_ptr(raw), m, k, L.F32 if f32 else L.F64, _ptr(idx), _ptr(coef),
+                                               _stream()))
+            torch.cuda.current_stream().synchronize()
+        return cls(idx, coef, n_src, coef_f32=f32, shape_1d=one_d)
+
+    def to_record(self):
+        """device SoA -> numpy structured array in the reference's file layout (K6 pack + D2H)."""
+        lib = require_cuda()
+        _bind_device(self.device)
+        dt = REC_F4 if self.coef_f32 else REC_F8
+        with torch.cuda.device(self.device):
+            raw = torch.empty((self.m * self.k * dt.itemsize,), dtype=torch.uint8, device=self.device)
+            L.check(lib.g2p_table_pack_rec(_ptr(self.idx), _ptr(self.coef), self.m, self.k,
+                                           L.F32 if self.coef_f32 else L.F64, _ptr(raw), _stream()))
+            host = raw.cpu().numpy()
+        rec = host.view(dt)
+        return rec.reshape((self.m,) if self.shape_1d else (self.m, self.k))
+
+    def indexes_coeffs(self):
+        """(indexes int64, coeffs) numpy arrays shaped like ScipyInterpolation.interpolate's output."""
+        rec = self.to_record()
+        return np.ascontiguousarray(rec['indexes']), np.ascontiguousarray(rec['coeffs'])
+
+    # ---- apply
+    def apply(self, src, mv_out, src_mask=None, mask_policy=L.MASK_AS_REFERENCE, out=None, out_mask=None):
+        """Batched K7 on device-resident messages.  src: float64 [b, n] (or [n]); returns out [b, m]
+        (and out_mask uint8 [b, m] under PROPAGATE).  Asynchronous on the current stream."""
+        lib = require_cuda()
+        _bind_device(self.device)
+        squeeze = src.dim() == 1
+        if squeeze:
+            src = src.unsqueeze(0)
+            src_mask = src_mask.unsqueeze(0) if src_mask is not None else None
+        if src.dtype != torch.float64 or src.device != self.device:
+            raise ValueError('src must be a float64 tensor on the table device')
+        b, n = src.shape
+        if n != self.n_src:
+            raise ValueError(f'source field has {n} values, intertable was built for {self.n_src}')
+        if src.stride(1) != 1:
+            src = src.contiguous()
+        propagate = mask_policy == L.MASK_PROPAGATE
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty((b, self.m), dtype=torch.float64, device=self.device)
+            if propagate:
+                if src_mask is None:
+                    raise ValueError('PROPAGATE needs src_mask')
+                if src_mask.dtype == torch.bool:
+                    src_mask = src_mask.view(torch.uint8)
+                if src_mask.stride(1) != 1 or src_mask.stride(0) != src.stride(0):
+                    # the C ABI uses one stride for values and masks
+                    src = src.contiguous()
+                    src_mask = src_mask.contiguous()
+                if out_mask is None:
+                    out_mask = torch.empty((b, self.m), dtype=torch.uint8, device=self.device)
+            if b > 0 and self.m > 0:
+                L.check(lib.g2p_apply(_ptr(self.idx), _ptr(self.coef) if self.k > 1 else None, self.m, self.k, _ptr(src),
+                                      _ptr(src_mask) if propagate else None, n, b, src.stride(0), out.stride(0),
+                                      float(mv_out), int(mask_policy), _ptr(out), _ptr(out_mask) if propagate else None,
+                                      _stream()))
+        if squeeze:
+            out = out[0]
+            out_mask = out_mask[0] if out_mask is not None else None
+        return (out, out_mask) if propagate else out
+
+
+def launch_count():
+    return int(L.lib().g2p_launch_count())
+
+
+def pinned_empty(shape, dtype=torch.float64):
+    """Page-locked host buffer (torch tensor; `.numpy()` gives a zero-copy ndarray view).  The GRIB
+    decoder writes message values here so that the H2D copy is a plain async DMA."""
+    require_cuda()
+    return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
+class HostApplyPipeline:
+    """Host-buffer front end of K7: messages in (pinned) host memory -> interpolated fields in pinned
+    host memory, chunked and double-buffered so that H2D, the apply kernel and D2H overlap.
+
+    This is the path behind `Interpolator.interpolate_batch`; the bench's `e2e` number times it."""
+
+    def __init__(self, table, chunk_messages=8, with_mask=False):
+        self.t = table
+        self.c = int(chunk_messages)
+        self.with_mask = bool(with_mask)
+        dev = table.device
+        n, m = table.n_src, table.m
+        with torch.cuda.device(dev):
+            self.d_src = [torch.empty((self.c, n), dtype=torch.float64, device=dev) for _ in range(2)]
+            self.d_out = [torch.empty((self.c, m), dtype=torch.float64, device=dev) for _ in range(2)]
+            self.d_msk = [torch.empty((self.c, n), dtype=torch.uint8, device=dev) for _ in range(2)] if with_mask else None
+            self.d_omk = [torch.empty((self.c, m), dtype=torch.uint8, device=dev) for _ in range(2)] if with_mask else None
+            self.s_in = torch.cuda.Stream(device=dev)
+            self.s_out = torch.cuda.Stream(device=dev)
+        self._stage = None          # pinned staging for pageable inputs, allocated on first use
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _staged(self, host, lo, hi, which):
+        """pageable numpy rows -> pinned staging slot (CPU memcpy); pinned tensors pass through."""
+        if isinstance(host, torch.Tensor):
+            return host[lo:hi]
+        if self._stage is None:
+            self._stage = {}
+        key = (which, host.dtype.str)
+        if key not in self._stage:
+            tdt = torch.float64 if host.dtype == np.float64 else torch.uint8
+            self._stage[key] = [pinned_empty((self.c, host.shape[1]), tdt) for _ in range(2)]
+        slot = self._stage[key][(lo // self.c) % 2]
+        view = slot[:hi - lo]
+        view.numpy()[...] = host[lo:hi]
+        return view
+
+    def run(self, src, mv_out, src_mask=None, mask_policy=L.MASK_AS_REFERENCE, out=None, out_mask=None):
+        """src: [b, n] float64 pinned tensor (or ndarray); src_mask: [b, n] uint8/bool or None.
+        Returns (out [b, m] pinned tensor, out_mask [b, m] pinned uint8 tensor or None)."""
+        t = self.t
+        propagate = mask_policy == L.MASK_PROPAGATE
+        if propagate and not self.with_mask:
+            raise ValueError('pipeline was created without mask buffers')
+        b = src.shape[0]
+        if src.shape[1] != t.n_src:
+            raise ValueError(f'source field has {src.shape[1]} values, intertable was built for {t.n_src}')
+        if isinstance(src_mask, np.ndarray) and src_mask.dtype == np.bool_:
+            src_mask = src_mask.view(np.uint8)
+        if isinstance(src_mask, torch.Tensor) and src_mask.dtype == torch.bool:
+            src_mask = src_mask.view(torch.uint8)
+        if out is None:
+            out = pinned_empty((b, t.m))
+        if propagate and out_mask is None:
+            out_mask = pinned_empty((b, t.m), torch.uint8)
+        cur = torch.cuda.current_stream(t.device)
+        ev_in = [None, None]
+        ev_k = [None, None]
+        ev_out = [None, None]
+        start = torch.cuda.Event()
+        start.record(cur)
+        self.s_in.wait_event(start)
+        self.s_out.wait_event(start)
+        for ci, lo in enumerate(range(0, b, self.c)):
+            hi = min(b, lo + self.c)
+            s = ci % 2
+            nb = hi - lo
+            if ev_in[s] is not None and not isinstance(src, torch.Tensor):
+                ev_in[s].synchronize()                     # staging slot is free again
+            hs = self._staged(src, lo, hi, 'v')
+            hm = self._staged(src_mask, lo, hi, 'm') if propagate else None
+            with torch.cuda.stream(self.s_in):
+                if ev_k[s] is not None:
+                    self.s_in.wait_event(ev_k[s])          # slot's previous kernel has consumed its input
+                self.d_src[s][:nb].copy_(hs, non_blocking=True)
+                self.h2d_bytes += hs.numel() * 8
+                if propagate:
+                    self.d_msk[s][:nb].copy_(hm, non_blocking=True)
+                    self.h2d_bytes += hm.numel()
+                ev_in[s] = torch.cuda.Event()
+                ev_in[s].record(self.s_in)
+            cur.wait_event(ev_in[s])
+            if ev_out[s] is not None:
+                cur.wait_event(ev_out[s])                  # slot's previous output has left the device
+            if propagate:
+                t.apply(self.d_src[s][:nb], mv_out, src_mask=self.d_msk[s][:nb], mask_policy=mask_policy,
+                        out=self.d_out[s][:nb], out_mask=self.d_omk[s][:nb])
+            else:
+                t.apply(self.d_src[s][:nb], mv_out, out=self.d_out[s][:nb])
+            ev_k[s] = torch.cuda.Event()
+            ev_k[s].record(cur)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(ev_k[s])
+                out[lo:hi].copy_(self.d_out[s][:nb], non_blocking=True)
+                self.d2h_bytes += nb * t.m * 8
+                if propagate:
+                    out_mask[lo:hi].copy_(self.d_omk[s][:nb], non_blocking=True)
+                    self.d2h_bytes += nb * t.m
+                ev_out[s] = torch.cuda.Event()
+                ev_out[s].record(self.s_out)
+        for e in ev_out:
+            if e is not None:
+                cur.wait_event(e)
+        return out, (out_mask if propagate else None)

@@ -1,0 +1,81 @@
+"""Multi-GPU sharding of the interpolation path (one process per GPU, torch.distributed).
+
+* intertable BUILD: the source index is replicated, target points are split into contiguous
+  blocks (the reference's `num_of_splits` row chunks, scipy_interpolation_lib.py:588-607, become
+  the rank partition); the only exchange is one all-gather of the finished table shards - and only
+  when every rank needs the whole table (NCCL over NVLink on GPUs, gloo in the CPU tests).
+* intertable APPLY: messages (step x ensemble member) are split by MEMBER so that the accumulation
+  V[t] - V[t-D] of one member stays on one GPU; no collective at all.
+
+Nothing here computes on the CPU: the functions take and return tensors on whatever device the
+process group works on.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(total, rank, world_size, align=1):
+    """[lo, hi) of `rank`'s contiguous block of `total` items; block starts are multiples of `align`
+    (e.g. the number of columns, to split whole target rows).  Blocks differ by at most one unit."""
+    units = -(-total // align)
+    base, rem = divmod(units, world_size)
+    lo_u = rank * base + min(rank, rem)
+    hi_u = lo_u + base + (1 if rank < rem else 0)
+    return min(lo_u * align, total), min(hi_u * align, total)
+
+
+def members_of_rank(n_members, rank, world_size):
+    """round-robin ensemble members -> rank (all steps of one member stay together)."""
+    return list(range(rank, n_members, world_size))
+
+
+def all_gather_table(idx_shard, coef_shard, m_total, group=None):
+    """Assemble SoA table shards ([k, m_r] per rank, contiguous target blocks in rank order) into the
+    full [k, m_total] table on every rank.  Shards may be ragged: they are padded to the largest."""
+    rank, ws = world()
+    if ws == 1:
+        return idx_shard, coef_shard
+    k, m_r = idx_shard.shape
+    sizes = torch.tensor([m_r], dtype=torch.int64, device=idx_shard.device)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(ws)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    all_sizes = [int(s.item()) for s in all_sizes]
+    if sum(all_sizes) != m_total:
+        raise ValueError(f'table shards cover {sum(all_sizes)} targets, expected {m_total}')
+    m_max = max(all_sizes)
+
+    def gather(shard):
+        pad = shard
+        if m_r != m_max:
+            pad = shard.new_zeros((k, m_max))
+            pad[:, :m_r] = shard
+        buf = shard.new_empty((ws, k, m_max))
+        dist.all_gather_into_tensor(buf, pad.contiguous(), group=group)
+        if all(s == m_max for s in all_sizes):
+            return buf.permute(1, 0, 2).reshape(k, ws * m_max)
+        return torch.cat([buf[r, :, :all_sizes[r]] for r in range(ws)], dim=1).contiguous()
+
+    return gather(idx_shard), gather(coef_shard)
+
+
+def max_over_ranks(value, device):
+    """device-timed duration -> max over ranks (the contract for every multi-GPU number)."""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    rank, ws = world()
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value, device):
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    rank, ws = world()
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())

@@ -82,7 +82,8 @@ def _ne_evaluate(expr, local_dict=None, global_dict=None, out=None, **kw):
     names = dict(frame.f_globals if global_dict is None else global_dict)
     names.update(frame.f_locals if local_dict is None else local_dict)
     tree = ast.fix_missing_locations(_Const().visit(ast.parse(expr, mode='eval')))
-    env = {'where': np.where, 'cos': np.cos, 'sin': np.sin, 'sqrt': np.sqrt, 'exp': np.exp,
+    # float32 sin/cos: numexpr calls libm sinf/cosf (oracle/libm32.py), not numpy's SIMD kernels
+    env = {'where': np.where, 'cos': libm32.cos, 'sin': libm32.sin, 'sqrt': np.sqrt, 'exp': np.exp,
            'log': np.log, 'abs': np.abs, '_f64': np.float64, '_i64': np.int64}
     for n in {x.id for x in ast.walk(tree) if isinstance(x, ast.Name)}:
         if n in env:
@@ -124,6 +125,7 @@ from pyg2p.main.manipulation.conversion import Converter  # noqa: E402
 from pyg2p.main.manipulation.correction import Corrector  # noqa: E402
 
 from pyg2p_b200 import synth  # noqa: E402  (input generators only)
+from oracle import libm32  # noqa: E402  (ctypes binding of glibc sinf/cosf)
 
 
 def quiet(fn, *a, **k):

@@ -1,0 +1,148 @@
+"""GPU parity of the batched intertable apply (K7) and the table record pack/unpack (K6),
+bit-exact against the oracle and the reference-generated golden vectors, through the C ABI."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import interp_ref as R
+from pyg2p_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    from pyg2p_b200 import device
+    device.require_cuda()
+    return device
+
+
+def _eq(a, b):
+    """bit equality that treats NaN == NaN."""
+    np.testing.assert_array_equal(np.asarray(a), np.asarray(b))
+
+
+@pytest.mark.parametrize('mode,k', [('nearest', 1), ('invdist', 4)])
+def test_apply_matches_reference_golden(dev, golden_dir, mode, k):
+    g = np.load(os.path.join(golden_dir, 'apply_regional.npz'))
+    t = np.load(os.path.join(golden_dir, 'build_regional_global_f64.npz'))
+    rec = R.to_record(t[f'{mode}_indexes'], t[f'{mode}_weights'])
+    n = g['v0'].size
+    tbl = dev.DeviceTable.from_record(rec, n)
+    assert (tbl.k, tbl.m) == (k, 5241)
+    src = torch.from_numpy(np.stack([g[f'v{b}'] for b in range(3)])).cuda()
+    out = tbl.apply(src, float(g['mv_out'])).cpu().numpy()
+    for b in range(3):
+        _eq(out[b], g[f'{mode}_plain{b}'])            # what the reference's own code produced
+        _eq(out[b], g[f'{mode}_masked{b}'])           # AS_REFERENCE: masks are dropped (App. C.1)
+    # PROPAGATE: intended semantics
+    mask = torch.from_numpy(np.stack([g[f'mask{b}'] for b in range(3)])).cuda()
+    o2, m2 = tbl.apply(src, float(g['mv_out']), src_mask=mask, mask_policy=L.MASK_PROPAGATE)
+    for b in range(3):
+        data, mk = R.apply_propagate(g[f'v{b}'], rec['coeffs'], rec['indexes'], k, float(g['mv_out']), g[f'mask{b}'])
+        _eq(o2[b].cpu().numpy(), data)
+        _eq(m2[b].cpu().numpy().astype(bool), mk)
+
+
+def test_record_roundtrip_and_reference_golden_table(dev, golden_dir):
+    with gzip.GzipFile(os.path.join(golden_dir, 'ref_tbl_pf10slhf_550800_scipy_nearest.npy.gz')) as f:
+        rec = np.load(f)
+    n = 511 * 415
+    tbl = dev.DeviceTable.from_record(rec, n)
+    back = tbl.to_record()
+    assert back.dtype == rec.dtype and back.shape == rec.shape
+    assert back.tobytes() == rec.tobytes()
+    mv = -3.4028234663852886e38
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal((5, n))
+    out = tbl.apply(torch.from_numpy(v).cuda(), mv).cpu().numpy()
+    for b in range(5):
+        _eq(out[b], R.apply_as_reference(v[b], rec['coeffs'], rec['indexes'], 1, mv))
+    assert (out[0] == mv).sum() == 362052
+
+
+@pytest.mark.parametrize('k', [1, 2, 3, 4, 11])
+@pytest.mark.parametrize('m,b', [(1, 1), (2, 3), (1001, 7), (65537, 9), (300000, 2)])
+def test_apply_random_tables(dev, k, m, b):
+    """ragged sizes (odd m -> unaligned rows), sentinels, NaN weights, all k the reference uses."""
+    rng = np.random.default_rng(100 * k + m % 97 + b)
+    n = 5000
+    idx = rng.integers(0, n + 1, size=(m, k))                 # n = sentinel
+    w = rng.random((m, k))
+    w /= w.sum(axis=1, keepdims=True)
+    w[rng.random(m) < 0.05] = np.nan
+    if k == 1:
+        idx, w = idx[:, 0], w[:, 0]
+    rec = R.to_record(idx, w)
+    tbl = dev.DeviceTable.from_record(rec, n)
+    assert tbl.to_record().tobytes() == np.ascontiguousarray(rec).tobytes()
+    v = rng.standard_normal((b, n)) * 100
+    mask = rng.random((b, n)) < 0.1
+    mv = 9.969209968386869e36
+    out = tbl.apply(torch.from_numpy(v).cuda(), mv).cpu().numpy()
+    o2, m2 = tbl.apply(torch.from_numpy(v).cuda(), mv, src_mask=torch.from_numpy(mask).cuda(),
+                       mask_policy=L.MASK_PROPAGATE)
+    for i in range(b):
+        with np.errstate(all='ignore'):
+            _eq(out[i], R.apply_sequential(v[i], rec['coeffs'], rec['indexes'], k, mv))
+            data, mk = R.apply_propagate(v[i], rec['coeffs'], rec['indexes'], k, mv, mask[i])
+        _eq(o2[i].cpu().numpy(), data)
+        _eq(m2[i].cpu().numpy().astype(bool), mk)
+
+
+def test_apply_f32_coeff_table(dev):
+    rng = np.random.default_rng(8)
+    m, n = 777, 300
+    idx = rng.integers(0, n + 1, size=m)
+    d = (rng.random(m) * 1e5).astype(np.float32)
+    rec = R.to_record(idx, d)
+    assert rec.dtype.itemsize == 12
+    tbl = dev.DeviceTable.from_record(rec, n)
+    assert tbl.coef_f32 and tbl.to_record().tobytes() == np.ascontiguousarray(rec).tobytes()
+
+
+def test_apply_strided_batch_and_empty(dev):
+    rng = np.random.default_rng(9)
+    m, n, k = 1000, 400, 4
+    idx = rng.integers(0, n, size=(m, k))
+    w = rng.random((m, k))
+    rec = R.to_record(idx, w)
+    tbl = dev.DeviceTable.from_record(rec, n)
+    big = torch.from_numpy(rng.standard_normal((6, n + 40))).cuda()
+    view = big[:, :n]                                         # src_stride > n
+    out = tbl.apply(view, 0.0).cpu().numpy()
+    for i in range(6):
+        _eq(out[i], R.apply_sequential(big[i, :n].cpu().numpy(), w, idx, k, 0.0))
+    empty = tbl.apply(torch.empty((0, n), dtype=torch.float64, device='cuda'), 0.0)
+    assert empty.shape == (0, m)
+    with pytest.raises(ValueError):
+        tbl.apply(torch.zeros((1, n + 1), dtype=torch.float64, device='cuda'), 0.0)
+
+
+def test_linearity_at_full_size(dev):
+    """Size-independent property at BASELINE scale (O1280 -> EFAS, 16 messages): the apply is linear
+    in the source field for finite weights, and a constant field maps to that constant."""
+    m, n, k, b = 950000, 6599680, 4, 16
+    g = torch.Generator(device='cuda').manual_seed(1)
+    base = torch.randint(0, n - 4000, (1, m), generator=g, device='cuda', dtype=torch.int64)
+    idx = (base + torch.randint(0, 4000, (k, m), generator=g, device='cuda')).to(torch.int32)
+    w = torch.rand((k, m), generator=g, device='cuda', dtype=torch.float64)
+    w = w / w.sum(0, keepdim=True)
+    tbl = dev.DeviceTable(idx.contiguous(), w.contiguous(), n)
+    src = torch.randn((b, n), generator=g, device='cuda', dtype=torch.float64)
+    out = tbl.apply(src, 0.0)
+    out2 = tbl.apply(src * 2.0, 0.0)
+    assert torch.equal(out2, out * 2.0)                       # exact: scaling by 2 commutes with rounding
+    ones = tbl.apply(torch.full((1, n), 3.0, device='cuda', dtype=torch.float64), 0.0)
+    assert torch.allclose(ones, torch.full_like(ones, 3.0), rtol=1e-15, atol=0)
+    # spot check rows against the oracle order
+    rows = torch.randint(0, m, (2000,), generator=g, device='cuda')
+    ii = idx[:, rows].long()
+    ww = w[:, rows]
+    acc = ww[0] * src[3][ii[0]]
+    for j in range(1, k):
+        acc = acc + ww[j] * src[3][ii[j]]
+    assert torch.equal(out[3][rows], acc)

@@ -1,0 +1,248 @@
+"""GPU parity of the intertable build (K1-K5) against the oracle and the golden vectors
+produced by the reference's own code.  Everything goes through the C ABI (pyg2p_b200.device).
+
+Contract:
+  (i)  given identical xyz bytes, neighbour ids and distances are bit-exact vs cKDTree on every
+       row that carries no exact-tie flag; flagged rows match as multisets of distances;
+  (ii) from lat/lon, GPU trig is within 2 ulp of numpy's, so a mismatch vs the golden vectors
+       is only allowed where the competing distances are within 1e-9 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import interp_ref as R
+from pyg2p_b200 import _lib as L
+from pyg2p_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+BUILD_CASES = ['o24_box_f64', 'o24_laea_f32mv', 'regional_global_f64', 'o24_coincident_f64']
+
+
+@pytest.fixture(scope='module')
+def dev():
+    from pyg2p_b200 import device
+    device.require_cuda()
+    return device
+
+
+def _ulp_diff(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float64).view(np.int64)
+    b = np.ascontiguousarray(b, dtype=np.float64).view(np.int64)
+    return np.abs(a - b)
+
+
+def _d2(q, p):
+    """squared distance in the cKDTree arithmetic."""
+    dx, dy, dz = q[0] - p[0], q[1] - p[1], q[2] - p[2]
+    return ((dx * dx) + (dy * dy)) + (dz * dz)
+
+
+def _check_raw_vs_tree(src_xyz, tgt_xyz, k, idx, dist, flags, f32):
+    """contract (i): cKDTree on the same xyz bytes.  Rows without the exact-tie flag must agree in
+    ids and order; on flagged rows an id may differ only from an id at EXACTLY the same distance
+    (inside the row or at the k/k+1 boundary)."""
+    tree = R.build_tree(src_xyz)
+    d, i = R.query(tree, tgt_xyz.astype(np.float32) if f32 else tgt_xyz, k)
+    d = np.asarray(d, dtype=np.float64).reshape(len(tgt_xyz), k)
+    i = i.reshape(len(tgt_xyz), k)
+    np.testing.assert_array_equal(dist, d)            # distances are bit-equal even on tie rows
+    tie = (flags & L.FLAG_TIE) != 0
+    np.testing.assert_array_equal(idx[~tie], i[~tie])
+    for r in np.nonzero(tie)[0]:
+        assert sorted(idx[r]) == sorted(set(idx[r]))  # no duplicates
+        for a, b in zip(idx[r], i[r]):
+            if a != b:
+                assert _d2(tgt_xyz[r], src_xyz[a]) == _d2(tgt_xyz[r], src_xyz[b])
+    return int(tie.sum())
+
+
+@pytest.mark.parametrize('case', BUILD_CASES)
+@pytest.mark.parametrize('k', [1, 2, 4])
+def test_knn_raw_bit_exact_on_same_xyz(dev, golden_dir, case, k):
+    g = np.load(os.path.join(golden_dir, f'build_{case}.npz'))
+    ix = dev.SourceIndex(g['src_lon'], g['src_lat'], float(g['radius']))
+    out = ix.knn(g['tgt_lon'], g['tgt_lat'], k=k, mode=L.MODE_RAW, want_xyz=True)
+    f32 = g['tgt_lat'].dtype == np.float32
+    idx = out['idx'].cpu().numpy().T.astype(np.int64)
+    dist = out['coef'].cpu().numpy().T
+    flags = out['flags'].cpu().numpy()
+    _check_raw_vs_tree(ix.xyz().cpu().numpy(), out['xyz'].cpu().numpy(), k, idx, dist, flags, f32)
+
+
+@pytest.mark.parametrize('case', BUILD_CASES)
+def test_xyz_within_2ulp_of_numpy(dev, golden_dir, case):
+    g = np.load(os.path.join(golden_dir, f'build_{case}.npz'))
+    r = float(g['radius'])
+    sx = dev.latlon_to_xyz(g['src_lon'], g['src_lat'], r).cpu().numpy()
+    ox = R.stack_xyz(*R.to_3d(g['src_lon'], g['src_lat'], r))
+    # absolute bound: 2 ulp of the radius (components near zero have tiny ulps of their own)
+    assert np.max(np.abs(sx - ox)) <= 2 * np.spacing(r)
+    tx = dev.latlon_to_xyz(g['tgt_lon'], g['tgt_lat'], r).cpu().numpy()
+    ot = R.stack_xyz(*R.to_3d(g['tgt_lon'], g['tgt_lat'], r)).astype(np.float64)
+    if g['tgt_lat'].dtype == np.float32:
+        assert np.all(tx == tx.astype(np.float32))
+        ok = np.abs(g['tgt_lat'].ravel()) < 1e6     # garbage (MV) coordinates: any point of the sphere is fine
+        assert np.max(np.abs(tx[ok] - ot[ok])) <= 2 * np.spacing(np.float32(r))
+        assert np.allclose(np.linalg.norm(tx, axis=1), r, rtol=1e-6)
+    else:
+        assert np.max(np.abs(tx - ot)) <= 2 * np.spacing(r)
+
+
+def _near_tie_rows(src_xyz, tgt_xyz, idx_a, idx_b, rel=1e-9):
+    """rows where idx_a != idx_b must have |d(a) - d(b)| <= rel*d for every differing column."""
+    bad = np.nonzero((idx_a != idx_b).any(axis=1))[0]
+    n = len(src_xyz)
+    for r in bad:
+        for a, b in zip(idx_a[r], idx_b[r]):
+            if a == b:
+                continue
+            if a >= n or b >= n:
+                return bad, False
+            da = np.linalg.norm(tgt_xyz[r] - src_xyz[a])
+            db = np.linalg.norm(tgt_xyz[r] - src_xyz[b])
+            if abs(da - db) > rel * max(da, db):
+                return bad, False
+    return bad, True
+
+
+@pytest.mark.parametrize('case', BUILD_CASES)
+@pytest.mark.parametrize('mode,k', [('nearest', 1), ('invdist', 4)])
+def test_table_vs_reference_golden(dev, golden_dir, case, mode, k):
+    """contract (ii) + K5: full build from lat/lon compared with what the reference produced."""
+    g = np.load(os.path.join(golden_dir, f'build_{case}.npz'))
+    n = g['src_lon'].size
+    ix = dev.SourceIndex(g['src_lon'], g['src_lat'], float(g['radius']))
+    mub = ix.min_upper_bound(int(g['nj']))
+    assert mub == pytest.approx(float(g[f'{mode}_mub']), rel=1e-12)
+    out = ix.knn(g['tgt_lon'], g['tgt_lat'], k=k, mode=L.MODE_NEAREST if mode == 'nearest' else L.MODE_INVDIST,
+                 mub=mub, want_xyz=True)
+    f32 = g['tgt_lat'].dtype == np.float32
+    tbl = dev.DeviceTable(out['idx'], out['coef'], n, coef_f32=(f32 and mode == 'nearest'))
+    idx, w = tbl.indexes_coeffs()
+    gi, gw = g[f'{mode}_indexes'], g[f'{mode}_weights']
+    assert idx.shape == gi.shape and idx.dtype == gi.dtype
+    assert w.shape == gw.shape and w.dtype == gw.dtype
+    i2, g2 = idx.reshape(len(idx), -1), gi.reshape(len(gi), -1)
+    bad, ok = _near_tie_rows(ix.xyz().cpu().numpy(), out['xyz'].cpu().numpy(), i2, g2, rel=1e-6 if f32 else 1e-9)
+    assert ok, f'{len(bad)} rows differ from the reference beyond near-ties'
+    if not f32:
+        # a row may differ only if the GPU itself saw (near-)equal distances there
+        fl = out['flags'].cpu().numpy()
+        unflagged = [r for r in bad if not fl[r] & (L.FLAG_TIE | L.FLAG_NEAR_TIE) and (g2[r] < n).all()]
+        assert len(unflagged) == 0, unflagged
+    good = np.ones(len(idx), bool)
+    good[bad] = False
+    w2, gw2 = w.reshape(len(w), -1)[good], gw.reshape(len(gw), -1)[good]
+    sane = np.abs(np.asarray(g['tgt_lat'], dtype=np.float64).ravel()[good]) < 1e6   # MV (garbage) coordinates
+    if mode == 'nearest':
+        # coeffs = distances.  f64: GPU trig moves xyz by <= 2 ulp.  f32 maps: libm's sinf/cosf (numexpr) and
+        # the float32-rounded float64 trig used on the GPU differ by one float32 ulp in ~1.3 % of the
+        # values, i.e. target positions move by up to ~1 m (one float32 ulp of the radius, 3 components).
+        if f32:
+            np.testing.assert_allclose(w2[sane].astype(np.float64), gw2[sane].astype(np.float64), rtol=0, atol=2.0)
+            assert np.mean(w2[sane] == gw2[sane]) > 0.9
+        else:
+            np.testing.assert_allclose(w2, gw2, rtol=1e-12, atol=1e-8)
+    else:
+        assert np.array_equal(np.isnan(w2[sane]), np.isnan(gw2[sane]))
+        fin = ~np.isnan(gw2) & ~np.isnan(w2) & sane[:, None]
+        if f32:
+            # d(w)/w ~ 2 d(dist)/dist with d(dist) <= 2 m and dist ~ 1e5 m on this coarse grid
+            np.testing.assert_allclose(w2[fin], gw2[fin], rtol=2e-3, atol=1e-6)
+            assert np.mean(w2[fin] == gw2[fin]) > 0.9
+        else:
+            np.testing.assert_allclose(w2[fin], gw2[fin], rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize('case', ['o24_box_f64', 'o24_laea_f32mv', 'o24_coincident_f64'])
+def test_weights_bit_exact_given_same_distances(dev, golden_dir, case):
+    """K5 in isolation: feed the oracle's own (idx, dist) through g2p_weights -> bit-exact weights."""
+    g = np.load(os.path.join(golden_dir, f'build_{case}.npz'))
+    o = R.BuildOracle(g['src_lon'], g['src_lat'], synth.GridDetails(radius=float(g['radius']), Nj=int(g['nj'])),
+                      g['z'], 4, float(g['mv_target']), synth.GRIB_MV, mode='invdist')
+    _, w_ref, i_ref = o.interpolate(g['tgt_lon'], g['tgt_lat'])
+    f32 = g['tgt_lat'].dtype == np.float32
+    idx = torch.from_numpy(np.ascontiguousarray(o.raw_indexes.T).astype(np.int32)).cuda()
+    coef = torch.from_numpy(np.ascontiguousarray(o.raw_distances.T).astype(np.float64)).cuda()
+    dev.weights(L.MODE_INVDIST, idx, coef, g['z'].size, o.min_upper_bound, L.F32 if f32 else L.F64)
+    np.testing.assert_array_equal(idx.cpu().numpy().T.astype(np.int64), i_ref)
+    np.testing.assert_array_equal(coef.cpu().numpy().T, w_ref)
+    np.testing.assert_array_equal(coef.cpu().numpy().T, g['invdist_weights'])      # == the reference's own output
+
+
+@pytest.mark.parametrize('k,f32', [(1, False), (4, False), (4, True)])
+def test_o320_to_efas_bit_exact(dev, k, f32):
+    """BASELINE config 1 shape: O320 -> EFAS 5 km LAEA (950x1000), cKDTree on the same xyz."""
+    lat, lon, det = synth.octahedral_grid(320)
+    tl, tlo = synth.efas_target(dtype=np.float32 if f32 else np.float64)
+    ix = dev.SourceIndex(lon, lat, det['radius'])
+    src_xyz = ix.xyz().cpu().numpy()
+    tree = R.build_tree(src_xyz)
+    mub = ix.min_upper_bound(det['Nj'])
+    assert mub == R.min_upper_bound(tree, src_xyz, det['Nj'], workers=-1)
+    out = ix.knn(tlo, tl, k=k, mode=L.MODE_RAW, want_xyz=True)
+    txyz = out['xyz'].cpu().numpy()
+    d, i = tree.query(txyz, k=k, workers=-1)
+    if f32:
+        d = np.float32(d).astype(np.float64)
+    flags = out['flags'].cpu().numpy()
+    tie = (flags & L.FLAG_TIE) != 0
+    idx = out['idx'].cpu().numpy().T.astype(np.int64).reshape(i.shape)
+    dist = out['coef'].cpu().numpy().T.reshape(d.shape)
+    np.testing.assert_array_equal(dist, d)
+    np.testing.assert_array_equal(idx[~tie], i[~tie])
+    assert tie.sum() < 100
+
+
+def test_regular_target_with_exact_ties(dev):
+    """Regular 0.25-degree target over an O48 source: exact fp64 ties occur."""
+    lat, lon, det = synth.octahedral_grid(48)
+    tl, tlo = synth.latlon_target(0.25)
+    ix = dev.SourceIndex(lon, lat, det['radius'])
+    out = ix.knn(tlo, tl, k=4, mode=L.MODE_RAW, want_xyz=True)
+    idx = out['idx'].cpu().numpy().T.astype(np.int64)
+    dist = out['coef'].cpu().numpy().T
+    n_tie = _check_raw_vs_tree(ix.xyz().cpu().numpy(), out['xyz'].cpu().numpy(), 4, idx, dist,
+                               out['flags'].cpu().numpy(), False)
+    assert n_tie > 0
+    # deterministic GPU tie rule: equal distances are ordered by ascending source id
+    for r in np.nonzero((out['flags'].cpu().numpy() & L.FLAG_TIE) != 0)[0][:200]:
+        for c in range(3):
+            if dist[r, c] == dist[r, c + 1]:
+                assert idx[r, c] < idx[r, c + 1]
+
+
+def test_far_targets_unbounded_search(dev):
+    """Regional source, targets on the other side of the globe: the true nearest neighbour and its
+    distance must still be found (nearest tables store it for every row)."""
+    lat, lon, det = synth.regular_ll_grid(60.0, 40.0, 41, 0.0, 30.0, 61)
+    rng = np.random.default_rng(5)
+    tl = rng.uniform(-90, 90, 4000)
+    tlo = rng.uniform(-180, 180, 4000)
+    ix = dev.SourceIndex(lon, lat, det['radius'])
+    out = ix.knn(tlo, tl, k=4, mode=L.MODE_RAW, want_xyz=True)
+    _check_raw_vs_tree(ix.xyz().cpu().numpy(), out['xyz'].cpu().numpy(), 4,
+                       out['idx'].cpu().numpy().T.astype(np.int64), out['coef'].cpu().numpy().T,
+                       out['flags'].cpu().numpy(), False)
+
+
+def test_fewer_sources_than_k(dev):
+    ix = dev.SourceIndex([10.0, 11.0], [45.0, 45.0], 6371229.0)
+    out = ix.knn(np.array([10.2]), np.array([45.0]), k=4, mode=L.MODE_RAW)
+    idx = out['idx'].cpu().numpy()[:, 0]
+    d = out['coef'].cpu().numpy()[:, 0]
+    assert list(idx) == [0, 1, 2, 2] and np.isinf(d[2:]).all() and np.isfinite(d[:2]).all()
+    assert out['flags'].cpu().numpy()[0] & L.FLAG_SHORT
+
+
+def test_rotated_source(dev, golden_dir):
+    """`to_regular` branch (:673-678): rotated_ll sources land on the unit sphere."""
+    g = np.load(os.path.join(golden_dir, 'build_o24_box_f64.npz'))
+    rot = (-40.0, 10.0)
+    got = dev.latlon_to_xyz(g['src_lon'], g['src_lat'], 1.0, rotation=rot).cpu().numpy()
+    want = R.stack_xyz(*R.to_3d(g['src_lon'], g['src_lat'], 1.0, rotation=rot))
+    assert np.max(np.abs(got - want)) <= 4 * np.spacing(1.0)
