@@ -151,6 +151,36 @@ int g2p_apply(const int32_t* idx, const double* coef, int64_t m, int k, const do
               const uint8_t* src_mask, int64_t n, int b, int64_t src_stride, int64_t out_stride,
               double mv_out, int mask_policy, double* out, uint8_t* out_mask, void* stream);
 
+/* K7w  windowed apply: the same operation as g2p_apply with the source values staged through shared
+ * memory by TMA bulk copies (see pyg2p_b200/csrc/g2p_apply_win.cu).  It needs a plan, built once per
+ * table: the targets are cut into 2-D tiles (rows x cols is the target map shape as in
+ * `result.reshape(lonefas.shape)`, interpolation/__init__.py:263; pass rows = cols = 0 for a flat
+ * table) and every tile gets the list of contiguous source index ranges its neighbours fall in.
+ * g2p_plan_create returns G2P_ERR_UNSUPPORTED when the table's indexes are too scattered for a
+ * shared-memory window; callers then use g2p_apply (still on the GPU). */
+typedef struct g2p_plan g2p_plan;
+
+typedef struct g2p_plan_info {
+  int64_t m, n;
+  int32_t k, tile_rows, tile_cols, n_tiles;
+  int32_t max_window;   /* largest per-tile window, in source values */
+  int32_t max_ranges;   /* largest number of index ranges of one tile */
+  double mean_window;   /* mean per-tile window, in source values */
+  int64_t bytes;        /* device memory held by the plan */
+} g2p_plan_info;
+
+/* idx: int32 [k][m] device (the SoA table indexes; values >= n are "no value").  Synchronises `stream`. */
+int g2p_plan_create(const int32_t* idx, int64_t m, int k, int64_t n, int64_t rows, int64_t cols, g2p_plan** out,
+                    void* stream);
+int g2p_plan_destroy(g2p_plan* plan);
+int g2p_plan_get_info(const g2p_plan* plan, g2p_plan_info* info /* host */);
+/* arguments as g2p_apply; the indexes come from the plan.  Requirements (else G2P_ERR_UNSUPPORTED):
+ * k in {1, 4}; src 16-byte aligned with src_stride a multiple of 2 and >= n rounded up to 16;
+ * under PROPAGATE also src_mask 16-byte aligned and src_stride a multiple of 16. */
+int g2p_apply_planned(const g2p_plan* plan, const double* coef, const double* src, const uint8_t* src_mask, int b,
+                      int64_t src_stride, int64_t out_stride, double mv_out, int mask_policy, double* out,
+                      uint8_t* out_mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libg2pgpu.so')
 
 OK = 0
+ERR_UNSUPPORTED = -5
 F64, F32 = 0, 1
 MODE_RAW, MODE_NEAREST, MODE_INVDIST = 0, 1, 2
 MASK_AS_REFERENCE, MASK_PROPAGATE = 0, 1
@@ -30,6 +31,12 @@ class Rotation(C.Structure):
 class IndexInfo(C.Structure):
     _fields_ = [('n', C.c_int64), ('cells_per_face_side', C.c_int32), ('n_cells', C.c_int64),
                 ('radius', C.c_double), ('mean_spacing', C.c_double), ('bytes', C.c_int64)]
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [('m', C.c_int64), ('n', C.c_int64), ('k', C.c_int32), ('tile_rows', C.c_int32),
+                ('tile_cols', C.c_int32), ('n_tiles', C.c_int32), ('max_window', C.c_int32),
+                ('max_ranges', C.c_int32), ('mean_window', C.c_double), ('bytes', C.c_int64)]
 
 
 _vp, _i64, _i32, _f64 = C.c_void_p, C.c_int64, C.c_int, C.c_double
@@ -54,6 +61,10 @@ PROTOTYPES = {
     'g2p_table_pack_rec': (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     'g2p_table_unpack_rec': (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     'g2p_apply': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _i32, _i64, _i64, _f64, _i32, _vp, _vp, _vp]),
+    'g2p_plan_create': (C.c_int, [_vp, _i64, _i32, _i64, _i64, _i64, C.POINTER(_vp), _vp]),
+    'g2p_plan_destroy': (C.c_int, [_vp]),
+    'g2p_plan_get_info': (C.c_int, [_vp, C.POINTER(PlanInfo)]),
+    'g2p_apply_planned': (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f64, _i32, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,642 @@
+// K7w: windowed (shared-memory staged) batched intertable apply for sm_100a, plus the tile plan it needs.
+//
+// Same arithmetic and semantics as g2p_apply (g2p_apply.cu; reference
+// src/pyg2p/main/interpolation/__init__.py:142-162), different data movement.  The generic kernel
+// gathers straight from global memory: every warp-level gather touches 10-16 sectors, the L1
+// wavefront queue - not HBM - is the limit (ncu: 15.7 sectors/request, 14 % of HBM peak).
+// Here the targets are cut into 2-D tiles of 1024; the source points a tile references form a few
+// contiguous index ranges (pieces of neighbouring latitude rings).  A plan, built once per table,
+// lists those ranges per tile (16-element aligned) and rewrites the table's int32 indexes as
+// uint16 offsets into the tile's window.  The apply kernel then, per (tile, message):
+//   * one warp issues cp.async.bulk (TMA 1-D bulk copies, UBLKCP) of the ranges - values and
+//     mask bytes - into a shared-memory stage, completion on an mbarrier; 2-4 stages in flight;
+//   * all threads gather their k neighbours from shared memory (bank-conflict-light because
+//     neighbouring lanes own neighbouring targets), do the no-FMA weighted sum and write the
+//     outputs with 128-bit streaming stores.
+// Every source value is read from L2/HBM once per tile instead of once per referencing target, and
+// index/weight registers are loaded once per (tile, message chunk).
+#include <algorithm>
+#include <climits>
+#include <cstring>
+#include <vector>
+
+#include "g2p_common.cuh"
+
+namespace g2p {
+
+constexpr int kWinThreads = 256;
+constexpr int kWinTPT = 4;                               // targets per thread: 2 adjacent pairs
+constexpr int kTileTargets = kWinThreads * kWinTPT;      // 1024
+constexpr int kMaxRanges = 96;                           // source index ranges per tile
+constexpr int kMaxStages = 4;
+constexpr int kBlockElems = 16;                          // range granularity: 16 values = 128 B, 16 mask bytes
+constexpr int kPlanSpanBlocks = 1 << 17;                 // bitmap span per tile: 2 M source elements
+constexpr int kMaxWindowElems = 20480;                   // 160 KB of values per stage at most (1 stage)
+constexpr uint16_t kLocalSentinel = 0xffff;
+
+struct __align__(16) Range {
+  int32_t src_start;   // first source element (multiple of 16)
+  int32_t n_elem;      // multiple of 16
+  int32_t smem_off;    // element offset inside the stage window
+  int32_t pad;
+};
+
+}  // namespace g2p
+
+struct g2p_plan {
+  int device;
+  int64_t m, n, n_pad;
+  int k;
+  int64_t rows, cols;
+  int tile_rows, tile_cols, tiles_r, tiles_c, n_tiles;
+  int max_window;      // elements, over tiles
+  int max_ranges;
+  double mean_window;
+  uint16_t* lidx;      // [k][m]
+  g2p::Range* ranges;  // [n_tiles][kMaxRanges]
+  int32_t* tile_info;  // [n_tiles][2] = {n_ranges, window_elems}
+};
+
+namespace g2p {
+
+// ------------------------------------------------------------------ tile geometry (shared by plan and apply)
+struct TileGeom {
+  int64_t rows, cols;
+  int tile_rows, tile_cols, tiles_c, threads_per_row;
+};
+
+// target columns owned by thread x of a tile row: pairs {2x, 2x+1} and {half + 2x, half + 2x + 1}
+__device__ __forceinline__ void thread_targets(const TileGeom& g, int tile, int tid, int64_t& r, int64_t (&c)[kWinTPT]) {
+  const int ty = tile / g.tiles_c, tx = tile - ty * g.tiles_c;
+  const int tr = tid / g.threads_per_row, x = tid - tr * g.threads_per_row;
+  const int half = g.tile_cols >> 1;
+  r = (int64_t)ty * g.tile_rows + tr;
+  const int64_t c0 = (int64_t)tx * g.tile_cols;
+  c[0] = c0 + 2 * x;
+  c[1] = c[0] + 1;
+  c[2] = c0 + half + 2 * x;
+  c[3] = c[2] + 1;
+}
+
+// ------------------------------------------------------------------ plan kernel: one CTA per tile
+struct PlanArgs {
+  const int32_t* idx;
+  int64_t m, n, n_pad;
+  int k;
+  TileGeom g;
+  uint16_t* lidx;
+  Range* ranges;
+  int32_t* tile_info;
+  int32_t* status;  // [0] = first failing reason (0 ok), [1] = max window, [2] = max ranges
+  unsigned long long* total_window;
+  int dry;          // only measure (no lidx / ranges written): used to choose the tile shape
+};
+
+__global__ void __launch_bounds__(kWinThreads) plan_kernel(const PlanArgs a) {
+  extern __shared__ uint32_t s_bits[];  // kPlanSpanBlocks / 32 words
+  __shared__ int s_min, s_max, s_nr, s_fail;
+  __shared__ Range s_ranges[kMaxRanges];
+  const int tile = blockIdx.x;
+  const int tid = threadIdx.x;
+  int64_t r, c[kWinTPT];
+  thread_targets(a.g, tile, tid, r, c);
+  if (tid == 0) {
+    s_min = INT_MAX;
+    s_max = -1;
+    s_nr = 0;
+    s_fail = 0;
+  }
+  __syncthreads();
+  // pass 1: block span
+  int32_t my[kWinTPT][16];
+  int lo = INT_MAX, hi = -1;
+#pragma unroll
+  for (int t = 0; t < kWinTPT; ++t) {
+    const bool ok = r < a.g.rows && c[t] < a.g.cols;
+    const int64_t j = r * a.g.cols + c[t];
+    for (int kk = 0; kk < a.k; ++kk) {
+      int32_t v = ok ? a.idx[(int64_t)kk * a.m + j] : -1;
+      if (v < 0 || v >= a.n) v = -1;  // sentinel / invalid
+      my[t][kk] = v;
+      if (v >= 0) {
+        lo = min(lo, v / kBlockElems);
+        hi = max(hi, v / kBlockElems);
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((tid & 31) == 0) {
+    atomicMin(&s_min, lo);
+    atomicMax(&s_max, hi);
+  }
+  __syncthreads();
+  const int bmin = s_min, bmax = s_max;
+  const int span = (bmax >= 0) ? (bmax - bmin + 1) : 0;
+  if (span > kPlanSpanBlocks) {
+    if (tid == 0) atomicCAS(&a.status[0], 0, 1);  // indexes too scattered for a window
+    return;
+  }
+  const int words = (span + 31) / 32;
+  for (int w = tid; w < words; w += kWinThreads) s_bits[w] = 0u;
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < kWinTPT; ++t)
+    for (int kk = 0; kk < a.k; ++kk)
+      if (my[t][kk] >= 0) {
+        const int b = my[t][kk] / kBlockElems - bmin;
+        atomicOr(&s_bits[b >> 5], 1u << (b & 31));
+      }
+  __syncthreads();
+  // runs of set blocks -> ranges (sequential walk: a tile has a few dozen runs)
+  if (tid == 0) {
+    int nr = 0, win = 0, run_start = -1;
+    for (int b = 0; b <= span; ++b) {
+      const bool set = (b < span) && ((s_bits[b >> 5] >> (b & 31)) & 1u);
+      if (set && run_start < 0) run_start = b;
+      if (!set && run_start >= 0) {
+        if (nr < kMaxRanges) {
+          Range rg;
+          rg.src_start = (bmin + run_start) * kBlockElems;
+          int64_t end = (int64_t)(bmin + b) * kBlockElems;
+          if (end > a.n_pad) end = a.n_pad;
+          rg.n_elem = (int32_t)(end - rg.src_start);
+          rg.smem_off = win;
+          rg.pad = 0;
+          s_ranges[nr] = rg;
+          win += rg.n_elem;
+        }
+        ++nr;
+        run_start = -1;
+      }
+      // skip whole empty / full words quickly
+      if (run_start < 0 && (b & 31) == 31 && b + 1 < span) {
+        while (b + 32 < span && s_bits[(b + 1) >> 5] == 0u) b += 32;
+      }
+    }
+    s_nr = nr;
+    if (nr > kMaxRanges) {
+      s_fail = 1;
+      atomicCAS(&a.status[0], 0, 2);
+    } else if (win > kMaxWindowElems) {
+      s_fail = 1;
+      atomicCAS(&a.status[0], 0, 3);
+    } else {
+      atomicMax(&a.status[1], win);
+      atomicMax(&a.status[2], nr);
+      atomicAdd(a.total_window, (unsigned long long)win);
+      if (!a.dry) {
+        a.tile_info[2 * tile] = nr;
+        a.tile_info[2 * tile + 1] = win;
+      }
+    }
+  }
+  __syncthreads();
+  if (s_fail || a.dry) return;
+  const int nr = s_nr;
+  for (int i = tid; i < nr; i += kWinThreads) a.ranges[(int64_t)tile * kMaxRanges + i] = s_ranges[i];
+  // pass 3: local offsets
+#pragma unroll
+  for (int t = 0; t < kWinTPT; ++t) {
+    const bool ok = r < a.g.rows && c[t] < a.g.cols;
+    if (!ok) continue;
+    const int64_t j = r * a.g.cols + c[t];
+    for (int kk = 0; kk < a.k; ++kk) {
+      const int32_t v = my[t][kk];
+      uint16_t l = kLocalSentinel;
+      if (v >= 0) {
+        int lo_r = 0, hi_r = nr - 1;  // last range with src_start <= v
+        while (lo_r < hi_r) {
+          const int mid = (lo_r + hi_r + 1) >> 1;
+          if (s_ranges[mid].src_start <= v) lo_r = mid; else hi_r = mid - 1;
+        }
+        l = (uint16_t)(s_ranges[lo_r].smem_off + (v - s_ranges[lo_r].src_start));
+      }
+      a.lidx[(int64_t)kk * a.m + j] = l;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ PTX helpers: mbarrier + bulk copy
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (1-D TMA); dst, src and bytes are multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------ apply kernel
+struct WinArgs {
+  const uint16_t* lidx;
+  const double* coef;
+  const Range* ranges;
+  const int32_t* tile_info;
+  const double* src;
+  const uint8_t* src_mask;
+  double* out;
+  uint8_t* out_mask;
+  int64_t m, src_stride, out_stride;
+  TileGeom g;
+  int b, n_tiles, msgs_per_chunk, stages, stage_elems;
+  int64_t n_items;
+  double mv_out;
+  int vec_store, vec_mask;
+};
+
+template <int K>
+__device__ __forceinline__ double weighted_sum(const double (&w)[K], const double (&v)[K]) {
+  if (K == 1) return v[0];
+  double acc = __dmul_rn(w[0], v[0]);
+#pragma unroll
+  for (int kk = 1; kk < K; ++kk) acc = __dadd_rn(acc, __dmul_rn(w[kk], v[kk]));
+  return acc;
+}
+
+template <int K, bool MASK>
+__global__ void __launch_bounds__(kWinThreads) apply_window_kernel(const WinArgs a) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ __align__(8) uint64_t s_full[kMaxStages];
+  __shared__ Range s_ranges[kMaxRanges];
+  __shared__ int s_tile_info[2];
+  double* s_val = reinterpret_cast<double*>(s_raw);                                    // [stages][stage_elems]
+  uint8_t* s_msk = s_raw + (size_t)a.stages * a.stage_elems * sizeof(double);          // [stages][stage_elems]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int S = a.stages;
+  const int sent = a.stage_elems - 1;  // slot that always holds mv_out / mask 0
+  if (tid < S) {
+    mbar_init(&s_full[tid], 1);
+    s_val[(size_t)tid * a.stage_elems + sent] = a.mv_out;
+    if (MASK) s_msk[(size_t)tid * a.stage_elems + sent] = 0;
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  uint32_t phase = 0;  // bit s = parity to wait for on stage s
+
+  for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    const int tile = (int)(item % a.n_tiles);
+    const int chunk = (int)(item / a.n_tiles);
+    const int msg_begin = chunk * a.msgs_per_chunk;
+    const int msg_end = min(a.b, msg_begin + a.msgs_per_chunk);
+    // ---- tile plan
+    if (tid < 2) s_tile_info[tid] = a.tile_info[2 * tile + tid];
+    __syncthreads();
+    const int nr = s_tile_info[0];
+    const uint32_t win_bytes = (uint32_t)s_tile_info[1] * (MASK ? 9u : 8u);
+    for (int i = tid; i < nr; i += kWinThreads) s_ranges[i] = a.ranges[(int64_t)tile * kMaxRanges + i];
+    __syncthreads();
+
+    auto issue = [&](int msg, int stage) {  // warp 0 only
+      if (lane == 0) mbar_expect_tx(&s_full[stage], win_bytes);
+      __syncwarp();
+      const double* gv = a.src + (int64_t)msg * a.src_stride;
+      double* sv = s_val + (size_t)stage * a.stage_elems;
+      for (int i = lane; i < nr; i += 32) {
+        const Range rg = s_ranges[i];
+        bulk_g2s(sv + rg.smem_off, gv + rg.src_start, (uint32_t)rg.n_elem * 8u, &s_full[stage]);
+        if (MASK)
+          bulk_g2s(s_msk + (size_t)stage * a.stage_elems + rg.smem_off,
+                   a.src_mask + (int64_t)msg * a.src_stride + rg.src_start, (uint32_t)rg.n_elem, &s_full[stage]);
+      }
+    };
+    if (warp == 0 && nr > 0)
+      for (int s = 0; s < S && msg_begin + s < msg_end; ++s) issue(msg_begin + s, s);
+
+    // ---- this thread's targets: local indexes and weights stay in registers for the whole chunk
+    int64_t r, c[kWinTPT];
+    thread_targets(a.g, tile, tid, r, c);
+    bool ok[kWinTPT];
+    int64_t j[kWinTPT];
+    int li[kWinTPT][K];
+    double w[kWinTPT][K];
+#pragma unroll
+    for (int t = 0; t < kWinTPT; ++t) {
+      ok[t] = r < a.g.rows && c[t] < a.g.cols;
+      j[t] = r * a.g.cols + c[t];
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk) {
+        const uint16_t l = ok[t] ? __ldg(a.lidx + (int64_t)kk * a.m + j[t]) : kLocalSentinel;
+        li[t][kk] = (l == kLocalSentinel) ? sent : (int)l;
+        w[t][kk] = (K > 1 && ok[t]) ? __ldg(a.coef + (int64_t)kk * a.m + j[t]) : 1.0;
+      }
+    }
+
+    // ---- messages
+    for (int msg = msg_begin, it = 0; msg < msg_end; ++msg, ++it) {
+      const int stage = it % S;
+      if (nr > 0) {
+        mbar_wait(&s_full[stage], (phase >> stage) & 1u);
+        phase ^= 1u << stage;
+      }
+      const double* sv = s_val + (size_t)stage * a.stage_elems;
+      const uint8_t* sm = s_msk + (size_t)stage * a.stage_elems;
+      double res[kWinTPT];
+      uint32_t mk[kWinTPT];
+#pragma unroll
+      for (int t = 0; t < kWinTPT; ++t) {
+        double v[K];
+        uint32_t mm = 0;
+#pragma unroll
+        for (int kk = 0; kk < K; ++kk) {
+          v[kk] = sv[li[t][kk]];
+          if (MASK) mm |= sm[li[t][kk]];
+        }
+        res[t] = weighted_sum<K>(w[t], v);
+        mk[t] = mm ? 1u : 0u;
+      }
+      double* o = a.out + (int64_t)msg * a.out_stride;
+#pragma unroll
+      for (int p = 0; p < kWinTPT; p += 2) {
+        if (a.vec_store && ok[p + 1]) {
+          __stcs(reinterpret_cast<double2*>(o + j[p]), make_double2(res[p], res[p + 1]));
+        } else {
+          if (ok[p]) __stcs(o + j[p], res[p]);
+          if (ok[p + 1]) __stcs(o + j[p + 1], res[p + 1]);
+        }
+      }
+      if (MASK) {
+        uint8_t* om = a.out_mask + (int64_t)msg * a.out_stride;
+#pragma unroll
+        for (int p = 0; p < kWinTPT; p += 2) {
+          if (a.vec_mask && ok[p + 1]) {
+            *reinterpret_cast<uint16_t*>(om + j[p]) = (uint16_t)(mk[p] | (mk[p + 1] << 8));
+          } else {
+            if (ok[p]) om[j[p]] = (uint8_t)mk[p];
+            if (ok[p + 1]) om[j[p + 1]] = (uint8_t)mk[p + 1];
+          }
+        }
+      }
+      __syncthreads();  // everyone is done with this stage
+      if (warp == 0 && nr > 0 && msg + S < msg_end) issue(msg + S, stage);
+    }
+  }
+}
+
+static size_t win_smem_bytes(int stages, int stage_elems, bool mask) {
+  return (size_t)stages * stage_elems * (mask ? 9 : 8);
+}
+
+template <int K, bool MASK>
+static int launch_window(const g2p_plan* p, WinArgs a, cudaStream_t st) {
+  // stages: as many as fit in ~100 KB per CTA (two CTAs per SM), at least 1
+  const int stage_elems = ((p->max_window + 1 + 15) / 16) * 16;  // +1: the sentinel slot
+  int stages = kMaxStages;
+  while (stages > 1 && win_smem_bytes(stages, stage_elems, MASK) > 100 * 1024) --stages;
+  const size_t smem = win_smem_bytes(stages, stage_elems, MASK);
+  if (smem > 200 * 1024) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: window of %d elements needs %zu B of shared memory", p->max_window, smem);
+  auto kern = apply_window_kernel<K, MASK>;
+  G2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  G2P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWinThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t grid_cap = (int64_t)per_sm * num_sms();
+  a.stages = stages;
+  a.stage_elems = stage_elems;
+  // message chunks: long enough to amortise the per-item index/weight loads, short enough to
+  // give every CTA several items
+  int64_t want_chunks = ceil_div(8 * grid_cap, p->n_tiles);
+  int64_t max_chunks = ceil_div(a.b, 8);
+  int64_t n_chunks = std::max<int64_t>(1, std::min(want_chunks, max_chunks));
+  a.msgs_per_chunk = (int)ceil_div(a.b, n_chunks);
+  n_chunks = ceil_div(a.b, a.msgs_per_chunk);
+  a.n_items = (int64_t)p->n_tiles * n_chunks;
+  const int grid = (int)std::min<int64_t>(a.n_items, grid_cap);
+  kern<<<grid, kWinThreads, smem, st>>>(a);
+  G2P_LAUNCHED();
+  return G2P_OK;
+}
+
+}  // namespace g2p
+
+using namespace g2p;
+
+extern "C" {
+
+int g2p_plan_create(const int32_t* idx, int64_t m, int k, int64_t n, int64_t rows, int64_t cols, g2p_plan** out,
+                    void* stream) {
+  if (!out) return set_error(G2P_ERR_INVALID, "g2p_plan_create: out is null");
+  *out = nullptr;
+  if (!idx || m < 1 || k < 1 || k > 16 || n < 1 || n > 0x7fffffffLL)
+    return set_error(G2P_ERR_INVALID, "g2p_plan_create: bad arguments");
+  if (rows <= 0 || cols <= 0) {
+    rows = 1;
+    cols = m;
+  }
+  if (rows * cols != m) return set_error(G2P_ERR_INVALID, "g2p_plan_create: rows*cols != m");
+  cudaStream_t st = as_stream(stream);
+  g2p_plan* p = new g2p_plan();
+  p->m = m;
+  p->n = n;
+  p->n_pad = ceil_div(n, kBlockElems) * kBlockElems;
+  p->k = k;
+  p->rows = rows;
+  p->cols = cols;
+  // tile shape: 1024 targets as tile_rows x tile_cols (powers of two).  A flat table is one row; for a 2-D
+  // target map the candidates are measured on the table itself and the one with the smallest total
+  // window wins (compact tiles suit projected grids whose rows cut across the source rings).
+  struct Shape { int tr, tc; };
+  std::vector<Shape> cand;
+  if (rows == 1) {
+    cand.push_back({1, kTileTargets});
+  } else {
+    for (int tc : {64, 128, 32, 256, 16, 512, 1024}) {
+      const int tr = kTileTargets / tc;
+      if ((tc / 2 >= cols && tc > 4) || (tr / 2 >= rows && tr > 1)) continue;  // mostly empty tiles
+      cand.push_back({tr, tc});
+    }
+    if (cand.empty()) cand.push_back({1, kTileTargets});
+  }
+  cudaGetDevice(&p->device);
+  int32_t* d_status = nullptr;
+  unsigned long long* d_total = nullptr;
+  cudaError_t e = cudaMalloc(&p->lidx, (size_t)k * m * sizeof(uint16_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_status, 4 * sizeof(int32_t) + sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    g2p_plan_destroy(p);
+    return cuda_fail(e, "g2p_plan_create: cudaMalloc", __FILE__, __LINE__);
+  }
+  d_total = reinterpret_cast<unsigned long long*>(d_status + 4);
+  int32_t status[6] = {0, 0, 0, 0, 0, 0};
+  auto run = [&](Shape sh, int dry) -> cudaError_t {
+    p->tile_rows = sh.tr;
+    p->tile_cols = sh.tc;
+    p->tiles_c = (int)ceil_div(cols, sh.tc);
+    p->tiles_r = (int)ceil_div(rows, sh.tr);
+    p->n_tiles = p->tiles_c * p->tiles_r;
+    cudaError_t err = cudaMemsetAsync(d_status, 0, 4 * sizeof(int32_t) + sizeof(unsigned long long), st);
+    if (err != cudaSuccess) return err;
+    if (!dry) {
+      if (p->ranges) cudaFree(p->ranges);
+      if (p->tile_info) cudaFree(p->tile_info);
+      p->ranges = nullptr;
+      p->tile_info = nullptr;
+      err = cudaMalloc(&p->ranges, (size_t)p->n_tiles * kMaxRanges * sizeof(Range));
+      if (err == cudaSuccess) err = cudaMalloc(&p->tile_info, (size_t)p->n_tiles * 2 * sizeof(int32_t));
+      if (err == cudaSuccess) err = cudaMemsetAsync(p->tile_info, 0, (size_t)p->n_tiles * 2 * sizeof(int32_t), st);
+      if (err != cudaSuccess) return err;
+    }
+    PlanArgs a{};
+    a.idx = idx;
+    a.m = m;
+    a.n = n;
+    a.n_pad = p->n_pad;
+    a.k = k;
+    a.g.rows = rows;
+    a.g.cols = cols;
+    a.g.tile_rows = sh.tr;
+    a.g.tile_cols = sh.tc;
+    a.g.tiles_c = p->tiles_c;
+    a.g.threads_per_row = sh.tc / kWinTPT;
+    a.lidx = p->lidx;
+    a.ranges = p->ranges;
+    a.tile_info = p->tile_info;
+    a.status = d_status;
+    a.total_window = d_total;
+    a.dry = dry;
+    plan_kernel<<<p->n_tiles, kWinThreads, kPlanSpanBlocks / 8, st>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaMemcpyAsync(status, d_status, sizeof(status), cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    return err;
+  };
+  int rc = G2P_OK;
+  int best = -1, last_fail = 0;
+  unsigned long long best_total = ~0ull;
+  if ((int64_t)ceil_div(cols, 4) * rows > 0x7fffffffLL) e = cudaErrorInvalidValue;
+  for (size_t i = 0; e == cudaSuccess && cand.size() > 1 && i < cand.size(); ++i) {
+    e = run(cand[i], 1);
+    if (e != cudaSuccess) break;
+    unsigned long long total;
+    memcpy(&total, &status[4], sizeof(total));
+    if (status[0] == 0 && total < best_total) {
+      best_total = total;
+      best = (int)i;
+    } else if (status[0] != 0) {
+      last_fail = status[0];
+    }
+  }
+  if (e == cudaSuccess) {
+    if (cand.size() == 1) best = 0;
+    if (best < 0) {
+      status[0] = last_fail ? last_fail : 1;
+    } else {
+      e = run(cand[best], 0);
+    }
+  }
+  cudaFree(d_status);
+  if (e != cudaSuccess) rc = cuda_fail(e, "g2p_plan_create", __FILE__, __LINE__);
+  else if (status[0] != 0) {
+    static const char* why[] = {"", "a tile's indexes span more than 2 M source points", "a tile needs more than 96 index ranges",
+                                "a tile's window exceeds 20480 source values"};
+    rc = set_error(G2P_ERR_UNSUPPORTED, "g2p_plan_create: table is not windowable (%s); use g2p_apply", why[status[0] & 3]);
+  }
+  if (rc != G2P_OK) {
+    g2p_plan_destroy(p);
+    return rc;
+  }
+  {
+    unsigned long long total;
+    memcpy(&total, &status[4], sizeof(total));
+    p->mean_window = (double)total / (double)p->n_tiles;
+  }
+  p->max_window = status[1];
+  p->max_ranges = status[2];
+  *out = p;
+  return G2P_OK;
+}
+
+int g2p_plan_destroy(g2p_plan* p) {
+  if (!p) return G2P_OK;
+  if (p->lidx) cudaFree(p->lidx);
+  if (p->ranges) cudaFree(p->ranges);
+  if (p->tile_info) cudaFree(p->tile_info);
+  delete p;
+  return G2P_OK;
+}
+
+int g2p_plan_get_info(const g2p_plan* p, g2p_plan_info* info) {
+  if (!p || !info) return set_error(G2P_ERR_INVALID, "g2p_plan_get_info: null argument");
+  info->m = p->m;
+  info->n = p->n;
+  info->k = p->k;
+  info->tile_rows = p->tile_rows;
+  info->tile_cols = p->tile_cols;
+  info->n_tiles = p->n_tiles;
+  info->max_window = p->max_window;
+  info->max_ranges = p->max_ranges;
+  info->mean_window = p->mean_window;
+  info->bytes = (int64_t)p->k * p->m * 2 + (int64_t)p->n_tiles * (kMaxRanges * (int64_t)sizeof(Range) + 8);
+  return G2P_OK;
+}
+
+int g2p_apply_planned(const g2p_plan* p, const double* coef, const double* src, const uint8_t* src_mask, int b,
+                      int64_t src_stride, int64_t out_stride, double mv_out, int mask_policy, double* out,
+                      uint8_t* out_mask, void* stream) {
+  if (!p || !src || !out) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: null plan/src/out");
+  if (p->k > 1 && !coef) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: coef is required for k > 1");
+  if (p->k != 1 && p->k != 4) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: k=%d (1 and 4 are planned; use g2p_apply)", p->k);
+  if (b < 0) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: b < 0");
+  if (mask_policy != G2P_MASK_PROPAGATE && mask_policy != G2P_MASK_AS_REFERENCE)
+    return set_error(G2P_ERR_INVALID, "g2p_apply_planned: unknown mask_policy %d", mask_policy);
+  const bool mask = (mask_policy == G2P_MASK_PROPAGATE);
+  if (mask && (!src_mask || !out_mask)) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: PROPAGATE needs src_mask and out_mask");
+  if (src_stride < p->n_pad || out_stride < p->m) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: strides shorter than rows (src rows must be padded to a multiple of 16)");
+  // bulk copies need 16-byte aligned sources: value rows at 16 B, mask rows at 16 B
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (src_stride % 2) != 0)
+    return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: src rows must be 16-byte aligned; use g2p_apply");
+  if (mask && ((reinterpret_cast<uintptr_t>(src_mask) & 15) || (src_stride % 16) != 0))
+    return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: mask rows must be 16-byte aligned (stride %% 16 == 0); use g2p_apply");
+  if (b == 0) return G2P_OK;
+  WinArgs a{};
+  a.lidx = p->lidx;
+  a.coef = coef;
+  a.ranges = p->ranges;
+  a.tile_info = p->tile_info;
+  a.src = src;
+  a.src_mask = src_mask;
+  a.out = out;
+  a.out_mask = out_mask;
+  a.m = p->m;
+  a.src_stride = src_stride;
+  a.out_stride = out_stride;
+  a.g.rows = p->rows;
+  a.g.cols = p->cols;
+  a.g.tile_rows = p->tile_rows;
+  a.g.tile_cols = p->tile_cols;
+  a.g.tiles_c = p->tiles_c;
+  a.g.threads_per_row = p->tile_cols / kWinTPT;
+  a.b = b;
+  a.n_tiles = p->n_tiles;
+  a.mv_out = mv_out;
+  a.vec_store = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (out_stride % 2 == 0) && (p->cols % 2 == 0);
+  a.vec_mask = mask && ((reinterpret_cast<uintptr_t>(out_mask) & 1) == 0) && (out_stride % 2 == 0) && (p->cols % 2 == 0);
+  cudaStream_t st = as_stream(stream);
+  if (p->k == 1) return mask ? launch_window<1, true>(p, a, st) : launch_window<1, false>(p, a, st);
+  return mask ? launch_window<4, true>(p, a, st) : launch_window<4, false>(p, a, st);
+}
+
+}  // extern "C"

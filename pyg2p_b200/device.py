@@ -6,6 +6,7 @@ There is no CPU fallback: every function here needs libg2pgpu.so and a CUDA devi
 raises otherwise.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -189,7 +190,7 @@ class DeviceTable:
     {int64 indexes, f8|f4 coeffs}, shape (m,) for k=1 and (m,k) otherwise
     (reference interpolation/__init__.py:251)."""
 
-    def __init__(self, idx, coef, n_src, coef_f32=False, shape_1d=None):
+    def __init__(self, idx, coef, n_src, coef_f32=False, shape_1d=None, grid_shape=None):
         self.idx = idx
         self.coef = coef
         self.k, self.m = idx.shape
@@ -197,10 +198,50 @@ class DeviceTable:
         self.coef_f32 = bool(coef_f32)
         self.shape_1d = (self.k == 1) if shape_1d is None else shape_1d
         self.device = idx.device
+        self.grid_shape = tuple(int(x) for x in grid_shape) if grid_shape is not None else None
+        if self.grid_shape is not None and self.grid_shape[0] * self.grid_shape[1] != self.m:
+            raise ValueError(f'grid_shape {self.grid_shape} does not hold {self.m} targets')
+        self._plan = None            # C.c_void_p of a g2p_plan, False once found not windowable
+        self.plan_error = None
+
+    # ---- window plan for the shared-memory staged apply (K7w)
+    def plan(self):
+        """g2p_plan handle for this table (built on first use), or None when the table's indexes are too
+        scattered for a shared-memory window (the generic gather kernel is used then)."""
+        if self._plan is None:
+            lib = require_cuda()
+            _bind_device(self.device)
+            h = C.c_void_p()
+            rows, cols = self.grid_shape if self.grid_shape is not None else (0, 0)
+            with torch.cuda.device(self.device):
+                rc = lib.g2p_plan_create(_ptr(self.idx), self.m, self.k, self.n_src, rows, cols, C.byref(h), _stream())
+            if rc == L.ERR_UNSUPPORTED:
+                self._plan = False
+                self.plan_error = lib.g2p_last_error().decode('utf-8', 'replace')
+            else:
+                L.check(rc)
+                self._plan = h
+        return self._plan or None
+
+    def plan_info(self):
+        h = self.plan()
+        if h is None:
+            return None
+        inf = L.PlanInfo()
+        L.check(L.lib().g2p_plan_get_info(h, C.byref(inf)))
+        return {f: getattr(inf, f) for f, _ in L.PlanInfo._fields_}
+
+    def __del__(self):
+        try:
+            if self._plan:
+                L.lib().g2p_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:
+            pass
 
     # ---- record layout
     @classmethod
-    def from_record(cls, rec, n_src, device=None):
+    def from_record(cls, rec, n_src, device=None, grid_shape=None):
         """structured array as loaded from an intertable file -> device SoA (K6 unpack)."""
         lib = require_cuda()
         dev = _bind_device(device)
@@ -222,7 +263,7 @@ class DeviceTable:
             L.check(lib.g2p_table_unpack_rec(_ptr(raw), m, k, L.F32 if f32 else L.F64, _ptr(idx), _ptr(coef),
                                                _stream()))
             torch.cuda.current_stream().synchronize()
-        return cls(idx, coef, n_src, coef_f32=f32, shape_1d=one_d)
+        return cls(idx, coef, n_src, coef_f32=f32, shape_1d=one_d, grid_shape=grid_shape)
 
     def to_record(self):
         """device SoA -> numpy structured array in the reference's file layout (K6 pack + D2H)."""
@@ -243,9 +284,22 @@ class DeviceTable:
         return np.ascontiguousarray(rec['indexes']), np.ascontiguousarray(rec['coeffs'])
 
     # ---- apply
+    def _window_ok(self, src, src_mask, propagate):
+        """alignment rules of g2p_apply_planned (TMA bulk copies need 16-byte aligned rows)."""
+        if self.k not in (1, 4) or os.environ.get('G2P_APPLY_PATH', 'auto') == 'generic':
+            return False
+        n_pad = -(-self.n_src // 16) * 16
+        if src.data_ptr() % 16 or src.stride(0) % 2 or src.stride(0) < n_pad:
+            return False
+        if propagate and (src_mask.data_ptr() % 16 or src.stride(0) % 16):
+            return False
+        return self.plan() is not None
+
     def apply(self, src, mv_out, src_mask=None, mask_policy=L.MASK_AS_REFERENCE, out=None, out_mask=None):
         """Batched K7 on device-resident messages.  src: float64 [b, n] (or [n]); returns out [b, m]
-        (and out_mask uint8 [b, m] under PROPAGATE).  Asynchronous on the current stream."""
+        (and out_mask uint8 [b, m] under PROPAGATE).  Asynchronous on the current stream.
+        Uses the windowed kernel (g2p_apply_planned) when the table and the buffers allow it, else the
+        generic gather kernel (g2p_apply); both are bit-identical."""
         lib = require_cuda()
         _bind_device(self.device)
         squeeze = src.dim() == 1
@@ -274,7 +328,14 @@ class DeviceTable:
                     src_mask = src_mask.contiguous()
                 if out_mask is None:
                     out_mask = torch.empty((b, self.m), dtype=torch.uint8, device=self.device)
-            if b > 0 and self.m > 0:
+            if b > 0 and self.m > 0 and self._window_ok(src, src_mask, propagate):
+                self.last_path = 'window'
+                L.check(lib.g2p_apply_planned(self.plan(), _ptr(self.coef) if self.k > 1 else None, _ptr(src),
+                                              _ptr(src_mask) if propagate else None, b, src.stride(0), out.stride(0),
+                                              float(mv_out), int(mask_policy), _ptr(out),
+                                              _ptr(out_mask) if propagate else None, _stream()))
+            elif b > 0 and self.m > 0:
+                self.last_path = 'generic'
                 L.check(lib.g2p_apply(_ptr(self.idx), _ptr(self.coef) if self.k > 1 else None, self.m, self.k, _ptr(src),
                                       _ptr(src_mask) if propagate else None, n, b, src.stride(0), out.stride(0),
                                       float(mv_out), int(mask_policy), _ptr(out), _ptr(out_mask) if propagate else None,

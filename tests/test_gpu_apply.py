@@ -146,3 +146,103 @@ def test_linearity_at_full_size(dev):
     for j in range(1, k):
         acc = acc + ww[j] * src[3][ii[j]]
     assert torch.equal(out[3][rows], acc)
+
+
+def _padded(v, align=16):
+    """[b, n] ndarray -> device view [b, n] of a [b, ceil16(n)] buffer (what the windowed kernel needs)."""
+    b, n = v.shape
+    n_pad = -(-n // align) * align
+    buf = torch.zeros((b, n_pad), dtype=torch.from_numpy(v[:0]).dtype, device='cuda')
+    buf[:, :n] = torch.from_numpy(v).cuda()
+    return buf[:, :n]
+
+
+@pytest.mark.parametrize('mode,k', [('nearest', 1), ('invdist', 4)])
+def test_window_path_matches_reference_golden(dev, golden_dir, mode, k):
+    g = np.load(os.path.join(golden_dir, 'apply_regional.npz'))
+    t = np.load(os.path.join(golden_dir, 'build_regional_global_f64.npz'))
+    rec = R.to_record(t[f'{mode}_indexes'], t[f'{mode}_weights'])
+    n = g['v0'].size
+    tbl = dev.DeviceTable.from_record(rec, n)
+    assert tbl.plan_info()['max_window'] >= 16
+    src = _padded(np.stack([g[f'v{b}'] for b in range(3)]))
+    mask = _padded(np.stack([g[f'mask{b}'] for b in range(3)]).view(np.uint8))
+    out = tbl.apply(src, float(g['mv_out'])).cpu().numpy()
+    assert tbl.last_path == 'window'
+    o2, m2 = tbl.apply(src, float(g['mv_out']), src_mask=mask, mask_policy=L.MASK_PROPAGATE)
+    assert tbl.last_path == 'window'
+    for b in range(3):
+        _eq(out[b], g[f'{mode}_plain{b}'])
+        data, mk = R.apply_propagate(g[f'v{b}'], rec['coeffs'], rec['indexes'], k, float(g['mv_out']), g[f'mask{b}'])
+        _eq(o2[b].cpu().numpy(), data)
+        _eq(m2[b].cpu().numpy().astype(bool), mk)
+
+
+@pytest.mark.parametrize('k', [1, 4])
+@pytest.mark.parametrize('shape,b', [((1, 1), 1), ((1, 2), 3), ((7, 143), 5), ((33, 257), 9), ((300, 1000), 2),
+                                     ((1, 65537), 4), ((5, 4), 70)])
+def test_window_path_random_tables(dev, k, shape, b):
+    """the windowed kernel against the oracle on ragged grids (odd columns, partial tiles), sentinels and
+    NaN weights; batch sizes that exercise the stage ring (b > stages) and several message chunks."""
+    rows, cols = shape
+    m = rows * cols
+    rng = np.random.default_rng(7 * k + m % 1013 + b)
+    n = 4001                                                   # not a multiple of 16: rows are padded
+    centre = rng.integers(0, n, size=m)
+    idx = np.clip(centre[:, None] + rng.integers(-40, 41, size=(m, k)), 0, n)   # n = sentinel
+    idx[rng.random(m) < 0.03] = n
+    w = rng.random((m, k))
+    w /= w.sum(axis=1, keepdims=True)
+    w[rng.random(m) < 0.05] = np.nan
+    if k == 1:
+        idx, w = idx[:, 0], w[:, 0]
+    rec = R.to_record(idx, w)
+    v = rng.standard_normal((b, n)) * 100
+    mask = rng.random((b, n)) < 0.1
+    mv = 9.969209968386869e36
+    for grid_shape in (None, shape):
+        tbl = dev.DeviceTable.from_record(rec, n, grid_shape=grid_shape)
+        src, msk = _padded(v), _padded(mask.view(np.uint8))
+        out = tbl.apply(src, mv).cpu().numpy()
+        assert tbl.last_path == 'window', tbl.plan_error
+        o2, m2 = tbl.apply(src, mv, src_mask=msk, mask_policy=L.MASK_PROPAGATE)
+        for i in range(b):
+            with np.errstate(all='ignore'):
+                _eq(out[i], R.apply_sequential(v[i], rec['coeffs'], rec['indexes'], k, mv))
+                data, mk = R.apply_propagate(v[i], rec['coeffs'], rec['indexes'], k, mv, mask[i])
+            _eq(o2[i].cpu().numpy(), data)
+            _eq(m2[i].cpu().numpy().astype(bool), mk)
+
+
+def test_scattered_table_falls_back_to_generic_gpu_kernel(dev):
+    rng = np.random.default_rng(4)
+    n, m, k = 4_000_000, 5000, 4
+    idx = rng.integers(0, n, size=(m, k))
+    w = rng.random((m, k))
+    tbl = dev.DeviceTable.from_record(R.to_record(idx, w), n)
+    v = rng.standard_normal((2, n))
+    out = tbl.apply(torch.from_numpy(v).cuda(), 0.0).cpu().numpy()
+    assert tbl.last_path == 'generic' and 'not windowable' in tbl.plan_error
+    for i in range(2):
+        _eq(out[i], R.apply_sequential(v[i], w, idx, k, 0.0))
+
+
+def test_window_equals_generic_on_real_geometry(dev, monkeypatch):
+    """O320 -> EFAS invdist table built on the GPU: both apply kernels give identical bytes."""
+    from pyg2p_b200 import synth
+    lat, lon, det = synth.octahedral_grid(320)
+    tl, tlo = synth.efas_target()
+    ix = dev.SourceIndex(lon, lat, det['radius'])
+    out = ix.knn(tlo, tl, k=4, mode=L.MODE_INVDIST, mub=ix.min_upper_bound(det['Nj']), want_flags=False)
+    tbl = dev.DeviceTable(out['idx'], out['coef'], lat.size, grid_shape=tl.shape)
+    info = tbl.plan_info()
+    assert info['tile_cols'] * info['tile_rows'] == 1024 and info['max_window'] < 4096
+    g = torch.Generator(device='cuda').manual_seed(2)
+    src = torch.randn((37, lat.size), generator=g, device='cuda', dtype=torch.float64)
+    msk = (torch.rand((37, lat.size), generator=g, device='cuda') < 0.05).to(torch.uint8)
+    a, am = tbl.apply(src, 1e20, src_mask=msk, mask_policy=L.MASK_PROPAGATE)
+    assert tbl.last_path == 'window'
+    monkeypatch.setenv('G2P_APPLY_PATH', 'generic')
+    b_, bm = tbl.apply(src, 1e20, src_mask=msk, mask_policy=L.MASK_PROPAGATE)
+    assert tbl.last_path == 'generic'
+    assert torch.equal(a.view(torch.int64), b_.view(torch.int64)) and torch.equal(am, bm)
