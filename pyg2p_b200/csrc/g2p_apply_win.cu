@@ -8,8 +8,11 @@
 // contiguous index ranges (pieces of neighbouring latitude rings).  A plan, built once per table,
 // lists those ranges per tile (16-element aligned) and rewrites the table's int32 indexes as
 // uint16 offsets into the tile's window.  The apply kernel then, per (tile, message):
-//   * one warp issues cp.async.bulk (TMA 1-D bulk copies, UBLKCP) of the ranges - values and
-//     mask bytes - into a shared-memory stage, completion on an mbarrier; 2-4 stages in flight;
+//   * all threads copy the ranges - values and mask bytes - into a shared-memory stage with 16-byte
+//     cp.async (LDGSTS, L2-only), 2-4 stages in flight.  (A first version issued one cp.async.bulk
+//     per range from one warp: the ranges are ~32 values long, 44 bulk copies per tile and message,
+//     and UBLKCP takes its operands from uniform registers, so the issuing warp serialised them at
+//     ~20 instructions each and every other warp waited at the barrier - see profiles/.)
 //   * all threads gather their k neighbours from shared memory (bank-conflict-light because
 //     neighbouring lanes own neighbouring targets), do the no-FMA weighted sum and write the
 //     outputs with 128-bit streaming stores.
@@ -31,7 +34,7 @@ constexpr int kMaxRanges = 96;                           // source index ranges 
 constexpr int kMaxStages = 4;
 constexpr int kBlockElems = 16;                          // range granularity: 16 values = 128 B, 16 mask bytes
 constexpr int kPlanSpanBlocks = 1 << 17;                 // bitmap span per tile: 2 M source elements
-constexpr int kMaxWindowElems = 20480;                   // 160 KB of values per stage at most (1 stage)
+constexpr int kMaxWindowElems = 8192;                    // 16 x 16-byte value chunks per thread and message
 constexpr uint16_t kLocalSentinel = 0xffff;
 
 struct __align__(16) Range {
@@ -219,34 +222,27 @@ __global__ void __launch_bounds__(kWinThreads) plan_kernel(const PlanArgs a) {
   }
 }
 
-// ------------------------------------------------------------------ PTX helpers: mbarrier + bulk copy
+// ------------------------------------------------------------------ PTX helpers: cp.async (LDGSTS)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// 16-byte global -> shared asynchronous copy, L2 only (.cg): the staged values are read once per tile
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
 }
-// global -> shared bulk copy (1-D TMA); dst, src and bytes are multiples of 16
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 
 // ------------------------------------------------------------------ apply kernel
@@ -276,61 +272,82 @@ __device__ __forceinline__ double weighted_sum(const double (&w)[K], const doubl
   return acc;
 }
 
-template <int K, bool MASK>
+// source element of window element `elem` (ranges are sorted by smem_off); -1 past the window
+__device__ __forceinline__ int window_to_source(const Range* ranges, int nr, int window, int elem) {
+  if (elem >= window) return -1;
+  int lo = 0, hi = nr - 1;  // last range with smem_off <= elem
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (ranges[mid].smem_off <= elem) lo = mid; else hi = mid - 1;
+  }
+  return ranges[lo].src_start + (elem - ranges[lo].smem_off);
+}
+
+// CV = 16-byte value chunks copied per thread and message (window <= 512*CV values)
+template <int K, bool MASK, int CV>
 __global__ void __launch_bounds__(kWinThreads) apply_window_kernel(const WinArgs a) {
   extern __shared__ __align__(128) unsigned char s_raw[];
-  __shared__ __align__(8) uint64_t s_full[kMaxStages];
   __shared__ Range s_ranges[kMaxRanges];
   __shared__ int s_tile_info[2];
-  double* s_val = reinterpret_cast<double*>(s_raw);                                    // [stages][stage_elems]
-  uint8_t* s_msk = s_raw + (size_t)a.stages * a.stage_elems * sizeof(double);          // [stages][stage_elems]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int CM = (CV + 7) / 8;  // 16-byte mask chunks per thread
+  const int tid = threadIdx.x;
   const int S = a.stages;
-  const int sent = a.stage_elems - 1;  // slot that always holds mv_out / mask 0
+  const uint32_t val_base = smem_u32(s_raw);                                             // [stages][stage_elems] f64
+  const uint32_t msk_base = val_base + (uint32_t)S * a.stage_elems * 8u;                 // [stages][stage_elems] u8
+  const uint32_t stage_vbytes = (uint32_t)a.stage_elems * 8u;
+  const int sent = a.stage_elems - 1;  // slot that always holds mv_out / mask 0 (copies never reach it)
   if (tid < S) {
-    mbar_init(&s_full[tid], 1);
-    s_val[(size_t)tid * a.stage_elems + sent] = a.mv_out;
-    if (MASK) s_msk[(size_t)tid * a.stage_elems + sent] = 0;
+    reinterpret_cast<double*>(s_raw)[(size_t)tid * a.stage_elems + sent] = a.mv_out;
+    if (MASK) s_raw[(size_t)S * a.stage_elems * 8 + (size_t)tid * a.stage_elems + sent] = 0;
   }
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
-  uint32_t phase = 0;  // bit s = parity to wait for on stage s
 
   for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
     const int tile = (int)(item % a.n_tiles);
     const int chunk = (int)(item / a.n_tiles);
     const int msg_begin = chunk * a.msgs_per_chunk;
-    const int msg_end = min(a.b, msg_begin + a.msgs_per_chunk);
+    const int n_msg = min(a.b, msg_begin + a.msgs_per_chunk) - msg_begin;
     // ---- tile plan
+    __syncthreads();  // previous item is finished with s_ranges and the stages
     if (tid < 2) s_tile_info[tid] = a.tile_info[2 * tile + tid];
     __syncthreads();
     const int nr = s_tile_info[0];
-    const uint32_t win_bytes = (uint32_t)s_tile_info[1] * (MASK ? 9u : 8u);
+    const int window = s_tile_info[1];
     for (int i = tid; i < nr; i += kWinThreads) s_ranges[i] = a.ranges[(int64_t)tile * kMaxRanges + i];
     __syncthreads();
+    // ---- this thread's share of the staging copies: CV value chunks, CM mask chunks (source offsets)
+    int vsrc[CV], msrc[CM];
+#pragma unroll
+    for (int i = 0; i < CV; ++i) vsrc[i] = window_to_source(s_ranges, nr, window, 2 * (tid + kWinThreads * i));
+#pragma unroll
+    for (int i = 0; i < CM; ++i) msrc[i] = MASK ? window_to_source(s_ranges, nr, window, 16 * (tid + kWinThreads * i)) : -1;
 
-    auto issue = [&](int msg, int stage) {  // warp 0 only
-      if (lane == 0) mbar_expect_tx(&s_full[stage], win_bytes);
-      __syncwarp();
-      const double* gv = a.src + (int64_t)msg * a.src_stride;
-      double* sv = s_val + (size_t)stage * a.stage_elems;
-      for (int i = lane; i < nr; i += 32) {
-        const Range rg = s_ranges[i];
-        bulk_g2s(sv + rg.smem_off, gv + rg.src_start, (uint32_t)rg.n_elem * 8u, &s_full[stage]);
-        if (MASK)
-          bulk_g2s(s_msk + (size_t)stage * a.stage_elems + rg.smem_off,
-                   a.src_mask + (int64_t)msg * a.src_stride + rg.src_start, (uint32_t)rg.n_elem, &s_full[stage]);
+    auto prefetch = [&](int it) {  // message msg_begin + it -> stage it % S
+      if (it < n_msg) {
+        const int stage = it % S;
+        const int64_t row = (int64_t)(msg_begin + it) * a.src_stride;
+        const double* gv = a.src + row;
+        const uint32_t sv = val_base + (uint32_t)stage * stage_vbytes + 16u * tid;
+#pragma unroll
+        for (int i = 0; i < CV; ++i)
+          if (vsrc[i] >= 0) cp_async16(sv + 16u * kWinThreads * i, gv + vsrc[i]);
+        if (MASK) {
+          const uint8_t* gm = a.src_mask + row;
+          const uint32_t sm = msk_base + (uint32_t)stage * a.stage_elems + 16u * tid;
+#pragma unroll
+          for (int i = 0; i < CM; ++i)
+            if (msrc[i] >= 0) cp_async16(sm + 16u * kWinThreads * i, gm + msrc[i]);
+        }
       }
+      cp_async_commit();  // always: keeps the group count uniform
     };
-    if (warp == 0 && nr > 0)
-      for (int s = 0; s < S && msg_begin + s < msg_end; ++s) issue(msg_begin + s, s);
+    for (int s = 0; s < S - 1; ++s) prefetch(s);
 
-    // ---- this thread's targets: local indexes and weights stay in registers for the whole chunk
+    // ---- this thread's targets: window offsets and weights stay in registers for the whole chunk
     int64_t r, c[kWinTPT];
     thread_targets(a.g, tile, tid, r, c);
     bool ok[kWinTPT];
     int64_t j[kWinTPT];
-    int li[kWinTPT][K];
+    uint32_t li[kWinTPT][K];
     double w[kWinTPT][K];
 #pragma unroll
     for (int t = 0; t < kWinTPT; ++t) {
@@ -339,20 +356,21 @@ __global__ void __launch_bounds__(kWinThreads) apply_window_kernel(const WinArgs
 #pragma unroll
       for (int kk = 0; kk < K; ++kk) {
         const uint16_t l = ok[t] ? __ldg(a.lidx + (int64_t)kk * a.m + j[t]) : kLocalSentinel;
-        li[t][kk] = (l == kLocalSentinel) ? sent : (int)l;
+        li[t][kk] = (l == kLocalSentinel) ? (uint32_t)sent : (uint32_t)l;
         w[t][kk] = (K > 1 && ok[t]) ? __ldg(a.coef + (int64_t)kk * a.m + j[t]) : 1.0;
       }
     }
+    double* o = a.out + (int64_t)msg_begin * a.out_stride;
+    uint8_t* om = MASK ? a.out_mask + (int64_t)msg_begin * a.out_stride : nullptr;
 
     // ---- messages
-    for (int msg = msg_begin, it = 0; msg < msg_end; ++msg, ++it) {
+    for (int it = 0; it < n_msg; ++it) {
+      if (S >= 4) cp_async_wait<2>(); else if (S == 3) cp_async_wait<1>(); else cp_async_wait<0>();
+      __syncthreads();        // message `it` is in shared memory; everyone is done with message it-1
+      prefetch(it + S - 1);   // into the stage message it-1 used
       const int stage = it % S;
-      if (nr > 0) {
-        mbar_wait(&s_full[stage], (phase >> stage) & 1u);
-        phase ^= 1u << stage;
-      }
-      const double* sv = s_val + (size_t)stage * a.stage_elems;
-      const uint8_t* sm = s_msk + (size_t)stage * a.stage_elems;
+      const uint32_t sv = val_base + (uint32_t)stage * stage_vbytes;
+      const uint32_t sm = msk_base + (uint32_t)stage * a.stage_elems;
       double res[kWinTPT];
       uint32_t mk[kWinTPT];
 #pragma unroll
@@ -361,13 +379,12 @@ __global__ void __launch_bounds__(kWinThreads) apply_window_kernel(const WinArgs
         uint32_t mm = 0;
 #pragma unroll
         for (int kk = 0; kk < K; ++kk) {
-          v[kk] = sv[li[t][kk]];
-          if (MASK) mm |= sm[li[t][kk]];
+          v[kk] = lds_f64(sv + 8u * li[t][kk]);
+          if (MASK) mm |= lds_u8(sm + li[t][kk]);
         }
         res[t] = weighted_sum<K>(w[t], v);
-        mk[t] = mm ? 1u : 0u;
+        mk[t] = mm;
       }
-      double* o = a.out + (int64_t)msg * a.out_stride;
 #pragma unroll
       for (int p = 0; p < kWinTPT; p += 2) {
         if (a.vec_store && ok[p + 1]) {
@@ -378,7 +395,6 @@ __global__ void __launch_bounds__(kWinThreads) apply_window_kernel(const WinArgs
         }
       }
       if (MASK) {
-        uint8_t* om = a.out_mask + (int64_t)msg * a.out_stride;
 #pragma unroll
         for (int p = 0; p < kWinTPT; p += 2) {
           if (a.vec_mask && ok[p + 1]) {
@@ -388,10 +404,11 @@ __global__ void __launch_bounds__(kWinThreads) apply_window_kernel(const WinArgs
             if (ok[p + 1]) om[j[p + 1]] = (uint8_t)mk[p + 1];
           }
         }
+        om += a.out_stride;
       }
-      __syncthreads();  // everyone is done with this stage
-      if (warp == 0 && nr > 0 && msg + S < msg_end) issue(msg + S, stage);
+      o += a.out_stride;
     }
+    cp_async_wait<0>();
   }
 }
 
@@ -399,15 +416,14 @@ static size_t win_smem_bytes(int stages, int stage_elems, bool mask) {
   return (size_t)stages * stage_elems * (mask ? 9 : 8);
 }
 
-template <int K, bool MASK>
-static int launch_window(const g2p_plan* p, WinArgs a, cudaStream_t st) {
-  // stages: as many as fit in ~100 KB per CTA (two CTAs per SM), at least 1
-  const int stage_elems = ((p->max_window + 1 + 15) / 16) * 16;  // +1: the sentinel slot
+template <int K, bool MASK, int CV>
+static int launch_window_cv(const g2p_plan* p, WinArgs a, int stage_elems, cudaStream_t st) {
+  // stages: as many as fit in ~72 KB per CTA (three CTAs per SM), at least 2
   int stages = kMaxStages;
-  while (stages > 1 && win_smem_bytes(stages, stage_elems, MASK) > 100 * 1024) --stages;
+  while (stages > 2 && win_smem_bytes(stages, stage_elems, MASK) > 72 * 1024) --stages;
   const size_t smem = win_smem_bytes(stages, stage_elems, MASK);
   if (smem > 200 * 1024) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: window of %d elements needs %zu B of shared memory", p->max_window, smem);
-  auto kern = apply_window_kernel<K, MASK>;
+  auto kern = apply_window_kernel<K, MASK, CV>;
   G2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   G2P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWinThreads, smem));
@@ -427,6 +443,16 @@ static int launch_window(const g2p_plan* p, WinArgs a, cudaStream_t st) {
   kern<<<grid, kWinThreads, smem, st>>>(a);
   G2P_LAUNCHED();
   return G2P_OK;
+}
+
+template <int K, bool MASK>
+static int launch_window(const g2p_plan* p, WinArgs a, cudaStream_t st) {
+  const int stage_elems = ((p->max_window + 1 + 15) / 16) * 16;  // +1: the sentinel slot
+  const int chunks = (p->max_window / 2 + kWinThreads - 1) / kWinThreads;  // 16-byte value chunks per thread
+  if (chunks <= 2) return launch_window_cv<K, MASK, 2>(p, a, stage_elems, st);
+  if (chunks <= 4) return launch_window_cv<K, MASK, 4>(p, a, stage_elems, st);
+  if (chunks <= 8) return launch_window_cv<K, MASK, 8>(p, a, stage_elems, st);
+  return launch_window_cv<K, MASK, 16>(p, a, stage_elems, st);
 }
 
 }  // namespace g2p
@@ -551,7 +577,7 @@ int g2p_plan_create(const int32_t* idx, int64_t m, int k, int64_t n, int64_t row
   if (e != cudaSuccess) rc = cuda_fail(e, "g2p_plan_create", __FILE__, __LINE__);
   else if (status[0] != 0) {
     static const char* why[] = {"", "a tile's indexes span more than 2 M source points", "a tile needs more than 96 index ranges",
-                                "a tile's window exceeds 20480 source values"};
+                                "a tile's window exceeds 8192 source values"};
     rc = set_error(G2P_ERR_UNSUPPORTED, "g2p_plan_create: table is not windowable (%s); use g2p_apply", why[status[0] & 3]);
   }
   if (rc != G2P_OK) {
