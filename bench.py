@@ -283,11 +283,17 @@ def run_b200(args):
     ii = table.idx[:, rows].long()
     ww = table.coef[:, rows]
     inside = ii[0] < n
-    acc = ww[0] * src[B // 2][ii[0].clamp(max=n - 1)]
+    iic = ii.clamp(max=n - 1)
+    acc = ww[0] * src[B // 2][iic[0]]
+    masked = src_mask[B // 2][iic[0]].bool()
     for j in range(1, K_INVDIST):
-        acc = acc + ww[j] * src[B // 2][ii[j].clamp(max=n - 1)]
+        acc = acc + ww[j] * src[B // 2][iic[j]]
+        masked |= src_mask[B // 2][iic[j]].bool()
+    masked &= inside
+    acc = torch.where(masked, torch.full_like(acc, synth.NC_FILL_F64), acc)
     got = out_t[B // 2][rows]
     assert torch.equal(got[inside], acc[inside]), 'timed apply output differs from the reference evaluation order'
+    assert torch.equal(out_m[B // 2][rows].bool(), masked), 'timed apply mask differs'
     assert torch.isnan(got[~inside]).all()
 
     # ---- e2e: host (pinned) messages -> host results through the host-buffer pipeline

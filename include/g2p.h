@@ -46,7 +46,7 @@ enum {
 
 enum { G2P_F64 = 0, G2P_F32 = 1 };                 /* dtype of lat/lon maps, distances, coeffs */
 enum { G2P_MODE_RAW = 0, G2P_MODE_NEAREST = 1, G2P_MODE_INVDIST = 2 };
-enum { G2P_MASK_AS_REFERENCE = 0, G2P_MASK_PROPAGATE = 1 };
+enum { G2P_MASK_AS_REFERENCE = 0, G2P_MASK_PROPAGATE = 1, G2P_MASK_FILL = 2 };
 
 /* per-target flags written by g2p_knn */
 enum {
@@ -142,11 +142,13 @@ int g2p_table_unpack_rec(const void* rec, int64_t m, int k, int coeff_dtype, int
  *   src        : float64, message i at src + i*src_stride, n values each
  *   src_mask   : uint8 (1 = missing), message i at src_mask + i*src_stride; nullable
  *   out        : float64, message i at out + i*out_stride, m values each
- *   out_mask   : uint8, same striding as out; required iff mask_policy == PROPAGATE
+ *   out_mask   : uint8, same striding as out; required iff mask_policy == PROPAGATE (ignored otherwise)
  *   k == 1     : out = src[idx], or mv_out where idx == n (the appended slot, :147)
  *   k  > 1     : out = ((w0*v0 + w1*v1) + w2*v2) + ..., separate multiply and add
  *   mask_policy: AS_REFERENCE ignores src_mask (the reference drops it);
- *                PROPAGATE sets out_mask = OR of the k source masks */
+ *                PROPAGATE is the intended semantics of :148-161: out_mask = OR of the k source masks and
+ *                the masked outputs hold mv_out (`ma.filled(result, mv_out)`, what the writers do with a
+ *                masked result: util/numeric.py:21-27); FILL is PROPAGATE without the out_mask array */
 int g2p_apply(const int32_t* idx, const double* coef, int64_t m, int k, const double* src,
               const uint8_t* src_mask, int64_t n, int b, int64_t src_stride, int64_t out_stride,
               double mv_out, int mask_policy, double* out, uint8_t* out_mask, void* stream);

@@ -237,12 +237,15 @@ def apply_sequential(v, weights, indexes, nnear, mv_out):
 def apply_propagate(v, weights, indexes, nnear, mv_out, src_mask):
     """Intended mask semantics of :148-161 (what the code would do with `ma.append`): the
     output is masked where ANY of the k source points is masked; the sentinel slot N is
-    never masked.  Returns (data, mask)."""
+    never masked.  Returns (`ma.filled(result, mv_out)`, mask): the data under a mask is
+    unspecified in numpy.ma, and every consumer in the reference fills it with the target
+    missing value (`result_masked`, util/numeric.py:21-27), so that is the pinned form."""
     data = apply_sequential(np.asarray(ma.getdata(v)), weights, indexes, nnear, mv_out)
     m = np.append(np.asarray(src_mask, dtype=bool), False)
     if nnear == 1:
-        return data, m[indexes]
-    out = np.zeros(indexes.shape[0], dtype=bool)
-    for j in range(indexes.shape[1]):
-        out |= m[indexes[:, j]]
-    return data, out
+        out = m[indexes]
+    else:
+        out = np.zeros(indexes.shape[0], dtype=bool)
+        for j in range(indexes.shape[1]):
+            out |= m[indexes[:, j]]
+    return np.where(out, mv_out, data), out

@@ -14,7 +14,7 @@ OK = 0
 ERR_UNSUPPORTED = -5
 F64, F32 = 0, 1
 MODE_RAW, MODE_NEAREST, MODE_INVDIST = 0, 1, 2
-MASK_AS_REFERENCE, MASK_PROPAGATE = 0, 1
+MASK_AS_REFERENCE, MASK_PROPAGATE, MASK_FILL = 0, 1, 2
 FLAG_TIE, FLAG_NEAR_TIE, FLAG_SHORT = 1, 2, 4
 
 

@@ -75,6 +75,10 @@ __device__ __forceinline__ void apply_messages(const ApplyArgs& a, int msg, int6
   for (int u = 0; u < U; ++u) {
     double r0 = weighted<K>(w0, v0[u]);
     double r1 = weighted<K>(w1, v1[u]);
+    if (MASK) {  // masked outputs carry the target missing value (`ma.filled(result, mv_out)`)
+      if (mk0[u]) r0 = a.mv_out;
+      if (mk1[u]) r1 = a.mv_out;
+    }
     double* o = a.out + (int64_t)(msg + u) * a.out_stride + j0;
     if (a.vec_store && has1) {
       __stcs(reinterpret_cast<double2*>(o), make_double2(r0, r1));
@@ -82,7 +86,7 @@ __device__ __forceinline__ void apply_messages(const ApplyArgs& a, int msg, int6
       __stcs(o, r0);
       if (has1) __stcs(o + 1, r1);
     }
-    if (MASK) {
+    if (MASK && a.out_mask) {
       uint8_t* om = a.out_mask + (int64_t)(msg + u) * a.out_stride + j0;
       om[0] = mk0[u];
       if (has1) om[1] = mk1[u];
@@ -142,8 +146,9 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel_anyk(const ApplyAr
       acc = (kk == 0) ? p : __dadd_rn(acc, p);
       if (MASK && in) mk |= __ldg(a.src_mask + (int64_t)msg * a.src_stride + i);
     }
+    if (MASK && mk) acc = a.mv_out;
     __stcs(a.out + (int64_t)msg * a.out_stride + j, acc);
-    if (MASK) a.out_mask[(int64_t)msg * a.out_stride + j] = mk ? 1 : 0;
+    if (MASK && a.out_mask) a.out_mask[(int64_t)msg * a.out_stride + j] = mk ? 1 : 0;
   }
 }
 
@@ -252,11 +257,13 @@ int g2p_apply(const int32_t* idx, const double* coef, int64_t m, int k, const do
   if (k > 1 && !coef) return set_error(G2P_ERR_INVALID, "g2p_apply: coef is required for k > 1");
   if (m < 0 || n < 0 || n > 0x7fffffffLL || b < 0) return set_error(G2P_ERR_INVALID, "g2p_apply: bad sizes");
   if (src_stride < n || out_stride < m) return set_error(G2P_ERR_INVALID, "g2p_apply: strides shorter than rows");
-  const bool mask = (mask_policy == G2P_MASK_PROPAGATE);
-  if (mask_policy != G2P_MASK_PROPAGATE && mask_policy != G2P_MASK_AS_REFERENCE)
+  const bool mask = (mask_policy == G2P_MASK_PROPAGATE || mask_policy == G2P_MASK_FILL);
+  if (!mask && mask_policy != G2P_MASK_AS_REFERENCE)
     return set_error(G2P_ERR_INVALID, "g2p_apply: unknown mask_policy %d", mask_policy);
-  if (mask && (!src_mask || !out_mask))
-    return set_error(G2P_ERR_INVALID, "g2p_apply: PROPAGATE needs src_mask and out_mask");
+  if (mask && !src_mask) return set_error(G2P_ERR_INVALID, "g2p_apply: PROPAGATE / FILL need src_mask");
+  if (mask_policy == G2P_MASK_PROPAGATE && !out_mask)
+    return set_error(G2P_ERR_INVALID, "g2p_apply: PROPAGATE needs out_mask");
+  if (mask_policy == G2P_MASK_FILL) out_mask = nullptr;
   if (m == 0 || b == 0) return G2P_OK;
   ApplyArgs a{};
   a.idx = idx;

@@ -68,17 +68,16 @@ struct TileGeom {
   int tile_rows, tile_cols, tiles_c, threads_per_row;
 };
 
-// target columns owned by thread x of a tile row: pairs {2x, 2x+1} and {half + 2x, half + 2x + 1}
+// target columns owned by thread x of a tile row: x, x + T, x + 2T, x + 3T with T = threads per row, so that
+// neighbouring lanes own neighbouring targets: their k-th neighbours are the same or adjacent source points
+// (broadcast / distinct banks in shared memory) and a half-warp stores 128 contiguous bytes
 __device__ __forceinline__ void thread_targets(const TileGeom& g, int tile, int tid, int64_t& r, int64_t (&c)[kWinTPT]) {
   const int ty = tile / g.tiles_c, tx = tile - ty * g.tiles_c;
   const int tr = tid / g.threads_per_row, x = tid - tr * g.threads_per_row;
-  const int half = g.tile_cols >> 1;
   r = (int64_t)ty * g.tile_rows + tr;
-  const int64_t c0 = (int64_t)tx * g.tile_cols;
-  c[0] = c0 + 2 * x;
-  c[1] = c[0] + 1;
-  c[2] = c0 + half + 2 * x;
-  c[3] = c[2] + 1;
+  const int64_t c0 = (int64_t)tx * g.tile_cols + x;
+#pragma unroll
+  for (int t = 0; t < kWinTPT; ++t) c[t] = c0 + (int64_t)t * g.threads_per_row;
 }
 
 // ------------------------------------------------------------------ plan kernel: one CTA per tile
@@ -260,7 +259,6 @@ struct WinArgs {
   int b, n_tiles, msgs_per_chunk, stages, stage_elems;
   int64_t n_items;
   double mv_out;
-  int vec_store, vec_mask;
 };
 
 template <int K>
@@ -272,7 +270,7 @@ __device__ __forceinline__ double weighted_sum(const double (&w)[K], const doubl
   return acc;
 }
 
-// source element of window element `elem` (ranges are sorted by smem_off); -1 past the window
+// source element of window element `elem` (ranges are sorted by smem_off); -1 in a gap or past the window
 __device__ __forceinline__ int window_to_source(const Range* ranges, int nr, int window, int elem) {
   if (elem >= window) return -1;
   int lo = 0, hi = nr - 1;  // last range with smem_off <= elem
@@ -280,15 +278,23 @@ __device__ __forceinline__ int window_to_source(const Range* ranges, int nr, int
     const int mid = (lo + hi + 1) >> 1;
     if (ranges[mid].smem_off <= elem) lo = mid; else hi = mid - 1;
   }
-  return ranges[lo].src_start + (elem - ranges[lo].smem_off);
+  const int d = elem - ranges[lo].smem_off;
+  return (d >= 0 && d < ranges[lo].n_elem) ? ranges[lo].src_start + d : -1;
 }
 
-// CV = 16-byte value chunks copied per thread and message (window <= 512*CV values)
-template <int K, bool MASK, int CV>
+// A masked source value is replaced, in shared memory, by this quiet NaN: the weighted sum of a target
+// with a masked neighbour is then NaN and the (rare) slow path looks for the marker among its operands,
+// so the k mask-byte gathers per target disappear from the inner loop.
+constexpr unsigned long long kMaskMarker = 0x7ff86d61736b0001ull;
+
+// MP: 0 = no masks (AS_REFERENCE), 1 = PROPAGATE (out_mask written), 2 = FILL
+// CV: 16-byte value chunks copied per thread and message (window <= 512*CV values)
+template <int K, int MP, int CV>
 __global__ void __launch_bounds__(kWinThreads) apply_window_kernel(const WinArgs a) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ Range s_ranges[kMaxRanges];
   __shared__ int s_tile_info[2];
+  constexpr bool MASK = MP != 0;
   constexpr int CM = (CV + 7) / 8;  // 16-byte mask chunks per thread
   const int tid = threadIdx.x;
   const int S = a.stages;
@@ -340,73 +346,81 @@ __global__ void __launch_bounds__(kWinThreads) apply_window_kernel(const WinArgs
       }
       cp_async_commit();  // always: keeps the group count uniform
     };
+    // fold the mask bytes of a landed message into its values (4 window elements per thread and step)
+    auto fold = [&](int it) {
+      if (it >= n_msg) return;
+      const int stage = it % S;
+      const uint32_t sv = val_base + (uint32_t)stage * stage_vbytes;
+      const uint32_t sm = msk_base + (uint32_t)stage * a.stage_elems;
+      for (int e = 4 * tid; e < window; e += 4 * kWinThreads) {
+        uint32_t m4;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m4) : "r"(sm + e));
+        if (m4) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if ((m4 >> (8 * q)) & 0xffu)
+              asm volatile("st.shared.u64 [%0], %1;" ::"r"(sv + 8u * (e + q)), "l"(kMaskMarker) : "memory");
+        }
+      }
+    };
     for (int s = 0; s < S - 1; ++s) prefetch(s);
 
     // ---- this thread's targets: window offsets and weights stay in registers for the whole chunk
     int64_t r, c[kWinTPT];
     thread_targets(a.g, tile, tid, r, c);
     bool ok[kWinTPT];
-    int64_t j[kWinTPT];
     uint32_t li[kWinTPT][K];
     double w[kWinTPT][K];
+    const int64_t j0 = r * a.g.cols + c[0];
 #pragma unroll
     for (int t = 0; t < kWinTPT; ++t) {
       ok[t] = r < a.g.rows && c[t] < a.g.cols;
-      j[t] = r * a.g.cols + c[t];
+      const int64_t j = j0 + (int64_t)t * a.g.threads_per_row;
 #pragma unroll
       for (int kk = 0; kk < K; ++kk) {
-        const uint16_t l = ok[t] ? __ldg(a.lidx + (int64_t)kk * a.m + j[t]) : kLocalSentinel;
-        li[t][kk] = (l == kLocalSentinel) ? (uint32_t)sent : (uint32_t)l;
-        w[t][kk] = (K > 1 && ok[t]) ? __ldg(a.coef + (int64_t)kk * a.m + j[t]) : 1.0;
+        const uint16_t l = ok[t] ? __ldg(a.lidx + (int64_t)kk * a.m + j) : kLocalSentinel;
+        li[t][kk] = 8u * ((l == kLocalSentinel) ? (uint32_t)sent : (uint32_t)l);
+        w[t][kk] = (K > 1 && ok[t]) ? __ldg(a.coef + (int64_t)kk * a.m + j) : 1.0;
       }
     }
-    double* o = a.out + (int64_t)msg_begin * a.out_stride;
-    uint8_t* om = MASK ? a.out_mask + (int64_t)msg_begin * a.out_stride : nullptr;
+    double* o = a.out + (int64_t)msg_begin * a.out_stride + j0;
+    uint8_t* om = (MP == 1) ? a.out_mask + (int64_t)msg_begin * a.out_stride + j0 : nullptr;
 
+    if (MASK) {  // message 0 must be folded before the first gather
+      if (S >= 4) cp_async_wait<2>(); else cp_async_wait<1>();
+      __syncthreads();
+      fold(0);
+    }
     // ---- messages
     for (int it = 0; it < n_msg; ++it) {
-      if (S >= 4) cp_async_wait<2>(); else if (S == 3) cp_async_wait<1>(); else cp_async_wait<0>();
-      __syncthreads();        // message `it` is in shared memory; everyone is done with message it-1
+      if (MASK) {  // message it+1 has landed (it is folded below, one message ahead of the gathers)
+        if (S >= 4) cp_async_wait<1>(); else cp_async_wait<0>();
+      } else {     // message it has landed
+        if (S >= 4) cp_async_wait<2>(); else if (S == 3) cp_async_wait<1>(); else cp_async_wait<0>();
+      }
+      __syncthreads();        // copies / folds of the others are visible; everyone is done with message it-1
       prefetch(it + S - 1);   // into the stage message it-1 used
-      const int stage = it % S;
-      const uint32_t sv = val_base + (uint32_t)stage * stage_vbytes;
-      const uint32_t sm = msk_base + (uint32_t)stage * a.stage_elems;
-      double res[kWinTPT];
-      uint32_t mk[kWinTPT];
+      if (MASK) fold(it + 1);
+      const uint32_t sv = val_base + (uint32_t)(it % S) * stage_vbytes;
 #pragma unroll
       for (int t = 0; t < kWinTPT; ++t) {
         double v[K];
-        uint32_t mm = 0;
 #pragma unroll
-        for (int kk = 0; kk < K; ++kk) {
-          v[kk] = lds_f64(sv + 8u * li[t][kk]);
-          if (MASK) mm |= lds_u8(sm + li[t][kk]);
-        }
-        res[t] = weighted_sum<K>(w[t], v);
-        mk[t] = mm;
-      }
+        for (int kk = 0; kk < K; ++kk) v[kk] = lds_f64(sv + li[t][kk]);
+        double res = weighted_sum<K>(w[t], v);
+        uint32_t mk = 0;
+        if (MASK && res != res) {  // NaN: a masked neighbour, or NaN weights / inputs (then it stays NaN)
 #pragma unroll
-      for (int p = 0; p < kWinTPT; p += 2) {
-        if (a.vec_store && ok[p + 1]) {
-          __stcs(reinterpret_cast<double2*>(o + j[p]), make_double2(res[p], res[p + 1]));
-        } else {
-          if (ok[p]) __stcs(o + j[p], res[p]);
-          if (ok[p + 1]) __stcs(o + j[p + 1], res[p + 1]);
+          for (int kk = 0; kk < K; ++kk) mk |= (uint32_t)(__double_as_longlong(v[kk]) == (long long)kMaskMarker);
+          if (mk) res = a.mv_out;
         }
-      }
-      if (MASK) {
-#pragma unroll
-        for (int p = 0; p < kWinTPT; p += 2) {
-          if (a.vec_mask && ok[p + 1]) {
-            *reinterpret_cast<uint16_t*>(om + j[p]) = (uint16_t)(mk[p] | (mk[p + 1] << 8));
-          } else {
-            if (ok[p]) om[j[p]] = (uint8_t)mk[p];
-            if (ok[p + 1]) om[j[p + 1]] = (uint8_t)mk[p + 1];
-          }
+        if (ok[t]) {
+          __stcs(o + t * a.g.threads_per_row, res);
+          if (MP == 1) om[t * a.g.threads_per_row] = (uint8_t)mk;
         }
-        om += a.out_stride;
       }
       o += a.out_stride;
+      if (MP == 1) om += a.out_stride;
     }
     cp_async_wait<0>();
   }
@@ -416,14 +430,16 @@ static size_t win_smem_bytes(int stages, int stage_elems, bool mask) {
   return (size_t)stages * stage_elems * (mask ? 9 : 8);
 }
 
-template <int K, bool MASK, int CV>
+template <int K, int MP, int CV>
 static int launch_window_cv(const g2p_plan* p, WinArgs a, int stage_elems, cudaStream_t st) {
   // stages: as many as fit in ~72 KB per CTA (three CTAs per SM), at least 2
+  constexpr bool MASK = MP != 0;
+  constexpr int kMinStages = MASK ? 3 : 2;  // the mask fold runs one message ahead of the gathers
   int stages = kMaxStages;
-  while (stages > 2 && win_smem_bytes(stages, stage_elems, MASK) > 72 * 1024) --stages;
+  while (stages > kMinStages && win_smem_bytes(stages, stage_elems, MASK) > 72 * 1024) --stages;
   const size_t smem = win_smem_bytes(stages, stage_elems, MASK);
   if (smem > 200 * 1024) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: window of %d elements needs %zu B of shared memory", p->max_window, smem);
-  auto kern = apply_window_kernel<K, MASK, CV>;
+  auto kern = apply_window_kernel<K, MP, CV>;
   G2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   G2P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWinThreads, smem));
@@ -445,14 +461,14 @@ static int launch_window_cv(const g2p_plan* p, WinArgs a, int stage_elems, cudaS
   return G2P_OK;
 }
 
-template <int K, bool MASK>
+template <int K, int MP>
 static int launch_window(const g2p_plan* p, WinArgs a, cudaStream_t st) {
   const int stage_elems = ((p->max_window + 1 + 15) / 16) * 16;  // +1: the sentinel slot
   const int chunks = (p->max_window / 2 + kWinThreads - 1) / kWinThreads;  // 16-byte value chunks per thread
-  if (chunks <= 2) return launch_window_cv<K, MASK, 2>(p, a, stage_elems, st);
-  if (chunks <= 4) return launch_window_cv<K, MASK, 4>(p, a, stage_elems, st);
-  if (chunks <= 8) return launch_window_cv<K, MASK, 8>(p, a, stage_elems, st);
-  return launch_window_cv<K, MASK, 16>(p, a, stage_elems, st);
+  if (chunks <= 2) return launch_window_cv<K, MP, 2>(p, a, stage_elems, st);
+  if (chunks <= 4) return launch_window_cv<K, MP, 4>(p, a, stage_elems, st);
+  if (chunks <= 8) return launch_window_cv<K, MP, 8>(p, a, stage_elems, st);
+  return launch_window_cv<K, MP, 16>(p, a, stage_elems, st);
 }
 
 }  // namespace g2p
@@ -626,10 +642,11 @@ int g2p_apply_planned(const g2p_plan* p, const double* coef, const double* src, 
   if (p->k > 1 && !coef) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: coef is required for k > 1");
   if (p->k != 1 && p->k != 4) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: k=%d (1 and 4 are planned; use g2p_apply)", p->k);
   if (b < 0) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: b < 0");
-  if (mask_policy != G2P_MASK_PROPAGATE && mask_policy != G2P_MASK_AS_REFERENCE)
+  const bool mask = (mask_policy == G2P_MASK_PROPAGATE || mask_policy == G2P_MASK_FILL);
+  if (!mask && mask_policy != G2P_MASK_AS_REFERENCE)
     return set_error(G2P_ERR_INVALID, "g2p_apply_planned: unknown mask_policy %d", mask_policy);
-  const bool mask = (mask_policy == G2P_MASK_PROPAGATE);
-  if (mask && (!src_mask || !out_mask)) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: PROPAGATE needs src_mask and out_mask");
+  if (mask && !src_mask) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: PROPAGATE / FILL need src_mask");
+  if (mask_policy == G2P_MASK_PROPAGATE && !out_mask) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: PROPAGATE needs out_mask");
   if (src_stride < p->n_pad || out_stride < p->m) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: strides shorter than rows (src rows must be padded to a multiple of 16)");
   // bulk copies need 16-byte aligned sources: value rows at 16 B, mask rows at 16 B
   if ((reinterpret_cast<uintptr_t>(src) & 15) || (src_stride % 2) != 0)
@@ -658,11 +675,13 @@ int g2p_apply_planned(const g2p_plan* p, const double* coef, const double* src, 
   a.b = b;
   a.n_tiles = p->n_tiles;
   a.mv_out = mv_out;
-  a.vec_store = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (out_stride % 2 == 0) && (p->cols % 2 == 0);
-  a.vec_mask = mask && ((reinterpret_cast<uintptr_t>(out_mask) & 1) == 0) && (out_stride % 2 == 0) && (p->cols % 2 == 0);
   cudaStream_t st = as_stream(stream);
-  if (p->k == 1) return mask ? launch_window<1, true>(p, a, st) : launch_window<1, false>(p, a, st);
-  return mask ? launch_window<4, true>(p, a, st) : launch_window<4, false>(p, a, st);
+  if (p->k == 1) {
+    if (mask_policy == G2P_MASK_PROPAGATE) return launch_window<1, 1>(p, a, st);
+    return mask ? launch_window<1, 2>(p, a, st) : launch_window<1, 0>(p, a, st);
+  }
+  if (mask_policy == G2P_MASK_PROPAGATE) return launch_window<4, 1>(p, a, st);
+  return mask ? launch_window<4, 2>(p, a, st) : launch_window<4, 0>(p, a, st);
 }
 
 }  // extern "C"

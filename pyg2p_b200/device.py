@@ -297,7 +297,8 @@ class DeviceTable:
 
     def apply(self, src, mv_out, src_mask=None, mask_policy=L.MASK_AS_REFERENCE, out=None, out_mask=None):
         """Batched K7 on device-resident messages.  src: float64 [b, n] (or [n]); returns out [b, m]
-        (and out_mask uint8 [b, m] under PROPAGATE).  Asynchronous on the current stream.
+        (and out_mask uint8 [b, m] under PROPAGATE; masked outputs hold mv_out under PROPAGATE and FILL).
+        Asynchronous on the current stream.
         Uses the windowed kernel (g2p_apply_planned) when the table and the buffers allow it, else the
         generic gather kernel (g2p_apply); both are bit-identical."""
         lib = require_cuda()
@@ -313,37 +314,38 @@ class DeviceTable:
             raise ValueError(f'source field has {n} values, intertable was built for {self.n_src}')
         if src.stride(1) != 1:
             src = src.contiguous()
-        propagate = mask_policy == L.MASK_PROPAGATE
+        propagate = mask_policy in (L.MASK_PROPAGATE, L.MASK_FILL)
         with torch.cuda.device(self.device):
             if out is None:
                 out = torch.empty((b, self.m), dtype=torch.float64, device=self.device)
             if propagate:
                 if src_mask is None:
-                    raise ValueError('PROPAGATE needs src_mask')
+                    raise ValueError('PROPAGATE / FILL need src_mask')
                 if src_mask.dtype == torch.bool:
                     src_mask = src_mask.view(torch.uint8)
                 if src_mask.stride(1) != 1 or src_mask.stride(0) != src.stride(0):
                     # the C ABI uses one stride for values and masks
                     src = src.contiguous()
                     src_mask = src_mask.contiguous()
-                if out_mask is None:
+                if out_mask is None and mask_policy == L.MASK_PROPAGATE:
                     out_mask = torch.empty((b, self.m), dtype=torch.uint8, device=self.device)
             if b > 0 and self.m > 0 and self._window_ok(src, src_mask, propagate):
                 self.last_path = 'window'
                 L.check(lib.g2p_apply_planned(self.plan(), _ptr(self.coef) if self.k > 1 else None, _ptr(src),
                                               _ptr(src_mask) if propagate else None, b, src.stride(0), out.stride(0),
                                               float(mv_out), int(mask_policy), _ptr(out),
-                                              _ptr(out_mask) if propagate else None, _stream()))
+                                              _ptr(out_mask) if mask_policy == L.MASK_PROPAGATE else None,
+                                              _stream()))
             elif b > 0 and self.m > 0:
                 self.last_path = 'generic'
                 L.check(lib.g2p_apply(_ptr(self.idx), _ptr(self.coef) if self.k > 1 else None, self.m, self.k, _ptr(src),
                                       _ptr(src_mask) if propagate else None, n, b, src.stride(0), out.stride(0),
-                                      float(mv_out), int(mask_policy), _ptr(out), _ptr(out_mask) if propagate else None,
-                                      _stream()))
+                                      float(mv_out), int(mask_policy), _ptr(out),
+                                      _ptr(out_mask) if mask_policy == L.MASK_PROPAGATE else None, _stream()))
         if squeeze:
             out = out[0]
             out_mask = out_mask[0] if out_mask is not None else None
-        return (out, out_mask) if propagate else out
+        return (out, out_mask) if mask_policy == L.MASK_PROPAGATE else out
 
 
 def launch_count():
@@ -399,7 +401,8 @@ class HostApplyPipeline:
         """src: [b, n] float64 pinned tensor (or ndarray); src_mask: [b, n] uint8/bool or None.
         Returns (out [b, m] pinned tensor, out_mask [b, m] pinned uint8 tensor or None)."""
         t = self.t
-        propagate = mask_policy == L.MASK_PROPAGATE
+        propagate = mask_policy in (L.MASK_PROPAGATE, L.MASK_FILL)   # masks go in
+        want_omask = mask_policy == L.MASK_PROPAGATE                # ... and a mask array comes out
         if propagate and not self.with_mask:
             raise ValueError('pipeline was created without mask buffers')
         b = src.shape[0]
@@ -411,7 +414,7 @@ class HostApplyPipeline:
             src_mask = src_mask.view(torch.uint8)
         if out is None:
             out = pinned_empty((b, t.m))
-        if propagate and out_mask is None:
+        if want_omask and out_mask is None:
             out_mask = pinned_empty((b, t.m), torch.uint8)
         cur = torch.cuda.current_stream(t.device)
         ev_in = [None, None]
@@ -444,7 +447,7 @@ class HostApplyPipeline:
                 cur.wait_event(ev_out[s])                  # slot's previous output has left the device
             if propagate:
                 t.apply(self.d_src[s][:nb], mv_out, src_mask=self.d_msk[s][:nb], mask_policy=mask_policy,
-                        out=self.d_out[s][:nb], out_mask=self.d_omk[s][:nb])
+                        out=self.d_out[s][:nb], out_mask=self.d_omk[s][:nb] if want_omask else None)
             else:
                 t.apply(self.d_src[s][:nb], mv_out, out=self.d_out[s][:nb])
             ev_k[s] = torch.cuda.Event()
@@ -453,7 +456,7 @@ class HostApplyPipeline:
                 self.s_out.wait_event(ev_k[s])
                 out[lo:hi].copy_(self.d_out[s][:nb], non_blocking=True)
                 self.d2h_bytes += nb * t.m * 8
-                if propagate:
+                if want_omask:
                     out_mask[lo:hi].copy_(self.d_omk[s][:nb], non_blocking=True)
                     self.d2h_bytes += nb * t.m
                 ev_out[s] = torch.cuda.Event()
@@ -461,4 +464,4 @@ class HostApplyPipeline:
         for e in ev_out:
             if e is not None:
                 cur.wait_event(e)
-        return out, (out_mask if propagate else None)
+        return out, (out_mask if want_omask else None)

@@ -206,12 +206,15 @@ def test_window_path_random_tables(dev, k, shape, b):
         out = tbl.apply(src, mv).cpu().numpy()
         assert tbl.last_path == 'window', tbl.plan_error
         o2, m2 = tbl.apply(src, mv, src_mask=msk, mask_policy=L.MASK_PROPAGATE)
+        o3 = tbl.apply(src, mv, src_mask=msk, mask_policy=L.MASK_FILL)
+        assert tbl.last_path == 'window'
         for i in range(b):
             with np.errstate(all='ignore'):
                 _eq(out[i], R.apply_sequential(v[i], rec['coeffs'], rec['indexes'], k, mv))
                 data, mk = R.apply_propagate(v[i], rec['coeffs'], rec['indexes'], k, mv, mask[i])
             _eq(o2[i].cpu().numpy(), data)
             _eq(m2[i].cpu().numpy().astype(bool), mk)
+            _eq(o3[i].cpu().numpy(), data)
 
 
 def test_scattered_table_falls_back_to_generic_gpu_kernel(dev):
@@ -241,8 +244,15 @@ def test_window_equals_generic_on_real_geometry(dev, monkeypatch):
     src = torch.randn((37, lat.size), generator=g, device='cuda', dtype=torch.float64)
     msk = (torch.rand((37, lat.size), generator=g, device='cuda') < 0.05).to(torch.uint8)
     a, am = tbl.apply(src, 1e20, src_mask=msk, mask_policy=L.MASK_PROPAGATE)
+    af = tbl.apply(src, 1e20, src_mask=msk, mask_policy=L.MASK_FILL)
+    ar = tbl.apply(src, 1e20)
     assert tbl.last_path == 'window'
     monkeypatch.setenv('G2P_APPLY_PATH', 'generic')
     b_, bm = tbl.apply(src, 1e20, src_mask=msk, mask_policy=L.MASK_PROPAGATE)
+    bf = tbl.apply(src, 1e20, src_mask=msk, mask_policy=L.MASK_FILL)
+    br = tbl.apply(src, 1e20)
     assert tbl.last_path == 'generic'
     assert torch.equal(a.view(torch.int64), b_.view(torch.int64)) and torch.equal(am, bm)
+    assert torch.equal(af.view(torch.int64), bf.view(torch.int64)) and torch.equal(af, a)
+    assert torch.equal(ar.view(torch.int64), br.view(torch.int64))
+    assert 0.05 < am.float().mean() < 0.5 and torch.equal(a == 1e20, am.bool())
