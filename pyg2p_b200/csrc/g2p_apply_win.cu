@@ -289,15 +289,14 @@ constexpr unsigned long long kMaskMarker = 0x7ff86d61736b0001ull;
 
 // MP: 0 = no masks (AS_REFERENCE), 1 = PROPAGATE (out_mask written), 2 = FILL
 // CV: 16-byte value chunks copied per thread and message (window <= 512*CV values)
-template <int K, int MP, int CV>
-__global__ void __launch_bounds__(kWinThreads) apply_window_kernel(const WinArgs a) {
+template <int K, int MP, int CV, int S>
+__global__ void __launch_bounds__(kWinThreads, 3) apply_window_kernel(const WinArgs a) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ Range s_ranges[kMaxRanges];
   __shared__ int s_tile_info[2];
   constexpr bool MASK = MP != 0;
   constexpr int CM = (CV + 7) / 8;  // 16-byte mask chunks per thread
   const int tid = threadIdx.x;
-  const int S = a.stages;
   const uint32_t val_base = smem_u32(s_raw);                                             // [stages][stage_elems] f64
   const uint32_t msk_base = val_base + (uint32_t)S * a.stage_elems * 8u;                 // [stages][stage_elems] u8
   const uint32_t stage_vbytes = (uint32_t)a.stage_elems * 8u;
@@ -327,31 +326,43 @@ __global__ void __launch_bounds__(kWinThreads) apply_window_kernel(const WinArgs
 #pragma unroll
     for (int i = 0; i < CM; ++i) msrc[i] = MASK ? window_to_source(s_ranges, nr, window, 16 * (tid + kWinThreads * i)) : -1;
 
-    auto prefetch = [&](int it) {  // message msg_begin + it -> stage it % S
-      if (it < n_msg) {
-        const int stage = it % S;
-        const int64_t row = (int64_t)(msg_begin + it) * a.src_stride;
-        const double* gv = a.src + row;
-        const uint32_t sv = val_base + (uint32_t)stage * stage_vbytes + 16u * tid;
+    // this thread's copy chunks: running global pointers (advanced one source row per message) and the
+    // byte offset of the chunk inside a stage
+    const char* gsrc_v[CV];
+    const char* gsrc_m[CM];
+    const int64_t vrow = a.src_stride * 8, mrow = a.src_stride;
 #pragma unroll
-        for (int i = 0; i < CV; ++i)
-          if (vsrc[i] >= 0) cp_async16(sv + 16u * kWinThreads * i, gv + vsrc[i]);
-        if (MASK) {
-          const uint8_t* gm = a.src_mask + row;
-          const uint32_t sm = msk_base + (uint32_t)stage * a.stage_elems + 16u * tid;
+    for (int i = 0; i < CV; ++i)
+      gsrc_v[i] = reinterpret_cast<const char*>(a.src) + (int64_t)msg_begin * vrow + 8 * (int64_t)max(vsrc[i], 0);
 #pragma unroll
-          for (int i = 0; i < CM; ++i)
-            if (msrc[i] >= 0) cp_async16(sm + 16u * kWinThreads * i, gm + msrc[i]);
+    for (int i = 0; i < CM; ++i)
+      gsrc_m[i] = MASK ? reinterpret_cast<const char*>(a.src_mask) + (int64_t)msg_begin * mrow + (int64_t)max(msrc[i], 0)
+                       : nullptr;
+    const uint32_t stage_mbytes = (uint32_t)a.stage_elems;
+    const uint32_t val_end = val_base + (uint32_t)S * stage_vbytes;
+    int n_left = n_msg;  // messages not yet prefetched
+
+    // next message of the chunk -> the stage whose value / mask addresses are (sv, sm)
+    auto prefetch = [&](uint32_t sv, uint32_t sm) {
+      if (n_left > 0) {
+#pragma unroll
+        for (int i = 0; i < CV; ++i) {
+          if (vsrc[i] >= 0) cp_async16(sv + 16u * tid + 16u * kWinThreads * i, gsrc_v[i]);
+          gsrc_v[i] += vrow;
         }
+        if (MASK) {
+#pragma unroll
+          for (int i = 0; i < CM; ++i) {
+            if (msrc[i] >= 0) cp_async16(sm + 16u * tid + 16u * kWinThreads * i, gsrc_m[i]);
+            gsrc_m[i] += mrow;
+          }
+        }
+        --n_left;
       }
       cp_async_commit();  // always: keeps the group count uniform
     };
     // fold the mask bytes of a landed message into its values (4 window elements per thread and step)
-    auto fold = [&](int it) {
-      if (it >= n_msg) return;
-      const int stage = it % S;
-      const uint32_t sv = val_base + (uint32_t)stage * stage_vbytes;
-      const uint32_t sm = msk_base + (uint32_t)stage * a.stage_elems;
+    auto fold = [&](uint32_t sv, uint32_t sm) {
       for (int e = 4 * tid; e < window; e += 4 * kWinThreads) {
         uint32_t m4;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m4) : "r"(sm + e));
@@ -363,7 +374,21 @@ __global__ void __launch_bounds__(kWinThreads) apply_window_kernel(const WinArgs
         }
       }
     };
-    for (int s = 0; s < S - 1; ++s) prefetch(s);
+    // running stage cursors (value address, mask address) instead of `it % S` (S is a runtime value)
+    uint32_t pv = val_base, pm = msk_base;  // stage the next prefetch goes to
+    auto advance = [&](uint32_t& v, uint32_t& mk) {
+      v += stage_vbytes;
+      mk += stage_mbytes;
+      if (v == val_end) {
+        v = val_base;
+        mk = msk_base;
+      }
+    };
+#pragma unroll
+    for (int s = 0; s < S - 1; ++s) {
+      prefetch(pv, pm);
+      advance(pv, pm);
+    }
 
     // ---- this thread's targets: window offsets and weights stay in registers for the whole chunk
     int64_t r, c[kWinTPT];
@@ -372,10 +397,12 @@ __global__ void __launch_bounds__(kWinThreads) apply_window_kernel(const WinArgs
     uint32_t li[kWinTPT][K];
     double w[kWinTPT][K];
     const int64_t j0 = r * a.g.cols + c[0];
+    uint32_t ob[kWinTPT];  // byte offset of the target in an output row
 #pragma unroll
     for (int t = 0; t < kWinTPT; ++t) {
       ok[t] = r < a.g.rows && c[t] < a.g.cols;
       const int64_t j = j0 + (int64_t)t * a.g.threads_per_row;
+      ob[t] = 8u * (uint32_t)j;
 #pragma unroll
       for (int kk = 0; kk < K; ++kk) {
         const uint16_t l = ok[t] ? __ldg(a.lidx + (int64_t)kk * a.m + j) : kLocalSentinel;
@@ -383,30 +410,33 @@ __global__ void __launch_bounds__(kWinThreads) apply_window_kernel(const WinArgs
         w[t][kk] = (K > 1 && ok[t]) ? __ldg(a.coef + (int64_t)kk * a.m + j) : 1.0;
       }
     }
-    double* o = a.out + (int64_t)msg_begin * a.out_stride + j0;
-    uint8_t* om = (MP == 1) ? a.out_mask + (int64_t)msg_begin * a.out_stride + j0 : nullptr;
+    char* o = reinterpret_cast<char*>(a.out) + (int64_t)msg_begin * a.out_stride * 8;       // block-uniform
+    char* om = (MP == 1) ? reinterpret_cast<char*>(a.out_mask) + (int64_t)msg_begin * a.out_stride : nullptr;
 
+    uint32_t gv_s = val_base;                // stage of the message being gathered
+    uint32_t fv_s = val_base, fm_s = msk_base;  // stage of the message being folded (one ahead)
     if (MASK) {  // message 0 must be folded before the first gather
-      if (S >= 4) cp_async_wait<2>(); else cp_async_wait<1>();
+      cp_async_wait<S - 2>();
       __syncthreads();
-      fold(0);
+      fold(fv_s, fm_s);
+      advance(fv_s, fm_s);
     }
     // ---- messages
     for (int it = 0; it < n_msg; ++it) {
-      if (MASK) {  // message it+1 has landed (it is folded below, one message ahead of the gathers)
-        if (S >= 4) cp_async_wait<1>(); else cp_async_wait<0>();
-      } else {     // message it has landed
-        if (S >= 4) cp_async_wait<2>(); else if (S == 3) cp_async_wait<1>(); else cp_async_wait<0>();
-      }
+      // masked: message it+1 has landed (it is folded below, one message ahead of the gathers); else message it
+      cp_async_wait<MASK ? S - 3 : S - 2>();
       __syncthreads();        // copies / folds of the others are visible; everyone is done with message it-1
-      prefetch(it + S - 1);   // into the stage message it-1 used
-      if (MASK) fold(it + 1);
-      const uint32_t sv = val_base + (uint32_t)(it % S) * stage_vbytes;
+      prefetch(pv, pm);       // message it+S-1, into the stage message it-1 used
+      advance(pv, pm);
+      if (MASK) {
+        if (it + 1 < n_msg) fold(fv_s, fm_s);
+        advance(fv_s, fm_s);
+      }
 #pragma unroll
       for (int t = 0; t < kWinTPT; ++t) {
         double v[K];
 #pragma unroll
-        for (int kk = 0; kk < K; ++kk) v[kk] = lds_f64(sv + li[t][kk]);
+        for (int kk = 0; kk < K; ++kk) v[kk] = lds_f64(gv_s + li[t][kk]);
         double res = weighted_sum<K>(w[t], v);
         uint32_t mk = 0;
         if (MASK && res != res) {  // NaN: a masked neighbour, or NaN weights / inputs (then it stays NaN)
@@ -415,11 +445,13 @@ __global__ void __launch_bounds__(kWinThreads) apply_window_kernel(const WinArgs
           if (mk) res = a.mv_out;
         }
         if (ok[t]) {
-          __stcs(o + t * a.g.threads_per_row, res);
-          if (MP == 1) om[t * a.g.threads_per_row] = (uint8_t)mk;
+          __stcs(reinterpret_cast<double*>(o + ob[t]), res);
+          if (MP == 1) *reinterpret_cast<uint8_t*>(om + (ob[t] >> 3)) = (uint8_t)mk;
         }
       }
-      o += a.out_stride;
+      gv_s += stage_vbytes;
+      if (gv_s == val_end) gv_s = val_base;
+      o += a.out_stride * 8;
       if (MP == 1) om += a.out_stride;
     }
     cp_async_wait<0>();
@@ -430,22 +462,17 @@ static size_t win_smem_bytes(int stages, int stage_elems, bool mask) {
   return (size_t)stages * stage_elems * (mask ? 9 : 8);
 }
 
-template <int K, int MP, int CV>
-static int launch_window_cv(const g2p_plan* p, WinArgs a, int stage_elems, cudaStream_t st) {
-  // stages: as many as fit in ~72 KB per CTA (three CTAs per SM), at least 2
+template <int K, int MP, int CV, int S>
+static int launch_window_s(const g2p_plan* p, WinArgs a, int stage_elems, cudaStream_t st) {
   constexpr bool MASK = MP != 0;
-  constexpr int kMinStages = MASK ? 3 : 2;  // the mask fold runs one message ahead of the gathers
-  int stages = kMaxStages;
-  while (stages > kMinStages && win_smem_bytes(stages, stage_elems, MASK) > 72 * 1024) --stages;
-  const size_t smem = win_smem_bytes(stages, stage_elems, MASK);
-  if (smem > 200 * 1024) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: window of %d elements needs %zu B of shared memory", p->max_window, smem);
-  auto kern = apply_window_kernel<K, MP, CV>;
+  const size_t smem = win_smem_bytes(S, stage_elems, MASK);
+  auto kern = apply_window_kernel<K, MP, CV, S>;
   G2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   G2P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWinThreads, smem));
   if (per_sm < 1) per_sm = 1;
   const int64_t grid_cap = (int64_t)per_sm * num_sms();
-  a.stages = stages;
+  a.stages = S;
   a.stage_elems = stage_elems;
   // message chunks: long enough to amortise the per-item index/weight loads, short enough to
   // give every CTA several items
@@ -459,6 +486,16 @@ static int launch_window_cv(const g2p_plan* p, WinArgs a, int stage_elems, cudaS
   kern<<<grid, kWinThreads, smem, st>>>(a);
   G2P_LAUNCHED();
   return G2P_OK;
+}
+
+template <int K, int MP, int CV>
+static int launch_window_cv(const g2p_plan* p, WinArgs a, int stage_elems, cudaStream_t st) {
+  // four stages when they fit in ~72 KB per CTA (three CTAs per SM), else three (the mask fold runs one
+  // message ahead of the gathers, so three is the minimum)
+  if (win_smem_bytes(4, stage_elems, MP != 0) <= 72 * 1024) return launch_window_s<K, MP, CV, 4>(p, a, stage_elems, st);
+  if (win_smem_bytes(3, stage_elems, MP != 0) > 220 * 1024)
+    return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: window of %d elements does not fit in shared memory", p->max_window);
+  return launch_window_s<K, MP, CV, 3>(p, a, stage_elems, st);
 }
 
 template <int K, int MP>
