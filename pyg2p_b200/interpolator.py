@@ -1,0 +1,220 @@
+"""Drop-in for the reference's `Interpolator` (main/interpolation/__init__.py:20-395) on the scipy path:
+same constructor (`exec_ctx`, `mv_input`), same context keys, intertable naming / lookup / on-disk layout,
+same `interpolate` / `interpolate_scipy` signatures and error codes - with the table build and the table
+apply running on the GPU (pyg2p_b200.device), and `interpolate_batch` added so that callers can hand over
+all messages (steps x members) of a run at once instead of looping per step (writers/__init__.py:55,96).
+"""
+import gzip
+import logging
+import os
+import re
+from functools import partial
+
+import numpy as np
+import numpy.ma as ma
+import torch
+
+from . import _lib as L
+from . import device
+from .exceptions import (MALFORMED_GRIB_LATLON, NO_INTERTABLE_CREATED, NOT_IMPLEMENTED, ApplicationException)
+from .maps import LatLong
+from .scipy_interpolation import ScipyInterpolation
+
+
+def _normalize_filename(name):
+    """util/files.py:98-110: lower-case stem without long digit runs and separators, first 10 characters."""
+    stem = os.path.splitext(name)[0].lower()
+    stem = re.sub(r'([0-9]{8,10})', '', stem) or stem
+    stem = stem.replace('-', '').replace('_', '').replace('.', '')
+    return name.replace('.', '_') if len(stem) < 3 else stem[:10]
+
+
+class Interpolator:
+    _LOADED_INTERTABLES = {}      # path -> numpy record array (as the reference, :21)
+    _DEVICE_TABLES = {}           # (path, device index) -> DeviceTable
+    _prefix = 'I'
+    scipy_modes_nnear = {'nearest': 1, 'invdist': 4, 'adw': 11, 'cdd': 11, 'bilinear': 4, 'triangulation': 3,
+                         'bilinear_delaunay': 4}
+    suffixes = {'grib_nearest': 'grib_nearest', 'grib_invdist': 'grib_invdist', 'nearest': 'scipy_nearest',
+                'invdist': 'scipy_invdist', 'adw': 'scipy_adw', 'cdd': 'scipy_cdd', 'bilinear': 'scipy_bilinear',
+                'triangulation': 'scipy_triangulation', 'bilinear_delaunay': 'scipy_bilinear_delaunay'}
+    _format_intertable = 'tbl{prognum}_{source_file}_{target_size}_{suffix}.npy.gz'.format
+    gzip_level = 1                # file content is identical at any level; level 9 costs ~40 s per million rows
+
+    def __init__(self, exec_ctx, mv_input, mask_policy='as_reference'):
+        self._logger = logging.getLogger()
+        self._mv_grib = mv_input
+        self.interpolate_with_grib = exec_ctx.is_with_grib_interpolation
+        self._mode = exec_ctx.get('interpolation.mode')
+        self._num_of_splits = exec_ctx.get('interpolation.num_of_splits')
+        self._source_filename = os.path.basename(exec_ctx.get('input.file'))
+        self._suffix = self.suffixes[self._mode]
+        self._intertable_dirs = exec_ctx.get('interpolation.dirs')
+        self._rotated_target_grid = exec_ctx.get('interpolation.rotated_target')
+        lat_map, lon_map = exec_ctx.get('interpolation.latMap'), exec_ctx.get('interpolation.lonMap')
+        self._target_coords = lat_map if isinstance(lat_map, LatLong) else LatLong(lat_map, lon_map)
+        self.mv_out = self._target_coords.mv
+        self.parallel = exec_ctx.get('interpolation.parallel')
+        self.format_intertablename = partial(self._format_intertable,
+                                             source_file=_normalize_filename(self._source_filename),
+                                             target_size=self._target_coords.lats.size, suffix=self._suffix)
+        self._aux_val = self._aux_gid = self._aux_2nd_res_gid = self._aux_2nd_res_val = None
+        self.create_if_missing = exec_ctx.get('interpolation.create')
+        self.intertables_config = exec_ctx.configuration.intertables
+        # 'as_reference': masks of the input are ignored, as the reference does;
+        # 'propagate': the result is a MaskedArray, masked where any of the k source points is masked
+        self.mask_policy = mask_policy
+        self.tie_rows = None
+
+    # ------------------------------------------------------------------ reference API
+    def interpolate(self, lats, longs, v, grid_id, geodetic_info, gid=-1, is_second_res=False):
+        if self.interpolate_with_grib:
+            return self.interpolate_grib(v, gid, grid_id, is_second_res=is_second_res)
+        return self.interpolate_scipy(lats, longs, v, grid_id, geodetic_info)
+
+    def interpolate_grib(self, v, gid, grid_id, is_second_res=False):
+        raise ApplicationException.get_exc(
+            NOT_IMPLEMENTED, 'grib_nearest / grib_invdist are ecCodes-internal searches, outside the GPU path')
+
+    def interpolate_scipy(self, latgrib, longrib, v, grid_id, grid_details=None):
+        out = self.interpolate_batch(latgrib, longrib, [v], grid_id, grid_details)
+        return out[0]
+
+    def interpolate_batch(self, latgrib, longrib, values, grid_id, grid_details=None):
+        """`values`: sequence of source fields [n] (ndarray / MaskedArray) or a 2-D array [b, n] - all messages
+        of the run that share `grid_id`.  Returns an array [b, rows, cols] (MaskedArray under 'propagate')."""
+        table = self._table_for(latgrib, longrib, values[0], grid_id, grid_details)
+        shape = self._target_coords.lons.shape
+        b = len(values)
+        n = table.n_src
+        masked_in = [isinstance(x, ma.MaskedArray) and x.mask is not ma.nomask for x in values]
+        propagate = self.mask_policy == 'propagate' and any(masked_in)
+        pipe = self._pipeline(table, propagate)
+        h_src = device.pinned_empty((b, n))
+        h_np = h_src.numpy()
+        h_msk = device.pinned_empty((b, n), torch.uint8) if propagate else None
+        for i, x in enumerate(values):
+            h_np[i] = np.asarray(ma.getdata(x), dtype=np.float64).ravel()
+            if propagate:
+                h_msk.numpy()[i] = np.broadcast_to(ma.getmaskarray(x).ravel(), (n,)) if masked_in[i] else 0
+        out, omask = pipe.run(h_src, float(self.mv_output), src_mask=h_msk,
+                              mask_policy=L.MASK_PROPAGATE if propagate else L.MASK_AS_REFERENCE)
+        torch.cuda.current_stream(table.device).synchronize()
+        res = out.numpy().reshape((b,) + shape)
+        if propagate:
+            return ma.masked_array(res, mask=omask.numpy().reshape((b,) + shape).astype(bool), fill_value=self.mv_output)
+        if table.k == 1 and any(isinstance(x, ma.MaskedArray) for x in values):
+            return ma.masked_array(res)          # `v[indexes]` of a MaskedArray stays one, with no mask (:153)
+        return res
+
+    def aux_for_intertable_generation(self, aux_g, aux_v, aux_g2, aux_v2):
+        self._aux_gid, self._aux_val, self._aux_2nd_res_gid, self._aux_2nd_res_val = aux_g, aux_v, aux_g2, aux_v2
+
+    @property
+    def mv_output(self):
+        return self.mv_out
+
+    # ------------------------------------------------------------------ intertable lookup / creation
+    def _intertable_filename(self, grid_id):
+        """id `I{grid_id}_{maps id}{suffix}` -> (id, path); lookup order user dir, global dir, `.gz` optional
+        (:68-101)."""
+        intertable_id = '{}{}_{}{}'.format(self._prefix, grid_id.replace('$', '_'), self._target_coords.identifier,
+                                           self._suffix)
+        user_dir, global_dir = self._intertable_dirs.get('user'), self._intertable_dirs.get('global')
+        known = self.intertables_config.vars
+
+        def present(path):
+            return os.path.exists(path) or os.path.exists(path + '.gz')
+
+        if intertable_id not in known:
+            if not self.create_if_missing:
+                raise ApplicationException.get_exc(NO_INTERTABLE_CREATED, details=f'Using {intertable_id}')
+            self.intertables_config.check_write()
+            i, name = 0, self.format_intertablename(prognum='')
+            while os.path.exists(os.path.normpath(os.path.join(user_dir, name))):
+                i += 1
+                name = self.format_intertablename(prognum=f'_{i}')
+            return intertable_id, os.path.normpath(os.path.join(user_dir, name))
+        filename = known[intertable_id]['filename']
+        path = os.path.normpath(os.path.join(user_dir, filename)) if user_dir else None
+        if not path or not present(path):
+            path = os.path.normpath(os.path.join(global_dir, filename))
+            if not present(path):
+                if not self.create_if_missing:
+                    raise ApplicationException.get_exc(NO_INTERTABLE_CREATED, details=f'Tried to create {path}')
+                self.intertables_config.check_write()
+                path = os.path.normpath(os.path.join(user_dir, filename))
+                path = path if path.endswith('.gz') else path + '.gz'
+                self._logger.warning(f'An entry in configuration was found for {filename} but intertable does not exist.')
+        return intertable_id, path
+
+    def _read_intertable(self, tbl_fullpath):
+        """-> (indexes, coeffs) strided field views of the record array, cached per path (:103-139)."""
+        rec = self._LOADED_INTERTABLES.get(tbl_fullpath)
+        if rec is None:
+            path = tbl_fullpath
+            if not path.endswith('.gz') and not os.path.exists(path):
+                path += '.gz'
+                if not os.path.exists(path):
+                    raise ApplicationException.get_exc(
+                        NO_INTERTABLE_CREATED, details=f'Tried to read both {tbl_fullpath} and {path} but none was found')
+            if path.endswith('.gz'):
+                with gzip.GzipFile(path, 'r') as f:
+                    rec = np.load(f)
+            else:
+                rec = np.load(path)
+            self._LOADED_INTERTABLES[tbl_fullpath] = rec
+            self._logger.info(f'Using interpolation table: {tbl_fullpath}')
+        return rec['indexes'], rec['coeffs']
+
+    def _table_for(self, latgrib, longrib, v, grid_id, grid_details):
+        intertable_id, path = self._intertable_filename(grid_id)
+        dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+        key = (path, dev)
+        if key in self._DEVICE_TABLES:
+            return self._DEVICE_TABLES[key]
+        nnear = self.scipy_modes_nnear[self._mode]
+        shape = self._target_coords.lons.shape
+        n_src = int(np.asarray(ma.getdata(v)).size)
+        if os.path.exists(path) or os.path.exists(path + '.gz'):
+            self._read_intertable(path)
+            table = device.DeviceTable.from_record(self._LOADED_INTERTABLES[path], n_src, grid_shape=shape)
+        elif self.create_if_missing:
+            self.intertables_config.check_write()
+            if latgrib is None:
+                self._logger.error('Trying to interpolate without grib lat/lons. Probably a malformed grib!')
+                raise ApplicationException.get_exc(MALFORMED_GRIB_LATLON)
+            self._logger.warning(f'\nInterpolating table not found\n Id: {intertable_id}\nWill create file: {path}')
+            si = ScipyInterpolation(longrib, latgrib, grid_details, np.asarray(ma.getdata(v)).ravel(), nnear,
+                                    self.mv_out, self._mv_grib, target_is_rotated=self._rotated_target_grid,
+                                    parallel=self.parallel, mode=self._mode, num_of_splits=self._num_of_splits)
+            table = si.build_table(self._target_coords.lons, self._target_coords.lats)
+            self.tie_rows = si.tie_rows()
+            rec = table.to_record()
+            if path.endswith('.gz'):
+                with gzip.GzipFile(path, 'w', compresslevel=self.gzip_level) as f:
+                    np.save(f, rec)
+            else:
+                np.save(path, rec)
+            self.update_intertable_conf(rec, intertable_id, path, np.asarray(v).shape)
+        else:
+            raise ApplicationException.get_exc(NO_INTERTABLE_CREATED, details=path)
+        assert (table.k == 1 and nnear == 1) or table.k == nnear, f'table has k={table.k}, mode {self._mode} needs {nnear}'
+        self._DEVICE_TABLES[key] = table
+        return table
+
+    def _pipeline(self, table, with_mask):
+        pipes = table.__dict__.setdefault('_host_pipes', {})
+        if with_mask not in pipes:
+            chunk = max(1, min(16, (256 << 20) // (table.n_src * 8)))      # ~256 MB of pinned staging per slot
+            pipes[with_mask] = device.HostApplyPipeline(table, chunk_messages=chunk, with_mask=with_mask)
+        return pipes[with_mask]
+
+    def update_intertable_conf(self, intertable, intertable_id, intertable_name, source_shape):
+        """:373-384 - remember the new table in the (user) intertables configuration."""
+        self._LOADED_INTERTABLES[intertable_name] = intertable
+        item = {'filename': os.path.basename(intertable_name), 'method': self._mode, 'source_shape': source_shape,
+                'target_shape': self._target_coords.lons.shape}
+        self.intertables_config.vars[intertable_id] = item
+        self.intertables_config.user_vars[intertable_id] = item
+        self.intertables_config.dump()
