@@ -55,8 +55,9 @@ def all_gather_table(idx_shard, coef_shard, m_total, group=None):
         if m_r != m_max:
             pad = shard.new_zeros((k, m_max))
             pad[:, :m_r] = shard
-        buf = shard.new_empty((ws, k, m_max))
-        dist.all_gather_into_tensor(buf, pad.contiguous(), group=group)
+        flat = shard.new_empty((ws * k, m_max))          # concatenation along dim 0 (the form gloo and nccl share)
+        dist.all_gather_into_tensor(flat, pad.contiguous(), group=group)
+        buf = flat.view(ws, k, m_max)
         if all(s == m_max for s in all_sizes):
             return buf.permute(1, 0, 2).reshape(k, ws * m_max)
         return torch.cat([buf[r, :, :all_sizes[r]] for r in range(ws)], dim=1).contiguous()
