@@ -421,7 +421,7 @@ def main():
     ap.add_argument('--messages', type=int, default=383, help='resident messages per GPU (3060 / 8)')
     ap.add_argument('--e2e-messages', type=int, default=32)
     ap.add_argument('--e2e-chunk', type=int, default=4)
-    ap.add_argument('--cpu-messages', type=int, default=96)
+    ap.add_argument('--cpu-messages', type=int, default=400)
     ap.add_argument('--skip-build', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
     args = ap.parse_args()
