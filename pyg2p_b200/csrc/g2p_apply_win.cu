@@ -40,8 +40,8 @@ constexpr uint16_t kLocalSentinel = 0xffff;
 struct __align__(16) Range {
   int32_t src_start;   // first source element (multiple of 16)
   int32_t n_elem;      // multiple of 16
-  int32_t smem_off;    // element offset inside the stage window
-  int32_t pad;
+  int32_t smem_off;    // element offset of the values inside the stage window (skewed, even)
+  int32_t mask_off;    // element offset of the mask bytes inside the stage's mask window (dense)
 };
 
 }  // namespace g2p
@@ -57,7 +57,8 @@ struct g2p_plan {
   double mean_window;
   uint16_t* lidx;      // [k][m]
   g2p::Range* ranges;  // [n_tiles][kMaxRanges]
-  int32_t* tile_info;  // [n_tiles][2] = {n_ranges, window_elems}
+  int32_t* tile_info;  // [n_tiles][4] = {n_ranges, value window (skewed), mask window (dense), 0}
+  int max_mwindow;     // largest dense (mask) window
 };
 
 namespace g2p {
@@ -89,14 +90,15 @@ struct PlanArgs {
   uint16_t* lidx;
   Range* ranges;
   int32_t* tile_info;
-  int32_t* status;  // [0] = first failing reason (0 ok), [1] = max window, [2] = max ranges
+  int32_t* status;  // [0] = first failing reason (0 ok), [1] = max value window, [2] = max ranges, [3] = max mask window
   unsigned long long* total_window;
   int dry;          // only measure (no lidx / ranges written): used to choose the tile shape
 };
 
 __global__ void __launch_bounds__(kWinThreads) plan_kernel(const PlanArgs a) {
   extern __shared__ uint32_t s_bits[];  // kPlanSpanBlocks / 32 words
-  __shared__ int s_min, s_max, s_nr, s_fail;
+  __shared__ int s_min, s_max, s_nr, s_fail, s_mwin;
+  __shared__ int s_dsum[kMaxRanges], s_dcnt[kMaxRanges];
   __shared__ Range s_ranges[kMaxRanges];
   const int tile = blockIdx.x;
   const int tid = threadIdx.x;
@@ -165,57 +167,114 @@ __global__ void __launch_bounds__(kWinThreads) plan_kernel(const PlanArgs a) {
           int64_t end = (int64_t)(bmin + b) * kBlockElems;
           if (end > a.n_pad) end = a.n_pad;
           rg.n_elem = (int32_t)(end - rg.src_start);
-          rg.smem_off = win;
-          rg.pad = 0;
+          rg.smem_off = win;   // provisional: replaced by the skewed offset below
+          rg.mask_off = win;   // mask bytes are staged densely (they are only read by the fold pass)
           s_ranges[nr] = rg;
           win += rg.n_elem;
         }
         ++nr;
         run_start = -1;
       }
-      // skip whole empty / full words quickly
+      // skip whole empty words quickly
       if (run_start < 0 && (b & 31) == 31 && b + 1 < span) {
         while (b + 32 < span && s_bits[(b + 1) >> 5] == 0u) b += 32;
       }
     }
     s_nr = nr;
+    s_mwin = win;
     if (nr > kMaxRanges) {
       s_fail = 1;
       atomicCAS(&a.status[0], 0, 2);
-    } else if (win > kMaxWindowElems) {
+    }
+  }
+  for (int i = tid; i < kMaxRanges; i += kWinThreads) {
+    s_dsum[i] = 0;
+    s_dcnt[i] = 0;
+  }
+  __syncthreads();
+  if (s_fail) return;
+  const int nr = s_nr;
+  // ---- range and position of every reference; alignment statistics between consecutive ranges.
+  // Consecutive ranges are pieces of neighbouring latitude rings.  When one target references position
+  // p_a of range r and p_b of range r+1, the two source points lie at about the same longitude, so
+  // D_r = mean(p_a - p_b) tells how the two ranges are shifted against each other.
+  int16_t rr[kWinTPT][16];
+#pragma unroll
+  for (int t = 0; t < kWinTPT; ++t) {
+    for (int kk = 0; kk < a.k; ++kk) {
+      const int32_t v = my[t][kk];
+      int lo_r = -1;
+      if (v >= 0) {
+        lo_r = 0;
+        int hi_r = nr - 1;  // last range with src_start <= v
+        while (lo_r < hi_r) {
+          const int mid = (lo_r + hi_r + 1) >> 1;
+          if (s_ranges[mid].src_start <= v) lo_r = mid; else hi_r = mid - 1;
+        }
+      }
+      rr[t][kk] = (int16_t)lo_r;
+    }
+    for (int ka = 0; ka < a.k; ++ka)
+      for (int kb = 0; kb < a.k; ++kb)
+        if (rr[t][ka] >= 0 && rr[t][kb] == rr[t][ka] + 1) {
+          const int pa = my[t][ka] - s_ranges[rr[t][ka]].src_start;
+          const int pb = my[t][kb] - s_ranges[rr[t][kb]].src_start;
+          atomicAdd(&s_dsum[rr[t][ka]], pa - pb);
+          atomicAdd(&s_dcnt[rr[t][ka]], 1);
+        }
+  }
+  __syncthreads();
+  // ---- skewed shared-memory offsets: with u(r) the position of range r that lines up with position 0 of
+  // range 0, a value at "longitude" x = p - u(r) of ring r goes to bank (x + 8*(r & 1)) mod 16 (8-byte banks):
+  // lanes of a half-warp that read neighbouring rings then hit disjoint bank groups (measured on
+  // O1280 -> EFAS: 1.67 wavefronts per half-warp gather instead of 2.34 with dense offsets).
+  if (tid == 0) {
+    int u = 0, cur = 0;
+    for (int i = 0; i < nr; ++i) {
+      if (i > 0) {
+        const int cnt = s_dcnt[i - 1];
+        int d = 0;
+        if (cnt > 0) {
+          const int sum = s_dsum[i - 1];
+          d = (sum >= 0) ? (sum + cnt / 2) / cnt : -((-sum + cnt / 2) / cnt);
+        }
+        u -= d;
+      }
+      int want = ((8 * (i & 1) - u) % 16 + 16) % 16;
+      want &= ~1;                                   // 16-byte cp.async chunks: even element offsets
+      const int off = cur + (((want - cur) % 16) + 16) % 16;
+      s_ranges[i].smem_off = off;
+      cur = off + s_ranges[i].n_elem;
+    }
+    const int win = (cur + 15) & ~15;
+    if (win > kMaxWindowElems) {
       s_fail = 1;
       atomicCAS(&a.status[0], 0, 3);
     } else {
       atomicMax(&a.status[1], win);
       atomicMax(&a.status[2], nr);
-      atomicAdd(a.total_window, (unsigned long long)win);
+      atomicMax(&a.status[3], s_mwin);
+      atomicAdd(a.total_window, (unsigned long long)s_mwin);
       if (!a.dry) {
-        a.tile_info[2 * tile] = nr;
-        a.tile_info[2 * tile + 1] = win;
+        a.tile_info[4 * tile] = nr;
+        a.tile_info[4 * tile + 1] = win;
+        a.tile_info[4 * tile + 2] = s_mwin;
+        a.tile_info[4 * tile + 3] = 0;
       }
     }
   }
   __syncthreads();
   if (s_fail || a.dry) return;
-  const int nr = s_nr;
   for (int i = tid; i < nr; i += kWinThreads) a.ranges[(int64_t)tile * kMaxRanges + i] = s_ranges[i];
-  // pass 3: local offsets
+  // ---- local offsets
 #pragma unroll
   for (int t = 0; t < kWinTPT; ++t) {
     const bool ok = r < a.g.rows && c[t] < a.g.cols;
     if (!ok) continue;
     const int64_t j = r * a.g.cols + c[t];
     for (int kk = 0; kk < a.k; ++kk) {
-      const int32_t v = my[t][kk];
       uint16_t l = kLocalSentinel;
-      if (v >= 0) {
-        int lo_r = 0, hi_r = nr - 1;  // last range with src_start <= v
-        while (lo_r < hi_r) {
-          const int mid = (lo_r + hi_r + 1) >> 1;
-          if (s_ranges[mid].src_start <= v) lo_r = mid; else hi_r = mid - 1;
-        }
-        l = (uint16_t)(s_ranges[lo_r].smem_off + (v - s_ranges[lo_r].src_start));
-      }
+      if (rr[t][kk] >= 0) l = (uint16_t)(s_ranges[rr[t][kk]].smem_off + (my[t][kk] - s_ranges[rr[t][kk]].src_start));
       a.lidx[(int64_t)kk * a.m + j] = l;
     }
   }
@@ -256,7 +315,7 @@ struct WinArgs {
   uint8_t* out_mask;
   int64_t m, src_stride, out_stride;
   TileGeom g;
-  int b, n_tiles, msgs_per_chunk, stages, stage_elems;
+  int b, n_tiles, msgs_per_chunk, stages, stage_elems, stage_melems;
   int64_t n_items;
   double mv_out;
 };
@@ -270,16 +329,25 @@ __device__ __forceinline__ double weighted_sum(const double (&w)[K], const doubl
   return acc;
 }
 
-// source element of window element `elem` (ranges are sorted by smem_off); -1 in a gap or past the window
-__device__ __forceinline__ int window_to_source(const Range* ranges, int nr, int window, int elem) {
-  if (elem >= window) return -1;
+// source element staged at value-window element `elem` (ranges are sorted by smem_off); -1 in a gap
+__device__ __forceinline__ int value_window_to_source(const Range* ranges, int nr, int elem) {
   int lo = 0, hi = nr - 1;  // last range with smem_off <= elem
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
     if (ranges[mid].smem_off <= elem) lo = mid; else hi = mid - 1;
   }
   const int d = elem - ranges[lo].smem_off;
-  return (d >= 0 && d < ranges[lo].n_elem) ? ranges[lo].src_start + d : -1;
+  return (nr > 0 && d >= 0 && d < ranges[lo].n_elem) ? ranges[lo].src_start + d : -1;
+}
+// range that holds mask-window element `elem` (dense offsets); -1 past the window
+__device__ __forceinline__ int mask_window_range(const Range* ranges, int nr, int mwindow, int elem) {
+  if (elem >= mwindow) return -1;
+  int lo = 0, hi = nr - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (ranges[mid].mask_off <= elem) lo = mid; else hi = mid - 1;
+  }
+  return lo;
 }
 
 // A masked source value is replaced, in shared memory, by this quiet NaN: the weighted sum of a target
@@ -288,23 +356,25 @@ __device__ __forceinline__ int window_to_source(const Range* ranges, int nr, int
 constexpr unsigned long long kMaskMarker = 0x7ff86d61736b0001ull;
 
 // MP: 0 = no masks (AS_REFERENCE), 1 = PROPAGATE (out_mask written), 2 = FILL
-// CV: 16-byte value chunks copied per thread and message (window <= 512*CV values)
+// CV: 16-byte value chunks copied per thread and message (value window <= 512*CV elements)
+// S : stages
 template <int K, int MP, int CV, int S>
 __global__ void __launch_bounds__(kWinThreads, 3) apply_window_kernel(const WinArgs a) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ Range s_ranges[kMaxRanges];
-  __shared__ int s_tile_info[2];
+  __shared__ int s_tile_info[4];
   constexpr bool MASK = MP != 0;
-  constexpr int CM = (CV + 7) / 8;  // 16-byte mask chunks per thread
+  constexpr int CM = (CV + 7) / 8;  // 16-byte mask chunks per thread; also 4-element fold groups per thread / 4
+  constexpr int CF = (CV + 1) / 2;  // fold groups (4 mask bytes) per thread
   const int tid = threadIdx.x;
-  const uint32_t val_base = smem_u32(s_raw);                                             // [stages][stage_elems] f64
-  const uint32_t msk_base = val_base + (uint32_t)S * a.stage_elems * 8u;                 // [stages][stage_elems] u8
+  const uint32_t val_base = smem_u32(s_raw);                                             // [S][stage_elems] f64
+  const uint32_t msk_base = val_base + (uint32_t)S * a.stage_elems * 8u;                 // [S][stage_melems] u8
   const uint32_t stage_vbytes = (uint32_t)a.stage_elems * 8u;
-  const int sent = a.stage_elems - 1;  // slot that always holds mv_out / mask 0 (copies never reach it)
-  if (tid < S) {
-    reinterpret_cast<double*>(s_raw)[(size_t)tid * a.stage_elems + sent] = a.mv_out;
-    if (MASK) s_raw[(size_t)S * a.stage_elems * 8 + (size_t)tid * a.stage_elems + sent] = 0;
-  }
+  const uint32_t stage_mbytes = (uint32_t)a.stage_melems;
+  const uint32_t val_end = val_base + (uint32_t)S * stage_vbytes;
+  const int sent = a.stage_elems - 1;  // slot that always holds mv_out (copies and folds never reach it)
+  if (tid < S) reinterpret_cast<double*>(s_raw)[(size_t)tid * a.stage_elems + sent] = a.mv_out;
+  const int64_t vrow = a.src_stride * 8, mrow = a.src_stride;
 
   for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
     const int tile = (int)(item % a.n_tiles);
@@ -313,68 +383,77 @@ __global__ void __launch_bounds__(kWinThreads, 3) apply_window_kernel(const WinA
     const int n_msg = min(a.b, msg_begin + a.msgs_per_chunk) - msg_begin;
     // ---- tile plan
     __syncthreads();  // previous item is finished with s_ranges and the stages
-    if (tid < 2) s_tile_info[tid] = a.tile_info[2 * tile + tid];
+    if (tid < 4) s_tile_info[tid] = a.tile_info[4 * tile + tid];
     __syncthreads();
     const int nr = s_tile_info[0];
-    const int window = s_tile_info[1];
+    const int mwindow = s_tile_info[2];
     for (int i = tid; i < nr; i += kWinThreads) s_ranges[i] = a.ranges[(int64_t)tile * kMaxRanges + i];
     __syncthreads();
-    // ---- this thread's share of the staging copies: CV value chunks, CM mask chunks (source offsets)
-    int vsrc[CV], msrc[CM];
+    // ---- this thread's share of the staging work, as byte offsets (-1 = nothing):
+    //   vsrc[i]: source-row offset of the 16-byte value chunk that goes to stage bytes 16*(tid + 256 i)
+    //   msrc[i]: source-row offset of the 16-byte mask chunk that goes to mask-stage bytes 16*(tid + 256 i)
+    //   fdst[i]: stage byte offset of the 4 values whose mask bytes are mask-stage bytes 4*(tid + 256 i)
+    int vsrc[CV], msrc[CM], fdst[CF];
 #pragma unroll
-    for (int i = 0; i < CV; ++i) vsrc[i] = window_to_source(s_ranges, nr, window, 2 * (tid + kWinThreads * i));
+    for (int i = 0; i < CV; ++i) {
+      const int e = value_window_to_source(s_ranges, nr, 2 * (tid + kWinThreads * i));
+      vsrc[i] = e < 0 ? -1 : 8 * e;
+    }
 #pragma unroll
-    for (int i = 0; i < CM; ++i) msrc[i] = MASK ? window_to_source(s_ranges, nr, window, 16 * (tid + kWinThreads * i)) : -1;
-
-    // this thread's copy chunks: running global pointers (advanced one source row per message) and the
-    // byte offset of the chunk inside a stage
-    const char* gsrc_v[CV];
-    const char* gsrc_m[CM];
-    const int64_t vrow = a.src_stride * 8, mrow = a.src_stride;
+    for (int i = 0; i < CM; ++i) {
+      msrc[i] = -1;
+      if (MASK) {
+        const int e = 16 * (tid + kWinThreads * i);
+        const int rg = mask_window_range(s_ranges, nr, mwindow, e);
+        if (rg >= 0) msrc[i] = s_ranges[rg].src_start + (e - s_ranges[rg].mask_off);
+      }
+    }
 #pragma unroll
-    for (int i = 0; i < CV; ++i)
-      gsrc_v[i] = reinterpret_cast<const char*>(a.src) + (int64_t)msg_begin * vrow + 8 * (int64_t)max(vsrc[i], 0);
-#pragma unroll
-    for (int i = 0; i < CM; ++i)
-      gsrc_m[i] = MASK ? reinterpret_cast<const char*>(a.src_mask) + (int64_t)msg_begin * mrow + (int64_t)max(msrc[i], 0)
-                       : nullptr;
-    const uint32_t stage_mbytes = (uint32_t)a.stage_elems;
-    const uint32_t val_end = val_base + (uint32_t)S * stage_vbytes;
+    for (int i = 0; i < CF; ++i) {
+      fdst[i] = -1;
+      if (MASK) {
+        const int e = 4 * (tid + kWinThreads * i);
+        const int rg = mask_window_range(s_ranges, nr, mwindow, e);
+        if (rg >= 0) fdst[i] = 8 * (s_ranges[rg].smem_off + (e - s_ranges[rg].mask_off));
+      }
+    }
+    const char* grow_v = reinterpret_cast<const char*>(a.src) + (int64_t)msg_begin * vrow;        // block-uniform
+    const char* grow_m = MASK ? reinterpret_cast<const char*>(a.src_mask) + (int64_t)msg_begin * mrow : nullptr;
     int n_left = n_msg;  // messages not yet prefetched
 
     // next message of the chunk -> the stage whose value / mask addresses are (sv, sm)
     auto prefetch = [&](uint32_t sv, uint32_t sm) {
       if (n_left > 0) {
 #pragma unroll
-        for (int i = 0; i < CV; ++i) {
-          if (vsrc[i] >= 0) cp_async16(sv + 16u * tid + 16u * kWinThreads * i, gsrc_v[i]);
-          gsrc_v[i] += vrow;
-        }
+        for (int i = 0; i < CV; ++i)
+          if (vsrc[i] >= 0) cp_async16(sv + 16u * tid + 16u * kWinThreads * i, grow_v + vsrc[i]);
         if (MASK) {
 #pragma unroll
-          for (int i = 0; i < CM; ++i) {
-            if (msrc[i] >= 0) cp_async16(sm + 16u * tid + 16u * kWinThreads * i, gsrc_m[i]);
-            gsrc_m[i] += mrow;
-          }
+          for (int i = 0; i < CM; ++i)
+            if (msrc[i] >= 0) cp_async16(sm + 16u * tid + 16u * kWinThreads * i, grow_m + msrc[i]);
+          grow_m += mrow;
         }
+        grow_v += vrow;
         --n_left;
       }
       cp_async_commit();  // always: keeps the group count uniform
     };
-    // fold the mask bytes of a landed message into its values (4 window elements per thread and step)
+    // fold the mask bytes of a landed message into its values
     auto fold = [&](uint32_t sv, uint32_t sm) {
-      for (int e = 4 * tid; e < window; e += 4 * kWinThreads) {
+#pragma unroll
+      for (int i = 0; i < CF; ++i) {
+        if (fdst[i] < 0) continue;
         uint32_t m4;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m4) : "r"(sm + e));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m4) : "r"(sm + 4u * tid + 4u * kWinThreads * i));
         if (m4) {
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             if ((m4 >> (8 * q)) & 0xffu)
-              asm volatile("st.shared.u64 [%0], %1;" ::"r"(sv + 8u * (e + q)), "l"(kMaskMarker) : "memory");
+              asm volatile("st.shared.u64 [%0], %1;" ::"r"(sv + (uint32_t)fdst[i] + 8u * q), "l"(kMaskMarker) : "memory");
         }
       }
     };
-    // running stage cursors (value address, mask address) instead of `it % S` (S is a runtime value)
+    // running stage cursors (value address, mask address)
     uint32_t pv = val_base, pm = msk_base;  // stage the next prefetch goes to
     auto advance = [&](uint32_t& v, uint32_t& mk) {
       v += stage_vbytes;
@@ -413,7 +492,7 @@ __global__ void __launch_bounds__(kWinThreads, 3) apply_window_kernel(const WinA
     char* o = reinterpret_cast<char*>(a.out) + (int64_t)msg_begin * a.out_stride * 8;       // block-uniform
     char* om = (MP == 1) ? reinterpret_cast<char*>(a.out_mask) + (int64_t)msg_begin * a.out_stride : nullptr;
 
-    uint32_t gv_s = val_base;                // stage of the message being gathered
+    uint32_t gv_s = val_base;                   // stage of the message being gathered
     uint32_t fv_s = val_base, fm_s = msk_base;  // stage of the message being folded (one ahead)
     if (MASK) {  // message 0 must be folded before the first gather
       cp_async_wait<S - 2>();
@@ -458,14 +537,14 @@ __global__ void __launch_bounds__(kWinThreads, 3) apply_window_kernel(const WinA
   }
 }
 
-static size_t win_smem_bytes(int stages, int stage_elems, bool mask) {
-  return (size_t)stages * stage_elems * (mask ? 9 : 8);
+static size_t win_smem_bytes(int stages, int stage_elems, int stage_melems, bool mask) {
+  return (size_t)stages * ((size_t)stage_elems * 8 + (mask ? stage_melems : 0));
 }
 
 template <int K, int MP, int CV, int S>
-static int launch_window_s(const g2p_plan* p, WinArgs a, int stage_elems, cudaStream_t st) {
+static int launch_window_s(const g2p_plan* p, WinArgs a, cudaStream_t st) {
   constexpr bool MASK = MP != 0;
-  const size_t smem = win_smem_bytes(S, stage_elems, MASK);
+  const size_t smem = win_smem_bytes(S, a.stage_elems, a.stage_melems, MASK);
   auto kern = apply_window_kernel<K, MP, CV, S>;
   G2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
@@ -473,7 +552,6 @@ static int launch_window_s(const g2p_plan* p, WinArgs a, int stage_elems, cudaSt
   if (per_sm < 1) per_sm = 1;
   const int64_t grid_cap = (int64_t)per_sm * num_sms();
   a.stages = S;
-  a.stage_elems = stage_elems;
   // message chunks: long enough to amortise the per-item index/weight loads, short enough to
   // give every CTA several items
   int64_t want_chunks = ceil_div(8 * grid_cap, p->n_tiles);
@@ -489,23 +567,25 @@ static int launch_window_s(const g2p_plan* p, WinArgs a, int stage_elems, cudaSt
 }
 
 template <int K, int MP, int CV>
-static int launch_window_cv(const g2p_plan* p, WinArgs a, int stage_elems, cudaStream_t st) {
+static int launch_window_cv(const g2p_plan* p, WinArgs a, cudaStream_t st) {
   // four stages when they fit in ~72 KB per CTA (three CTAs per SM), else three (the mask fold runs one
   // message ahead of the gathers, so three is the minimum)
-  if (win_smem_bytes(4, stage_elems, MP != 0) <= 72 * 1024) return launch_window_s<K, MP, CV, 4>(p, a, stage_elems, st);
-  if (win_smem_bytes(3, stage_elems, MP != 0) > 220 * 1024)
+  if (win_smem_bytes(4, a.stage_elems, a.stage_melems, MP != 0) <= 72 * 1024) return launch_window_s<K, MP, CV, 4>(p, a, st);
+  if (win_smem_bytes(3, a.stage_elems, a.stage_melems, MP != 0) > 220 * 1024)
     return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: window of %d elements does not fit in shared memory", p->max_window);
-  return launch_window_s<K, MP, CV, 3>(p, a, stage_elems, st);
+  return launch_window_s<K, MP, CV, 3>(p, a, st);
 }
 
 template <int K, int MP>
 static int launch_window(const g2p_plan* p, WinArgs a, cudaStream_t st) {
-  const int stage_elems = ((p->max_window + 1 + 15) / 16) * 16;  // +1: the sentinel slot
+  a.stage_elems = ((p->max_window + 1 + 15) / 16) * 16;  // +1: the sentinel slot
+  a.stage_melems = ((p->max_mwindow + 15) / 16) * 16;
   const int chunks = (p->max_window / 2 + kWinThreads - 1) / kWinThreads;  // 16-byte value chunks per thread
-  if (chunks <= 2) return launch_window_cv<K, MP, 2>(p, a, stage_elems, st);
-  if (chunks <= 4) return launch_window_cv<K, MP, 4>(p, a, stage_elems, st);
-  if (chunks <= 8) return launch_window_cv<K, MP, 8>(p, a, stage_elems, st);
-  return launch_window_cv<K, MP, 16>(p, a, stage_elems, st);
+  if (chunks <= 2) return launch_window_cv<K, MP, 2>(p, a, st);
+  if (chunks <= 3) return launch_window_cv<K, MP, 3>(p, a, st);
+  if (chunks <= 4) return launch_window_cv<K, MP, 4>(p, a, st);
+  if (chunks <= 8) return launch_window_cv<K, MP, 8>(p, a, st);
+  return launch_window_cv<K, MP, 16>(p, a, st);
 }
 
 }  // namespace g2p
@@ -573,8 +653,8 @@ int g2p_plan_create(const int32_t* idx, int64_t m, int k, int64_t n, int64_t row
       p->ranges = nullptr;
       p->tile_info = nullptr;
       err = cudaMalloc(&p->ranges, (size_t)p->n_tiles * kMaxRanges * sizeof(Range));
-      if (err == cudaSuccess) err = cudaMalloc(&p->tile_info, (size_t)p->n_tiles * 2 * sizeof(int32_t));
-      if (err == cudaSuccess) err = cudaMemsetAsync(p->tile_info, 0, (size_t)p->n_tiles * 2 * sizeof(int32_t), st);
+      if (err == cudaSuccess) err = cudaMalloc(&p->tile_info, (size_t)p->n_tiles * 4 * sizeof(int32_t));
+      if (err == cudaSuccess) err = cudaMemsetAsync(p->tile_info, 0, (size_t)p->n_tiles * 4 * sizeof(int32_t), st);
       if (err != cudaSuccess) return err;
     }
     PlanArgs a{};
@@ -643,6 +723,7 @@ int g2p_plan_create(const int32_t* idx, int64_t m, int k, int64_t n, int64_t row
     p->mean_window = (double)total / (double)p->n_tiles;
   }
   p->max_window = status[1];
+  p->max_mwindow = status[3];
   p->max_ranges = status[2];
   *out = p;
   return G2P_OK;
@@ -668,7 +749,7 @@ int g2p_plan_get_info(const g2p_plan* p, g2p_plan_info* info) {
   info->max_window = p->max_window;
   info->max_ranges = p->max_ranges;
   info->mean_window = p->mean_window;
-  info->bytes = (int64_t)p->k * p->m * 2 + (int64_t)p->n_tiles * (kMaxRanges * (int64_t)sizeof(Range) + 8);
+  info->bytes = (int64_t)p->k * p->m * 2 + (int64_t)p->n_tiles * (kMaxRanges * (int64_t)sizeof(Range) + 16);
   return G2P_OK;
 }
 
