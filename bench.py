@@ -278,6 +278,32 @@ def run_b200(args):
     avg_kernel_ms = float(np.mean(kern_ms))
     achieved = bytes_launch / (avg_kernel_ms * 1e-3) / 1e9
 
+    # other mask policies / the generic kernel on the same batch (informational, 5 launches each)
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        a_, b__ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        for _ in range(reps):
+            fn()
+        b__.record()
+        torch.cuda.synchronize()
+        return a_.elapsed_time(b__) / reps
+
+    variants = {}
+    ms = timed(lambda: table.apply(src, synth.NC_FILL_F64, src_mask=src_mask, mask_policy=L.MASK_FILL, out=out_t))
+    variants['fill (no out_mask array)'] = {'ms': ms, 'frac': bytes_launch / (ms * 1e-3) / 1e9 / hbm_peak}
+    nb = algorithmic_bytes_apply(B, n_touched, m, K_INVDIST, False)
+    ms = timed(lambda: table.apply(src, synth.NC_FILL_F64, out=out_t))
+    variants['as_reference (masks ignored)'] = {'ms': ms, 'frac': nb / (ms * 1e-3) / 1e9 / hbm_peak}
+    os.environ['G2P_APPLY_PATH'] = 'generic'
+    ms = timed(lambda: table.apply(src, synth.NC_FILL_F64, src_mask=src_mask, mask_policy=L.MASK_PROPAGATE, out=out_t,
+                                   out_mask=out_m), reps=2)
+    variants['generic gather kernel, propagate'] = {'ms': ms, 'frac': bytes_launch / (ms * 1e-3) / 1e9 / hbm_peak}
+    del os.environ['G2P_APPLY_PATH']
+    step()
+    torch.cuda.synchronize()
+
     # parity spot check of the timed output against the torch restatement of the reference order
     rows = torch.randint(0, m, (4096,), generator=g, device=dev)
     ii = table.idx[:, rows].long()
@@ -404,7 +430,7 @@ def run_b200(args):
                          'n_touched': n_touched, 'peak_source': peak_src},
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
             'messages_per_s': B * args.steps * ws / (total_ms * 1e-3),
-            'clocks': clocks, 'wall_s_timed_region': t_wall, 'build': build,
+            'clocks': clocks, 'wall_s_timed_region': t_wall, 'apply_variants': variants, 'build': build,
         }
         print(json.dumps(line), flush=True)
     if ws > 1:

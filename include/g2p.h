@@ -183,6 +183,73 @@ int g2p_apply_planned(const g2p_plan* plan, const double* coef, const double* sr
                       int64_t src_stride, int64_t out_stride, double mv_out, int mask_policy, double* out,
                       uint8_t* out_mask, void* stream);
 
+/* K8  the stages the reference runs around the interpolation, for all output messages of a run.
+ *
+ * g2p_manip: unit conversion -> step aggregation -> cut-off of negatives on the source grid
+ * (controller.py:106-132; manipulation/conversion.py:21,33-52; manipulation/aggregator.py:72-279), one
+ * launch for all outputs.  Conversion is `where(x != mv_grib, op2(op1(x)), mv_grib)` with op in
+ * {none, x*c, x+c, x/c} - this covers every function of configuration/global/parameters.json (`x*1000`,
+ * `-x*1000` = x*(-1000), `x-273.15` = x+(-273.15), `x*(-0.0353)`, ...) and the gem formula `(z/9.81)*0.0065`.
+ * Each output message is one g2p_manip_item:
+ *   PICK     out = 0.0 + c(V[in0])                         (instantaneous; in0 < 0: zeros)
+ *   ACCUM    out = ((0.0 + c(V[in0])) - c(V[in1])) * unit_time / divisor      (in1 < 0: zeros at step 0)
+ *   AVERAGE  out = (0.0 + c(V[in0]) + c(V[in1]) + ...) / divisor              (one add per hourly iterator)
+ * out_mask follows the reference literally: ACCUM keeps only the mask of V[in1] (the current step loses its
+ * mask in `v_iter_ma += V[t]`, aggregator.py:142-148), AVERAGE the OR of its inputs - of ALL b_in messages
+ * when mask_all is set, which is what _average does (:232) -, PICK none (:264-276).  With `touched` (device, int32[nc], sorted source indexes) the
+ * outputs are compact fields out[o][c] = manip(V[..][touched[c]]); NULL = whole grid (nc = n). */
+#define G2P_MANIP_MAX_IN 32
+enum { G2P_OP_NONE = 0, G2P_OP_MUL = 1, G2P_OP_ADD = 2, G2P_OP_DIV = 3 };
+enum { G2P_AGG_PICK = 0, G2P_AGG_ACCUM = 1, G2P_AGG_AVERAGE = 2 };
+
+typedef struct g2p_manip_item {
+  int32_t kind;                     /* G2P_AGG_* */
+  int32_t n_in;                     /* PICK 1, ACCUM 2, AVERAGE 1..G2P_MANIP_MAX_IN */
+  int32_t in[G2P_MANIP_MAX_IN];     /* input message numbers, in the order they are added */
+  int32_t mask_all;
+  double unit_time;                 /* ACCUM */
+  double divisor;                   /* ACCUM: aggregation step; AVERAGE: count */
+} g2p_manip_item;
+
+typedef struct g2p_manip_desc {
+  int32_t conv_op1;
+  double conv_c1;
+  int32_t conv_op2;
+  double conv_c2;
+  double mv_grib;                   /* GRIB missingValue guarded by the conversion */
+  int32_t cut_off_negative;
+  int32_t n_out;
+  const g2p_manip_item* items;      /* host, n_out entries */
+} g2p_manip_desc;
+
+int g2p_manip(const g2p_manip_desc* desc /* host */, const double* src, const uint8_t* src_mask /* nullable */,
+              int64_t n, int b_in, int64_t src_stride, const int32_t* touched /* nullable */, int64_t nc,
+              int64_t out_stride, double* out, uint8_t* out_mask /* iff src_mask */, void* stream);
+
+/* V[a] + (V[b] - V[a]) * frac: a missing step synthesised linearly in time (aggregator.py:105,128) */
+int g2p_time_interp(const double* va, const double* vb, double frac, int64_t n, double* out, void* stream);
+
+/* Corrector (manipulation/correction.py:46,59-82): `where((dem!=dem_mv) & (p!=mv) & (gem!=gem_mv),
+ * p + gem - dem*coeff, mv)` with mv = the netCDF f8 fill value.  g2p_correction_prepare computes the
+ * per-target terms once (dem_term = dem*coeff, valid = dem and gem present); g2p_apply_planned_corrected
+ * applies the formula in the epilogue of the windowed apply kernel, before the store. */
+typedef struct g2p_correction {
+  const double* gem;        /* device, m */
+  const double* dem_term;   /* device, m */
+  const uint8_t* valid;     /* device, m */
+  double mv;                /* 9.969209968386869e36 */
+} g2p_correction;
+
+int g2p_correction_prepare(const void* dem, int dem_dtype, double dem_mv, const double* gem, double gem_mv, double coeff,
+                           int64_t m, double* dem_term_out, uint8_t* valid_out, void* stream);
+/* the same formula in place on [b][m] outputs (after g2p_apply, for tables without a plan); mask nullable */
+int g2p_correct(double* values, const uint8_t* mask, int64_t m, int b, int64_t stride, const g2p_correction* corr,
+                void* stream);
+int g2p_apply_planned_corrected(const g2p_plan* plan, const double* coef, const double* src, const uint8_t* src_mask,
+                                int b, int64_t src_stride, int64_t out_stride, double mv_out, int mask_policy,
+                                const g2p_correction* corr /* host struct of device pointers */, double* out,
+                                uint8_t* out_mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

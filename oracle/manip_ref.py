@@ -155,6 +155,9 @@ def gem_from_geopotential(z, mv, gem_formula='(z/9.81)*0.0065'):
 def correct(values, dem, gem, dem_mv, gem_mv, formula='p+gem-dem*0.0065'):
     """correction.py:46,59-82: guarded formula on the target grid, `mv` = netCDF f8 fill."""
     p = values
+    # numexpr typing: the literal 0.0065 is a double, so a float32 dem (PCRaster REAL4 map) is promoted to
+    # double before the product; numpy >= 2 would keep `dem*0.0065` in float32 (weak Python scalars)
+    dem = np.asarray(dem, dtype=np.float64) if np.asarray(dem).dtype == np.float32 else dem
     mv = NC_FILL_F64 if ma.getdata(values).dtype == np.float64 else 9.969209968386869e36
     with np.errstate(over='ignore', invalid='ignore'):
         res = _eval(f'where((dem!=dem_mv) & (p!=mv) & (gem!=gem_mv), {formula}, mv)',

@@ -39,6 +39,26 @@ class PlanInfo(C.Structure):
                 ('max_ranges', C.c_int32), ('mean_window', C.c_double), ('bytes', C.c_int64)]
 
 
+MANIP_MAX_IN = 32
+OP_NONE, OP_MUL, OP_ADD, OP_DIV = 0, 1, 2, 3
+AGG_PICK, AGG_ACCUM, AGG_AVERAGE = 0, 1, 2
+
+
+class ManipItem(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('n_in', C.c_int32), ('inputs', C.c_int32 * MANIP_MAX_IN), ('mask_all', C.c_int32),
+                ('unit_time', C.c_double), ('divisor', C.c_double)]
+
+
+class ManipDesc(C.Structure):
+    _fields_ = [('conv_op1', C.c_int32), ('conv_c1', C.c_double), ('conv_op2', C.c_int32), ('conv_c2', C.c_double),
+                ('mv_grib', C.c_double), ('cut_off_negative', C.c_int32), ('n_out', C.c_int32),
+                ('items', C.POINTER(ManipItem))]
+
+
+class Correction(C.Structure):
+    _fields_ = [('gem', C.c_void_p), ('dem_term', C.c_void_p), ('valid', C.c_void_p), ('mv', C.c_double)]
+
+
 _vp, _i64, _i32, _f64 = C.c_void_p, C.c_int64, C.c_int, C.c_double
 _rotp = C.POINTER(Rotation)
 
@@ -65,6 +85,12 @@ PROTOTYPES = {
     'g2p_plan_destroy': (C.c_int, [_vp]),
     'g2p_plan_get_info': (C.c_int, [_vp, C.POINTER(PlanInfo)]),
     'g2p_apply_planned': (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f64, _i32, _vp, _vp, _vp]),
+    'g2p_manip': (C.c_int, [C.POINTER(ManipDesc), _vp, _vp, _i64, _i32, _i64, _vp, _i64, _i64, _vp, _vp, _vp]),
+    'g2p_time_interp': (C.c_int, [_vp, _vp, _f64, _i64, _vp, _vp]),
+    'g2p_correction_prepare': (C.c_int, [_vp, _i32, _f64, _vp, _f64, _f64, _i64, _vp, _vp, _vp]),
+    'g2p_correct': (C.c_int, [_vp, _vp, _i64, _i32, _i64, C.POINTER(Correction), _vp]),
+    'g2p_apply_planned_corrected': (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f64, _i32, C.POINTER(Correction),
+                                              _vp, _vp, _vp]),
 }
 
 _lib = None

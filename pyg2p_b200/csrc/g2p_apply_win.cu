@@ -318,6 +318,10 @@ struct WinArgs {
   int b, n_tiles, msgs_per_chunk, stages, stage_elems, stage_melems;
   int64_t n_items;
   double mv_out;
+  const double* corr_gem;
+  const double* corr_dem_term;
+  const uint8_t* corr_valid;
+  double corr_mv;
 };
 
 template <int K>
@@ -358,8 +362,9 @@ constexpr unsigned long long kMaskMarker = 0x7ff86d61736b0001ull;
 // MP: 0 = no masks (AS_REFERENCE), 1 = PROPAGATE (out_mask written), 2 = FILL
 // CV: 16-byte value chunks copied per thread and message (value window <= 512*CV elements)
 // S : stages
-template <int K, int MP, int CV, int S>
-__global__ void __launch_bounds__(kWinThreads, 3) apply_window_kernel(const WinArgs a) {
+// CORR: Corrector epilogue `where(valid & (p != mv), (p + gem) - dem_term, mv)` (manipulation/correction.py:46,74-81)
+template <int K, int MP, int CV, int S, bool CORR>
+__global__ void __launch_bounds__(kWinThreads, CORR ? 2 : 3) apply_window_kernel(const WinArgs a) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ Range s_ranges[kMaxRanges];
   __shared__ int s_tile_info[4];
@@ -477,6 +482,8 @@ __global__ void __launch_bounds__(kWinThreads, 3) apply_window_kernel(const WinA
     double w[kWinTPT][K];
     const int64_t j0 = r * a.g.cols + c[0];
     uint32_t ob[kWinTPT];  // byte offset of the target in an output row
+    double cgem[CORR ? kWinTPT : 1], cdt[CORR ? kWinTPT : 1];
+    bool cvalid[CORR ? kWinTPT : 1];
 #pragma unroll
     for (int t = 0; t < kWinTPT; ++t) {
       ok[t] = r < a.g.rows && c[t] < a.g.cols;
@@ -487,6 +494,11 @@ __global__ void __launch_bounds__(kWinThreads, 3) apply_window_kernel(const WinA
         const uint16_t l = ok[t] ? __ldg(a.lidx + (int64_t)kk * a.m + j) : kLocalSentinel;
         li[t][kk] = 8u * ((l == kLocalSentinel) ? (uint32_t)sent : (uint32_t)l);
         w[t][kk] = (K > 1 && ok[t]) ? __ldg(a.coef + (int64_t)kk * a.m + j) : 1.0;
+      }
+      if (CORR) {
+        cgem[t] = ok[t] ? __ldg(a.corr_gem + j) : 0.0;
+        cdt[t] = ok[t] ? __ldg(a.corr_dem_term + j) : 0.0;
+        cvalid[t] = ok[t] ? __ldg(a.corr_valid + j) != 0 : false;
       }
     }
     char* o = reinterpret_cast<char*>(a.out) + (int64_t)msg_begin * a.out_stride * 8;       // block-uniform
@@ -523,6 +535,8 @@ __global__ void __launch_bounds__(kWinThreads, 3) apply_window_kernel(const WinA
           for (int kk = 0; kk < K; ++kk) mk |= (uint32_t)(__double_as_longlong(v[kk]) == (long long)kMaskMarker);
           if (mk) res = a.mv_out;
         }
+        if (CORR && !mk)  // a masked output stays the missing value; p = NaN passes the guards and stays NaN
+          res = (cvalid[t] && res != a.corr_mv) ? __dsub_rn(__dadd_rn(res, cgem[t]), cdt[t]) : a.corr_mv;
         if (ok[t]) {
           __stcs(reinterpret_cast<double*>(o + ob[t]), res);
           if (MP == 1) *reinterpret_cast<uint8_t*>(om + (ob[t] >> 3)) = (uint8_t)mk;
@@ -541,11 +555,11 @@ static size_t win_smem_bytes(int stages, int stage_elems, int stage_melems, bool
   return (size_t)stages * ((size_t)stage_elems * 8 + (mask ? stage_melems : 0));
 }
 
-template <int K, int MP, int CV, int S>
-static int launch_window_s(const g2p_plan* p, WinArgs a, cudaStream_t st) {
+template <int K, int MP, int CV, int S, bool CORR>
+static int launch_window_c(const g2p_plan* p, WinArgs a, cudaStream_t st) {
   constexpr bool MASK = MP != 0;
   const size_t smem = win_smem_bytes(S, a.stage_elems, a.stage_melems, MASK);
-  auto kern = apply_window_kernel<K, MP, CV, S>;
+  auto kern = apply_window_kernel<K, MP, CV, S, CORR>;
   G2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   G2P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWinThreads, smem));
@@ -564,6 +578,11 @@ static int launch_window_s(const g2p_plan* p, WinArgs a, cudaStream_t st) {
   kern<<<grid, kWinThreads, smem, st>>>(a);
   G2P_LAUNCHED();
   return G2P_OK;
+}
+
+template <int K, int MP, int CV, int S>
+static int launch_window_s(const g2p_plan* p, WinArgs a, cudaStream_t st) {
+  return a.corr_gem ? launch_window_c<K, MP, CV, S, true>(p, a, st) : launch_window_c<K, MP, CV, S, false>(p, a, st);
 }
 
 template <int K, int MP, int CV>
@@ -753,9 +772,9 @@ int g2p_plan_get_info(const g2p_plan* p, g2p_plan_info* info) {
   return G2P_OK;
 }
 
-int g2p_apply_planned(const g2p_plan* p, const double* coef, const double* src, const uint8_t* src_mask, int b,
-                      int64_t src_stride, int64_t out_stride, double mv_out, int mask_policy, double* out,
-                      uint8_t* out_mask, void* stream) {
+static int apply_planned(const g2p_plan* p, const double* coef, const double* src, const uint8_t* src_mask, int b,
+                         int64_t src_stride, int64_t out_stride, double mv_out, int mask_policy, const g2p_correction* corr,
+                         double* out, uint8_t* out_mask, void* stream) {
   if (!p || !src || !out) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: null plan/src/out");
   if (p->k > 1 && !coef) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: coef is required for k > 1");
   if (p->k != 1 && p->k != 4) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: k=%d (1 and 4 are planned; use g2p_apply)", p->k);
@@ -793,6 +812,13 @@ int g2p_apply_planned(const g2p_plan* p, const double* coef, const double* src, 
   a.b = b;
   a.n_tiles = p->n_tiles;
   a.mv_out = mv_out;
+  if (corr) {
+    if (!corr->gem || !corr->dem_term || !corr->valid) return set_error(G2P_ERR_INVALID, "g2p_apply_planned_corrected: null correction arrays");
+    a.corr_gem = corr->gem;
+    a.corr_dem_term = corr->dem_term;
+    a.corr_valid = corr->valid;
+    a.corr_mv = corr->mv;
+  }
   cudaStream_t st = as_stream(stream);
   if (p->k == 1) {
     if (mask_policy == G2P_MASK_PROPAGATE) return launch_window<1, 1>(p, a, st);
@@ -800,6 +826,19 @@ int g2p_apply_planned(const g2p_plan* p, const double* coef, const double* src, 
   }
   if (mask_policy == G2P_MASK_PROPAGATE) return launch_window<4, 1>(p, a, st);
   return mask ? launch_window<4, 2>(p, a, st) : launch_window<4, 0>(p, a, st);
+}
+
+int g2p_apply_planned(const g2p_plan* p, const double* coef, const double* src, const uint8_t* src_mask, int b,
+                      int64_t src_stride, int64_t out_stride, double mv_out, int mask_policy, double* out,
+                      uint8_t* out_mask, void* stream) {
+  return apply_planned(p, coef, src, src_mask, b, src_stride, out_stride, mv_out, mask_policy, nullptr, out, out_mask, stream);
+}
+
+int g2p_apply_planned_corrected(const g2p_plan* p, const double* coef, const double* src, const uint8_t* src_mask, int b,
+                                int64_t src_stride, int64_t out_stride, double mv_out, int mask_policy,
+                                const g2p_correction* corr, double* out, uint8_t* out_mask, void* stream) {
+  if (!corr) return set_error(G2P_ERR_INVALID, "g2p_apply_planned_corrected: corr is null");
+  return apply_planned(p, coef, src, src_mask, b, src_stride, out_stride, mv_out, mask_policy, corr, out, out_mask, stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,245 @@
+// K8a: the source-grid manipulation stages that precede the intertable apply, fused into one
+// gather-and-compute kernel: unit conversion -> step aggregation -> cut-off of negatives.
+//
+// Replaces, for all output messages of a run in one launch,
+//   Converter.convert           where(x != mv, f(x), mv)              (manipulation/conversion.py:21,33-42)
+//   Aggregator._accumulation    ((0.0 + V[t]) - V[t-D]) * unit / D    (manipulation/aggregator.py:72-153)
+//   Aggregator._average         (0.0 + V[i1] + V[i2] + ...) / count   (:155-236), one add per hourly iterator
+//   Aggregator._instantaneous   0.0 + V[t]                            (:244-279)
+//   Converter.cut_off_negative  where(v < 0, 0, v)                    (conversion.py:44-52)
+// in the reference's evaluation order (numexpr evaluates left to right in float64; every operation below
+// is a separate IEEE multiply / add / divide, no FMA contraction).  The controller's stage order is
+// convert -> aggregate -> cut-off, all on the source grid, before interpolation (controller.py:106-132).
+//
+// With a `touched` list (the sorted source indexes an intertable references) the kernel writes COMPACT
+// fields: out[o][c] = manip(V[..][touched[c]]), so only the 4 % of an O1280 field that the EFAS table
+// reads is ever converted, aggregated and handed to the apply kernel (whose table is remapped to the
+// compact numbering).  Without it the kernel is the plain elementwise stage on the whole grid.
+#include <vector>
+
+#include "g2p_common.cuh"
+
+namespace g2p {
+
+constexpr int kManipMaxIn = G2P_MANIP_MAX_IN;
+
+struct ManipItem {       // device copy of g2p_manip_item
+  int kind, n_in, mask_all, pad;
+  int in[kManipMaxIn];
+  double unit_time, divisor;
+};
+
+struct ManipArgs {
+  const double* src;
+  const uint8_t* src_mask;
+  const int32_t* touched;
+  const ManipItem* items;
+  double* out;
+  uint8_t* out_mask;
+  int64_t n, nc, src_stride, out_stride;
+  int b_in, n_out;
+  int op1, op2;
+  double c1, c2, mv_grib;
+  int cut_off;
+};
+
+__device__ __forceinline__ double conv_op(int op, double c, double x) {
+  switch (op) {
+    case G2P_OP_MUL: return __dmul_rn(x, c);
+    case G2P_OP_ADD: return __dadd_rn(x, c);
+    case G2P_OP_DIV: return __ddiv_rn(x, c);
+    default: return x;
+  }
+}
+
+// where(x != mv, f(x), mv)  (conversion.py:21)
+__device__ __forceinline__ double convert(const ManipArgs& a, double x) {
+  if (a.op1 == G2P_OP_NONE) return x;  // 'x=x' is the identity: no guard either (conversion.py:34-35)
+  if (x == a.mv_grib) return a.mv_grib;
+  return conv_op(a.op2, a.c2, conv_op(a.op1, a.c1, x));
+}
+
+__global__ void __launch_bounds__(256) manip_kernel(const ManipArgs a) {
+  const int o = blockIdx.y;
+  const ManipItem& it = a.items[o];
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < a.nc; c += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = a.touched ? (int64_t)__ldg(a.touched + c) : c;
+    double res;
+    uint8_t mk = 0;
+    if (it.kind == G2P_AGG_ACCUM) {
+      // v_iter = 0.0 + V[t]; ((v_iter - V[t-D]) * unit_time) / D   (aggregator.py:142-147)
+      const double cur = __dadd_rn(0.0, convert(a, __ldg(a.src + (int64_t)it.in[0] * a.src_stride + i)));
+      const double prev = it.in[1] >= 0 ? convert(a, __ldg(a.src + (int64_t)it.in[1] * a.src_stride + i)) : 0.0;
+      res = __ddiv_rn(__dmul_rn(__dsub_rn(cur, prev), it.unit_time), it.divisor);
+    } else if (it.kind == G2P_AGG_AVERAGE) {
+      // temp_sum = 0.0; temp_sum += V[next available step >= hour] per hourly iterator; / count (:209-230)
+      double s = 0.0;
+      for (int q = 0; q < it.n_in; ++q) s = __dadd_rn(s, convert(a, __ldg(a.src + (int64_t)it.in[q] * a.src_stride + i)));
+      res = __ddiv_rn(s, it.divisor);
+    } else {
+      // res = zeros; res += V[t]   (:264-276); in[0] < 0: step 0 absent -> zeros
+      res = it.in[0] >= 0 ? __dadd_rn(0.0, convert(a, __ldg(a.src + (int64_t)it.in[0] * a.src_stride + i))) : 0.0;
+    }
+    if (a.cut_off && res < 0.0) res = 0.0;  // where(v < 0, 0, v): NaN stays NaN
+    a.out[(int64_t)o * a.out_stride + c] = res;
+    if (a.src_mask) {
+      if (it.mask_all == 1) {  // _average masks with the OR of ALL inputs of the run (aggregator.py:232)
+        for (int q = 0; q < a.b_in; ++q) mk |= __ldg(a.src_mask + (int64_t)q * a.src_stride + i);
+      } else if (it.kind == G2P_AGG_ACCUM) {
+        // the current step is copied into a fresh ndarray (`v_iter_ma += V[t]`, :142-143) and loses its
+        // mask there: only the mask of V[t-D] survives (:148)
+        if (it.in[1] >= 0) mk = __ldg(a.src_mask + (int64_t)it.in[1] * a.src_stride + i);
+      } else if (it.kind == G2P_AGG_AVERAGE) {
+        for (int q = 0; q < it.n_in; ++q) mk |= __ldg(a.src_mask + (int64_t)it.in[q] * a.src_stride + i);
+      }                          // PICK: `res_inst += V[t]` on a plain ndarray drops the mask (:264-276)
+      a.out_mask[(int64_t)o * a.out_stride + c] = mk ? 1 : 0;
+    }
+  }
+}
+
+// V[a] + (V[b] - V[a]) * frac : linear-in-time synthesis of a missing step (aggregator.py:105,128)
+__global__ void time_interp_kernel(const double* __restrict__ va, const double* __restrict__ vb, double frac, int64_t n,
+                                   double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __dadd_rn(va[i], __dmul_rn(__dsub_rn(vb[i], va[i]), frac));
+}
+
+// per-target terms of Corrector.correct (correction.py:46,74-81): dem_term = dem * coeff, valid = both present
+__global__ void correction_prepare_kernel(const void* __restrict__ dem, int dem_f32, double dem_mv,
+                                          const double* __restrict__ gem, double gem_mv, double coeff, int64_t m,
+                                          double* __restrict__ dem_term, uint8_t* __restrict__ valid) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (int64_t)gridDim.x * blockDim.x) {
+    // a float32 dem map meets the float64 constant in numexpr: promoted to double before the product
+    const double d = dem_f32 ? (double)reinterpret_cast<const float*>(dem)[j] : reinterpret_cast<const double*>(dem)[j];
+    dem_term[j] = __dmul_rn(d, coeff);
+    valid[j] = (d != dem_mv && gem[j] != gem_mv) ? 1 : 0;
+  }
+}
+
+// standalone Corrector.correct on [b][m] outputs (used after the generic apply kernel); masked outputs stay as they are
+__global__ void correct_kernel(double* __restrict__ v, const uint8_t* __restrict__ mask, int64_t m, int b, int64_t stride,
+                               const double* __restrict__ gem, const double* __restrict__ dem_term,
+                               const uint8_t* __restrict__ valid, double mv) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (int64_t)gridDim.x * blockDim.x) {
+    const double g = gem[j], dt = dem_term[j];
+    const bool ok = valid[j] != 0;
+    for (int q = 0; q < b; ++q) {
+      const int64_t at = (int64_t)q * stride + j;
+      if (mask && mask[at]) continue;
+      const double p = v[at];
+      v[at] = (ok && p != mv) ? __dsub_rn(__dadd_rn(p, g), dt) : mv;
+    }
+  }
+}
+
+}  // namespace g2p
+
+using namespace g2p;
+
+extern "C" {
+
+int g2p_manip(const g2p_manip_desc* desc, const double* src, const uint8_t* src_mask, int64_t n, int b_in,
+              int64_t src_stride, const int32_t* touched, int64_t nc, int64_t out_stride, double* out, uint8_t* out_mask,
+              void* stream) {
+  if (!desc || !src || !out) return set_error(G2P_ERR_INVALID, "g2p_manip: null desc/src/out");
+  if (desc->n_out < 0 || (desc->n_out > 0 && !desc->items)) return set_error(G2P_ERR_INVALID, "g2p_manip: bad items");
+  if (n < 0 || b_in < 1 || src_stride < n) return set_error(G2P_ERR_INVALID, "g2p_manip: bad sizes");
+  if (!touched) nc = n;
+  if (nc < 0 || out_stride < nc) return set_error(G2P_ERR_INVALID, "g2p_manip: out_stride shorter than the output rows");
+  if (src_mask && !out_mask) return set_error(G2P_ERR_INVALID, "g2p_manip: src_mask without out_mask");
+  for (int op : {desc->conv_op1, desc->conv_op2})
+    if (op < G2P_OP_NONE || op > G2P_OP_DIV) return set_error(G2P_ERR_INVALID, "g2p_manip: unknown conversion op %d", op);
+  if (desc->n_out == 0 || nc == 0) return G2P_OK;
+  if (desc->n_out > 65535) return set_error(G2P_ERR_UNSUPPORTED, "g2p_manip: more than 65535 output messages per call");
+  std::vector<ManipItem> items(desc->n_out);
+  for (int o = 0; o < desc->n_out; ++o) {
+    const g2p_manip_item& s = desc->items[o];
+    if (s.kind < G2P_AGG_PICK || s.kind > G2P_AGG_AVERAGE) return set_error(G2P_ERR_INVALID, "g2p_manip: item %d: unknown kind %d", o, s.kind);
+    const int need = s.kind == G2P_AGG_ACCUM ? 2 : (s.kind == G2P_AGG_PICK ? 1 : s.n_in);
+    if (s.n_in != need || need < 1 || need > kManipMaxIn) return set_error(G2P_ERR_INVALID, "g2p_manip: item %d: n_in = %d", o, s.n_in);
+    ManipItem& d = items[o];
+    d.kind = s.kind;
+    d.n_in = s.n_in;
+    d.mask_all = s.mask_all;
+    d.pad = 0;
+    for (int q = 0; q < kManipMaxIn; ++q) {
+      d.in[q] = q < s.n_in ? s.in[q] : -1;
+      if (q < s.n_in && (s.in[q] >= b_in || (s.in[q] < 0 && !(s.kind == G2P_AGG_ACCUM && q == 1) && s.kind != G2P_AGG_PICK)))
+        return set_error(G2P_ERR_INVALID, "g2p_manip: item %d references message %d of %d", o, s.in[q], b_in);
+    }
+    d.unit_time = s.unit_time;
+    d.divisor = s.divisor;
+  }
+  cudaStream_t st = as_stream(stream);
+  ManipItem* d_items = nullptr;
+  G2P_CUDA(cudaMallocAsync(&d_items, items.size() * sizeof(ManipItem), st));
+  cudaError_t e = cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(ManipItem), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `items` lives on this stack frame
+  if (e != cudaSuccess) {
+    cudaFreeAsync(d_items, st);
+    return cuda_fail(e, "g2p_manip: items upload", __FILE__, __LINE__);
+  }
+  ManipArgs a{};
+  a.src = src;
+  a.src_mask = src_mask;
+  a.touched = touched;
+  a.items = d_items;
+  a.out = out;
+  a.out_mask = out_mask;
+  a.n = n;
+  a.nc = nc;
+  a.src_stride = src_stride;
+  a.out_stride = out_stride;
+  a.b_in = b_in;
+  a.n_out = desc->n_out;
+  a.op1 = desc->conv_op1;
+  a.op2 = desc->conv_op2;
+  a.c1 = desc->conv_c1;
+  a.c2 = desc->conv_c2;
+  a.mv_grib = desc->mv_grib;
+  a.cut_off = desc->cut_off_negative;
+  int64_t bx = ceil_div(nc, 256);
+  const int64_t cap = std::max<int64_t>(1, (int64_t)num_sms() * 16 / desc->n_out);
+  if (bx > cap) bx = cap;
+  manip_kernel<<<dim3((unsigned)bx, (unsigned)desc->n_out), 256, 0, st>>>(a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  e = cudaGetLastError();
+  cudaFreeAsync(d_items, st);
+  if (e != cudaSuccess) return cuda_fail(e, "manip_kernel launch", __FILE__, __LINE__);
+  return G2P_OK;
+}
+
+int g2p_time_interp(const double* va, const double* vb, double frac, int64_t n, double* out, void* stream) {
+  if (!va || !vb || !out || n < 0) return set_error(G2P_ERR_INVALID, "g2p_time_interp: bad arguments");
+  if (n == 0) return G2P_OK;
+  int64_t blocks = std::min<int64_t>(ceil_div(n, 256), (int64_t)num_sms() * 16);
+  time_interp_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(va, vb, frac, n, out);
+  G2P_LAUNCHED();
+  return G2P_OK;
+}
+
+int g2p_correction_prepare(const void* dem, int dem_dtype, double dem_mv, const double* gem, double gem_mv, double coeff,
+                           int64_t m, double* dem_term_out, uint8_t* valid_out, void* stream) {
+  if (!dem || !gem || !dem_term_out || !valid_out || m < 0) return set_error(G2P_ERR_INVALID, "g2p_correction_prepare: bad arguments");
+  if (dem_dtype != G2P_F64 && dem_dtype != G2P_F32) return set_error(G2P_ERR_INVALID, "g2p_correction_prepare: bad dtype");
+  if (m == 0) return G2P_OK;
+  int64_t blocks = std::min<int64_t>(ceil_div(m, 256), (int64_t)num_sms() * 16);
+  correction_prepare_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(dem, dem_dtype == G2P_F32, dem_mv, gem, gem_mv,
+                                                                            coeff, m, dem_term_out, valid_out);
+  G2P_LAUNCHED();
+  return G2P_OK;
+}
+
+int g2p_correct(double* values, const uint8_t* mask, int64_t m, int b, int64_t stride, const g2p_correction* corr,
+                void* stream) {
+  if (!values || !corr || !corr->gem || !corr->dem_term || !corr->valid || m < 0 || b < 0 || stride < m)
+    return set_error(G2P_ERR_INVALID, "g2p_correct: bad arguments");
+  if (m == 0 || b == 0) return G2P_OK;
+  int64_t blocks = std::min<int64_t>(ceil_div(m, 256), (int64_t)num_sms() * 16);
+  correct_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(values, mask, m, b, stride, corr->gem, corr->dem_term,
+                                                                 corr->valid, corr->mv);
+  G2P_LAUNCHED();
+  return G2P_OK;
+}
+
+}  // extern "C"

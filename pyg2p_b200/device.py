@@ -295,7 +295,23 @@ class DeviceTable:
             return False
         return self.plan() is not None
 
-    def apply(self, src, mv_out, src_mask=None, mask_policy=L.MASK_AS_REFERENCE, out=None, out_mask=None):
+    def compact(self):
+        """(table over the compact numbering of the touched source points, touched int32 [nc] sorted).
+        Only the source values an intertable references are needed downstream (4 % of an O1280 field for the
+        EFAS grid); `g2p_manip` gathers exactly those, and this table reads them back by compact index."""
+        if getattr(self, '_compact', None) is None:
+            flat = self.idx.reshape(-1)
+            touched = torch.unique(flat[(flat >= 0) & (flat < self.n_src)])
+            nc = int(touched.numel())
+            pos = torch.searchsorted(touched, self.idx.to(torch.int64).reshape(-1)).reshape(self.idx.shape)
+            inside = (self.idx >= 0) & (self.idx < self.n_src)
+            cidx = torch.where(inside, pos, torch.full_like(pos, nc)).to(torch.int32).contiguous()
+            self._compact = (DeviceTable(cidx, self.coef, nc, coef_f32=self.coef_f32, shape_1d=self.shape_1d,
+                                         grid_shape=self.grid_shape), touched.to(torch.int32).contiguous())
+        return self._compact
+
+    def apply(self, src, mv_out, src_mask=None, mask_policy=L.MASK_AS_REFERENCE, out=None, out_mask=None,
+              correction=None):
         """Batched K7 on device-resident messages.  src: float64 [b, n] (or [n]); returns out [b, m]
         (and out_mask uint8 [b, m] under PROPAGATE; masked outputs hold mv_out under PROPAGATE and FILL).
         Asynchronous on the current stream.
@@ -331,17 +347,27 @@ class DeviceTable:
                     out_mask = torch.empty((b, self.m), dtype=torch.uint8, device=self.device)
             if b > 0 and self.m > 0 and self._window_ok(src, src_mask, propagate):
                 self.last_path = 'window'
-                L.check(lib.g2p_apply_planned(self.plan(), _ptr(self.coef) if self.k > 1 else None, _ptr(src),
-                                              _ptr(src_mask) if propagate else None, b, src.stride(0), out.stride(0),
-                                              float(mv_out), int(mask_policy), _ptr(out),
-                                              _ptr(out_mask) if mask_policy == L.MASK_PROPAGATE else None,
-                                              _stream()))
+                if correction is not None:
+                    L.check(lib.g2p_apply_planned_corrected(
+                        self.plan(), _ptr(self.coef) if self.k > 1 else None, _ptr(src),
+                        _ptr(src_mask) if propagate else None, b, src.stride(0), out.stride(0), float(mv_out),
+                        int(mask_policy), C.byref(correction.c_struct()), _ptr(out),
+                        _ptr(out_mask) if mask_policy == L.MASK_PROPAGATE else None, _stream()))
+                else:
+                    L.check(lib.g2p_apply_planned(self.plan(), _ptr(self.coef) if self.k > 1 else None, _ptr(src),
+                                                  _ptr(src_mask) if propagate else None, b, src.stride(0),
+                                                  out.stride(0), float(mv_out), int(mask_policy), _ptr(out),
+                                                  _ptr(out_mask) if mask_policy == L.MASK_PROPAGATE else None,
+                                                  _stream()))
             elif b > 0 and self.m > 0:
                 self.last_path = 'generic'
                 L.check(lib.g2p_apply(_ptr(self.idx), _ptr(self.coef) if self.k > 1 else None, self.m, self.k, _ptr(src),
                                       _ptr(src_mask) if propagate else None, n, b, src.stride(0), out.stride(0),
                                       float(mv_out), int(mask_policy), _ptr(out),
                                       _ptr(out_mask) if mask_policy == L.MASK_PROPAGATE else None, _stream()))
+                if correction is not None:   # no plan for this table: the Corrector runs as its own pass
+                    L.check(lib.g2p_correct(_ptr(out), _ptr(out_mask) if mask_policy == L.MASK_PROPAGATE else None,
+                                            self.m, b, out.stride(0), C.byref(correction.c_struct()), _stream()))
         if squeeze:
             out = out[0]
             out_mask = out_mask[0] if out_mask is not None else None

@@ -1,0 +1,477 @@
+"""Host mirror of the reference's source-grid manipulation stages - `Converter`
+(main/manipulation/conversion.py), `Aggregator` (main/manipulation/aggregator.py), `Corrector`
+(main/manipulation/correction.py) - as planners for the fused CUDA stages (g2p_manip,
+g2p_apply_planned_corrected).  The classes keep the reference's constructor arguments and method names;
+the arithmetic runs on the GPU in the reference's evaluation order.  No CPU fallback.
+"""
+import ast
+import bisect
+import ctypes as C
+
+import numpy as np
+import numpy.ma as ma
+import torch
+
+from . import _lib as L
+from . import device
+from .exceptions import NOT_IMPLEMENTED, ApplicationException
+
+AVERAGE, ACCUMULATION, INSTANTANEOUS = 'average', 'accumulation', 'instantaneous'
+PARAM_INSTANT, PARAM_AVG, PARAM_CUM = 'instant', 'avg', 'accum'
+NC_FILL_F64 = 9.969209968386869e36
+
+
+class Step:
+    """hashable message key, as the reference's pyg2p.Step (src/pyg2p/__init__.py:30-54)."""
+
+    def __init__(self, start_step, end_step, points_meridian, input_step, level):
+        self.start_step, self.end_step = start_step, end_step
+        self.resolution, self.input_step, self.level = points_meridian, input_step, level
+
+    def _key(self):
+        return self.start_step, self.end_step, self.resolution, self.input_step, self.level
+
+    def __hash__(self):
+        return hash(self._key())
+
+    def __eq__(self, other):
+        return self._key() == other._key()
+
+    def __lt__(self, other):
+        return self.start_step < other.start_step
+
+    def __le__(self, other):
+        return self.start_step <= other.start_step
+
+    def __repr__(self):
+        return (f's:{self.start_step} e:{self.end_step} res:{self.resolution} step-lenght:{self.input_step} '
+                f'level:{self.level}')
+
+
+# --------------------------------------------------------------------------- conversion functions
+def parse_function(function_str, var='x'):
+    """'x=x*1000' / 'x=x-273.15' / 'x=-x*1000' / '(z/9.81)*0.0065' ... -> [(op, constant), ...] (<= 2 steps).
+
+    Only chains of `var (*|/|+|-) constant` are accepted - every function of the reference's
+    parameters.json and the gem formulas of its templates have this shape.  Each step is exact:
+    x-c == x+(-c), (-x)*c == x*(-c), c*x == x*c in IEEE arithmetic."""
+    expr = function_str.split('=', 1)[1] if '=' in function_str else function_str
+    tree = ast.parse(expr.strip(), mode='eval').body
+
+    def const(node):
+        if isinstance(node, ast.Constant) and isinstance(node.value, (int, float)):
+            return float(node.value)
+        if isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.USub, ast.UAdd)):
+            v = const(node.operand)
+            return None if v is None else (-v if isinstance(node.op, ast.USub) else v)
+        return None
+
+    def walk(node):
+        """-> (ops, negated) for a sub-expression that contains the variable"""
+        if isinstance(node, ast.Name) and node.id == var:
+            return [], False
+        if isinstance(node, ast.UnaryOp) and isinstance(node.op, ast.USub):
+            ops, neg = walk(node.operand)
+            return ops, not neg
+        if isinstance(node, ast.BinOp):
+            lc, rc = const(node.left), const(node.right)
+            if rc is not None and lc is None:
+                ops, neg = walk(node.left)
+                if isinstance(node.op, ast.Mult):
+                    return ops + [(L.OP_MUL, -rc if neg else rc)], False
+                if isinstance(node.op, ast.Div):
+                    return ops + [(L.OP_DIV, -rc if neg else rc)], False
+                if not neg and isinstance(node.op, ast.Add):
+                    return ops + [(L.OP_ADD, rc)], False
+                if not neg and isinstance(node.op, ast.Sub):
+                    return ops + [(L.OP_ADD, -rc)], False
+            if lc is not None and rc is None:
+                ops, neg = walk(node.right)
+                if isinstance(node.op, ast.Mult):
+                    return ops + [(L.OP_MUL, -lc if neg else lc)], False
+                if not neg and isinstance(node.op, ast.Add):
+                    return ops + [(L.OP_ADD, lc)], False
+        raise ApplicationException.get_exc(NOT_IMPLEMENTED, f'function {function_str!r} is not a chain of '
+                                                             f'{var} (*|/|+|-) constant steps')
+
+    ops, neg = walk(tree)
+    if neg:
+        ops = ops + [(L.OP_MUL, -1.0)]
+    if len(ops) > 2:
+        raise ApplicationException.get_exc(NOT_IMPLEMENTED, f'function {function_str!r} has more than two steps')
+    return ops
+
+
+class Converter:
+    """`Converter(func='x=x*1000', cut_off=False)`; `.set_missing_value(mv)`; `.convert(x)`;
+    `.cut_off_negative(values)` (conversion.py:10-59)."""
+
+    def __init__(self, func=None, cut_off=False):
+        self._mv = -1
+        self._function_str = func
+        self._do_cut_off = cut_off
+        self.ops = [] if func in (None, 'x=x') else parse_function(func)
+        self.identity = func in (None, 'x=x')
+
+    def set_missing_value(self, mv):
+        self._mv = mv
+
+    @property
+    def must_cut_off(self):
+        return self._do_cut_off
+
+    def desc_fields(self):
+        ops = self.ops + [(L.OP_NONE, 0.0)] * (2 - len(self.ops))
+        return dict(conv_op1=ops[0][0], conv_c1=ops[0][1], conv_op2=ops[1][0], conv_c2=ops[1][1], mv_grib=float(self._mv))
+
+    def convert(self, x):
+        """where(x != mv, f(x), mv), mask preserved (conversion.py:33-42) - on the GPU."""
+        if self.identity:
+            return x
+        out = run_manip([x], [ManipItem.pick(0)], converter=self)[0]
+        return ma.masked_where(x.mask, out, copy=False) if isinstance(x, ma.MaskedArray) else out
+
+    def cut_off_negative(self, values):
+        """where(v < 0, 0, v) on every message of a dict (or on one array), mask dropped (conversion.py:44-52)."""
+        if isinstance(values, dict):
+            keys = list(values)
+            outs = run_manip([values[k] for k in keys], [ManipItem.pick(i) for i in range(len(keys))], cut_off=True)
+            return dict(zip(keys, outs))
+        return run_manip([values], [ManipItem.pick(0)], cut_off=True)[0]
+
+
+# --------------------------------------------------------------------------- aggregation plans
+class ManipItem:
+    """one output message of g2p_manip."""
+
+    def __init__(self, kind, inputs, unit_time=0.0, divisor=1.0, mask_all=0):
+        self.kind, self.inputs, self.unit_time, self.divisor, self.mask_all = kind, list(inputs), unit_time, divisor, mask_all
+
+    @classmethod
+    def pick(cls, i):
+        return cls(L.AGG_PICK, [i])
+
+    def to_c(self):
+        if len(self.inputs) > L.MANIP_MAX_IN:
+            raise ApplicationException.get_exc(NOT_IMPLEMENTED, f'average over {len(self.inputs)} iterator steps '
+                                                                f'(max {L.MANIP_MAX_IN})')
+        it = L.ManipItem()
+        it.kind, it.n_in, it.mask_all = self.kind, len(self.inputs), self.mask_all
+        for q, v in enumerate(self.inputs):
+            it.inputs[q] = v
+        it.unit_time, it.divisor = float(self.unit_time), float(self.divisor)
+        return it
+
+
+class AggregationPlan:
+    """What `Aggregator.do_manipulation` would compute, as data: the input slots (end_step of the messages,
+    in slot order), the steps to synthesise first - (new_step, step_a, step_b, fraction) -> slot appended
+    at the end - and one ManipItem per output key (start, end)."""
+
+    def __init__(self, slots):
+        self.slots = list(slots)
+        self.synth = []
+        self.outputs = []        # [((start, end), ManipItem)]
+
+    def slot(self, step):
+        return self.slots.index(step)
+
+    def add_synth(self, step, a, b, frac):
+        self.synth.append((step, a, b, frac))
+        self.slots.append(step)
+
+
+def plan_accumulation(steps, start, end, aggr_step, unit_time, force_zero=False):
+    """aggregator.py:72-153, including its quirks: step 0 absent -> zeros, a missing step t is
+    V[a] + (V[b]-V[a])*((t-a)/(b-a)), a missing PREVIOUS step t-D is interpolated with the fraction of t."""
+    keys = sorted(steps)
+    plan = AggregationPlan(keys)
+    known = list(keys)            # v_ord keys; grows with the synthesised steps
+    zero_created = False
+    if start == 0:
+        start = aggr_step
+    for t in range(start, end + 1, aggr_step):
+        vkeys = list(known)       # insertion order, like the reference's OrderedDict scan (synthesised steps at the end)
+        if t not in vkeys:
+            i_next = bisect.bisect_left(vkeys, t)
+            nxt = vkeys[i_next]
+            i_org = bisect.bisect_right(vkeys, t)
+            if i_org == i_next:
+                i_org -= 1
+            org = vkeys[i_org]
+            plan.add_synth(t, org, nxt, (t - org) / (nxt - org))
+            known.append(t)
+        prev = t - aggr_step
+        if prev >= 0 and prev not in vkeys and not zero_created:
+            if prev == 0:
+                zero_created = True
+                known.append(0)
+            else:
+                i_next = bisect.bisect_left(vkeys, prev)
+                nxt = vkeys[i_next]
+                i_org = bisect.bisect_right(vkeys, prev)
+                if i_org == i_next:
+                    i_org -= 1
+                org = vkeys[i_org]
+                plan.add_synth(prev, org, nxt, (t - org) / (nxt - org))
+                known.append(prev)
+        zero_prev = (prev == 0 and (force_zero or 0 not in plan.slots))
+        item = ManipItem(L.AGG_ACCUM, [plan.slot(t), -1 if zero_prev else plan.slot(prev)], unit_time=unit_time,
+                         divisor=aggr_step)
+        plan.outputs.append(((prev, t), item))
+    return plan
+
+
+def plan_average(steps, start, end, aggr_step, second_t_res=False):
+    """aggregator.py:155-236 without half weights: one add per hourly iterator, the next available step when an
+    hour is absent, divided by the count; masked with the OR of all inputs."""
+    keys = sorted(steps)
+    plan = AggregationPlan(keys)
+    if start == 0 or second_t_res:
+        it0, it1 = start, end - aggr_step + 2
+    else:
+        it0, it1 = start - aggr_step, end - aggr_step + 1
+    for t in range(it0, it1, aggr_step):
+        ins = []
+        for h in range(t + 1, t + aggr_step + 1):
+            ins.append(plan.slot(h if h in keys else keys[bisect.bisect_left(keys, h)]))
+        plan.outputs.append(((t, t + aggr_step), ManipItem(L.AGG_AVERAGE, ins, divisor=float(len(ins)), mask_all=1)))
+    return plan
+
+
+def plan_instantaneous(steps, start, end, aggr_step, input_step=0, step_type=PARAM_INSTANT):
+    """aggregator.py:238-279."""
+    keys = sorted(steps)
+    plan = AggregationPlan(keys)
+    s = start - aggr_step if start - aggr_step > 0 else start
+    if step_type == PARAM_AVG:
+        s = start + input_step
+    for t in range(s, end + 1, aggr_step):
+        if t in keys:
+            src = plan.slot(t)
+        elif t == 0:
+            src = -1
+        else:
+            src = plan.slot(keys[bisect.bisect_right(keys, t)])
+        plan.outputs.append(((t, t), ManipItem(L.AGG_PICK, [src])))
+    return plan
+
+
+class Aggregator:
+    """Same keyword arguments as the reference's Aggregator (aggregator.py:26-60); `do_manipulation(values)`
+    takes / returns `{Step: array}` and runs conversion-free aggregation on the GPU."""
+
+    def __init__(self, **kwargs):
+        self._mv_grib = kwargs.get('mv_grib')
+        self._step_type = kwargs.get('step_type')
+        self._input_step = int(kwargs.get('input_step'))
+        self._unit_time = int(kwargs.get('unit_time'))
+        self._aggregation_step = int(kwargs.get('aggr_step'))
+        self._aggregation = kwargs.get('aggr_type')
+        self._aggregation_halfweights = kwargs.get('aggr_halfweights')
+        self._force_zero = kwargs.get('force_zero_array')
+        self._start = int(kwargs.get('start_step'))
+        self._end = int(kwargs.get('end_step'))
+        self._second_t_res = kwargs.get('sec_temp_res')
+        self._usable_start = max(self._start - self._aggregation_step, 0) if self._input_step != 0 else self._start
+
+    def change_end_step(self, end_first_res):
+        self._end = end_first_res
+
+    def get_real_start_end_steps(self):
+        return self._usable_start, self._end
+
+    def plan(self, end_steps):
+        if self._aggregation == ACCUMULATION:
+            return plan_accumulation(end_steps, self._start, self._end, self._aggregation_step, self._unit_time,
+                                     bool(self._force_zero))
+        if self._step_type == PARAM_CUM:
+            raise ApplicationException.get_exc(
+                NOT_IMPLEMENTED, details=f'Manipulation {self._aggregation} for parameter type: {self._step_type}')
+        if self._aggregation == AVERAGE:
+            if self._aggregation_halfweights:
+                raise ApplicationException.get_exc(NOT_IMPLEMENTED, 'average with half weights on the GPU path')
+            return plan_average(end_steps, self._start, self._end, self._aggregation_step, bool(self._second_t_res))
+        return plan_instantaneous(end_steps, self._start, self._end, self._aggregation_step, self._input_step,
+                                  self._step_type)
+
+    def do_manipulation(self, values):
+        first = next(iter(values))
+        by_end = dict(sorted((k.end_step, v) for k, v in values.items()))
+        plan = self.plan(list(by_end))
+        outs = run_plan(plan, [by_end[s] for s in plan.slots[:len(by_end)]])
+        res = {}
+        for ((s, e), _), o in zip(plan.outputs, outs):
+            res[Step(s, e, first.resolution, self._aggregation_step, first.level)] = o
+        return res
+
+
+# --------------------------------------------------------------------------- running plans on the device
+def _upload(fields):
+    """list of [n] arrays (some MaskedArrays) -> (src [b, n] device, mask [b, n] uint8 device or None)."""
+    device.require_cuda()
+    n = np.asarray(ma.getdata(fields[0])).size
+    src = torch.empty((len(fields), n), dtype=torch.float64, device='cuda')
+    any_mask = any(isinstance(f, ma.MaskedArray) and f.mask is not ma.nomask for f in fields)
+    msk = torch.zeros((len(fields), n), dtype=torch.uint8, device='cuda') if any_mask else None
+    for i, f in enumerate(fields):
+        src[i] = torch.from_numpy(np.ascontiguousarray(ma.getdata(f), dtype=np.float64).ravel())
+        if any_mask and isinstance(f, ma.MaskedArray) and f.mask is not ma.nomask:
+            msk[i] = torch.from_numpy(np.array(np.broadcast_to(ma.getmaskarray(f).ravel(), (n,))).view(np.uint8))
+    return src, msk
+
+
+def manip_device(src, src_mask, items, converter=None, cut_off=False, touched=None):
+    """g2p_manip on device tensors: src [b, n] -> out [n_out, nc] (+ mask).  `touched`: int32 device tensor."""
+    lib = device.require_cuda()
+    b_in, n = src.shape
+    nc = n if touched is None else touched.numel()
+    n_out = len(items)
+    carr = (L.ManipItem * max(n_out, 1))(*[it.to_c() for it in items])
+    desc = L.ManipDesc()
+    fields = converter.desc_fields() if converter is not None and not converter.identity else dict(
+        conv_op1=L.OP_NONE, conv_c1=0.0, conv_op2=L.OP_NONE, conv_c2=0.0, mv_grib=0.0)
+    for k, v in fields.items():
+        setattr(desc, k, v)
+    desc.cut_off_negative = 1 if cut_off else 0
+    desc.n_out = n_out
+    desc.items = C.cast(carr, C.POINTER(L.ManipItem))
+    nc_pad = -(-nc // 16) * 16                       # rows padded to 16 values: what the windowed apply needs
+    out = torch.empty((n_out, nc_pad), dtype=torch.float64, device=src.device)
+    omask = torch.empty((n_out, nc_pad), dtype=torch.uint8, device=src.device) if src_mask is not None else None
+    if nc_pad != nc:
+        out[:, nc:] = 0.0
+        if omask is not None:
+            omask[:, nc:] = 0
+    L.check(lib.g2p_set_device(src.device.index))
+    L.check(lib.g2p_manip(C.byref(desc), C.c_void_p(src.data_ptr()),
+                          C.c_void_p(src_mask.data_ptr()) if src_mask is not None else None, n, b_in, src.stride(0),
+                          C.c_void_p(touched.data_ptr()) if touched is not None else None, nc, out.stride(0),
+                          C.c_void_p(out.data_ptr()), C.c_void_p(omask.data_ptr()) if omask is not None else None,
+                          C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out[:, :nc], (omask[:, :nc] if omask is not None else None)
+
+
+def synthesise_steps(plan, src, src_mask):
+    """append the linearly-in-time interpolated messages a plan needs (g2p_time_interp); masks are OR-ed."""
+    if not plan.synth:
+        return src, src_mask
+    lib = device.require_cuda()
+    b0, n = src.shape
+    full = torch.empty((b0 + len(plan.synth), n), dtype=torch.float64, device=src.device)
+    full[:b0] = src
+    fmask = None
+    if src_mask is not None:
+        fmask = torch.zeros((b0 + len(plan.synth), n), dtype=torch.uint8, device=src.device)
+        fmask[:b0] = src_mask
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for i, (step, a, b, frac) in enumerate(plan.synth):
+        ia, ib = plan.slot(a), plan.slot(b)
+        L.check(lib.g2p_time_interp(C.c_void_p(full[ia].data_ptr()), C.c_void_p(full[ib].data_ptr()), float(frac), n,
+                                    C.c_void_p(full[b0 + i].data_ptr()), st))
+        if fmask is not None:
+            fmask[b0 + i] = fmask[ia] | fmask[ib]
+    return full, fmask
+
+
+def run_plan(plan, fields, converter=None, cut_off=False):
+    src, msk = _upload(fields)
+    src, msk = synthesise_steps(plan, src, msk)
+    out, omask = manip_device(src, msk, [it for _, it in plan.outputs], converter=converter, cut_off=cut_off)
+    return _download(out, omask, np.asarray(ma.getdata(fields[0])).shape)
+
+
+def run_manip(fields, items, converter=None, cut_off=False):
+    src, msk = _upload(fields)
+    out, omask = manip_device(src, msk if not cut_off else None, items, converter=converter, cut_off=cut_off)
+    return _download(out, omask, np.asarray(ma.getdata(fields[0])).shape)
+
+
+def _download(out, omask, shape):
+    o = out.cpu().numpy()
+    res = [o[i].reshape(shape) for i in range(o.shape[0])]
+    if omask is not None:
+        m = omask.cpu().numpy().astype(bool)
+        res = [ma.masked_where(m[i].reshape(shape), r, copy=False) if m[i].any() else r for i, r in enumerate(res)]
+    return res
+
+
+# --------------------------------------------------------------------------- correction
+class Corrector:
+    """DEM / geopotential lapse-rate correction (manipulation/correction.py:13-113) as per-target terms on the
+    device.  `gem_values` is the geopotential field ALREADY interpolated to the target grid with the same
+    intertable, after `gem_formula` was applied on the source grid (correction.py:84-108) - use
+    `Corrector.from_geopotential` to do both steps."""
+
+    def __init__(self, dem_values, dem_mv, gem_values, gem_mv, formula='p+gem-dem*0.0065'):
+        compact = formula.replace(' ', '')
+        if not (compact.startswith('p+gem-dem*')):
+            raise ApplicationException.get_exc(NOT_IMPLEMENTED, f'correction formula {formula!r} (only p+gem-dem*c)')
+        self.coeff = float(compact[len('p+gem-dem*'):])
+        lib = device.require_cuda()
+        dem = np.ascontiguousarray(dem_values)
+        if dem.dtype not in (np.float32, np.float64):
+            dem = dem.astype(np.float64)
+        self.shape = dem.shape
+        m = dem.size
+        d_dem = torch.from_numpy(dem.ravel()).cuda()
+        self.gem = device.to_device(np.asarray(ma.getdata(gem_values), dtype=np.float64).ravel(), torch.float64, 'cuda')
+        self.dem_term = torch.empty(m, dtype=torch.float64, device='cuda')
+        self.valid = torch.empty(m, dtype=torch.uint8, device='cuda')
+        L.check(lib.g2p_correction_prepare(C.c_void_p(d_dem.data_ptr()), L.F32 if dem.dtype == np.float32 else L.F64,
+                                           float(dem_mv), C.c_void_p(self.gem.data_ptr()), float(gem_mv), self.coeff, m,
+                                           C.c_void_p(self.dem_term.data_ptr()), C.c_void_p(self.valid.data_ptr()),
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self.mv = NC_FILL_F64
+        self._c = L.Correction(self.gem.data_ptr(), self.dem_term.data_ptr(), self.valid.data_ptr(), self.mv)
+
+    @classmethod
+    def from_geopotential(cls, table, z_values, z_mv, mv_out, dem_values, dem_mv, formula='p+gem-dem*0.0065',
+                          gem_formula='(z/9.81)*0.0065'):
+        """`_read_geo` (correction.py:84-108): gem = interpolate(where(z != mv, gem_formula(z), mv))."""
+        conv = Converter.__new__(Converter)
+        conv._mv, conv._do_cut_off, conv.identity = z_mv, False, False
+        conv.ops = parse_function(gem_formula, var='z')
+        src, _ = _upload([z_values])
+        g_src, _ = manip_device(src, None, [ManipItem.pick(0)], converter=conv)
+        # `0.0 + x` of PICK is exact except for -0.0, which the formula cannot produce from a geopotential
+        n_pad = -(-table.n_src // 16) * 16
+        buf = torch.zeros((1, n_pad), dtype=torch.float64, device='cuda')
+        buf[0, :table.n_src] = g_src[0]
+        gem = table.apply(buf[:, :table.n_src], float(mv_out))[0]
+        return cls(dem_values, dem_mv, gem.cpu().numpy(), z_mv, formula)
+
+    def c_struct(self):
+        return self._c
+
+    def correct(self, values):
+        """standalone `Corrector.correct(values)` on a target-grid array (correction.py:59-82)."""
+        lib = device.require_cuda()
+        v = torch.from_numpy(np.ascontiguousarray(ma.getdata(values), dtype=np.float64).reshape(1, -1)).cuda()
+        L.check(lib.g2p_correct(C.c_void_p(v.data_ptr()), None, v.shape[1], 1, v.stride(0), C.byref(self._c),
+                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        out = v.cpu().numpy().reshape(np.asarray(values).shape)
+        return ma.masked_where(values.mask, out, copy=False) if isinstance(values, ma.MaskedArray) else out
+
+
+# --------------------------------------------------------------------------- the fused pipeline
+class FusedPipeline:
+    """convert -> aggregate -> cut-off (source grid, compact) -> intertable apply -> correction, for all output
+    messages of a run: two kernel launches (g2p_manip on the touched source points, then the windowed apply
+    with the Corrector epilogue).  Stage order as the reference's controller / writers (controller.py:106-132,
+    writers/__init__.py:55-70)."""
+
+    def __init__(self, table):
+        self.table = table
+        self.compact, self.touched = table.compact()
+
+    def run(self, src, src_mask, plan, converter=None, cut_off=False, mv_out=NC_FILL_F64,
+            mask_policy=L.MASK_AS_REFERENCE, corrector=None):
+        """src: device [b, n] float64 (messages in `plan.slots` order), src_mask: device uint8 [b, n] or None.
+        -> out [n_out, m] device (+ out_mask under PROPAGATE)."""
+        src, src_mask = synthesise_steps(plan, src, src_mask)
+        use_mask = src_mask is not None and mask_policy != L.MASK_AS_REFERENCE
+        vals, vmask = manip_device(src, src_mask if use_mask else None, [it for _, it in plan.outputs],
+                                   converter=converter, cut_off=cut_off, touched=self.touched)
+        return self.compact.apply(vals, float(mv_out), src_mask=vmask, mask_policy=mask_policy if use_mask else
+                                  L.MASK_AS_REFERENCE, correction=corrector)

@@ -1,0 +1,185 @@
+"""GPU parity of the fused manipulation stages (K8): Converter / Aggregator / Corrector against the golden
+vectors produced by the reference's own classes (tests/golden/manip.npz) and the whole pipeline
+convert -> aggregate -> cut-off -> apply -> correct against the oracle chain.  Bit-exact throughout."""
+import os
+
+import numpy as np
+import numpy.ma as ma
+import pytest
+import torch
+
+from oracle import interp_ref as R
+from oracle import manip_ref as MR
+from pyg2p_b200 import _lib as L
+from pyg2p_b200 import synth
+
+pytestmark = pytest.mark.gpu
+RES = 640
+
+
+@pytest.fixture(scope='module')
+def M():
+    from pyg2p_b200 import device
+    device.require_cuda()
+    from pyg2p_b200 import manipulation
+    return manipulation
+
+
+@pytest.fixture(scope='module')
+def g(golden_dir):
+    return np.load(os.path.join(golden_dir, 'manip.npz'))
+
+
+def test_converter_matches_reference(M, g):
+    x = g['conv_x']
+    for i, f in enumerate(['x=x*1000', 'x=x-273.15', 'x=x*(-0.0353)', 'x=-x*1000', 'x=x']):
+        c = M.Converter(func=f, cut_off=True)
+        c.set_missing_value(synth.GRIB_MV)
+        y = c.convert(x.copy())
+        np.testing.assert_array_equal(np.asarray(y), g[f'conv{i}'])
+        np.testing.assert_array_equal(c.cut_off_negative(np.asarray(y).copy()), g[f'conv{i}_cut'])
+    xm = ma.masked_where(x > 0.01, x)
+    ym = M.Converter(func='x=x*1000').convert(xm)
+    assert isinstance(ym, ma.MaskedArray) and np.array_equal(ym.mask, xm.mask)
+    d = M.Converter(func='x=x*1000', cut_off=True).cut_off_negative({'a': x.copy(), 'b': -x})
+    np.testing.assert_array_equal(d['b'], np.where(-x < 0, 0, -x))
+
+
+def _check(g, tag, out):
+    keys = sorted(out.keys(), key=lambda s: (s.end_step, s.start_step))
+    np.testing.assert_array_equal(np.array([(s.start_step, s.end_step) for s in keys]), g[f'{tag}_keys'])
+    np.testing.assert_array_equal(np.array([np.asarray(ma.getdata(out[k])) for k in keys]), g[f'{tag}_vals'])
+    n = g['conv_x'].size
+    masks = np.array([np.broadcast_to(ma.getmaskarray(out[k]) if isinstance(out[k], ma.MaskedArray) else False, (n,))
+                      for k in keys])
+    np.testing.assert_array_equal(masks, g[f'{tag}_masks'])
+
+
+def test_aggregator_matches_reference(M, g):
+    steps = list(g['agg_steps'])
+    cum, mask, inst = g['agg_cum'], g['agg_mask'], g['inst_fields']
+
+    def vals(stepset, src=cum, masked=False, start_is_end=False):
+        d = {}
+        for s in stepset:
+            v = src[steps.index(s)].copy()
+            if masked:
+                v = ma.masked_where(mask, v, copy=True)
+            d[M.Step(int(s) if start_is_end else 0, int(s), RES, 6, 0)] = v
+        return d
+
+    def agg(**kw):
+        base = dict(aggr_step=24, aggr_type='accumulation', aggr_halfweights=False, input_step=6, step_type='accum',
+                    start_step=0, end_step=72, unit_time=24, mv_grib=synth.GRIB_MV, force_zero_array=False)
+        base.update(kw)
+        return M.Aggregator(**base)
+
+    _check(g, 'acc_full', agg().do_manipulation(vals(steps)))
+    _check(g, 'acc_nozero', agg().do_manipulation(vals(steps[1:])))
+    _check(g, 'acc_gap', agg().do_manipulation(vals([s for s in steps if s != 48])))
+    _check(g, 'acc_masked', agg().do_manipulation(vals(steps, masked=True)))
+    _check(g, 'acc_forcezero', agg(force_zero_array=True).do_manipulation(vals(steps)))
+    _check(g, 'acc_step12_unit6', agg(aggr_step=12, unit_time=6, start_step=12).do_manipulation(vals(steps)))
+    iv = dict(aggr_type='average', step_type='instant')
+    _check(g, 'avg_full', agg(**iv).do_manipulation(vals(steps, inst, start_is_end=True)))
+    _check(g, 'avg_start24', agg(start_step=24, **iv).do_manipulation(vals(steps, inst, start_is_end=True)))
+    ii = dict(aggr_type='instantaneous', step_type='instant', aggr_step=12)
+    _check(g, 'inst_full', agg(**ii).do_manipulation(vals(steps, inst, start_is_end=True)))
+    _check(g, 'inst_gap', agg(**ii).do_manipulation(vals([s for s in steps if s not in (0, 36)], inst, start_is_end=True)))
+    out = agg().do_manipulation(vals(steps))
+    assert next(iter(out)) == M.Step(0, 24, RES, 24, 0)
+    with pytest.raises(Exception):
+        agg(aggr_type='average').do_manipulation(vals(steps))          # average of an accumulated parameter
+
+
+def test_corrector_matches_reference(M, g):
+    c = M.Corrector(g['corr_dem'], float(g['corr_dem_mv']), g['corr_gem'], float(g['corr_gem_mv']))
+    np.testing.assert_array_equal(c.correct(g['corr_p'].copy()), g['corr_out'])
+    c32 = M.Corrector(g['corr_dem'].astype(np.float32), float(g['corr_dem_mv']), g['corr_gem'], float(g['corr_gem_mv']))
+    want = MR.correct(g['corr_p'].copy(), g['corr_dem'].astype(np.float32).astype(np.float64), g['corr_gem'],
+                      float(g['corr_dem_mv']), float(g['corr_gem_mv']))
+    np.testing.assert_array_equal(c32.correct(g['corr_p'].copy()), np.asarray(ma.filled(want)))
+    with pytest.raises(Exception):
+        M.Corrector(g['corr_dem'], 0.0, g['corr_gem'], 0.0, formula='p/gem*(10**((-0.159)*dem/1000))')
+
+
+@pytest.mark.parametrize('kind', ['accumulation', 'average', 'instantaneous'])
+def test_fused_pipeline_matches_oracle_chain(M, kind):
+    """messages (steps 0..72 by 6 h) of one member -> convert -> aggregate -> cut-off -> invdist apply ->
+    lapse-rate correction, two launches on the GPU, against the oracle's stage-by-stage chain on the same
+    table; with and without masks."""
+    from pyg2p_b200 import device
+    lat, lon, det = synth.regular_ll_grid(62.0, 38.0, 97, -8.0, 32.0, 161)
+    n = lat.size
+    tl, tlo = synth.efas_target(rows=96, cols=70, cell=20000.0, x_ul=3500000.0, y_ul=4000000.0)
+    ix = device.SourceIndex(lon, lat, det['radius'])
+    out = ix.knn(tlo, tl, k=4, mode=L.MODE_INVDIST, mub=ix.min_upper_bound(det['Nj']), want_flags=False)
+    table = device.DeviceTable(out['idx'], out['coef'], n, grid_shape=tl.shape)
+    idx, w = table.indexes_coeffs()
+    steps = list(range(0, 73, 6))
+    rng = np.random.default_rng(3)
+    if kind == 'accumulation':
+        fields = np.cumsum(np.maximum(0, rng.standard_normal((len(steps), n))) * 2e-3 - 2e-4, axis=0)
+        func, cut, agg = 'x=x*1000', True, dict(aggr_type='accumulation', step_type='accum', aggr_step=24, unit_time=24)
+    else:
+        fields = 280.0 + 5 * rng.standard_normal((len(steps), n))
+        func, cut, agg = 'x=x-273.15', False, dict(aggr_type=kind, step_type='instant', aggr_step=24 if kind == 'average' else 12,
+                                                   unit_time=24)
+    mask = rng.random(n) < 0.03
+    fields[:, mask] = synth.GRIB_MV
+    conv = M.Converter(func=func, cut_off=cut)
+    conv.set_missing_value(synth.GRIB_MV)
+    a = M.Aggregator(input_step=6, start_step=0, end_step=72, mv_grib=synth.GRIB_MV, force_zero_array=False,
+                     aggr_halfweights=False, **agg)
+    plan = a.plan(steps)
+    dem = synth.field_dem(tl, tlo, synth.PCR_MV_F32).astype(np.float32)
+    z = synth.field_geopotential(lat, lon)
+    z[::97] = synth.GRIB_MV
+    mv_out = synth.NC_FILL_F64
+    corr = M.Corrector.from_geopotential(table, z, synth.GRIB_MV, mv_out, dem, float(synth.PCR_MV_F32))
+    pipe = M.FusedPipeline(table)
+    assert pipe.compact.n_src == pipe.touched.numel() < n
+    src = torch.from_numpy(fields).cuda()
+    got = pipe.run(src, None, plan, converter=conv, cut_off=cut, mv_out=mv_out, corrector=corr).cpu().numpy()
+    assert pipe.compact.last_path == 'window'
+    # ---- oracle chain
+    converted = {s: MR.convert(fields[i].copy(), func, synth.GRIB_MV) for i, s in enumerate(steps)}
+    if kind == 'accumulation':
+        ref = MR.accumulation(converted, 0, 72, 24, 24)
+    elif kind == 'average':
+        ref = MR.average(converted, 0, 72, 24)
+    else:
+        ref = MR.instantaneous(converted, 0, 72, 12, input_step=6)
+    gem_src = MR.gem_from_geopotential(z, synth.GRIB_MV)
+    with np.errstate(all='ignore'):
+        gem = R.apply_sequential(gem_src, w, idx, 4, mv_out)
+    keys = sorted(ref, key=lambda k: (k[1], k[0]))
+    assert [k for k, _ in plan.outputs] == keys and got.shape == (len(keys), tl.size)
+    for o, k in enumerate(keys):
+        v = np.asarray(ma.getdata(ref[k]))
+        if cut:
+            v = MR.cut_off_negative(v)
+        with np.errstate(all='ignore'):
+            p = R.apply_sequential(v, w, idx, 4, mv_out)
+            want = MR.correct(p, dem.ravel(), gem, float(synth.PCR_MV_F32), synth.GRIB_MV)
+        np.testing.assert_array_equal(got[o], np.asarray(ma.filled(want)))
+    # ---- the same without correction, masks propagated (fill): masked wherever a used input is masked
+    msk = torch.from_numpy(np.broadcast_to(mask, fields.shape).copy().view(np.uint8)).cuda()
+    got2 = pipe.run(src, msk, plan, converter=conv, cut_off=cut, mv_out=mv_out, mask_policy=L.MASK_FILL).cpu().numpy()
+    masked_in = {s: ma.masked_where(mask, converted[s]) for s in steps}
+    if kind == 'accumulation':
+        refm = MR.accumulation(masked_in, 0, 72, 24, 24)
+    elif kind == 'average':
+        refm = MR.average(masked_in, 0, 72, 24)
+    else:
+        refm = MR.instantaneous(masked_in, 0, 72, 12, input_step=6)
+    for o, k in enumerate(keys):
+        v = np.asarray(ma.getdata(refm[k]))
+        if cut:
+            v = MR.cut_off_negative(v)
+        mk = ma.getmaskarray(refm[k]) if isinstance(refm[k], ma.MaskedArray) else np.zeros(n, bool)
+        if kind == 'accumulation' and k[0] == 0:
+            mk = np.zeros(n, bool) | (ma.getmaskarray(refm[k]) if isinstance(refm[k], ma.MaskedArray) else False)
+        with np.errstate(all='ignore'):
+            data, _ = R.apply_propagate(v, w, idx, 4, mv_out, np.broadcast_to(mk, (n,)))
+        np.testing.assert_array_equal(got2[o], data)
