@@ -213,6 +213,7 @@ def run_b200(args):
     dev = torch.device('cuda', local_rank)
     if ws > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')     # keep stdout for the one JSON line
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():

@@ -103,6 +103,9 @@ int g2p_index_get_xyz(const g2p_index* index, double* xyz_out, void* stream);
  * (scipy_interpolation_lib.py:568-570).  dmax is a HOST pointer; synchronises `stream`.
  * min_upper_bound = dmax + dmax*4/Nj is computed by the host (Python float arithmetic). */
 int g2p_index_max_nn_dist(g2p_index* index, double* dmax /* host */, void* stream);
+/* the same over the source records [first, last) of the (cell-sorted) index only: with the sources split over
+ * ranks, max over ranks of the partial results is the full result (one all-reduce of a double) */
+int g2p_index_max_nn_dist_part(g2p_index* index, int64_t first, int64_t last, double* dmax /* host */, void* stream);
 
 /* K1+K3(+K5)  k nearest source points of every target.
  * Replaces `tree.query(efas_locations, k=nnear)` (scipy_interpolation_lib.py:624-628) and,

@@ -76,6 +76,7 @@ PROTOTYPES = {
     'g2p_index_get_info': (C.c_int, [_vp, C.POINTER(IndexInfo)]),
     'g2p_index_get_xyz': (C.c_int, [_vp, _vp, _vp]),
     'g2p_index_max_nn_dist': (C.c_int, [_vp, C.POINTER(C.c_double), _vp]),
+    'g2p_index_max_nn_dist_part': (C.c_int, [_vp, _i64, _i64, C.POINTER(C.c_double), _vp]),
     'g2p_knn': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f64, _rotp, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp]),
     'g2p_weights': (C.c_int, [_i32, _i32, _i64, _i64, _f64, _i32, _vp, _vp, _vp]),
     'g2p_table_pack_rec': (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),

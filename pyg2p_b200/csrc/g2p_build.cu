@@ -334,11 +334,32 @@ static int grid_for(int64_t n, int threads, int waves = 8) {
   return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
 }
 
+// stream-ordered allocation from the device's default pool, which is told to keep its memory: a table
+// build allocates ~400 MB of index and scratch, and cudaMalloc / cudaFree cost more than the kernels
+template <typename T>
+static cudaError_t pool_alloc(T** p, size_t bytes, cudaStream_t st) {
+  static bool tuned[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !tuned[dev]) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    tuned[dev] = true;
+  }
+  return cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 1, st);
+}
+
 static void free_index(g2p_index* ix) {
   if (!ix) return;
-  if (ix->xyz) cudaFree(ix->xyz);
-  if (ix->pts) cudaFree(ix->pts);
-  if (ix->cell_start) cudaFree(ix->cell_start);
+  // wait for every stream (a query on any of them may still be reading the index), then hand the memory
+  // back to the pool - cudaFree would return it to the driver and the next build would pay for it again
+  cudaDeviceSynchronize();
+  if (ix->xyz) cudaFreeAsync(ix->xyz, nullptr);
+  if (ix->pts) cudaFreeAsync(ix->pts, nullptr);
+  if (ix->cell_start) cudaFreeAsync(ix->cell_start, nullptr);
   delete ix;
 }
 
@@ -359,8 +380,8 @@ static int build_cells(g2p_index* ix, cudaStream_t st) {
   const int n_coarse = 6 * Gc * Gc;
   double* d_stats = nullptr;
   uint8_t* d_coarse = nullptr;
-  G2P_CUDA(cudaMalloc(&d_stats, 2 * sizeof(double)));
-  G2P_CUDA(cudaMalloc(&d_coarse, n_coarse));
+  G2P_CUDA(pool_alloc(&d_stats, 2 * sizeof(double), st));
+  G2P_CUDA(pool_alloc(&d_coarse, n_coarse, st));
   const double init[2] = {DBL_MAX, 0.0};
   G2P_CUDA(cudaMemcpyAsync(d_stats, init, sizeof(init), cudaMemcpyHostToDevice, st));
   G2P_CUDA(cudaMemsetAsync(d_coarse, 0, n_coarse, st));
@@ -371,8 +392,8 @@ static int build_cells(g2p_index* ix, cudaStream_t st) {
   G2P_CUDA(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
   G2P_CUDA(cudaMemcpyAsync(coarse.data(), d_coarse, n_coarse, cudaMemcpyDeviceToHost, st));
   G2P_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_stats);
-  cudaFree(d_coarse);
+  cudaFreeAsync(d_stats, st);
+  cudaFreeAsync(d_coarse, st);
   const double rmin = stats[0], rmax = stats[1];
   if (!(rmax > 0.0) || !std::isfinite(rmax) || !(rmin > 0.0))
     return set_error(G2P_ERR_INVALID, "source coordinates are not finite / not on a sphere (|p| in [%g, %g])", rmin, rmax);
@@ -396,12 +417,12 @@ static int build_cells(g2p_index* ix, cudaStream_t st) {
   uint32_t *d_keys = nullptr, *d_counts = nullptr, *d_cursor = nullptr, *d_bsums = nullptr;
   const int64_t nc = ix->n_cells;
   const int nb = (int)ceil_div(nc, kScanBlock);
-  G2P_CUDA(cudaMalloc(&d_keys, (size_t)n * 4));
-  G2P_CUDA(cudaMalloc(&d_counts, (size_t)nc * 4));
-  G2P_CUDA(cudaMalloc(&d_cursor, (size_t)nc * 4));
-  G2P_CUDA(cudaMalloc(&d_bsums, (size_t)nb * 4));
-  G2P_CUDA(cudaMalloc(&ix->cell_start, (size_t)(nc + 1) * 4));
-  G2P_CUDA(cudaMalloc(&ix->pts, (size_t)n * sizeof(Pt)));
+  G2P_CUDA(pool_alloc(&d_keys, (size_t)n * 4, st));
+  G2P_CUDA(pool_alloc(&d_counts, (size_t)nc * 4, st));
+  G2P_CUDA(pool_alloc(&d_cursor, (size_t)nc * 4, st));
+  G2P_CUDA(pool_alloc(&d_bsums, (size_t)nb * 4, st));
+  G2P_CUDA(pool_alloc(&ix->cell_start, (size_t)(nc + 1) * 4, st));
+  G2P_CUDA(pool_alloc(&ix->pts, (size_t)n * sizeof(Pt), st));
   G2P_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nc * 4, st));
   key_hist_kernel<<<grid_for(n, 256), 256, 0, st>>>(ix->xyz, n, G, d_keys, d_counts);
   G2P_LAUNCHED();
@@ -414,10 +435,10 @@ static int build_cells(g2p_index* ix, cudaStream_t st) {
   scatter_kernel<<<grid_for(n, 256), 256, 0, st>>>(ix->xyz, d_keys, n, d_cursor, ix->pts);
   G2P_LAUNCHED();
   G2P_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_keys);
-  cudaFree(d_counts);
-  cudaFree(d_cursor);
-  cudaFree(d_bsums);
+  cudaFreeAsync(d_keys, st);
+  cudaFreeAsync(d_counts, st);
+  cudaFreeAsync(d_cursor, st);
+  cudaFreeAsync(d_bsums, st);
   ix->bytes = (int64_t)n * 24 + (int64_t)n * sizeof(Pt) + (nc + 1) * 4;
   return G2P_OK;
 }
@@ -446,6 +467,7 @@ struct KnnArgs {
   uint8_t* flags_out;
   double* xyz_out;
   double* dmax2_out;         // SELF mode: max over queries of d2[1]
+  int64_t q0;                // SELF mode: first source record of this call (sharded self query)
   unsigned long long* stats; // [0] extra passes, [1] candidates examined (debug counters; nullable)
 };
 
@@ -673,7 +695,7 @@ __global__ void __launch_bounds__(256) knn_kernel(const KnnArgs a) {
     double qx, qy, qz;
     if (QSRC == QUERY_SELF) {
       int self_id;
-      load_pt(a.ix.pts + q, qx, qy, qz, self_id);
+      load_pt(a.ix.pts + a.q0 + q, qx, qy, qz, self_id);
     } else if (QSRC == QUERY_XYZ) {
       qx = a.txyz[3 * q]; qy = a.txyz[3 * q + 1]; qz = a.txyz[3 * q + 2];
     } else {
@@ -844,14 +866,14 @@ int g2p_latlon_to_xyz(const void* lon, const void* lat, int64_t n, int dtype, do
   return G2P_OK;
 }
 
-static int index_alloc(int64_t n, g2p_index** out, g2p_index** ixp) {
+static int index_alloc(int64_t n, g2p_index** out, g2p_index** ixp, cudaStream_t st) {
   if (!out) return set_error(G2P_ERR_INVALID, "g2p_index_create: out is null");
   *out = nullptr;
   if (n < 1 || n > 0x7ffffff0LL) return set_error(G2P_ERR_INVALID, "g2p_index_create: n=%lld out of range", (long long)n);
   g2p_index* ix = new g2p_index();
   ix->n = n;
   G2P_CUDA(cudaGetDevice(&ix->device));
-  cudaError_t e = cudaMalloc(&ix->xyz, (size_t)n * 24);
+  cudaError_t e = pool_alloc(&ix->xyz, (size_t)n * 24, st);
   if (e != cudaSuccess) {
     delete ix;
     return cuda_fail(e, "cudaMalloc(xyz)", __FILE__, __LINE__);
@@ -864,7 +886,7 @@ int g2p_index_create(const double* lon, const double* lat, int64_t n, double rad
                      g2p_index** out, void* stream) {
   if (!lon || !lat) return set_error(G2P_ERR_INVALID, "g2p_index_create: null lon/lat");
   g2p_index* ix = nullptr;
-  int rc = index_alloc(n, out, &ix);
+  int rc = index_alloc(n, out, &ix, as_stream(stream));
   if (rc) return rc;
   ix->user_radius = radius;
   rc = g2p_latlon_to_xyz(lon, lat, n, G2P_F64, radius, rot, ix->xyz, stream);
@@ -880,7 +902,7 @@ int g2p_index_create(const double* lon, const double* lat, int64_t n, double rad
 int g2p_index_create_xyz(const double* xyz, int64_t n, g2p_index** out, void* stream) {
   if (!xyz) return set_error(G2P_ERR_INVALID, "g2p_index_create_xyz: null xyz");
   g2p_index* ix = nullptr;
-  int rc = index_alloc(n, out, &ix);
+  int rc = index_alloc(n, out, &ix, as_stream(stream));
   if (rc) return rc;
   cudaError_t e = cudaMemcpyAsync(ix->xyz, xyz, (size_t)n * 24, cudaMemcpyDeviceToDevice, as_stream(stream));
   rc = (e == cudaSuccess) ? build_cells(ix, as_stream(stream)) : cuda_fail(e, "cudaMemcpyAsync(xyz)", __FILE__, __LINE__);
@@ -915,14 +937,25 @@ int g2p_index_get_xyz(const g2p_index* ix, double* xyz_out, void* stream) {
 }
 
 int g2p_index_max_nn_dist(g2p_index* ix, double* dmax, void* stream) {
+  if (!ix) return set_error(G2P_ERR_INVALID, "g2p_index_max_nn_dist: null argument");
+  return g2p_index_max_nn_dist_part(ix, 0, ix->n, dmax, stream);
+}
+
+int g2p_index_max_nn_dist_part(g2p_index* ix, int64_t first, int64_t last, double* dmax, void* stream) {
   if (!ix || !dmax) return set_error(G2P_ERR_INVALID, "g2p_index_max_nn_dist: null argument");
+  if (first < 0 || last > ix->n || first > last) return set_error(G2P_ERR_INVALID, "g2p_index_max_nn_dist_part: bad range");
+  if (first == last) {
+    *dmax = 0.0;
+    return G2P_OK;
+  }
   cudaStream_t st = as_stream(stream);
   double* d_max = nullptr;
-  G2P_CUDA(cudaMalloc(&d_max, sizeof(double)));
+  G2P_CUDA(pool_alloc(&d_max, sizeof(double), st));
   G2P_CUDA(cudaMemsetAsync(d_max, 0, sizeof(double), st));
   KnnArgs a{};
   a.ix = view_of(ix);
-  a.m = ix->n;
+  a.m = last - first;
+  a.q0 = first;
   a.k = 2;
   a.mode = G2P_MODE_RAW;
   a.dmax2_out = d_max;
@@ -933,7 +966,7 @@ int g2p_index_max_nn_dist(g2p_index* ix, double* dmax, void* stream) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = cuda_fail(e, "max_nn_dist readback", __FILE__, __LINE__);
   }
-  cudaFree(d_max);
+  cudaFreeAsync(d_max, st);
   if (rc != G2P_OK) return rc;
   *dmax = sqrt(d2);  // sqrt is monotone and correctly rounded: sqrt(max d2) == max sqrt(d2)
   return G2P_OK;

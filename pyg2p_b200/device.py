@@ -105,12 +105,17 @@ class SourceIndex:
 
     def max_nn_dist(self):
         """max over sources of the distance to the nearest OTHER source (k=2 self query + np.max,
-        reference :568-570)."""
+        reference :568-570).  Under an initialised process group every rank queries its share of the
+        sources and the maximum is all-reduced (the result is identical on every rank and to the
+        single-process one: max is exact)."""
+        from . import parallel
         _bind_device(self.device)
         d = C.c_double()
+        rank, ws = parallel.world()
+        lo, hi = parallel.shard_bounds(self.n, rank, ws) if ws > 1 else (0, self.n)
         with torch.cuda.device(self.device):
-            L.check(self._lib.g2p_index_max_nn_dist(self._h, C.byref(d), _stream()))
-        return d.value
+            L.check(self._lib.g2p_index_max_nn_dist_part(self._h, lo, hi, C.byref(d), _stream()))
+        return parallel.max_over_ranks(d.value, self.device) if ws > 1 else d.value
 
     def min_upper_bound(self, nj):
         """`dmax + dmax*4/Nj` in Python float arithmetic, as the reference (:570)."""
