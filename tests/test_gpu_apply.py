@@ -256,3 +256,35 @@ def test_window_equals_generic_on_real_geometry(dev, monkeypatch):
     assert torch.equal(af.view(torch.int64), bf.view(torch.int64)) and torch.equal(af, a)
     assert torch.equal(ar.view(torch.int64), br.view(torch.int64))
     assert 0.05 < am.float().mean() < 0.5 and torch.equal(a == 1e20, am.bool())
+
+
+@pytest.mark.parametrize('res,k', [(0.1, 1), (0.05, 4)])
+def test_full_size_glofas_tables_window_equals_generic(dev, monkeypatch, res, k):
+    """BASELINE configs[1] / [2] tables at full size (O1280 -> 0.1 deg k=1, 5.4 M targets; 0.05 deg k=4, 21.6 M):
+    the windowed kernel (plan on a global lat/lon grid) and the generic kernel give identical bytes, with masks,
+    for a single message and for a short batch; a constant field maps to that constant."""
+    from pyg2p_b200 import synth
+    lat, lon, det = synth.octahedral_grid(1280)
+    tl, tlo = synth.latlon_target(res)
+    ix = dev.SourceIndex(lon, lat, det['radius'])
+    out = ix.knn(tlo, tl, k=k, mode=L.MODE_NEAREST if k == 1 else L.MODE_INVDIST, mub=ix.min_upper_bound(det['Nj']),
+                 want_flags=False)
+    tbl = dev.DeviceTable(out['idx'], out['coef'], lat.size, grid_shape=tl.shape)
+    info = tbl.plan_info()
+    assert info is not None and info['tile_rows'] * info['tile_cols'] == 1024, tbl.plan_error
+    g = torch.Generator(device='cuda').manual_seed(5)
+    for b in (1, 5):
+        src = torch.randn((b, lat.size), generator=g, device='cuda', dtype=torch.float64)
+        msk = (torch.rand((b, lat.size), generator=g, device='cuda') < 0.02).to(torch.uint8)
+        a, am = tbl.apply(src, 1e20, src_mask=msk, mask_policy=L.MASK_PROPAGATE)
+        ar = tbl.apply(src, 1e20)
+        assert tbl.last_path == 'window'
+        monkeypatch.setenv('G2P_APPLY_PATH', 'generic')
+        b_, bm = tbl.apply(src, 1e20, src_mask=msk, mask_policy=L.MASK_PROPAGATE)
+        br = tbl.apply(src, 1e20)
+        assert tbl.last_path == 'generic'
+        monkeypatch.delenv('G2P_APPLY_PATH')
+        assert torch.equal(a.view(torch.int64), b_.view(torch.int64)) and torch.equal(am, bm)
+        assert torch.equal(ar.view(torch.int64), br.view(torch.int64))
+    const = tbl.apply(torch.full((1, lat.size), 7.25, device='cuda', dtype=torch.float64), 0.0)
+    assert torch.allclose(const, torch.full_like(const, 7.25), rtol=2e-15, atol=0)

@@ -246,3 +246,54 @@ def test_rotated_source(dev, golden_dir):
     got = dev.latlon_to_xyz(g['src_lon'], g['src_lat'], 1.0, rotation=rot).cpu().numpy()
     want = R.stack_xyz(*R.to_3d(g['src_lon'], g['src_lat'], 1.0, rotation=rot))
     assert np.max(np.abs(got - want)) <= 4 * np.spacing(1.0)
+
+
+@pytest.mark.parametrize('res,mode,k', [(0.1, 'nearest', 1), (0.05, 'invdist', 4)])
+def test_full_size_o1280_to_glofas_sampled(dev, res, mode, k):
+    """BASELINE configs[1] / configs[2] at full size (O1280 -> GloFAS 0.1 deg nearest, 5.4 M targets; -> 0.05 deg
+    invdist, 21.6 M targets): the whole table is built on the GPU; 200 000 random rows are compared with
+    cKDTree + the oracle's weights on the same xyz bytes (bit-exact off exact ties), and size-independent
+    properties are checked on all rows (weights sum to 1, ids in range, distances ascending)."""
+    lat, lon, det = synth.octahedral_grid(1280)
+    n = lat.size
+    tl, tlo = synth.latlon_target(res)
+    m = tl.size
+    ix = dev.SourceIndex(lon, lat, det['radius'])
+    mub = ix.min_upper_bound(det['Nj'])
+    src_xyz = ix.xyz().cpu().numpy()
+    tree = R.build_tree(src_xyz)
+    assert mub == R.min_upper_bound(tree, src_xyz, det['Nj'], workers=-1)
+    raw = ix.knn(tlo, tl, k=k, mode=L.MODE_RAW, want_xyz=True)
+    tab = ix.knn(tlo, tl, k=k, mode=L.MODE_NEAREST if k == 1 else L.MODE_INVDIST, mub=mub, want_flags=False)
+    # ---- all rows
+    assert int(raw['idx'].min()) >= 0 and int(raw['idx'].max()) < n
+    if k > 1:
+        assert bool((raw['coef'][1:] >= raw['coef'][:-1]).all())
+        s = tab['coef'].sum(0)
+        inside = tab['idx'][0] < n
+        assert torch.allclose(s[inside], torch.ones_like(s[inside]), rtol=0, atol=4e-16 * k)
+        assert bool(torch.isnan(tab['coef'][:, ~inside]).all()) and int((~inside).sum()) == 0   # global source: all inside
+    flags = raw['flags'].cpu().numpy()
+    n_tie = int(((flags & L.FLAG_TIE) != 0).sum())
+    assert n_tie < 200                                     # 54 of 21.6 M on this pair (SURVEY A.5 found 14 with numpy trig)
+    # ---- sample
+    rng = np.random.default_rng(12)
+    rows = np.sort(rng.choice(m, 200_000, replace=False))
+    rows_d = torch.from_numpy(rows).cuda()
+    q = raw['xyz'][rows_d].cpu().numpy()
+    d, i = tree.query(q, k=k, workers=-1)
+    d, i = d.reshape(len(rows), k), i.reshape(len(rows), k)
+    gi = raw['idx'][:, rows_d].cpu().numpy().T.astype(np.int64)
+    gd = raw['coef'][:, rows_d].cpu().numpy().T
+    np.testing.assert_array_equal(gd, d)
+    tie = (flags[rows] & L.FLAG_TIE) != 0
+    np.testing.assert_array_equal(gi[~tie], i[~tie])
+    z = np.zeros(n)
+    if k == 1:
+        _, want_idx = R.build_nn(d[:, 0], i[:, 0], z, mub, 0.0)
+        np.testing.assert_array_equal(tab['idx'][0, rows_d].cpu().numpy().astype(np.int64)[~tie], want_idx[~tie])
+        np.testing.assert_array_equal(tab['coef'][0, rows_d].cpu().numpy(), d[:, 0])
+    else:
+        _, w_ref, i_ref = R.build_weights_invdist(d, i, z, mub, 0.0, k)
+        np.testing.assert_array_equal(tab['coef'][:, rows_d].cpu().numpy().T[~tie], w_ref[~tie])
+        np.testing.assert_array_equal(tab['idx'][:, rows_d].cpu().numpy().T.astype(np.int64)[~tie], i_ref[~tie])
