@@ -792,8 +792,11 @@ __global__ void weights_kernel(int mode, int k, int64_t m, int32_t nsrc, double 
 static int knn_lanes() {
   static int lanes = 0;
   if (lanes == 0) {
-    int v = (int)env_double("G2P_KNN_LANES", 8);
-    lanes = (v == 1 || v == 4 || v == 8 || v == 32) ? v : 8;
+    // threads per query.  Measured on B200, O1280 -> 0.05 deg k=4 (21.6 M queries): 1 lane 17.8 ms, 2 lanes 7.5 ms,
+    // 4 lanes 12.8 ms, 8 lanes 23.4 ms - with ~30 candidates per query the shuffle merge of wider groups
+    // costs more than the scan it parallelises (profiles/r01_build.md)
+    int v = (int)env_double("G2P_KNN_LANES", 2);
+    lanes = (v == 1 || v == 2 || v == 4 || v == 8 || v == 32) ? v : 2;
   }
   return lanes;
 }
@@ -819,9 +822,11 @@ template <int KK>
 static int launch_knn_l(const KnnArgs& a, int qsrc, cudaStream_t st) {
   switch (knn_lanes()) {
     case 1: return launch_knn_q<KK, 1>(a, qsrc, st);
+    case 2: return launch_knn_q<KK, 2>(a, qsrc, st);
     case 4: return launch_knn_q<KK, 4>(a, qsrc, st);
     case 32: return launch_knn_q<KK, 32>(a, qsrc, st);
-    default: return launch_knn_q<KK, 8>(a, qsrc, st);
+    case 8: return launch_knn_q<KK, 8>(a, qsrc, st);
+    default: return launch_knn_q<KK, 2>(a, qsrc, st);
   }
 }
 
