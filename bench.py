@@ -379,7 +379,7 @@ def run_b200(args):
             ixb = device.SourceIndex(d_lon, d_lat, det['radius'])
             mubb = ixb.min_upper_bound(det['Nj'])
             o = ixb.knn(d_tlo, d_tla, k=K_INVDIST, mode=L.MODE_INVDIST, mub=mubb, want_flags=True)
-            idx_f, coef_f = parallel.all_gather_table(o['idx'], o['coef'], M)
+            idx_f, coef_f = parallel.all_gather_table(o['idx'], o['coef'], M, align=gl.shape[1])
             return ixb, o, idx_f, coef_f
 
         build_once()

@@ -35,32 +35,33 @@ def members_of_rank(n_members, rank, world_size):
     return list(range(rank, n_members, world_size))
 
 
-def all_gather_table(idx_shard, coef_shard, m_total, group=None):
-    """Assemble SoA table shards ([k, m_r] per rank, contiguous target blocks in rank order) into the
-    full [k, m_total] table on every rank.  Shards may be ragged: they are padded to the largest."""
+def all_gather_table(idx_shard, coef_shard, m_total, align=1, group=None):
+    """Assemble SoA table shards ([k, m_r] per rank, the contiguous target blocks of `shard_bounds(m_total, r,
+    world, align)`) into the full [k, m_total] table on every rank.  The shard sizes follow from the arguments,
+    so nothing but the table itself crosses the wire: with equal shards each neighbour row is gathered straight
+    into its place (k collectives per array, no staging copy); ragged shards are padded to the largest."""
     rank, ws = world()
     if ws == 1:
         return idx_shard, coef_shard
     k, m_r = idx_shard.shape
-    sizes = torch.tensor([m_r], dtype=torch.int64, device=idx_shard.device)
-    all_sizes = [torch.zeros_like(sizes) for _ in range(ws)]
-    dist.all_gather(all_sizes, sizes, group=group)
-    all_sizes = [int(s.item()) for s in all_sizes]
-    if sum(all_sizes) != m_total:
-        raise ValueError(f'table shards cover {sum(all_sizes)} targets, expected {m_total}')
-    m_max = max(all_sizes)
+    bounds = [shard_bounds(m_total, r, ws, align) for r in range(ws)]
+    sizes = [hi - lo for lo, hi in bounds]
+    if sizes[rank] != m_r:
+        raise ValueError(f'rank {rank} holds {m_r} targets, its block has {sizes[rank]}')
+    m_max = max(sizes)
 
     def gather(shard):
-        pad = shard
-        if m_r != m_max:
-            pad = shard.new_zeros((k, m_max))
-            pad[:, :m_r] = shard
+        if all(s == m_max for s in sizes):
+            full = shard.new_empty((k, m_total))
+            for kk in range(k):
+                dist.all_gather_into_tensor(full[kk], shard[kk].contiguous(), group=group)
+            return full
+        pad = shard.new_zeros((k, m_max))
+        pad[:, :m_r] = shard
         flat = shard.new_empty((ws * k, m_max))          # concatenation along dim 0 (the form gloo and nccl share)
-        dist.all_gather_into_tensor(flat, pad.contiguous(), group=group)
+        dist.all_gather_into_tensor(flat, pad, group=group)
         buf = flat.view(ws, k, m_max)
-        if all(s == m_max for s in all_sizes):
-            return buf.permute(1, 0, 2).reshape(k, ws * m_max)
-        return torch.cat([buf[r, :, :all_sizes[r]] for r in range(ws)], dim=1).contiguous()
+        return torch.cat([buf[r, :, :sizes[r]] for r in range(ws)], dim=1).contiguous()
 
     return gather(idx_shard), gather(coef_shard)
 

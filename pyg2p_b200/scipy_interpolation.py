@@ -80,7 +80,7 @@ class ScipyInterpolation:
         idx, coef = out['idx'], out['coef']
         self.flags = out['flags']
         if ws > 1:
-            idx, coef = parallel.all_gather_table(idx, coef, m)
+            idx, coef = parallel.all_gather_table(idx, coef, m, align=cols)
         f32 = lonefas.dtype == np.float32 and self.mode == 'nearest'     # coeffs = float32 distances (:627-635)
         shape = lonefas.shape if lonefas.ndim == 2 else None
         self.table = device.DeviceTable(idx, coef, self.z.size, coef_f32=f32, grid_shape=shape)

@@ -28,7 +28,7 @@ def _worker(rank, ws, port, rows, cols, k, q):
         full_w = torch.arange(k * m, dtype=torch.float64).reshape(k, m) / 7.0
         lo, hi = parallel.shard_bounds(m, rank, ws, align=cols)
         assert lo % cols == 0 and (hi % cols == 0 or hi == m)
-        idx, w = parallel.all_gather_table(full_idx[:, lo:hi].contiguous(), full_w[:, lo:hi].contiguous(), m)
+        idx, w = parallel.all_gather_table(full_idx[:, lo:hi].contiguous(), full_w[:, lo:hi].contiguous(), m, align=cols)
         ok = torch.equal(idx, full_idx) and torch.equal(w, full_w)
         t = parallel.max_over_ranks(1.0 + rank, torch.device('cpu'))
         s = parallel.sum_over_ranks(1.0 + rank, torch.device('cpu'))
