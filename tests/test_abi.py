@@ -41,3 +41,15 @@ def test_no_cpu_fallback():
     lib = L.lib()
     assert lib.g2p_apply(None, None, 1, 1, None, None, 1, 1, 1, 1, 0.0, 0, None, None, None) == -1
     assert b'null' in lib.g2p_last_error()
+
+
+def test_product_never_touches_the_oracle():
+    """the oracle is test infrastructure: nothing under pyg2p_b200/ may import, call or mention it."""
+    pkg = os.path.join(REPO, 'pyg2p_b200')
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(root, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
+                # ... nor reach for a CPU implementation of the path (scipy's cKDTree, numexpr)
+                assert not re.search(r'^\s*(from|import)\s+(scipy|numexpr)\b', text, flags=re.M), f
