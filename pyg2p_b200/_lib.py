@@ -41,7 +41,7 @@ class PlanInfo(C.Structure):
 
 MANIP_MAX_IN = 32
 OP_NONE, OP_MUL, OP_ADD, OP_DIV = 0, 1, 2, 3
-AGG_PICK, AGG_ACCUM, AGG_AVERAGE = 0, 1, 2
+AGG_PICK, AGG_ACCUM, AGG_AVERAGE, AGG_COPY = 0, 1, 2, 3
 
 
 class ManipItem(C.Structure):

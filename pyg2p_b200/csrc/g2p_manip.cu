@@ -59,9 +59,12 @@ __device__ __forceinline__ double convert(const ManipArgs& a, double x) {
   return conv_op(a.op2, a.c2, conv_op(a.op1, a.c1, x));
 }
 
-__global__ void __launch_bounds__(256) manip_kernel(const ManipArgs a) {
-  const int o = blockIdx.y;
-  const ManipItem& it = a.items[o];
+constexpr int kManipInline = 16;   // items passed by value in the kernel parameters (no upload, no sync)
+struct ManipInline {
+  ManipItem items[kManipInline];
+};
+
+__device__ __forceinline__ void manip_body(const ManipArgs& a, const ManipItem& it, int o) {
   for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < a.nc; c += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = a.touched ? (int64_t)__ldg(a.touched + c) : c;
     double res;
@@ -76,6 +79,8 @@ __global__ void __launch_bounds__(256) manip_kernel(const ManipArgs a) {
       double s = 0.0;
       for (int q = 0; q < it.n_in; ++q) s = __dadd_rn(s, convert(a, __ldg(a.src + (int64_t)it.in[q] * a.src_stride + i)));
       res = __ddiv_rn(s, it.divisor);
+    } else if (it.kind == G2P_AGG_COPY) {
+      res = convert(a, a.src[(int64_t)it.in[0] * a.src_stride + i]);
     } else {
       // res = zeros; res += V[t]   (:264-276); in[0] < 0: step 0 absent -> zeros
       res = it.in[0] >= 0 ? __dadd_rn(0.0, convert(a, __ldg(a.src + (int64_t)it.in[0] * a.src_stride + i))) : 0.0;
@@ -91,10 +96,18 @@ __global__ void __launch_bounds__(256) manip_kernel(const ManipArgs a) {
         if (it.in[1] >= 0) mk = __ldg(a.src_mask + (int64_t)it.in[1] * a.src_stride + i);
       } else if (it.kind == G2P_AGG_AVERAGE) {
         for (int q = 0; q < it.n_in; ++q) mk |= __ldg(a.src_mask + (int64_t)it.in[q] * a.src_stride + i);
+      } else if (it.kind == G2P_AGG_COPY) {
+        mk = a.src_mask[(int64_t)it.in[0] * a.src_stride + i];
       }                          // PICK: `res_inst += V[t]` on a plain ndarray drops the mask (:264-276)
       a.out_mask[(int64_t)o * a.out_stride + c] = mk ? 1 : 0;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) manip_kernel(const ManipArgs a) { manip_body(a, a.items[blockIdx.y], blockIdx.y); }
+
+__global__ void __launch_bounds__(256) manip_kernel_inline(const ManipArgs a, const __grid_constant__ ManipInline in) {
+  manip_body(a, in.items[blockIdx.y], blockIdx.y);
 }
 
 // V[a] + (V[b] - V[a]) * frac : linear-in-time synthesis of a missing step (aggregator.py:105,128)
@@ -154,8 +167,8 @@ int g2p_manip(const g2p_manip_desc* desc, const double* src, const uint8_t* src_
   std::vector<ManipItem> items(desc->n_out);
   for (int o = 0; o < desc->n_out; ++o) {
     const g2p_manip_item& s = desc->items[o];
-    if (s.kind < G2P_AGG_PICK || s.kind > G2P_AGG_AVERAGE) return set_error(G2P_ERR_INVALID, "g2p_manip: item %d: unknown kind %d", o, s.kind);
-    const int need = s.kind == G2P_AGG_ACCUM ? 2 : (s.kind == G2P_AGG_PICK ? 1 : s.n_in);
+    if (s.kind < G2P_AGG_PICK || s.kind > G2P_AGG_COPY) return set_error(G2P_ERR_INVALID, "g2p_manip: item %d: unknown kind %d", o, s.kind);
+    const int need = s.kind == G2P_AGG_ACCUM ? 2 : ((s.kind == G2P_AGG_PICK || s.kind == G2P_AGG_COPY) ? 1 : s.n_in);
     if (s.n_in != need || need < 1 || need > kManipMaxIn) return set_error(G2P_ERR_INVALID, "g2p_manip: item %d: n_in = %d", o, s.n_in);
     ManipItem& d = items[o];
     d.kind = s.kind;
@@ -172,12 +185,15 @@ int g2p_manip(const g2p_manip_desc* desc, const double* src, const uint8_t* src_
   }
   cudaStream_t st = as_stream(stream);
   ManipItem* d_items = nullptr;
-  G2P_CUDA(cudaMallocAsync(&d_items, items.size() * sizeof(ManipItem), st));
-  cudaError_t e = cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(ManipItem), cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `items` lives on this stack frame
-  if (e != cudaSuccess) {
-    cudaFreeAsync(d_items, st);
-    return cuda_fail(e, "g2p_manip: items upload", __FILE__, __LINE__);
+  const bool inline_items = desc->n_out <= kManipInline;
+  if (!inline_items) {
+    G2P_CUDA(cudaMallocAsync(&d_items, items.size() * sizeof(ManipItem), st));
+    cudaError_t e = cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(ManipItem), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `items` lives on this stack frame
+    if (e != cudaSuccess) {
+      cudaFreeAsync(d_items, st);
+      return cuda_fail(e, "g2p_manip: items upload", __FILE__, __LINE__);
+    }
   }
   ManipArgs a{};
   a.src = src;
@@ -201,10 +217,16 @@ int g2p_manip(const g2p_manip_desc* desc, const double* src, const uint8_t* src_
   int64_t bx = ceil_div(nc, 256);
   const int64_t cap = std::max<int64_t>(1, (int64_t)num_sms() * 16 / desc->n_out);
   if (bx > cap) bx = cap;
-  manip_kernel<<<dim3((unsigned)bx, (unsigned)desc->n_out), 256, 0, st>>>(a);
+  if (inline_items) {
+    ManipInline in{};
+    for (int o = 0; o < desc->n_out; ++o) in.items[o] = items[o];
+    manip_kernel_inline<<<dim3((unsigned)bx, (unsigned)desc->n_out), 256, 0, st>>>(a, in);
+  } else {
+    manip_kernel<<<dim3((unsigned)bx, (unsigned)desc->n_out), 256, 0, st>>>(a);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  e = cudaGetLastError();
-  cudaFreeAsync(d_items, st);
+  cudaError_t e = cudaGetLastError();
+  if (d_items) cudaFreeAsync(d_items, st);
   if (e != cudaSuccess) return cuda_fail(e, "manip_kernel launch", __FILE__, __LINE__);
   return G2P_OK;
 }

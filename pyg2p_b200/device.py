@@ -496,3 +496,97 @@ class HostApplyPipeline:
             if e is not None:
                 cur.wait_event(e)
         return out, (out_mask if want_omask else None)
+
+
+def compact_gather(src_ptr, mask_ptr, n, b, src_stride, touched, out, out_mask):
+    """g2p_manip with COPY items: out[i][c] = src[i][touched[c]] for b messages.  `src_ptr` / `mask_ptr` are raw
+    addresses: device memory or PINNED HOST memory (unified addressing lets the kernel read it over PCIe)."""
+    lib = require_cuda()
+    items = (L.ManipItem * b)()
+    for i in range(b):
+        items[i].kind, items[i].n_in = L.AGG_COPY, 1
+        items[i].inputs[0] = i
+        items[i].divisor = 1.0
+    desc = L.ManipDesc()
+    desc.conv_op1 = desc.conv_op2 = L.OP_NONE
+    desc.n_out = b
+    desc.items = C.cast(items, C.POINTER(L.ManipItem))
+    L.check(lib.g2p_manip(C.byref(desc), C.c_void_p(src_ptr), C.c_void_p(mask_ptr) if mask_ptr else None, n, b,
+                          src_stride, _ptr(touched), touched.numel(), out.stride(0), _ptr(out),
+                          _ptr(out_mask) if mask_ptr else None, _stream()))
+
+
+class CompactHostPipeline:
+    """Host-buffer front end for tables that touch a small part of the source grid (regional targets: the EFAS
+    table reads 4 % of an O1280 field).  Instead of copying whole messages to the device, a gather kernel reads
+    exactly the touched values out of the pinned host buffers over PCIe (zero-copy), the windowed apply runs
+    on the compact fields through the renumbered table, and the results return by D2H - kernel and D2H of
+    neighbouring chunks overlap on two streams.  Same results as HostApplyPipeline, ~17x less H2D traffic."""
+
+    def __init__(self, table, chunk_messages=16, with_mask=False):
+        self.t = table
+        self.ct, self.touched = table.compact()
+        self.c = int(min(chunk_messages, 16))          # <= 16 items travel in the kernel parameters (no sync)
+        self.with_mask = bool(with_mask)
+        dev = table.device
+        nc_pad = -(-self.ct.n_src // 16) * 16
+        m = table.m
+        with torch.cuda.device(dev):
+            self.d_c = [torch.zeros((self.c, nc_pad), dtype=torch.float64, device=dev) for _ in range(2)]
+            self.d_cm = [torch.zeros((self.c, nc_pad), dtype=torch.uint8, device=dev) for _ in range(2)] if with_mask else None
+            self.d_out = [torch.empty((self.c, m), dtype=torch.float64, device=dev) for _ in range(2)]
+            self.d_omk = [torch.empty((self.c, m), dtype=torch.uint8, device=dev) for _ in range(2)] if with_mask else None
+            self.s_out = torch.cuda.Stream(device=dev)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def run(self, src, mv_out, src_mask=None, mask_policy=L.MASK_AS_REFERENCE, out=None, out_mask=None):
+        """src: [b, n] float64 PINNED tensor; src_mask: [b, n] uint8 pinned tensor or None -> (out, out_mask) pinned."""
+        t = self.t
+        masks_in = mask_policy in (L.MASK_PROPAGATE, L.MASK_FILL)
+        want_omask = mask_policy == L.MASK_PROPAGATE
+        if masks_in and not self.with_mask:
+            raise ValueError('pipeline was created without mask buffers')
+        if not (isinstance(src, torch.Tensor) and src.is_pinned() and src.dtype == torch.float64 and src.stride(1) == 1):
+            raise ValueError('src must be a pinned float64 tensor [b, n] (device.pinned_empty)')
+        if masks_in and not (isinstance(src_mask, torch.Tensor) and src_mask.is_pinned() and src_mask.stride(0) == src.stride(0)):
+            raise ValueError('src_mask must be a pinned uint8 tensor with the row stride of src')
+        b, n = src.shape
+        if n != t.n_src:
+            raise ValueError(f'source field has {n} values, intertable was built for {t.n_src}')
+        if out is None:
+            out = pinned_empty((b, t.m))
+        if want_omask and out_mask is None:
+            out_mask = pinned_empty((b, t.m), torch.uint8)
+        _bind_device(t.device)
+        nc = self.ct.n_src
+        cur = torch.cuda.current_stream(t.device)
+        ev_out = [None, None]
+        with torch.cuda.device(t.device):
+            for ci, lo in enumerate(range(0, b, self.c)):
+                hi = min(b, lo + self.c)
+                s, nb = ci % 2, hi - lo
+                if ev_out[s] is not None:
+                    cur.wait_event(ev_out[s])                  # the slot's previous results have left the device
+                compact_gather(src.data_ptr() + lo * src.stride(0) * 8,
+                               (src_mask.data_ptr() + lo * src.stride(0)) if masks_in else None, n, nb, src.stride(0),
+                               self.touched, self.d_c[s][:nb], self.d_cm[s][:nb] if masks_in else None)
+                self.h2d_bytes += nb * nc * (9 if masks_in else 8)     # what the gather pulls over PCIe (touched values)
+                self.ct.apply(self.d_c[s][:nb, :nc], mv_out, src_mask=self.d_cm[s][:nb, :nc] if masks_in else None,
+                              mask_policy=mask_policy, out=self.d_out[s][:nb],
+                              out_mask=self.d_omk[s][:nb] if want_omask else None)
+                ev_k = torch.cuda.Event()
+                ev_k.record(cur)
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(ev_k)
+                    out[lo:hi].copy_(self.d_out[s][:nb], non_blocking=True)
+                    self.d2h_bytes += nb * t.m * 8
+                    if want_omask:
+                        out_mask[lo:hi].copy_(self.d_omk[s][:nb], non_blocking=True)
+                        self.d2h_bytes += nb * t.m
+                    ev_out[s] = torch.cuda.Event()
+                    ev_out[s].record(self.s_out)
+            for e in ev_out:
+                if e is not None:
+                    cur.wait_event(e)
+        return out, (out_mask if want_omask else None)

@@ -206,8 +206,13 @@ class Interpolator:
     def _pipeline(self, table, with_mask):
         pipes = table.__dict__.setdefault('_host_pipes', {})
         if with_mask not in pipes:
-            chunk = max(1, min(16, (256 << 20) // (table.n_src * 8)))      # ~256 MB of pinned staging per slot
-            pipes[with_mask] = device.HostApplyPipeline(table, chunk_messages=chunk, with_mask=with_mask)
+            _, touched = table.compact()
+            if table.k in (1, 4) and touched.numel() * 4 < table.n_src:
+                # regional target: gather the touched values straight out of the pinned buffers (zero-copy)
+                pipes[with_mask] = device.CompactHostPipeline(table, chunk_messages=16, with_mask=with_mask)
+            else:
+                chunk = max(1, min(16, (256 << 20) // (table.n_src * 8)))  # ~256 MB of pinned staging per slot
+                pipes[with_mask] = device.HostApplyPipeline(table, chunk_messages=chunk, with_mask=with_mask)
         return pipes[with_mask]
 
     def update_intertable_conf(self, intertable, intertable_id, intertable_name, source_shape):

@@ -177,3 +177,36 @@ def test_scipy_interpolation_signature_and_outputs(api):
         np.testing.assert_allclose(np.asarray(ma.getdata(res))[ok], np.asarray(ma.filled(r_ref))[ok], rtol=1e-12)
     with pytest.raises(ApplicationException):
         ScipyInterpolation(lon, lat, det, z, 11, 0.0, 0.0, mode='adw')
+
+
+def test_compact_zero_copy_pipeline_equals_full_copy(api):
+    """the zero-copy host pipeline (gather of the touched values out of pinned memory) gives the bytes of the
+    whole-field pipeline and of the device-resident apply, with and without masks, b > 2 chunks."""
+    import torch
+    from pyg2p_b200 import _lib as L
+    from pyg2p_b200 import device
+    lat, lon, det = synth.octahedral_grid(160)
+    tl, tlo = synth.efas_target(rows=190, cols=200, cell=25000.0)
+    ix = device.SourceIndex(lon, lat, det['radius'])
+    out = ix.knn(tlo, tl, k=4, mode=L.MODE_INVDIST, mub=ix.min_upper_bound(det['Nj']), want_flags=False)
+    table = device.DeviceTable(out['idx'], out['coef'], lat.size, grid_shape=tl.shape)
+    b = 37
+    g = torch.Generator().manual_seed(4)
+    h_src = device.pinned_empty((b, lat.size))
+    h_src.copy_(torch.randn((b, lat.size), generator=g, dtype=torch.float64))
+    h_msk = device.pinned_empty((b, lat.size), torch.uint8)
+    h_msk.copy_((torch.rand((b, lat.size), generator=g) < 0.03).to(torch.uint8))
+    full = device.HostApplyPipeline(table, chunk_messages=5, with_mask=True)
+    comp = device.CompactHostPipeline(table, chunk_messages=16, with_mask=True)
+    assert comp.ct.n_src < lat.size // 4
+    for policy in (L.MASK_AS_REFERENCE, L.MASK_PROPAGATE, L.MASK_FILL):
+        o1, m1 = full.run(h_src, 1e20, src_mask=h_msk, mask_policy=policy)
+        o2, m2 = comp.run(h_src, 1e20, src_mask=h_msk, mask_policy=policy)
+        torch.cuda.synchronize()
+        assert torch.equal(o1.view(torch.int64), o2.view(torch.int64))
+        assert (m1 is None and m2 is None) or torch.equal(m1, m2)
+    ref = table.apply(h_src.cuda(), 1e20).cpu()
+    o3, _ = comp.run(h_src, 1e20)
+    torch.cuda.synchronize()
+    assert torch.equal(ref.view(torch.int64), o3.view(torch.int64))
+    assert comp.h2d_bytes < full.h2d_bytes / 4
