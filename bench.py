@@ -424,6 +424,49 @@ def run_b200(args):
                                    'numpy record array {int64 indexes, f8 coeffs} (m, 4) out'}
             del si, rec
 
+    # ---- fused pipeline (BASELINE configs[4], eue_r24-style): members x (steps 0..360 by 6 h) of one GPU's share
+    # of the 51-member ensemble -> x*1000 -> 24 h accumulation -> cut-off -> invdist apply -> lapse-rate
+    # correction, two launches (g2p_manip on the touched points + windowed apply with the Corrector epilogue)
+    pipeline = None
+    if not args.skip_pipeline:
+        from pyg2p_b200 import manipulation as MP
+        members = max(1, 51 // 8)
+        steps_h = list(range(0, 361, 6))
+        conv = MP.Converter(func='x=x*1000', cut_off=True)
+        conv.set_missing_value(synth.GRIB_MV)
+        agg = MP.Aggregator(aggr_step=24, aggr_type='accumulation', aggr_halfweights=False, input_step=6,
+                            step_type='accum', start_step=0, end_step=360, unit_time=24, mv_grib=synth.GRIB_MV,
+                            force_zero_array=False)
+        plan = agg.plan(steps_h)
+        psrc = torch.empty((members * len(steps_h), n), dtype=torch.float64, device=dev)
+        psrc.normal_(0.0, 1.0, generator=g).clamp_(min=0.0).mul_(2e-3)
+        psrc = psrc.view(members, len(steps_h), n).cumsum(1).view(members * len(steps_h), n).contiguous()
+        dem = synth.field_dem(tl, tlo, synth.PCR_MV_F32).astype(np.float32)
+        corr = MP.Corrector.from_geopotential(table, synth.field_geopotential(lat, lon), synth.GRIB_MV, synth.NC_FILL_F64,
+                                              dem, float(synth.PCR_MV_F32))
+        fused = MP.FusedPipeline(table)
+
+        def pipe_step():
+            return fused.run(psrc, None, plan, converter=conv, cut_off=True, mv_out=synth.NC_FILL_F64, corrector=corr,
+                             members=members)
+
+        pout = pipe_step()
+        n_out = pout.shape[0]
+        l0 = device.launch_count()
+        pms = timed(pipe_step, reps=5)
+        pl = (device.launch_count() - l0) // 6
+        pms = parallel.max_over_ranks(pms, dev)
+        # algorithmic bytes: 2 input steps x 8 B per touched point + 8 B per target and output, + gem/dem/table once
+        pbytes = n_out * (2 * 8 * n_touched + 8 * m) + m * (K_INVDIST * 12 + 17)
+        pipeline = {'metric': 'fused pipeline output messages/s', 'value': n_out * ws / (pms * 1e-3), 'unit': 'messages/s',
+                    'ms_per_pass': pms, 'outputs_per_gpu': n_out, 'inputs_per_gpu': int(psrc.shape[0]),
+                    'members_per_gpu': members, 'gpu_launches_per_pass': pl,
+                    'algorithmic_GBps_per_gpu': pbytes / (pms * 1e-3) / 1e9,
+                    'frac_of_hbm_peak': pbytes / (pms * 1e-3) / 1e9 / hbm_peak,
+                    'workload': 'BASELINE configs[4]: x*1000 -> 24 h accumulation (steps 0..360 by 6 h) -> cut-off -> '
+                                'invdist apply O1280 -> EFAS -> p+gem-dem*0.0065, 6 of 51 members per GPU'}
+        del psrc, pout, fused, corr
+
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only)
     cpu = None
     if rank == 0 and ws == 1 and not args.skip_cpu:
@@ -455,7 +498,7 @@ def run_b200(args):
                          'n_touched': n_touched, 'peak_source': peak_src},
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
             'messages_per_s': B * args.steps * ws / (total_ms * 1e-3),
-            'clocks': clocks, 'wall_s_timed_region': t_wall, 'apply_variants': variants, 'build': build,
+            'clocks': clocks, 'wall_s_timed_region': t_wall, 'apply_variants': variants, 'build': build, 'pipeline': pipeline,
         }
         print(json.dumps(line), flush=True)
     if ws > 1:
@@ -476,6 +519,7 @@ def main():
     ap.add_argument('--cpu-messages', type=int, default=400)
     ap.add_argument('--skip-build', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--skip-pipeline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

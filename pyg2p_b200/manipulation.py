@@ -466,12 +466,21 @@ class FusedPipeline:
         self.compact, self.touched = table.compact()
 
     def run(self, src, src_mask, plan, converter=None, cut_off=False, mv_out=NC_FILL_F64,
-            mask_policy=L.MASK_AS_REFERENCE, corrector=None):
-        """src: device [b, n] float64 (messages in `plan.slots` order), src_mask: device uint8 [b, n] or None.
-        -> out [n_out, m] device (+ out_mask under PROPAGATE)."""
-        src, src_mask = synthesise_steps(plan, src, src_mask)
+            mask_policy=L.MASK_AS_REFERENCE, corrector=None, members=1):
+        """src: device [b, n] float64 (messages in `plan.slots` order; with `members` > 1 the rows are
+        member-major: all steps of member 0, then member 1, ... and the plan is applied to each member),
+        src_mask: device uint8 [b, n] or None.  -> out [members * n_out, m] device (+ out_mask under PROPAGATE)."""
+        if members == 1:
+            src, src_mask = synthesise_steps(plan, src, src_mask)
+            items = [it for _, it in plan.outputs]
+        else:
+            if plan.synth:
+                raise ApplicationException.get_exc(NOT_IMPLEMENTED, 'synthesised steps with members > 1')
+            per = len(plan.slots)
+            items = [ManipItem(it.kind, [i + mb * per if i >= 0 else i for i in it.inputs], it.unit_time, it.divisor,
+                               it.mask_all) for mb in range(members) for _, it in plan.outputs]
         use_mask = src_mask is not None and mask_policy != L.MASK_AS_REFERENCE
-        vals, vmask = manip_device(src, src_mask if use_mask else None, [it for _, it in plan.outputs],
+        vals, vmask = manip_device(src, src_mask if use_mask else None, items,
                                    converter=converter, cut_off=cut_off, touched=self.touched)
         return self.compact.apply(vals, float(mv_out), src_mask=vmask, mask_policy=mask_policy if use_mask else
                                   L.MASK_AS_REFERENCE, correction=corrector)
