@@ -249,3 +249,29 @@ def apply_propagate(v, weights, indexes, nnear, mv_out, src_mask):
         for j in range(indexes.shape[1]):
             out |= m[indexes[:, j]]
     return np.where(out, mv_out, data), out
+
+
+# --------------------------------------------------------------------------- grib_* table layouts (apply only)
+def _result_masked(values, fill_value):
+    """util/numeric.py:21-27."""
+    if not isinstance(values, ma.core.MaskedArray):
+        return values
+    return ma.filled(ma.masked_where(values.mask, values.data, copy=False), fill_value)
+
+
+def apply_grib_nearest(v, xs, ys, idxs, shape, mv_out):
+    """interpolation/__init__.py:286-287, 312: `result.fill(mv); result[xs, ys] = result_masked(v[idxs], mv)`."""
+    result = np.empty(shape)
+    result.fill(mv_out)
+    result[xs, ys] = _result_masked(v[idxs], mv_out)
+    return result
+
+
+def apply_grib_invdist(v, rec, shape, mv_out):
+    """:327-328, 348, 369-370: `res = v[i1]*c1 + v[i2]*c2 + v[i3]*c3 + v[i4]*c4; result[xs, ys] = result_masked(res)`."""
+    ind, cf = rec['indexes'], rec['coeffs']
+    result = np.empty(shape)
+    result.fill(mv_out)
+    res = v[ind[2]] * cf[0] + v[ind[3]] * cf[1] + v[ind[4]] * cf[2] + v[ind[5]] * cf[3]
+    result[ind[0], ind[1]] = _result_masked(res, mv_out)
+    return result

@@ -270,6 +270,42 @@ class DeviceTable:
             torch.cuda.current_stream().synchronize()
         return cls(idx, coef, n_src, coef_f32=f32, shape_1d=one_d, grid_shape=grid_shape)
 
+    @classmethod
+    def from_grib_nearest(cls, intertable, n_src, grid_shape, device=None):
+        """`grib_nearest` intertable `[xs, ys, idxs]` (scatter form: target row / column -> source index,
+        reference interpolation/__init__.py:296,312) -> k=1 gather table over the whole target grid; targets the
+        table does not list get the sentinel (the reference pre-fills the result with mv_out, :286-287)."""
+        require_cuda()
+        dev = _bind_device(device)
+        t = np.asarray(intertable)
+        xs, ys, idxs = (torch.from_numpy(np.ascontiguousarray(t[i]).astype(np.int64)).to(dev) for i in range(3))
+        rows, cols = grid_shape
+        idx = torch.full((1, rows * cols), int(n_src), dtype=torch.int32, device=dev)
+        idx[0, xs * cols + ys] = idxs.to(torch.int32)
+        coef = torch.zeros((1, rows * cols), dtype=torch.float64, device=dev)
+        return cls(idx, coef, n_src, grid_shape=grid_shape)
+
+    @classmethod
+    def from_grib_invdist(cls, rec, n_src, grid_shape, device=None):
+        """`grib_invdist` intertable: record array of shape (6, M') with indexes = [xs, ys, idx1..idx4] and
+        coeffs = [c1..c4, 0, 0] (reference :348-350, :369-370) -> k=4 gather table; v1*c1 + v2*c2 + v3*c3 + v4*c4
+        is evaluated left to right, the order of the apply kernels.  Unlisted targets: sentinel with weights
+        [1, 0, 0, 0], i.e. exactly mv_out."""
+        require_cuda()
+        dev = _bind_device(device)
+        ind = np.asarray(rec['indexes'])
+        cf = np.asarray(rec['coeffs'], dtype=np.float64)
+        rows, cols = grid_shape
+        m = rows * cols
+        j = torch.from_numpy((ind[0].astype(np.int64) * cols + ind[1].astype(np.int64))).to(dev)
+        idx = torch.full((4, m), int(n_src), dtype=torch.int32, device=dev)
+        coef = torch.zeros((4, m), dtype=torch.float64, device=dev)
+        coef[0] = 1.0
+        for kk in range(4):
+            idx[kk, j] = torch.from_numpy(ind[2 + kk].astype(np.int32)).to(dev)
+            coef[kk, j] = torch.from_numpy(np.ascontiguousarray(cf[kk])).to(dev)
+        return cls(idx, coef, n_src, grid_shape=grid_shape)
+
     def to_record(self):
         """device SoA -> numpy structured array in the reference's file layout (K6 pack + D2H)."""
         lib = require_cuda()

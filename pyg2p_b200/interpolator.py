@@ -73,8 +73,47 @@ class Interpolator:
         return self.interpolate_scipy(lats, longs, v, grid_id, geodetic_info)
 
     def interpolate_grib(self, v, gid, grid_id, is_second_res=False):
-        raise ApplicationException.get_exc(
-            NOT_IMPLEMENTED, 'grib_nearest / grib_invdist are ecCodes-internal searches, outside the GPU path')
+        """`grib_nearest` / `grib_invdist` (reference :268-371): existing intertables of both layouts are APPLIED
+        on the GPU; creating one is an ecCodes-internal nearest-point search and stays with the reference."""
+        if self._mode not in ('grib_nearest', 'grib_invdist'):
+            raise ApplicationException.get_exc(NOT_IMPLEMENTED, f'mode {self._mode} with GRIB interpolation')
+        intertable_id, path = self._intertable_filename(grid_id)
+        dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+        key = (path, dev)
+        table = self._DEVICE_TABLES.get(key)
+        if table is None:
+            if not (os.path.exists(path) or os.path.exists(path + '.gz')):
+                if self.create_if_missing:
+                    raise ApplicationException.get_exc(
+                        NOT_IMPLEMENTED, f'creating {self._mode} intertables needs ecCodes (codes_grib_find_nearest): '
+                                         f'build {path} with pyg2p, or use nearest / invdist')
+                raise ApplicationException.get_exc(NO_INTERTABLE_CREATED, details=path)
+            self._read_intertable_raw(path)
+            raw = self._LOADED_INTERTABLES[path]
+            shape = self._target_coords.lons.shape
+            n_src = int(np.asarray(ma.getdata(v)).size)
+            table = (device.DeviceTable.from_grib_nearest(raw, n_src, shape) if self._mode == 'grib_nearest'
+                     else device.DeviceTable.from_grib_invdist(raw, n_src, shape))
+            self._DEVICE_TABLES[key] = table
+        src = torch.from_numpy(np.ascontiguousarray(ma.getdata(v), dtype=np.float64).reshape(1, -1)).to(table.device)
+        if isinstance(v, ma.MaskedArray) and v.mask is not ma.nomask:
+            # `result_masked` fills masked results with mv_out (util/numeric.py:21-27) = MASK_FILL
+            msk = torch.from_numpy(np.array(np.broadcast_to(ma.getmaskarray(v).ravel(), (src.shape[1],))).view(np.uint8))
+            out = table.apply(src, float(self.mv_output), src_mask=msk.reshape(1, -1).to(table.device),
+                              mask_policy=L.MASK_FILL)
+        else:
+            out = table.apply(src, float(self.mv_output))
+        return out[0].cpu().numpy().reshape(self._target_coords.lons.shape)
+
+    def _read_intertable_raw(self, tbl_fullpath):
+        if tbl_fullpath not in self._LOADED_INTERTABLES:
+            path = tbl_fullpath if os.path.exists(tbl_fullpath) else tbl_fullpath + '.gz'
+            if path.endswith('.gz'):
+                with gzip.GzipFile(path, 'r') as f:
+                    self._LOADED_INTERTABLES[tbl_fullpath] = np.load(f)
+            else:
+                self._LOADED_INTERTABLES[tbl_fullpath] = np.load(path)
+        return self._LOADED_INTERTABLES[tbl_fullpath]
 
     def interpolate_scipy(self, latgrib, longrib, v, grid_id, grid_details=None):
         out = self.interpolate_batch(latgrib, longrib, [v], grid_id, grid_details)

@@ -210,3 +210,43 @@ def test_compact_zero_copy_pipeline_equals_full_copy(api):
     torch.cuda.synchronize()
     assert torch.equal(ref.view(torch.int64), o3.view(torch.int64))
     assert comp.h2d_bytes < full.h2d_bytes / 4
+
+
+@pytest.mark.parametrize('mode', ['grib_nearest', 'grib_invdist'])
+def test_grib_layout_tables_apply(api, tmp_path, mode):
+    """intertables in the `grib_nearest` ([xs, ys, idxs]) and `grib_invdist` (record array (6, M'))
+    layouts are applied on the GPU, against the literal restatement of the reference's three lines."""
+    Interpolator, _ = api
+    Interpolator._LOADED_INTERTABLES.clear()
+    Interpolator._DEVICE_TABLES.clear()
+    rng = np.random.default_rng(6)
+    n, rows, cols = 5000, 60, 45
+    valid = rng.random((rows, cols)) < 0.8                         # targets outside the GRIB domain are not listed
+    xs, ys = np.nonzero(valid)
+    if mode == 'grib_nearest':
+        tbl = np.asarray([xs, ys, rng.integers(0, n, xs.size)])
+    else:
+        ind = np.asarray([xs, ys] + [rng.integers(0, n, xs.size) for _ in range(4)])
+        c = rng.random((4, xs.size))
+        c /= c.sum(0)
+        tbl = np.rec.fromarrays((ind, np.asarray(list(c) + [np.zeros(xs.size), np.zeros(xs.size)])),
+                                names=('indexes', 'coeffs'))
+    fname = f'tbl_input_2700_{mode}.npy'
+    np.save(tmp_path / fname, tbl)
+    lat_map, lon_map = _target_maps(tmp_path)
+    d = {'interpolation.dirs': {'user': str(tmp_path), 'global': str(tmp_path)}, 'interpolation.latMap': lat_map,
+         'interpolation.lonMap': lon_map, 'interpolation.mode': mode, 'input.file': 'tests/data/input.grib'}
+    ctx = MockedExecutionContext(d, True)
+    it = Interpolator(ctx, synth.GRIB_MV)
+    ctx.configuration.intertables.vars['Ig_1_' + it._target_coords.identifier + mode] = {'filename': fname}
+    v = rng.standard_normal(n) * 10 + 280
+    out = it.interpolate(None, None, v, 'g$1', None, gid=-1)
+    want = (R.apply_grib_nearest(v, xs, ys, tbl[2], (rows, cols), it.mv_output) if mode == 'grib_nearest'
+            else R.apply_grib_invdist(v, tbl, (rows, cols), it.mv_output))
+    np.testing.assert_array_equal(out, want)
+    assert (out == it.mv_output).sum() == (~valid).sum()
+    vm = ma.masked_where(rng.random(n) < 0.1, v)
+    outm = it.interpolate(None, None, vm, 'g$1', None, gid=-1)
+    wantm = (R.apply_grib_nearest(vm, xs, ys, tbl[2], (rows, cols), it.mv_output) if mode == 'grib_nearest'
+             else R.apply_grib_invdist(vm, tbl, (rows, cols), it.mv_output))
+    np.testing.assert_array_equal(outm, wantm)
