@@ -304,7 +304,23 @@ def make_manip_cases():
     print('manip cases written:', sorted(k for k in out if k.endswith('_keys')))
 
 
+def make_reference_fixture_copies():
+    """Inputs of the reference's own golden intertable (tests/data/tbl_pf10slhf_550800_scipy_nearest.npy.gz):
+    the EFAS lat/lon PCRaster maps (as float32 arrays, MV cells = -3.4028235e38 as GDAL delivers them) and the
+    first 400 bytes of tests/data/input.grib (indicator + product + grid description sections of message 1)."""
+    from pyg2p_b200.maps import LatLong
+    ll = LatLong('/root/reference/tests/data/lat.map', '/root/reference/tests/data/lon.map')
+    np.savez_compressed(os.path.join(HERE, 'ref_efas_latlon_maps.npz'), lat=ll.lats, lon=ll.lons,
+                        identifier=np.array(ll.identifier), mv=np.float64(ll.mv))
+    with open('/root/reference/tests/data/input.grib', 'rb') as f:
+        head = f.read(400)
+    with open(os.path.join(HERE, 'ref_input_grib_header.bin'), 'wb') as f:
+        f.write(head)
+    print('reference fixture copies written:', ll.identifier)
+
+
 if __name__ == '__main__':
+    make_reference_fixture_copies()
     make_build_cases()
     make_apply_cases()
     make_manip_cases()

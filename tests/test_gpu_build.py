@@ -297,3 +297,31 @@ def test_full_size_o1280_to_glofas_sampled(dev, res, mode, k):
         _, w_ref, i_ref = R.build_weights_invdist(d, i, z, mub, 0.0, k)
         np.testing.assert_array_equal(tab['coef'][:, rows_d].cpu().numpy().T[~tie], w_ref[~tie])
         np.testing.assert_array_equal(tab['idx'][:, rows_d].cpu().numpy().T.astype(np.int64)[~tie], i_ref[~tie])
+
+
+def test_gpu_reproduces_the_reference_golden_table(dev, golden_dir):
+    """The reference's own golden intertable (tests/data/tbl_pf10slhf_550800_scipy_nearest.npy.gz, COSMO
+    rotated_ll 511x415 -> EFAS 810x680 PCRaster maps, 66 % of the rows outside the source domain) rebuilt on
+    the GPU from the grid description of the reference's input.grib and its lat/lon maps: identical sentinel
+    rows, identical indexes but for a handful of near-ties, stored distances within 1 m - including the
+    unbounded search for the far rows and the garbage coordinates of the MV cells."""
+    import gzip
+    from pyg2p_b200 import grib1
+    from pyg2p_b200.scipy_interpolation import ScipyInterpolation
+    with open(os.path.join(golden_dir, 'ref_input_grib_header.bin'), 'rb') as f:
+        lat, lon, det = grib1.read_grid(f.read())
+    maps = np.load(os.path.join(golden_dir, 'ref_efas_latlon_maps.npz'))
+    with gzip.GzipFile(os.path.join(golden_dir, 'ref_tbl_pf10slhf_550800_scipy_nearest.npy.gz')) as f:
+        tbl = np.load(f)
+    n = lat.size
+    si = ScipyInterpolation(lon, lat, det, np.zeros(n), 1, float(maps['mv']), synth.GRIB_MV, parallel=True, mode='nearest')
+    _, w, idx = si.interpolate(maps['lon'], maps['lat'])
+    assert idx.shape == tbl['indexes'].shape and idx.dtype == tbl['indexes'].dtype
+    assert (idx == n).sum() == 362052
+    np.testing.assert_array_equal(idx == n, tbl['indexes'] == n)
+    assert (idx != tbl['indexes']).sum() <= 10
+    d = np.abs(np.asarray(w, dtype=np.float64) - tbl['coeffs'])
+    assert d.max() < 1.0 and np.median(d) < 0.05
+    mv_rows = maps['lat'].ravel() == np.float32(maps['mv'])
+    assert mv_rows.sum() == 291776 and np.allclose(tbl['coeffs'][mv_rows], 849298.329, atol=1.0)
+    assert np.allclose(np.asarray(w, dtype=np.float64)[mv_rows], 849298.329, atol=1.0)

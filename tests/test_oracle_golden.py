@@ -139,3 +139,38 @@ def test_manipulation_matches_reference(golden_dir):
     out = MR.correct(g['corr_p'].copy(), g['corr_dem'], g['corr_gem'], float(g['corr_dem_mv']), float(g['corr_gem_mv']),
                      formula='p/gem*(10**((-0.159)*dem/1000))')
     np.testing.assert_array_equal(np.asarray(ma.filled(out)), g['corr_out_pressure'])
+
+
+def _golden_table_inputs(golden_dir):
+    from pyg2p_b200 import grib1
+    with open(os.path.join(golden_dir, 'ref_input_grib_header.bin'), 'rb') as f:
+        lat, lon, det = grib1.read_grid(f.read())
+    maps = np.load(os.path.join(golden_dir, 'ref_efas_latlon_maps.npz'))
+    with gzip.GzipFile(os.path.join(golden_dir, 'ref_tbl_pf10slhf_550800_scipy_nearest.npy.gz')) as f:
+        tbl = np.load(f)
+    return lat, lon, det, maps, tbl
+
+
+def test_grib1_grid_reader(golden_dir):
+    lat, lon, det, maps, _ = _golden_table_inputs(golden_dir)
+    assert det['grid_id'] == '-15.75$16.125$511$415$212065$rotated_ll'     # reference tests/test_readers.py style id
+    assert (det['Ni'], det['Nj'], det['radius'], det['gridType']) == (511, 415, 6367470.0, 'rotated_ll')
+    assert (det['latitudeOfSouthernPoleInDegrees'], det['longitudeOfSouthernPoleInDegrees']) == (-40.0, 10.0)
+    assert lat.size == 212065 and 31.8 < lat.min() < 32.0 and 59.7 < lat.max() < 59.8
+    assert str(maps['identifier']) == '-1700000_2700000_5000_-5000_34.97_71.07_-1700000_2700000_5000_-5000_-24.35_51.35'
+
+
+def test_oracle_reproduces_the_reference_golden_table(golden_dir):
+    """Known-answer test on the reference's own artefacts: its golden `scipy_nearest` intertable
+    (COSMO rotated_ll 511x415 -> EFAS 810x680) is rebuilt from the grid description of its input.grib and its
+    lat/lon maps.  Sentinel rows agree exactly; indexes agree on all but a handful of near-tie rows; the stored
+    distances agree to < 1 m (the table predates the float32 rounding of distances and was made with another
+    ecCodes / libm)."""
+    lat, lon, det, maps, tbl = _golden_table_inputs(golden_dir)
+    o = R.BuildOracle(lon, lat, det, np.zeros(lat.size), 1, float(maps['mv']), synth.GRIB_MV, parallel=True)
+    _, w, idx = o.interpolate(maps['lon'], maps['lat'])
+    n = lat.size
+    assert (idx == n).sum() == (tbl['indexes'] == n).sum() == 362052
+    np.testing.assert_array_equal(idx == n, tbl['indexes'] == n)
+    assert (idx != tbl['indexes']).sum() <= 10
+    assert np.max(np.abs(np.asarray(w, dtype=np.float64) - tbl['coeffs'])) < 1.0
