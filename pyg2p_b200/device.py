@@ -327,7 +327,12 @@ class DeviceTable:
     # ---- apply
     def _window_ok(self, src, src_mask, propagate):
         """alignment rules of g2p_apply_planned (TMA bulk copies need 16-byte aligned rows)."""
-        if self.k not in (1, 4) or os.environ.get('G2P_APPLY_PATH', 'auto') == 'generic':
+        path = os.environ.get('G2P_APPLY_PATH', 'auto')
+        if self.k not in (1, 4) or path == 'generic':
+            return False
+        if self.k == 1 and path != 'window':
+            # one gather per target: staging the window costs more than it saves (measured on O1280 -> 0.1 deg,
+            # profiles/r01_apply_sweep.md: generic 67-77 % of HBM peak, windowed 49-80 %)
             return False
         n_pad = -(-self.n_src // 16) * 16
         if src.data_ptr() % 16 or src.stride(0) % 2 or src.stride(0) < n_pad:

@@ -122,29 +122,46 @@ class Interpolator:
     def interpolate_batch(self, latgrib, longrib, values, grid_id, grid_details=None):
         """`values`: sequence of source fields [n] (ndarray / MaskedArray) or a 2-D array [b, n] - all messages
         of the run that share `grid_id`.  Returns an array [b, rows, cols] (MaskedArray under 'propagate')."""
-        table = self._table_for(latgrib, longrib, values[0], grid_id, grid_details)
+        pinned = isinstance(values, torch.Tensor)
+        first = values[0].numpy() if pinned else values[0]
+        table = self._table_for(latgrib, longrib, first, grid_id, grid_details)
         shape = self._target_coords.lons.shape
         b = len(values)
         n = table.n_src
-        masked_in = [isinstance(x, ma.MaskedArray) and x.mask is not ma.nomask for x in values]
-        propagate = self.mask_policy == 'propagate' and any(masked_in)
-        pipe = self._pipeline(table, propagate)
-        h_src = device.pinned_empty((b, n))
-        h_np = h_src.numpy()
-        h_msk = device.pinned_empty((b, n), torch.uint8) if propagate else None
-        for i, x in enumerate(values):
-            h_np[i] = np.asarray(ma.getdata(x), dtype=np.float64).ravel()
-            if propagate:
-                h_msk.numpy()[i] = np.broadcast_to(ma.getmaskarray(x).ravel(), (n,)) if masked_in[i] else 0
+        if pinned:
+            # messages decoded straight into `pinned_source_buffer(b, n)`: no staging copy on the host
+            if not (values.is_pinned() and values.dtype == torch.float64 and values.dim() == 2 and values.shape[1] == n):
+                raise ValueError('a tensor batch must come from Interpolator.pinned_source_buffer')
+            masked_in, propagate = [False] * b, False
+            pipe = self._pipeline(table, False)
+            h_src, h_msk = values, None
+        else:
+            masked_in = [isinstance(x, ma.MaskedArray) and x.mask is not ma.nomask for x in values]
+            propagate = self.mask_policy == 'propagate' and any(masked_in)
+            pipe = self._pipeline(table, propagate)
+            h_src = device.pinned_empty((b, n))
+            h_np = h_src.numpy()
+            h_msk = device.pinned_empty((b, n), torch.uint8) if propagate else None
+            for i, x in enumerate(values):
+                h_np[i] = np.asarray(ma.getdata(x), dtype=np.float64).ravel()
+                if propagate:
+                    h_msk.numpy()[i] = np.broadcast_to(ma.getmaskarray(x).ravel(), (n,)) if masked_in[i] else 0
         out, omask = pipe.run(h_src, float(self.mv_output), src_mask=h_msk,
                               mask_policy=L.MASK_PROPAGATE if propagate else L.MASK_AS_REFERENCE)
         torch.cuda.current_stream(table.device).synchronize()
         res = out.numpy().reshape((b,) + shape)
         if propagate:
             return ma.masked_array(res, mask=omask.numpy().reshape((b,) + shape).astype(bool), fill_value=self.mv_output)
-        if table.k == 1 and any(isinstance(x, ma.MaskedArray) for x in values):
+        if table.k == 1 and not pinned and any(isinstance(x, ma.MaskedArray) for x in values):
             return ma.masked_array(res)          # `v[indexes]` of a MaskedArray stays one, with no mask (:153)
         return res
+
+    @staticmethod
+    def pinned_source_buffer(b, n):
+        """page-locked [b, n] float64 buffer (torch tensor; `.numpy()` is a zero-copy view) for the GRIB decoder
+        to write message values into (`codes_get_double_array` results); `interpolate_batch` then reads it
+        from the device without any host-side staging copy."""
+        return device.pinned_empty((b, n))
 
     def aux_for_intertable_generation(self, aux_g, aux_v, aux_g2, aux_v2):
         self._aux_gid, self._aux_val, self._aux_2nd_res_gid, self._aux_2nd_res_val = aux_g, aux_v, aux_g2, aux_v2

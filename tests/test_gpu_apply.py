@@ -158,7 +158,8 @@ def _padded(v, align=16):
 
 
 @pytest.mark.parametrize('mode,k', [('nearest', 1), ('invdist', 4)])
-def test_window_path_matches_reference_golden(dev, golden_dir, mode, k):
+def test_window_path_matches_reference_golden(dev, golden_dir, mode, k, monkeypatch):
+    monkeypatch.setenv('G2P_APPLY_PATH', 'window')          # k=1 tables default to the generic kernel
     g = np.load(os.path.join(golden_dir, 'apply_regional.npz'))
     t = np.load(os.path.join(golden_dir, 'build_regional_global_f64.npz'))
     rec = R.to_record(t[f'{mode}_indexes'], t[f'{mode}_weights'])
@@ -181,9 +182,10 @@ def test_window_path_matches_reference_golden(dev, golden_dir, mode, k):
 @pytest.mark.parametrize('k', [1, 4])
 @pytest.mark.parametrize('shape,b', [((1, 1), 1), ((1, 2), 3), ((7, 143), 5), ((33, 257), 9), ((300, 1000), 2),
                                      ((1, 65537), 4), ((5, 4), 70)])
-def test_window_path_random_tables(dev, k, shape, b):
+def test_window_path_random_tables(dev, k, shape, b, monkeypatch):
     """the windowed kernel against the oracle on ragged grids (odd columns, partial tiles), sentinels and
     NaN weights; batch sizes that exercise the stage ring (b > stages) and several message chunks."""
+    monkeypatch.setenv('G2P_APPLY_PATH', 'window')
     rows, cols = shape
     m = rows * cols
     rng = np.random.default_rng(7 * k + m % 1013 + b)
@@ -276,6 +278,7 @@ def test_full_size_glofas_tables_window_equals_generic(dev, monkeypatch, res, k)
     for b in (1, 5):
         src = torch.randn((b, lat.size), generator=g, device='cuda', dtype=torch.float64)
         msk = (torch.rand((b, lat.size), generator=g, device='cuda') < 0.02).to(torch.uint8)
+        monkeypatch.setenv('G2P_APPLY_PATH', 'window')
         a, am = tbl.apply(src, 1e20, src_mask=msk, mask_policy=L.MASK_PROPAGATE)
         ar = tbl.apply(src, 1e20)
         assert tbl.last_path == 'window'

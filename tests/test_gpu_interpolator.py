@@ -139,6 +139,10 @@ def test_batch_equals_per_message_and_mask_policies(api, tmp_path):
     assert batch.shape == (21, 60, 45) and not isinstance(batch, ma.MaskedArray)
     for i in (0, 7, 20):
         np.testing.assert_array_equal(batch[i], it.interpolate_scipy(lat, lon, fields[i], 'g$3', det))
+    # messages decoded into a pinned buffer go through without a host staging copy
+    buf = it.pinned_source_buffer(len(fields), lat.size)
+    buf.numpy()[:] = np.stack(fields)
+    np.testing.assert_array_equal(it.interpolate_batch(lat, lon, buf, 'g$3', det), batch)
     # as_reference: the masks are ignored, payloads (9999) flow into the sums - exactly the reference's output
     idx, coef = it._read_intertable(it._intertable_filename('g$3')[1])
     ref = it.interpolate_batch(lat, lon, masked, 'g$3', det)
