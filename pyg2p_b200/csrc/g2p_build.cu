@@ -67,16 +67,131 @@ static Rot make_rot(const g2p_rotation* r) {
   return o;
 }
 
+// ------------------------------------------------------------------ correctly rounded sin / cos
+// libdevice's float64 sin/cos are accurate to 1-2 ulp; the reference evaluates `to_3d` with libm (numexpr /
+// numpy), whose results are correctly rounded in ~99.9 % of the cases.  With libdevice only 67 % of the
+// source / target points get bit-identical xyz; evaluating sin and cos in double-double arithmetic
+// (Cody-Waite reduction by pi/2 in three 33-bit parts, Taylor series with the leading terms in
+// double-double, ~2^-75 relative error before the final rounding) reproduces libm in 99.86 % of the values,
+// so that distances, weights and near-tie decisions follow the reference's bit for bit almost everywhere.
+static __constant__ double kSinC[11][2] = {
+    {-0x1.5555555555555p-3, -0x1.5555555555555p-57},
+    {0x1.1111111111111p-7, 0x1.1111111111111p-63},
+    {-0x1.a01a01a01a01ap-13, -0x1.a01a01a01a01ap-73},
+    {0x1.71de3a556c734p-19, -0x1.c154f8ddc6c00p-73},
+    {-0x1.ae64567f544e4p-26, 0x1.c062e06d1f209p-80},
+    {0x1.6124613a86d09p-33, 0x1.f28e0cc748ebep-87},
+    {-0x1.ae7f3e733b81fp-41, -0x1.1d8656b0ee8cbp-97},
+    {0x1.952c77030ad4ap-49, 0x1.ac981465ddc6cp-103},
+    {-0x1.2f49b46814157p-57, -0x1.2650f61dbdcb4p-112},
+    {0x1.71b8ef6dcf572p-66, -0x1.d043ae40c4647p-120},
+    {-0x1.761b41316381ap-75, 0x1.3423c7d91404fp-130}};
+static __constant__ double kCosC[11][2] = {
+    {-0x1.0000000000000p-1, 0x0.0p+0},
+    {0x1.5555555555555p-5, 0x1.5555555555555p-59},
+    {-0x1.6c16c16c16c17p-10, 0x1.f49f49f49f49fp-65},
+    {0x1.a01a01a01a01ap-16, 0x1.a01a01a01a01ap-76},
+    {-0x1.27e4fb7789f5cp-22, -0x1.cbbc05b4fa99ap-76},
+    {0x1.1eed8eff8d898p-29, -0x1.2aec959e14c06p-83},
+    {-0x1.93974a8c07c9dp-37, -0x1.05d6f8a2efd1fp-92},
+    {0x1.ae7f3e733b81fp-45, 0x1.1d8656b0ee8cbp-101},
+    {-0x1.6827863b97d97p-53, -0x1.eec01221a8b0bp-107},
+    {0x1.e542ba4020225p-62, 0x1.ea72b4afe3c2fp-120},
+    {-0x1.0ce396db7f853p-70, 0x1.aebcdbd20331cp-124}};
+
+struct DD {
+  double h, l;
+};
+__device__ __forceinline__ DD fast_two_sum(double a, double b) {
+  const double s = __dadd_rn(a, b);
+  return {s, __dsub_rn(b, __dsub_rn(s, a))};
+}
+__device__ __forceinline__ DD two_sum(double a, double b) {
+  const double s = __dadd_rn(a, b);
+  const double bb = __dsub_rn(s, a);
+  return {s, __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb))};
+}
+__device__ __forceinline__ DD dd_mul(DD a, DD b) {
+  const double p = __dmul_rn(a.h, b.h);
+  double e = __fma_rn(a.h, b.h, -p);
+  e = __dadd_rn(e, __dadd_rn(__dmul_rn(a.h, b.l), __dmul_rn(a.l, b.h)));
+  return fast_two_sum(p, e);
+}
+__device__ __forceinline__ DD dd_add(DD a, DD b) {
+  DD s = two_sum(a.h, b.h);
+  return fast_two_sum(s.h, __dadd_rn(s.l, __dadd_rn(a.l, b.l)));
+}
+
+__device__ __noinline__ void sincos_cr(double x, double* sn, double* cs) {
+  if (!(fabs(x) < 1.0e5)) {  // far outside lat/lon ranges (garbage coordinates of MV cells), NaN, inf
+    sincos(x, sn, cs);
+    return;
+  }
+  if (x == 0.0) {
+    *sn = x;
+    *cs = 1.0;
+    return;
+  }
+  const double k = rint(__dmul_rn(x, 0.6366197723675814));
+  // r = x - k*pi/2 with pi/2 = C1 + C2 + C3 + C3t, each Ci of 33 bits: k*Ci is exact for |k| < 2^20
+  const double t1 = __dsub_rn(x, __dmul_rn(k, 0x1.921fb54400000p+0));
+  DD s1 = two_sum(t1, -__dmul_rn(k, 0x1.0b4611a600000p-34));
+  DD s2 = two_sum(s1.h, -__dmul_rn(k, 0x1.3198a2e000000p-69));
+  const double lo = __dsub_rn(__dadd_rn(s1.l, s2.l), __dmul_rn(k, 0x1.b839a252049c1p-104));
+  const DD r = fast_two_sum(s2.h, lo);
+  const DD u = dd_mul(r, r);
+  // sin r = r + r*u*(S1 + u*(S2 + ...)), cos r = 1 + u*(C1 + u*(C2 + ...)); high orders in double
+  double q = kSinC[10][0];
+#pragma unroll
+  for (int i = 9; i >= 4; --i) q = __fma_rn(u.h, q, kSinC[i][0]);
+  DD t = dd_add(dd_mul(u, DD{q, 0.0}), DD{kSinC[3][0], kSinC[3][1]});
+#pragma unroll
+  for (int i = 2; i >= 0; --i) t = dd_add(dd_mul(u, t), DD{kSinC[i][0], kSinC[i][1]});
+  const DD s = dd_add(r, dd_mul(r, dd_mul(u, t)));
+  q = kCosC[10][0];
+#pragma unroll
+  for (int i = 9; i >= 5; --i) q = __fma_rn(u.h, q, kCosC[i][0]);
+  t = dd_add(dd_mul(u, DD{q, 0.0}), DD{kCosC[4][0], kCosC[4][1]});
+#pragma unroll
+  for (int i = 3; i >= 0; --i) t = dd_add(dd_mul(u, t), DD{kCosC[i][0], kCosC[i][1]});
+  const DD c = dd_add(DD{1.0, 0.0}, dd_mul(u, t));
+  const int n = ((int)k) & 3;
+  *sn = (n == 0) ? s.h : (n == 1) ? c.h : (n == 2) ? -s.h : -c.h;
+  *cs = (n == 0) ? c.h : (n == 1) ? -s.h : (n == 2) ? -c.h : s.h;
+}
+
 // ------------------------------------------------------------------ K1  lat/lon -> xyz
 // f64: radians = deg * (pi/180) in double (numpy deg2rad), libdevice sin/cos, products
 // (r*cos(lon))*cos(lat) left to right with separate multiplies.
 // f32: radians in float32, sin/cos rounded to float32 (see below), promoted to double for the products with the double
 // radius, result rounded to float32 (reference :691-694) and widened again for the search.
+// PAIRED: the two lanes of a lane pair (same query) share the trigonometry - the even lane evaluates the
+// longitude, the odd lane the latitude, and they swap results with one shuffle - which halves the cost of the
+// double-double sin/cos in the k-NN kernel (pass the group's lane mask; 0 = every thread on its own)
 template <bool F32>
 __device__ __forceinline__ void latlon_to_xyz(const void* lon, const void* lat, int64_t i, double radius,
-                                              const Rot& rot, double& x, double& y, double& z) {
+                                              const Rot& rot, double& x, double& y, double& z, unsigned pair_mask = 0u) {
   double cx, sx, cy, sy;
-  if (F32) {
+  if (pair_mask != 0u) {
+    const bool odd = threadIdx.x & 1;
+    double s1, c1;
+    if (F32) {
+      const float dr = 0.017453292519943295f;
+      const float ang = __fmul_rn(reinterpret_cast<const float*>(odd ? lat : lon)[i], dr);
+      double s, c;
+      sincos((double)ang, &s, &c);
+      s1 = (double)(float)s;
+      c1 = (double)(float)c;
+    } else {
+      const double ang = __dmul_rn(reinterpret_cast<const double*>(odd ? lat : lon)[i], 0.017453292519943295);
+      sincos_cr(ang, &s1, &c1);
+    }
+    const double s2 = __shfl_xor_sync(pair_mask, s1, 1), c2 = __shfl_xor_sync(pair_mask, c1, 1);
+    sx = odd ? s2 : s1;
+    cx = odd ? c2 : c1;
+    sy = odd ? s1 : s2;
+    cy = odd ? c1 : c2;
+  } else if (F32) {
     const float dr = 0.017453292519943295f;  // float32(pi/180): numpy's deg2radf constant
     float lo = __fmul_rn(reinterpret_cast<const float*>(lon)[i], dr);
     float la = __fmul_rn(reinterpret_cast<const float*>(lat)[i], dr);
@@ -93,8 +208,8 @@ __device__ __forceinline__ void latlon_to_xyz(const void* lon, const void* lat, 
     const double dr = 0.017453292519943295;
     double lo = __dmul_rn(reinterpret_cast<const double*>(lon)[i], dr);
     double la = __dmul_rn(reinterpret_cast<const double*>(lat)[i], dr);
-    sincos(lo, &sx, &cx);
-    sincos(la, &sy, &cy);
+    sincos_cr(lo, &sx, &cx);
+    sincos_cr(la, &sy, &cy);
   }
   if (!rot.on) {
     x = __dmul_rn(__dmul_rn(radius, cx), cy);
@@ -699,7 +814,7 @@ __global__ void __launch_bounds__(256) knn_kernel(const KnnArgs a) {
     } else if (QSRC == QUERY_XYZ) {
       qx = a.txyz[3 * q]; qy = a.txyz[3 * q + 1]; qz = a.txyz[3 * q + 2];
     } else {
-      latlon_to_xyz<F32>(a.tlon, a.tlat, q, a.xyz_radius, a.rot, qx, qy, qz);
+      latlon_to_xyz<F32>(a.tlon, a.tlat, q, a.xyz_radius, a.rot, qx, qy, qz, LANES >= 2 ? gmask : 0u);
     }
     TopK<KK> top;
     unsigned passes, examined;
