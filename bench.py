@@ -325,25 +325,59 @@ def run_b200(args):
     assert torch.equal(out_m[B // 2][rows].bool(), masked), 'timed apply mask differs'
     assert torch.isnan(got[~inside]).all()
 
-    # ---- e2e: host (pinned) messages -> host results through the host-buffer pipeline
+    # ---- e2e: through the reference-facing class.  A pyg2p_b200 Interpolator is set up as pyg2p sets one up
+    # (execution context, target maps, intertable directory); its first call builds and saves the intertable
+    # (untimed).  Each timed step is one `Interpolator.interpolate_batch` call on messages lying in pinned host
+    # memory - where the GRIB decoder writes them - and returns host arrays: H2D (the gather kernel reads the
+    # touched values over PCIe), apply, D2H are all inside the timed region.
+    import tempfile
+
+    from pyg2p_b200.interpolator import Interpolator
+    from pyg2p_b200.maps import LatLong
+
+    class _Conf:
+        def __init__(self):
+            self.vars, self.user_vars = {}, {}
+
+        def check_write(self):
+            return True
+
+        def dump(self):
+            pass
+
+    class _Ctx:
+        is_with_grib_interpolation = False
+
+        def __init__(self, d):
+            self._d = d
+            self.configuration = type('C', (), {'intertables': _Conf()})()
+
+        def get(self, key, default=None):
+            return self._d.get(key, default)
+
+    tmpdir = tempfile.mkdtemp(prefix=f'g2p_bench_{rank}_')
+    ctx = _Ctx({'interpolation.mode': 'invdist', 'interpolation.create': True, 'interpolation.parallel': True,
+                'interpolation.dirs': {'user': tmpdir, 'global': tmpdir}, 'input.file': 'ens_o1280.grib',
+                'interpolation.latMap': LatLong(tl, tlo, mv=synth.NC_FILL_F64, identifier='efas5km_laea_1000x950'),
+                'interpolation.lonMap': None})
+    interp = Interpolator(ctx, synth.GRIB_MV, mask_policy='propagate')
     Be = min(args.e2e_messages, B)
-    h_src = device.pinned_empty((Be, n))
+    h_src = interp.pinned_source_buffer(Be, n)
     h_msk = device.pinned_empty((Be, n), torch.uint8)
     h_src.copy_(src[:Be])
     h_msk.copy_(src_mask[:Be])
-    h_out = device.pinned_empty((Be, m))
-    h_om = device.pinned_empty((Be, m), torch.uint8)
-    # the Interpolator picks the zero-copy compact pipeline for regional targets (EFAS reads 4 % of an O1280 field)
-    pipe = (device.CompactHostPipeline(table, chunk_messages=16, with_mask=True) if not args.e2e_full_copy
-            else device.HostApplyPipeline(table, chunk_messages=args.e2e_chunk, with_mask=True))
+    h_out = interp.pinned_output_buffer(Be)
+    h_om = interp.pinned_output_buffer(Be, torch.uint8)
+    grid_id = '0.0$359.929$0$2560$6599680$reduced_gg'
     torch.cuda.synchronize()
 
     def e2e_step():
-        pipe.run(h_src, synth.NC_FILL_F64, src_mask=h_msk, mask_policy=L.MASK_PROPAGATE, out=h_out, out_mask=h_om)
-        torch.cuda.current_stream().synchronize()      # the caller reads the result on the host
+        return interp.interpolate_batch(lat, lon, h_src, grid_id, det, masks=h_msk, out=h_out, out_mask=h_om)
 
-    for _ in range(2):
-        e2e_step()
+    first = e2e_step()                     # builds the table, writes tbl_*.npy.gz, creates the host pipeline
+    assert isinstance(first, np.ma.MaskedArray) and first.shape == (Be,) + tl.shape
+    e2e_step()
+    pipe = interp._pipeline(interp._table_for(lat, lon, h_src[0].numpy(), grid_id, det), True)
     pipe.h2d_bytes = pipe.d2h_bytes = 0
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -357,14 +391,18 @@ def run_b200(args):
     e2e_ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
     e2e_bytes = algorithmic_bytes_apply(Be, n_touched, m, K_INVDIST, True)
     e2e_value = e2e_bytes * args.steps * ws / (e2e_ms * 1e-3) / 1e9
-    assert torch.equal(h_out[:Be].to(dev), out_t[:Be]) or torch.allclose(h_out[:Be].to(dev), out_t[:Be], equal_nan=True)
+    assert torch.equal(h_out.to(dev), out_t[:Be]) or torch.allclose(h_out.to(dev), out_t[:Be], equal_nan=True)
+    assert torch.equal(h_om.to(dev), out_m[:Be])
     e2e = {'value': e2e_value, 'unit': 'GB/s', 'h2d_bytes_per_step': pipe.h2d_bytes // args.steps,
            'd2h_bytes_per_step': pipe.d2h_bytes // args.steps, 'messages_per_step': Be,
            'messages_per_s': Be * args.steps * ws / (e2e_ms * 1e-3),
-           'api': ('pyg2p_b200.device.CompactHostPipeline.run (behind Interpolator.interpolate_batch): pinned host '
-                   'messages -> gather kernel reads the touched values over PCIe -> windowed apply -> D2H; '
-                   'h2d_bytes_per_step counts the touched values the gather pulls') if not args.e2e_full_copy else
-                  'pyg2p_b200.device.HostApplyPipeline.run: pinned host messages -> H2D of whole fields -> apply -> D2H'}
+           'api': 'pyg2p_b200.interpolator.Interpolator.interpolate_batch (drop-in for pyg2p Interpolator, mask_policy '
+                  'propagate): messages in pinned host buffers -> ' + type(pipe).__name__ + ' (gather kernel reads the '
+                  'touched source values over PCIe, windowed apply, D2H) -> numpy MaskedArray views; '
+                  'h2d_bytes_per_step counts the touched values pulled over PCIe'}
+    import shutil
+    shutil.rmtree(tmpdir, ignore_errors=True)
+    del interp, first
     del h_src, h_msk, h_out, h_om, pipe, src, src_mask, out_t, out_m
     torch.cuda.empty_cache()
 
@@ -516,8 +554,6 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--messages', type=int, default=383, help='resident messages per GPU (3060 / 8)')
     ap.add_argument('--e2e-messages', type=int, default=64)
-    ap.add_argument('--e2e-chunk', type=int, default=4)
-    ap.add_argument('--e2e-full-copy', action='store_true', help='e2e with whole-field H2D copies instead of the gather')
     ap.add_argument('--cpu-messages', type=int, default=400)
     ap.add_argument('--skip-build', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')

@@ -119,9 +119,15 @@ class Interpolator:
         out = self.interpolate_batch(latgrib, longrib, [v], grid_id, grid_details)
         return out[0]
 
-    def interpolate_batch(self, latgrib, longrib, values, grid_id, grid_details=None):
+    def interpolate_batch(self, latgrib, longrib, values, grid_id, grid_details=None, masks=None, out=None,
+                          out_mask=None):
         """`values`: sequence of source fields [n] (ndarray / MaskedArray) or a 2-D array [b, n] - all messages
-        of the run that share `grid_id`.  Returns an array [b, rows, cols] (MaskedArray under 'propagate')."""
+        of the run that share `grid_id`.  Returns an array [b, rows, cols] (MaskedArray under 'propagate').
+
+        Fast path for decoders: `values` = the tensor from `pinned_source_buffer(b, n)` (and `masks` = a pinned
+        uint8 tensor of the same shape, 1 = missing, when `mask_policy == 'propagate'`); `out` / `out_mask` =
+        pinned tensors [b, rows*cols] from `pinned_output_buffer` to reuse between calls (the returned arrays
+        are views of them)."""
         pinned = isinstance(values, torch.Tensor)
         first = values[0].numpy() if pinned else values[0]
         table = self._table_for(latgrib, longrib, first, grid_id, grid_details)
@@ -132,9 +138,10 @@ class Interpolator:
             # messages decoded straight into `pinned_source_buffer(b, n)`: no staging copy on the host
             if not (values.is_pinned() and values.dtype == torch.float64 and values.dim() == 2 and values.shape[1] == n):
                 raise ValueError('a tensor batch must come from Interpolator.pinned_source_buffer')
-            masked_in, propagate = [False] * b, False
-            pipe = self._pipeline(table, False)
-            h_src, h_msk = values, None
+            masked_in = [masks is not None] * b
+            propagate = self.mask_policy == 'propagate' and masks is not None
+            pipe = self._pipeline(table, propagate)
+            h_src, h_msk = values, (masks if propagate else None)
         else:
             masked_in = [isinstance(x, ma.MaskedArray) and x.mask is not ma.nomask for x in values]
             propagate = self.mask_policy == 'propagate' and any(masked_in)
@@ -147,11 +154,13 @@ class Interpolator:
                 if propagate:
                     h_msk.numpy()[i] = np.broadcast_to(ma.getmaskarray(x).ravel(), (n,)) if masked_in[i] else 0
         out, omask = pipe.run(h_src, float(self.mv_output), src_mask=h_msk,
-                              mask_policy=L.MASK_PROPAGATE if propagate else L.MASK_AS_REFERENCE)
+                              mask_policy=L.MASK_PROPAGATE if propagate else L.MASK_AS_REFERENCE, out=out,
+                              out_mask=out_mask)
         torch.cuda.current_stream(table.device).synchronize()
         res = out.numpy().reshape((b,) + shape)
         if propagate:
-            return ma.masked_array(res, mask=omask.numpy().reshape((b,) + shape).astype(bool), fill_value=self.mv_output)
+            return ma.masked_array(res, mask=omask.numpy().view(np.bool_).reshape((b,) + shape), fill_value=self.mv_output,
+                                   copy=False)
         if table.k == 1 and not pinned and any(isinstance(x, ma.MaskedArray) for x in values):
             return ma.masked_array(res)          # `v[indexes]` of a MaskedArray stays one, with no mask (:153)
         return res
@@ -162,6 +171,10 @@ class Interpolator:
         to write message values into (`codes_get_double_array` results); `interpolate_batch` then reads it
         from the device without any host-side staging copy."""
         return device.pinned_empty((b, n))
+
+    def pinned_output_buffer(self, b, dtype=torch.float64):
+        """page-locked [b, rows*cols] result buffer to pass as `out=` (float64) / `out_mask=` (uint8)."""
+        return device.pinned_empty((b, self._target_coords.lons.size), dtype)
 
     def aux_for_intertable_generation(self, aux_g, aux_v, aux_g2, aux_v2):
         self._aux_gid, self._aux_val, self._aux_2nd_res_gid, self._aux_2nd_res_val = aux_g, aux_v, aux_g2, aux_v2
