@@ -101,3 +101,24 @@ def test_lookup_order_and_gz_reader(tmp_path):
     assert path in Interpolator._LOADED_INTERTABLES
     np.save(tmp_path / 'tbl_x.npy', rec)                            # the user dir wins once the file is there
     assert it._intertable_filename('g')[1] == str(tmp_path / 'tbl_x.npy')
+
+
+def test_parallel_gzip_table_is_read_by_the_reference_loader(tmp_path):
+    """multi-member gzip written by all cores == what `gzip.GzipFile` + `np.load` (the reference's reader) expect,
+    byte for byte the `.npy` stream of np.save."""
+    import io
+    from pyg2p_b200.interpolator import save_npy_gz_parallel
+    rng = np.random.default_rng(0)
+    m = 300_000
+    rec = np.rec.fromarrays((rng.integers(0, 6_599_681, (m, 4)), rng.random((m, 4))), names=('indexes', 'coeffs'))
+    path = tmp_path / 'tbl.npy.gz'
+    save_npy_gz_parallel(str(path), rec, level=1, chunk_bytes=1 << 20)
+    with gzip.GzipFile(path, 'r') as f:
+        back = np.load(f)
+    assert back.dtype == rec.dtype and back.shape == rec.shape and back.tobytes() == rec.tobytes()
+    ref = io.BytesIO()
+    np.save(ref, rec)
+    assert gzip.open(path).read() == ref.getvalue()
+    save_npy_gz_parallel(str(tmp_path / 'empty.npy.gz'), rec[:0])
+    with gzip.GzipFile(tmp_path / 'empty.npy.gz', 'r') as f:
+        assert np.load(f).shape == (0, 4)
