@@ -213,8 +213,20 @@ def run_b200(args):
     dev = torch.device('cuda', local_rank)
     if ws > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')     # keep stdout for the one JSON line
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator comes up: keep stdout for the one
+        # JSON line by pointing fd 1 at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     def barrier():
         if ws > 1:
