@@ -445,21 +445,45 @@ def run_b200(args):
         b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         b0.record()
         torch.cuda.nvtx.range_push('timed_build')
+        rep_wall = []
         for _ in range(reps):
+            t_rep = time.perf_counter()
             ixb, o, idx_f, coef_f = build_once()
+            torch.cuda.synchronize()
+            rep_wall.append((time.perf_counter() - t_rep) * 1e3)
         torch.cuda.nvtx.range_pop()
         b1.record()
         barrier()
-        build_ms = parallel.max_over_ranks(b0.elapsed_time(b1), dev) / reps
+        # median repetition (each bracketed by a device synchronisation): the stream-ordered memory pool can make
+        # a single repetition several times slower when it regrows after the previous index was returned
+        build_ms = parallel.max_over_ranks(float(np.median(rep_wall)), dev)
+        build_mean_ms = parallel.max_over_ranks(b0.elapsed_time(b1), dev) / reps
         n_tie = int((o['flags'] & L.FLAG_TIE).ne(0).sum().item())
         build = {'metric': 'intertable build target-pts/s', 'value': M / (build_ms * 1e-3), 'unit': 'target-pts/s',
-                 'ms_per_build': build_ms, 'targets': M, 'targets_per_gpu': hi_i - lo_i, 'k': K_INVDIST,
+                 'ms_per_build': build_ms, 'ms_per_build_mean': build_mean_ms, 'reps_ms': [round(x, 3) for x in rep_wall],
+                 'statistic': 'median of reps', 'targets': M, 'targets_per_gpu': hi_i - lo_i, 'k': K_INVDIST,
                  'mode': 'invdist', 'scaling': 'strong', 'reps': reps,
                  'includes': 'lat/lon->xyz, cube-sphere index, self k=2 query + max (min_upper_bound), k-NN, '
                              'invdist weights' + (', NCCL all-gather of table shards' if ws > 1 else ''),
                  'gpu_launches_per_build': (device.launch_count() - l0) // reps,
                  'exact_tie_rows_rank0': n_tie, 'index': ixb.info(),
                  'workload': 'BASELINE configs[2]: O1280 (6 599 680 pts) -> GloFAS 0.05 deg (7200x3000), invdist k=4'}
+        # the apply kernel on THIS table (global lat/lon target: rows run along the source rings), 16 messages
+        gt = device.DeviceTable(idx_f, coef_f, n, grid_shape=gl.shape)
+        gb = 16
+        gsrc = torch.randn((gb, n), generator=g, device=dev, dtype=torch.float64)
+        gmsk = (torch.rand((gb, n), generator=g, device=dev) < 0.02).to(torch.uint8)
+        gout = torch.empty((gb, M), dtype=torch.float64, device=dev)
+        gom = torch.empty((gb, M), dtype=torch.uint8, device=dev)
+        g_touched = int(torch.unique(idx_f[idx_f < n]).numel())
+        ms_m = timed(lambda: gt.apply(gsrc, synth.NC_FILL_F64, src_mask=gmsk, mask_policy=L.MASK_PROPAGATE, out=gout,
+                                      out_mask=gom), reps=5)
+        ms_p = timed(lambda: gt.apply(gsrc, synth.NC_FILL_F64, out=gout), reps=5)
+        build['apply_on_this_table'] = {
+            'messages': gb, 'kernel_path': gt.last_path, 'plan': gt.plan_info(),
+            'propagate': {'ms': ms_m, 'frac_of_hbm_peak': algorithmic_bytes_apply(gb, g_touched, M, K_INVDIST, True) / (ms_m * 1e-3) / 1e9 / hbm_peak},
+            'masks_ignored': {'ms': ms_p, 'frac_of_hbm_peak': algorithmic_bytes_apply(gb, g_touched, M, K_INVDIST, False) / (ms_p * 1e-3) / 1e9 / hbm_peak}}
+        del gt, gsrc, gmsk, gout, gom
         del ixb, o, idx_f, coef_f
         if ws == 1:
             # the same through the drop-in class, host arrays in -> host record (reference layout) out
