@@ -151,9 +151,10 @@ class SourceIndex:
             flags = torch.empty((m,), dtype=torch.uint8, device=self.device) if want_flags else None
             xyz = torch.empty((m, 3), dtype=torch.float64, device=self.device) if want_xyz else None
             r = float(radius) if radius is not None else (float(self.radius) if self.radius else 0.0)
-            L.check(self._lib.g2p_knn(self._h, _ptr(lo), _ptr(la), _ptr(tx), m, code, r, L.rotation_arg(rotation),
-                                      int(k), int(mode), float(mub), _ptr(idx), _ptr(coef), _ptr(flags), _ptr(xyz),
-                                      _stream()))
+            if m > 0:
+                L.check(self._lib.g2p_knn(self._h, _ptr(lo), _ptr(la), _ptr(tx), m, code, r, L.rotation_arg(rotation),
+                                          int(k), int(mode), float(mub), _ptr(idx), _ptr(coef), _ptr(flags), _ptr(xyz),
+                                          _stream()))
         return {'idx': idx, 'coef': coef, 'flags': flags, 'xyz': xyz, 'coef_dtype': code}
 
 

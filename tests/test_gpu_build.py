@@ -345,3 +345,36 @@ def test_xyz_bit_identical_to_libm_almost_everywhere(dev):
     got = dev.latlon_to_xyz(a, a[::-1].copy(), 1.0).cpu().numpy()
     want = R.stack_xyz(*R.to_3d(a, a[::-1].copy(), 1.0))
     np.testing.assert_array_equal(got, want)
+
+
+def test_edge_cases_of_the_boundary(dev):
+    """single source point, empty target set, k larger than the source, duplicate source points, a target on a
+    source point - what cKDTree does in each case."""
+    # one source point: every target gets it; k=4 pads with (n, inf)
+    ix = dev.SourceIndex([12.5], [47.0], 6371229.0)
+    out = ix.knn(np.array([12.5, -170.0]), np.array([47.0, -80.0]), k=4, mode=L.MODE_RAW, want_xyz=True)
+    src, tq = ix.xyz().cpu().numpy(), out['xyz'].cpu().numpy()
+    d, i = R.build_tree(src).query(tq, k=4)
+    np.testing.assert_array_equal(out['idx'].cpu().numpy().T, i)
+    np.testing.assert_array_equal(out['coef'].cpu().numpy().T, d)
+    assert ix.max_nn_dist() == 0.0 or np.isinf(ix.max_nn_dist()) or ix.max_nn_dist() >= 0.0
+    # empty target set
+    e = ix.knn(np.empty(0), np.empty(0), k=1, mode=L.MODE_RAW)
+    assert e['idx'].shape == (1, 0) and e['coef'].shape == (1, 0)
+    # duplicates and an exact hit: distance 0 first, duplicates ordered by id, flagged as a tie
+    lon = np.array([10.0, 10.0, 11.0, 12.0, 10.0])
+    lat = np.array([50.0, 50.0, 50.0, 50.0, 50.0])
+    ix = dev.SourceIndex(lon, lat, 6371229.0)
+    out = ix.knn(np.array([10.0]), np.array([50.0]), k=4, mode=L.MODE_RAW)
+    assert out['idx'].cpu().numpy()[:, 0].tolist() == [0, 1, 4, 2]
+    assert out['coef'].cpu().numpy()[:3, 0].tolist() == [0.0, 0.0, 0.0]
+    assert out['flags'].cpu().numpy()[0] & L.FLAG_TIE
+    assert ix.max_nn_dist() > 0.0          # the non-duplicated points have a neighbour at a positive distance
+    # invdist on the exact hit: weights [1, 0, 0, 0] (d0 <= 1e-10 branch), indexes kept
+    t = ix.knn(np.array([10.0]), np.array([50.0]), k=4, mode=L.MODE_INVDIST, mub=1e6)
+    assert t['coef'].cpu().numpy()[:, 0].tolist() == [1.0, 0.0, 0.0, 0.0]
+    # bad arguments are refused with the library's message
+    with pytest.raises(Exception, match='k='):
+        ix.knn(np.array([10.0]), np.array([50.0]), k=17)
+    with pytest.raises(Exception):
+        dev.SourceIndex(np.array([np.nan, 1.0]), np.array([0.0, 1.0]), 6371229.0)
