@@ -590,19 +590,28 @@ __device__ __forceinline__ bool lex_lt(double da, int ia, double db, int ib) {
   return (da < db) || (da == db && ia < ib);
 }
 
+// sorted best-KK list plus `nxt`, the smallest squared distance among everything examined that is NOT in the
+// list: that one value is all the tie / near-tie flags need from the (k+1)-th neighbour, and keeping KK = k
+// slots instead of k+1 saves a quarter of the insertion work for k = 4
 template <int KK>
 struct TopK {
   double d[KK];
   int id[KK];
+  double nxt;
   __device__ __forceinline__ void reset() {
 #pragma unroll
     for (int s = 0; s < KK; ++s) {
       d[s] = __longlong_as_double(0x7ff0000000000000LL);
       id[s] = INT_MAX;
     }
+    nxt = __longlong_as_double(0x7ff0000000000000LL);
   }
   __device__ __forceinline__ void insert(double nd, int ni) {
-    if (!lex_lt(nd, ni, d[KK - 1], id[KK - 1])) return;
+    if (!lex_lt(nd, ni, d[KK - 1], id[KK - 1])) {
+      nxt = fmin(nxt, nd);
+      return;
+    }
+    nxt = fmin(nxt, d[KK - 1]);  // the evicted one (inf while the list is not full)
     d[KK - 1] = nd;
     id[KK - 1] = ni;
 #pragma unroll
@@ -717,6 +726,11 @@ __device__ __forceinline__ void merge_group(TopK<KK>& top, unsigned gmask) {
     res.id[s] = bi;
     if (top.id[0] == bi && bi != INT_MAX) top.pop_front();
   }
+  // best of what is left anywhere in the group: the lanes' unselected heads and their own `nxt`
+  double nx = fmin(top.nxt, top.d[0]);
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) nx = fmin(nx, __shfl_xor_sync(gmask, nx, o));
+  res.nxt = nx;
   top = res;
 }
 
@@ -796,7 +810,7 @@ __device__ __forceinline__ void invdist_weights(const double* d, int k, double m
 enum { QUERY_LATLON_F64 = 0, QUERY_LATLON_F32 = 1, QUERY_XYZ = 2, QUERY_SELF = 3 };
 
 template <int KK, int LANES, int QSRC>
-__global__ void __launch_bounds__(256, (KK >= 5 && KK < 12) ? 3 : 1) knn_kernel(const KnnArgs a) {
+__global__ void __launch_bounds__(256, (KK >= 4 && KK < 11) ? 3 : 1) knn_kernel(const KnnArgs a) {
   constexpr bool F32 = (QSRC == QUERY_LATLON_F32);
   const int lane = threadIdx.x % LANES;
   const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31) / LANES * LANES));
@@ -840,10 +854,12 @@ __global__ void __launch_bounds__(256, (KK >= 5 && KK < 12) ? 3 : 1) knn_kernel(
         if (F32) d = (double)(float)d;
         dist[s] = d;
         if (top.id[s] == INT_MAX) flag |= G2P_FLAG_SHORT;
-      }
-      if (s + 1 < KK && s < k && top.d[s + 1] < inf) {
-        if (top.d[s] == top.d[s + 1]) flag |= G2P_FLAG_TIE;
-        else if (top.d[s + 1] - top.d[s] <= top.d[s + 1] * 5.7e-14) flag |= G2P_FLAG_NEAR_TIE;
+        // the next-best squared distance after slot s: the following slot, or `nxt` behind the last one
+        const double after = (s + 1 < KK) ? top.d[(s + 1 < KK) ? s + 1 : s] : top.nxt;
+        if (after < inf) {
+          if (top.d[s] == after) flag |= G2P_FLAG_TIE;
+          else if (after - top.d[s] <= after * 5.7e-14) flag |= G2P_FLAG_NEAR_TIE;
+        }
       }
     }
     if (a.flags_out) a.flags_out[q] = flag;
@@ -947,11 +963,11 @@ static int launch_knn_l(const KnnArgs& a, int qsrc, cudaStream_t st) {
 
 static int launch_knn(const KnnArgs& a, int qsrc, cudaStream_t st) {
   const int k = a.k;
-  if (k <= 1) return launch_knn_l<2>(a, qsrc, st);
-  if (k <= 2) return launch_knn_l<3>(a, qsrc, st);
-  if (k <= 4) return launch_knn_l<5>(a, qsrc, st);
-  if (k <= 11) return launch_knn_l<12>(a, qsrc, st);
-  return launch_knn_l<17>(a, qsrc, st);
+  if (k <= 1) return launch_knn_l<1>(a, qsrc, st);
+  if (k <= 2) return launch_knn_l<2>(a, qsrc, st);
+  if (k <= 4) return launch_knn_l<4>(a, qsrc, st);
+  if (k <= 11) return launch_knn_l<11>(a, qsrc, st);
+  return launch_knn_l<16>(a, qsrc, st);
 }
 
 static IndexView view_of(const g2p_index* ix) {
