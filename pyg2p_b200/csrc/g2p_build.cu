@@ -19,7 +19,10 @@
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
+#include <ctime>
+#include <mutex>
 #include <vector>
 
 #include "g2p_common.cuh"
@@ -449,22 +452,57 @@ static int grid_for(int64_t n, int threads, int waves = 8) {
   return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
 }
 
-// stream-ordered allocation from the device's default pool, which is told to keep its memory: a table
-// build allocates ~400 MB of index and scratch, and cudaMalloc / cudaFree cost more than the kernels
+// Device buffers of the index and its scratch are recycled through a small per-device free list: a table build
+// allocates ~450 MB in nine pieces, and both cudaMalloc and cudaMallocAsync (whose pool regrows unpredictably:
+// 0.02 - 55 ms measured for the same sequence) cost more than the 0.75 ms of kernels that build the index.
+// Buffers come back when an index is destroyed (after a device synchronisation) or when build_cells is done
+// with its scratch (same stream, so stream order protects the reuse).  Index calls on one device are expected
+// on one stream at a time.
+struct CachedBuf {
+  void* p;
+  size_t bytes;
+};
+static std::vector<CachedBuf> g_free_bufs[64];
+static std::mutex g_free_mutex;
+constexpr size_t kCacheMaxEntries = 24;
+constexpr size_t kCacheMaxBytes = (size_t)2 << 30;   // at most 2 GiB parked per device
+
 template <typename T>
 static cudaError_t pool_alloc(T** p, size_t bytes, cudaStream_t st) {
-  static bool tuned[64] = {false};
+  if (bytes == 0) bytes = 1;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !tuned[dev]) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  if (dev >= 0 && dev < 64) {
+    std::lock_guard<std::mutex> lock(g_free_mutex);
+    auto& fl = g_free_bufs[dev];
+    int best = -1;
+    for (int i = 0; i < (int)fl.size(); ++i)
+      if (fl[i].bytes >= bytes && fl[i].bytes <= bytes + bytes / 2 + 4096 && (best < 0 || fl[i].bytes < fl[best].bytes)) best = i;
+    if (best >= 0) {
+      *p = reinterpret_cast<T*>(fl[best].p);
+      fl.erase(fl.begin() + best);
+      return cudaSuccess;
     }
-    tuned[dev] = true;
   }
-  return cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 1, st);
+  (void)st;
+  return cudaMalloc(reinterpret_cast<void**>(p), bytes);
+}
+
+static void pool_free(void* p, size_t bytes) {
+  if (!p) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64) {
+    std::lock_guard<std::mutex> lock(g_free_mutex);
+    auto& fl = g_free_bufs[dev];
+    size_t held = 0;
+    for (const CachedBuf& b : fl) held += b.bytes;
+    if (fl.size() < kCacheMaxEntries && held + bytes <= kCacheMaxBytes) {
+      fl.push_back({p, bytes ? bytes : 1});
+      return;
+    }
+  }
+  cudaFree(p);
 }
 
 static void free_index(g2p_index* ix) {
@@ -472,9 +510,9 @@ static void free_index(g2p_index* ix) {
   // wait for every stream (a query on any of them may still be reading the index), then hand the memory
   // back to the pool - cudaFree would return it to the driver and the next build would pay for it again
   cudaDeviceSynchronize();
-  if (ix->xyz) cudaFreeAsync(ix->xyz, nullptr);
-  if (ix->pts) cudaFreeAsync(ix->pts, nullptr);
-  if (ix->cell_start) cudaFreeAsync(ix->cell_start, nullptr);
+  pool_free(ix->xyz, (size_t)ix->n * 24);
+  pool_free(ix->pts, (size_t)ix->n * sizeof(g2p::Pt));
+  pool_free(ix->cell_start, (size_t)(ix->n_cells + 1) * 4);
   delete ix;
 }
 
@@ -487,8 +525,18 @@ static double env_double(const char* name, double dflt) {
 }
 
 // builds cells from ix->xyz (already on device)
+static double now_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 static int build_cells(g2p_index* ix, cudaStream_t st) {
   const int64_t n = ix->n;
+  const bool timing = getenv("G2P_TIMING") != nullptr;
+  double t0 = now_ms();
+  if (timing) cudaStreamSynchronize(st);
+  const double t_enter = now_ms();
   // 1. norm range + coarse occupancy (density estimate for regional sources)
   int Gc = (int)floor(sqrt((double)n / 96.0));
   Gc = Gc < 1 ? 1 : (Gc > 64 ? 64 : Gc);
@@ -507,8 +555,9 @@ static int build_cells(g2p_index* ix, cudaStream_t st) {
   G2P_CUDA(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
   G2P_CUDA(cudaMemcpyAsync(coarse.data(), d_coarse, n_coarse, cudaMemcpyDeviceToHost, st));
   G2P_CUDA(cudaStreamSynchronize(st));
-  cudaFreeAsync(d_stats, st);
-  cudaFreeAsync(d_coarse, st);
+  const double t_stats = now_ms();
+  pool_free(d_stats, 2 * sizeof(double));
+  pool_free(d_coarse, n_coarse);
   const double rmin = stats[0], rmax = stats[1];
   if (!(rmax > 0.0) || !std::isfinite(rmax) || !(rmin > 0.0))
     return set_error(G2P_ERR_INVALID, "source coordinates are not finite / not on a sphere (|p| in [%g, %g])", rmin, rmax);
@@ -538,6 +587,8 @@ static int build_cells(g2p_index* ix, cudaStream_t st) {
   G2P_CUDA(pool_alloc(&d_bsums, (size_t)nb * 4, st));
   G2P_CUDA(pool_alloc(&ix->cell_start, (size_t)(nc + 1) * 4, st));
   G2P_CUDA(pool_alloc(&ix->pts, (size_t)n * sizeof(Pt), st));
+  if (timing) cudaStreamSynchronize(st);
+  const double t_alloc = now_ms();
   G2P_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nc * 4, st));
   key_hist_kernel<<<grid_for(n, 256), 256, 0, st>>>(ix->xyz, n, G, d_keys, d_counts);
   G2P_LAUNCHED();
@@ -550,10 +601,13 @@ static int build_cells(g2p_index* ix, cudaStream_t st) {
   scatter_kernel<<<grid_for(n, 256), 256, 0, st>>>(ix->xyz, d_keys, n, d_cursor, ix->pts);
   G2P_LAUNCHED();
   G2P_CUDA(cudaStreamSynchronize(st));
-  cudaFreeAsync(d_keys, st);
-  cudaFreeAsync(d_counts, st);
-  cudaFreeAsync(d_cursor, st);
-  cudaFreeAsync(d_bsums, st);
+  if (timing)
+    fprintf(stderr, "[g2p] index n=%lld: wait-for-xyz %.2f ms, stats+readback %.2f ms, allocations %.2f ms, sort kernels %.2f ms\n",
+            (long long)n, t_enter - t0, t_stats - t_enter, t_alloc - t_stats, now_ms() - t_alloc);
+  pool_free(d_keys, (size_t)n * 4);
+  pool_free(d_counts, (size_t)nc * 4);
+  pool_free(d_cursor, (size_t)nc * 4);
+  pool_free(d_bsums, (size_t)nb * 4);
   ix->bytes = (int64_t)n * 24 + (int64_t)n * sizeof(Pt) + (nc + 1) * 4;
   return G2P_OK;
 }
@@ -1102,7 +1156,7 @@ int g2p_index_max_nn_dist_part(g2p_index* ix, int64_t first, int64_t last, doubl
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = cuda_fail(e, "max_nn_dist readback", __FILE__, __LINE__);
   }
-  cudaFreeAsync(d_max, st);
+  pool_free(d_max, sizeof(double));
   if (rc != G2P_OK) return rc;
   *dmax = sqrt(d2);  // sqrt is monotone and correctly rounded: sqrt(max d2) == max sqrt(d2)
   return G2P_OK;
