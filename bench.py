@@ -529,7 +529,9 @@ def run_b200(args):
         pout = pipe_step()
         n_out = pout.shape[0]
         l0 = device.launch_count()
+        torch.cuda.nvtx.range_push('timed_pipeline')
         pms = timed(pipe_step, reps=5)
+        torch.cuda.nvtx.range_pop()
         pl = (device.launch_count() - l0) // 6
         pms = parallel.max_over_ranks(pms, dev)
         # algorithmic bytes: 2 input steps x 8 B per touched point + 8 B per target and output, + gem/dem/table once

@@ -33,7 +33,6 @@ struct ManipArgs {
   const double* src;
   const uint8_t* src_mask;
   const int32_t* touched;
-  const ManipItem* items;
   double* out;
   uint8_t* out_mask;
   int64_t n, nc, src_stride, out_stride;
@@ -104,10 +103,10 @@ __device__ __forceinline__ void manip_body(const ManipArgs& a, const ManipItem& 
   }
 }
 
-__global__ void __launch_bounds__(256) manip_kernel(const ManipArgs a) { manip_body(a, a.items[blockIdx.y], blockIdx.y); }
-
-__global__ void __launch_bounds__(256) manip_kernel_inline(const ManipArgs a, const __grid_constant__ ManipInline in) {
-  manip_body(a, in.items[blockIdx.y], blockIdx.y);
+// up to 16 output messages per launch, their descriptions in the kernel parameters (no upload, no sync);
+// blockIdx.y = output message within the group, one source point per thread
+__global__ void __launch_bounds__(256) manip_kernel(const ManipArgs a, const __grid_constant__ ManipInline in, int o_base) {
+  manip_body(a, in.items[blockIdx.y], o_base + blockIdx.y);
 }
 
 // V[a] + (V[b] - V[a]) * frac : linear-in-time synthesis of a missing step (aggregator.py:105,128)
@@ -184,22 +183,10 @@ int g2p_manip(const g2p_manip_desc* desc, const double* src, const uint8_t* src_
     d.divisor = s.divisor;
   }
   cudaStream_t st = as_stream(stream);
-  ManipItem* d_items = nullptr;
-  const bool inline_items = desc->n_out <= kManipInline;
-  if (!inline_items) {
-    G2P_CUDA(cudaMallocAsync(&d_items, items.size() * sizeof(ManipItem), st));
-    cudaError_t e = cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(ManipItem), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `items` lives on this stack frame
-    if (e != cudaSuccess) {
-      cudaFreeAsync(d_items, st);
-      return cuda_fail(e, "g2p_manip: items upload", __FILE__, __LINE__);
-    }
-  }
   ManipArgs a{};
   a.src = src;
   a.src_mask = src_mask;
   a.touched = touched;
-  a.items = d_items;
   a.out = out;
   a.out_mask = out_mask;
   a.n = n;
@@ -214,20 +201,14 @@ int g2p_manip(const g2p_manip_desc* desc, const double* src, const uint8_t* src_
   a.c2 = desc->conv_c2;
   a.mv_grib = desc->mv_grib;
   a.cut_off = desc->cut_off_negative;
-  int64_t bx = ceil_div(nc, 256);
-  const int64_t cap = std::max<int64_t>(1, (int64_t)num_sms() * 16 / desc->n_out);
-  if (bx > cap) bx = cap;
-  if (inline_items) {
+  const int64_t bx = std::min<int64_t>(ceil_div(nc, 256), 0x7fffffffLL);
+  for (int o0 = 0; o0 < desc->n_out; o0 += kManipInline) {
+    const int cnt = std::min(kManipInline, desc->n_out - o0);
     ManipInline in{};
-    for (int o = 0; o < desc->n_out; ++o) in.items[o] = items[o];
-    manip_kernel_inline<<<dim3((unsigned)bx, (unsigned)desc->n_out), 256, 0, st>>>(a, in);
-  } else {
-    manip_kernel<<<dim3((unsigned)bx, (unsigned)desc->n_out), 256, 0, st>>>(a);
+    for (int o = 0; o < cnt; ++o) in.items[o] = items[o0 + o];
+    manip_kernel<<<dim3((unsigned)bx, (unsigned)cnt), 256, 0, st>>>(a, in, o0);
+    G2P_LAUNCHED();
   }
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  cudaError_t e = cudaGetLastError();
-  if (d_items) cudaFreeAsync(d_items, st);
-  if (e != cudaSuccess) return cuda_fail(e, "manip_kernel launch", __FILE__, __LINE__);
   return G2P_OK;
 }
 
