@@ -573,6 +573,7 @@ def run_b200(args):
                          'frac': achieved / hbm_peak, 'traffic': traffic, 'kernel': 'g2p::apply_window_kernel<4, true>' if table.last_path == 'window'
                          else 'g2p::apply_kernel<4, true>', 'plan': table.plan_info() or table.plan_error,
                          'algorithmic_bytes_per_launch': bytes_launch, 'avg_launch_ms': avg_kernel_ms,
+                         'launch_ms_min_median_max': [float(np.min(kern_ms)), float(np.median(kern_ms)), float(np.max(kern_ms))],
                          'n_touched': n_touched, 'peak_source': peak_src},
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
             'messages_per_s': B * args.steps * ws / (total_ms * 1e-3),
