@@ -467,6 +467,12 @@ def run_b200(args):
                              'invdist weights' + (', NCCL all-gather of table shards' if ws > 1 else ''),
                  'gpu_launches_per_build': (device.launch_count() - l0) // reps,
                  'exact_tie_rows_rank0': n_tie, 'index': ixb.info(),
+                 # M*(16 in + k*(8+8) out) + N*(16 in + 24 xyz); the k-NN is instruction / latency
+                 # bound (profiles/r01_build.md), the HBM figure is informational
+                 'roofline': {'bound': 'hbm', 'unit': 'GB/s', 'peak': hbm_peak,
+                              'algorithmic_bytes_per_build': M * (16 + K_INVDIST * 16) + n * 40,
+                              'achieved': (M * (16 + K_INVDIST * 16) + n * 40) / (build_ms * 1e-3) / 1e9,
+                              'frac': (M * (16 + K_INVDIST * 16) + n * 40) / (build_ms * 1e-3) / 1e9 / hbm_peak},
                  'workload': 'BASELINE configs[2]: O1280 (6 599 680 pts) -> GloFAS 0.05 deg (7200x3000), invdist k=4'}
         # the apply kernel on THIS table (global lat/lon target: rows run along the source rings), 16 messages
         gt = device.DeviceTable(idx_f, coef_f, n, grid_shape=gl.shape)
