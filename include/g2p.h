@@ -256,6 +256,17 @@ int g2p_apply_planned_corrected(const g2p_plan* plan, const double* coef, const 
                                 const g2p_correction* corr /* host struct of device pointers */, double* out,
                                 uint8_t* out_mask, void* stream);
 
+/* The whole pipeline in ONE launch: convert -> aggregate -> cut-off (in the staging step of the windowed
+ * apply kernel, on exactly the source values the tile gathers) -> interpolate -> correct.  `desc` as for
+ * g2p_manip, with at most two inputs per output item (PICK, COPY, ACCUM, AVERAGE of <= 2) and no mask_all items
+ * under a mask policy - otherwise G2P_ERR_UNSUPPORTED and the caller uses g2p_manip + g2p_apply_planned.
+ * src / src_mask hold the b_in INPUT messages (whole source fields, rows as for g2p_apply_planned); out has
+ * desc->n_out rows; corr may be NULL. */
+int g2p_apply_planned_fused(const g2p_plan* plan, const double* coef, const g2p_manip_desc* desc /* host */,
+                            const double* src, const uint8_t* src_mask, int b_in, int64_t src_stride,
+                            int64_t out_stride, double mv_out, int mask_policy,
+                            const g2p_correction* corr /* nullable */, double* out, uint8_t* out_mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

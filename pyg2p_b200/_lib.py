@@ -92,6 +92,8 @@ PROTOTYPES = {
     'g2p_correct': (C.c_int, [_vp, _vp, _i64, _i32, _i64, C.POINTER(Correction), _vp]),
     'g2p_apply_planned_corrected': (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f64, _i32, C.POINTER(Correction),
                                               _vp, _vp, _vp]),
+    'g2p_apply_planned_fused': (C.c_int, [_vp, _vp, C.POINTER(ManipDesc), _vp, _vp, _i32, _i64, _i64, _f64, _i32,
+                                          C.POINTER(Correction), _vp, _vp, _vp]),
 }
 
 _lib = None

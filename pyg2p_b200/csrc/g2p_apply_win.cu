@@ -304,6 +304,12 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
   return v;
 }
 
+// one output message of the fused pipeline: which input messages it combines and how (g2p_manip_item, <= 2 inputs)
+struct AggItem {
+  int32_t kind, in0, in1, pad;
+  double unit_time, divisor;
+};
+
 // ------------------------------------------------------------------ apply kernel
 struct WinArgs {
   const uint16_t* lidx;
@@ -323,6 +329,10 @@ struct WinArgs {
   const double* corr_dem_term;
   const uint8_t* corr_valid;
   double corr_mv;
+  // AGG: the source-grid stages fused into the staging step (see apply_window_kernel)
+  const AggItem* agg_items;   // device, one per output message
+  int op1, op2, cut_off;
+  double c1, c2, mv_grib;
 };
 
 template <int K>
@@ -363,23 +373,41 @@ constexpr unsigned long long kMaskMarker = 0x7ff86d61736b0001ull;
 // MP: 0 = no masks (AS_REFERENCE), 1 = PROPAGATE (out_mask written), 2 = FILL
 // CV: 16-byte value chunks copied per thread and message (value window <= 512*CV elements)
 // S : stages
+// where(x != mv, op2(op1(x)), mv)  (manipulation/conversion.py:21); op1 == NONE is the identity 'x=x'
+__device__ __forceinline__ double agg_convert(const WinArgs& a, double x) {
+  if (a.op1 == G2P_OP_NONE) return x;
+  if (x == a.mv_grib) return a.mv_grib;
+  double y = a.op1 == G2P_OP_MUL ? __dmul_rn(x, a.c1) : a.op1 == G2P_OP_ADD ? __dadd_rn(x, a.c1) : __ddiv_rn(x, a.c1);
+  if (a.op2 != G2P_OP_NONE)
+    y = a.op2 == G2P_OP_MUL ? __dmul_rn(y, a.c2) : a.op2 == G2P_OP_ADD ? __dadd_rn(y, a.c2) : __ddiv_rn(y, a.c2);
+  return y;
+}
+
 // CORR: Corrector epilogue `where(valid & (p != mv), (p + gem) - dem_term, mv)` (manipulation/correction.py:46,74-81)
-template <int K, int MP, int CV, int S, bool CORR>
-__global__ void __launch_bounds__(kWinThreads, CORR ? 2 : 3) apply_window_kernel(const WinArgs a) {
+// AGG : the source-grid stages run inside the staging step: an output message stages the windows of its (<= 2)
+//       input messages, and the fold pass - one message ahead of the gathers, where the mask bytes are folded
+//       anyway - evaluates conversion, aggregation (PICK / ACCUM / AVERAGE of <= 2 / COPY, g2p_manip's arithmetic)
+//       and the cut-off on every staged source value before the targets gather it.  convert -> aggregate ->
+//       cut-off -> interpolate -> correct is then ONE launch that reads every needed source value once.
+template <int K, int MP, int CV, int S, bool CORR, bool AGG>
+__global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_window_kernel(const WinArgs a) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ Range s_ranges[kMaxRanges];
   __shared__ int s_tile_info[4];
   constexpr bool MASK = MP != 0;
+  constexpr bool FOLD = MASK || AGG;
+  constexpr int NIN = AGG ? 2 : 1;  // staged input windows per message
   constexpr int CM = (CV + 7) / 8;  // 16-byte mask chunks per thread; also 4-element fold groups per thread / 4
   constexpr int CF = (CV + 1) / 2;  // fold groups (4 mask bytes) per thread
   const int tid = threadIdx.x;
-  const uint32_t val_base = smem_u32(s_raw);                                             // [S][stage_elems] f64
-  const uint32_t msk_base = val_base + (uint32_t)S * a.stage_elems * 8u;                 // [S][stage_melems] u8
-  const uint32_t stage_vbytes = (uint32_t)a.stage_elems * 8u;
-  const uint32_t stage_mbytes = (uint32_t)a.stage_melems;
+  const uint32_t val_base = smem_u32(s_raw);                                             // [S][NIN][stage_elems] f64
+  const uint32_t msk_base = val_base + (uint32_t)S * NIN * a.stage_elems * 8u;           // [S][NIN][stage_melems] u8
+  const uint32_t in_vbytes = (uint32_t)a.stage_elems * 8u, in_mbytes = (uint32_t)a.stage_melems;
+  const uint32_t stage_vbytes = NIN * in_vbytes;
+  const uint32_t stage_mbytes = NIN * in_mbytes;
   const uint32_t val_end = val_base + (uint32_t)S * stage_vbytes;
   const int sent = a.stage_elems - 1;  // slot that always holds mv_out (copies and folds never reach it)
-  if (tid < S) reinterpret_cast<double*>(s_raw)[(size_t)tid * a.stage_elems + sent] = a.mv_out;
+  if (tid < S) reinterpret_cast<double*>(s_raw)[(size_t)tid * NIN * a.stage_elems + sent] = a.mv_out;
   const int64_t vrow = a.src_stride * 8, mrow = a.src_stride;
 
   for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
@@ -417,7 +445,7 @@ __global__ void __launch_bounds__(kWinThreads, CORR ? 2 : 3) apply_window_kernel
 #pragma unroll
     for (int i = 0; i < CF; ++i) {
       fdst[i] = -1;
-      if (MASK) {
+      if (FOLD) {
         const int e = 4 * (tid + kWinThreads * i);
         const int rg = mask_window_range(s_ranges, nr, mwindow, e);
         if (rg >= 0) fdst[i] = 8 * (s_ranges[rg].smem_off + (e - s_ranges[rg].mask_off));
@@ -430,32 +458,89 @@ __global__ void __launch_bounds__(kWinThreads, CORR ? 2 : 3) apply_window_kernel
     // next message of the chunk -> the stage whose value / mask addresses are (sv, sm)
     auto prefetch = [&](uint32_t sv, uint32_t sm) {
       if (n_left > 0) {
+        if (AGG) {
+          const AggItem it = a.agg_items[msg_begin + (n_msg - n_left)];
 #pragma unroll
-        for (int i = 0; i < CV; ++i)
-          if (vsrc[i] >= 0) cp_async16(sv + 16u * tid + 16u * kWinThreads * i, grow_v + vsrc[i]);
-        if (MASK) {
+          for (int q = 0; q < 2; ++q) {
+            const int in = q == 0 ? it.in0 : it.in1;
+            if (in < 0) continue;
+            const char* gv = reinterpret_cast<const char*>(a.src) + (int64_t)in * vrow;
 #pragma unroll
-          for (int i = 0; i < CM; ++i)
-            if (msrc[i] >= 0) cp_async16(sm + 16u * tid + 16u * kWinThreads * i, grow_m + msrc[i]);
-          grow_m += mrow;
+            for (int i = 0; i < CV; ++i)
+              if (vsrc[i] >= 0) cp_async16(sv + q * in_vbytes + 16u * tid + 16u * kWinThreads * i, gv + vsrc[i]);
+            if (MASK) {
+              const char* gm = reinterpret_cast<const char*>(a.src_mask) + (int64_t)in * mrow;
+#pragma unroll
+              for (int i = 0; i < CM; ++i)
+                if (msrc[i] >= 0) cp_async16(sm + q * in_mbytes + 16u * tid + 16u * kWinThreads * i, gm + msrc[i]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < CV; ++i)
+            if (vsrc[i] >= 0) cp_async16(sv + 16u * tid + 16u * kWinThreads * i, grow_v + vsrc[i]);
+          if (MASK) {
+#pragma unroll
+            for (int i = 0; i < CM; ++i)
+              if (msrc[i] >= 0) cp_async16(sm + 16u * tid + 16u * kWinThreads * i, grow_m + msrc[i]);
+            grow_m += mrow;
+          }
+          grow_v += vrow;
         }
-        grow_v += vrow;
         --n_left;
       }
       cp_async_commit();  // always: keeps the group count uniform
     };
-    // fold the mask bytes of a landed message into its values
+    // the pass over a landed message, one message ahead of the gathers: (AGG) combine the staged input windows
+    // into the values the targets will gather, then fold the mask bytes into them
+    int fold_it = 0;  // message of the chunk the next fold works on
     auto fold = [&](uint32_t sv, uint32_t sm) {
+      AggItem it{};
+      if (AGG) it = a.agg_items[msg_begin + fold_it];
+      ++fold_it;
 #pragma unroll
       for (int i = 0; i < CF; ++i) {
         if (fdst[i] < 0) continue;
-        uint32_t m4;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m4) : "r"(sm + 4u * tid + 4u * kWinThreads * i));
-        if (m4) {
+        if (AGG) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if ((m4 >> (8 * q)) & 0xffu)
-              asm volatile("st.shared.u64 [%0], %1;" ::"r"(sv + (uint32_t)fdst[i] + 8u * q), "l"(kMaskMarker) : "memory");
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t at = sv + (uint32_t)fdst[i] + 8u * q;
+            const double xa = it.in0 >= 0 ? agg_convert(a, lds_f64(at)) : 0.0;
+            const double xb = it.in1 >= 0 ? agg_convert(a, lds_f64(at + in_vbytes)) : 0.0;
+            double v;
+            if (it.kind == G2P_AGG_ACCUM) {
+              v = __ddiv_rn(__dmul_rn(__dsub_rn(__dadd_rn(0.0, xa), xb), it.unit_time), it.divisor);
+            } else if (it.kind == G2P_AGG_AVERAGE) {
+              v = __dadd_rn(0.0, xa);
+              if (it.in1 >= 0) v = __dadd_rn(v, xb);
+              v = __ddiv_rn(v, it.divisor);
+            } else if (it.kind == G2P_AGG_COPY) {
+              v = xa;
+            } else {
+              v = it.in0 >= 0 ? __dadd_rn(0.0, xa) : 0.0;
+            }
+            if (a.cut_off && v < 0.0) v = 0.0;
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(at), "d"(v) : "memory");
+          }
+        }
+        if (MASK) {
+          uint32_t m4 = 0;
+          const uint32_t ma = sm + 4u * tid + 4u * kWinThreads * i;
+          if (!AGG) {
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m4) : "r"(ma));
+          } else {
+            // ACCUM keeps only the mask of V[t-D], AVERAGE the OR of its inputs, COPY its input's, PICK none
+            uint32_t m_a = 0, m_b = 0;
+            if (it.in0 >= 0) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m_a) : "r"(ma));
+            if (it.in1 >= 0) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m_b) : "r"(ma + in_mbytes));
+            m4 = it.kind == G2P_AGG_ACCUM ? m_b : it.kind == G2P_AGG_AVERAGE ? (m_a | m_b) : it.kind == G2P_AGG_COPY ? m_a : 0u;
+          }
+          if (m4) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if ((m4 >> (8 * q)) & 0xffu)
+                asm volatile("st.shared.u64 [%0], %1;" ::"r"(sv + (uint32_t)fdst[i] + 8u * q), "l"(kMaskMarker) : "memory");
+          }
         }
       }
     };
@@ -507,7 +592,7 @@ __global__ void __launch_bounds__(kWinThreads, CORR ? 2 : 3) apply_window_kernel
 
     uint32_t gv_s = val_base;                   // stage of the message being gathered
     uint32_t fv_s = val_base, fm_s = msk_base;  // stage of the message being folded (one ahead)
-    if (MASK) {  // message 0 must be folded before the first gather
+    if (FOLD) {  // message 0 must be folded before the first gather
       cp_async_wait<S - 2>();
       __syncthreads();
       fold(fv_s, fm_s);
@@ -516,11 +601,11 @@ __global__ void __launch_bounds__(kWinThreads, CORR ? 2 : 3) apply_window_kernel
     // ---- messages
     for (int it = 0; it < n_msg; ++it) {
       // masked: message it+1 has landed (it is folded below, one message ahead of the gathers); else message it
-      cp_async_wait<MASK ? S - 3 : S - 2>();
+      cp_async_wait<FOLD ? S - 3 : S - 2>();
       __syncthreads();        // copies / folds of the others are visible; everyone is done with message it-1
       prefetch(pv, pm);       // message it+S-1, into the stage message it-1 used
       advance(pv, pm);
-      if (MASK) {
+      if (FOLD) {
         if (it + 1 < n_msg) fold(fv_s, fm_s);
         advance(fv_s, fm_s);
       }
@@ -552,15 +637,15 @@ __global__ void __launch_bounds__(kWinThreads, CORR ? 2 : 3) apply_window_kernel
   }
 }
 
-static size_t win_smem_bytes(int stages, int stage_elems, int stage_melems, bool mask) {
-  return (size_t)stages * ((size_t)stage_elems * 8 + (mask ? stage_melems : 0));
+static size_t win_smem_bytes(int stages, int stage_elems, int stage_melems, bool mask, int nin) {
+  return (size_t)stages * nin * ((size_t)stage_elems * 8 + (mask ? stage_melems : 0));
 }
 
-template <int K, int MP, int CV, int S, bool CORR>
+template <int K, int MP, int CV, int S, bool CORR, bool AGG>
 static int launch_window_c(const g2p_plan* p, WinArgs a, cudaStream_t st) {
   constexpr bool MASK = MP != 0;
-  const size_t smem = win_smem_bytes(S, a.stage_elems, a.stage_melems, MASK);
-  auto kern = apply_window_kernel<K, MP, CV, S, CORR>;
+  const size_t smem = win_smem_bytes(S, a.stage_elems, a.stage_melems, MASK, AGG ? 2 : 1);
+  auto kern = apply_window_kernel<K, MP, CV, S, CORR, AGG>;
   G2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   G2P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWinThreads, smem));
@@ -583,17 +668,26 @@ static int launch_window_c(const g2p_plan* p, WinArgs a, cudaStream_t st) {
 
 template <int K, int MP, int CV, int S>
 static int launch_window_s(const g2p_plan* p, WinArgs a, cudaStream_t st) {
-  return a.corr_gem ? launch_window_c<K, MP, CV, S, true>(p, a, st) : launch_window_c<K, MP, CV, S, false>(p, a, st);
+  if (a.agg_items) {
+    // the fused pipeline is instantiated for the window sizes it is used with (CV <= 4: windows up to 2048 values)
+    if (CV > 4) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned_fused: window of %d values is too large; use g2p_manip + g2p_apply_planned", p->max_window);
+    if (CV <= 4)
+      return a.corr_gem ? launch_window_c<K, MP, (CV <= 4 ? CV : 2), S, true, true>(p, a, st)
+                        : launch_window_c<K, MP, (CV <= 4 ? CV : 2), S, false, true>(p, a, st);
+  }
+  return a.corr_gem ? launch_window_c<K, MP, CV, S, true, false>(p, a, st) : launch_window_c<K, MP, CV, S, false, false>(p, a, st);
 }
 
 template <int K, int MP, int CV>
 static int launch_window_cv(const g2p_plan* p, WinArgs a, cudaStream_t st) {
-  // four stages when they fit in ~72 KB per CTA (three CTAs per SM), else three (the mask fold runs one
+  // four stages when they fit in ~72 KB per CTA (three CTAs per SM), else three (the fold pass runs one
   // message ahead of the gathers, so three is the minimum)
   // (measured on O1280 -> EFAS, masks: 3 stages 1.25 ms, 4 stages 1.11 ms, 5 stages 1.16 ms, 6 stages 1.25 ms - more
   // shared memory per CTA leaves less L1 for the table and output traffic)
-  if (win_smem_bytes(4, a.stage_elems, a.stage_melems, MP != 0) <= 72 * 1024) return launch_window_s<K, MP, CV, 4>(p, a, st);
-  if (win_smem_bytes(3, a.stage_elems, a.stage_melems, MP != 0) > 220 * 1024)
+  const int nin = a.agg_items ? 2 : 1;
+  if (win_smem_bytes(4, a.stage_elems, a.stage_melems, MP != 0, nin) <= (size_t)(nin == 2 ? 100 : 72) * 1024)
+    return launch_window_s<K, MP, CV, 4>(p, a, st);
+  if (win_smem_bytes(3, a.stage_elems, a.stage_melems, MP != 0, nin) > 220 * 1024)
     return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: window of %d elements does not fit in shared memory", p->max_window);
   return launch_window_s<K, MP, CV, 3>(p, a, st);
 }
@@ -777,7 +871,7 @@ int g2p_plan_get_info(const g2p_plan* p, g2p_plan_info* info) {
 
 static int apply_planned(const g2p_plan* p, const double* coef, const double* src, const uint8_t* src_mask, int b,
                          int64_t src_stride, int64_t out_stride, double mv_out, int mask_policy, const g2p_correction* corr,
-                         double* out, uint8_t* out_mask, void* stream) {
+                         double* out, uint8_t* out_mask, void* stream, const g2p_manip_desc* fused = nullptr, int b_in = 0) {
   if (!p || !src || !out) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: null plan/src/out");
   if (p->k > 1 && !coef) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: coef is required for k > 1");
   if (p->k != 1 && p->k != 4) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: k=%d (1 and 4 are planned; use g2p_apply)", p->k);
@@ -815,6 +909,43 @@ static int apply_planned(const g2p_plan* p, const double* coef, const double* sr
   a.b = b;
   a.n_tiles = p->n_tiles;
   a.mv_out = mv_out;
+  AggItem* d_items = nullptr;
+  if (fused) {
+    // b = number of OUTPUT messages (fused->n_out), src holds b_in input messages
+    if (fused->n_out != b || b_in < 1 || !fused->items) return set_error(G2P_ERR_INVALID, "g2p_apply_planned_fused: bad item list");
+    std::vector<AggItem> items(b);
+    for (int o = 0; o < b; ++o) {
+      const g2p_manip_item& it = fused->items[o];
+      const bool one = it.kind == G2P_AGG_PICK || it.kind == G2P_AGG_COPY;
+      if (it.kind < G2P_AGG_PICK || it.kind > G2P_AGG_COPY || it.n_in < 1 || it.n_in > 2 || (one && it.n_in != 1) ||
+          (it.kind == G2P_AGG_ACCUM && it.n_in != 2))
+        return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned_fused: item %d (kind %d, %d inputs): at most two inputs per output; use g2p_manip", o, it.kind, it.n_in);
+      if (mask && it.mask_all) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned_fused: mask_all items need g2p_manip");
+      AggItem& d = items[o];
+      d.kind = it.kind;
+      d.in0 = it.in[0];
+      d.in1 = it.n_in > 1 ? it.in[1] : -1;
+      d.pad = 0;
+      d.unit_time = it.unit_time;
+      d.divisor = it.divisor;
+      if (d.in0 >= b_in || d.in1 >= b_in || (d.in0 < 0 && it.kind != G2P_AGG_PICK) || (d.in1 < 0 && it.kind == G2P_AGG_AVERAGE && it.n_in > 1))
+        return set_error(G2P_ERR_INVALID, "g2p_apply_planned_fused: item %d references a message outside 0..%d", o, b_in - 1);
+    }
+    G2P_CUDA(cudaMallocAsync(&d_items, items.size() * sizeof(AggItem), as_stream(stream)));
+    // pageable source: the copy is staged before the call returns, `items` may go out of scope
+    cudaError_t e = cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(AggItem), cudaMemcpyHostToDevice, as_stream(stream));
+    if (e != cudaSuccess) {
+      cudaFreeAsync(d_items, as_stream(stream));
+      return cuda_fail(e, "g2p_apply_planned_fused: item upload", __FILE__, __LINE__);
+    }
+    a.agg_items = d_items;
+    a.op1 = fused->conv_op1;
+    a.op2 = fused->conv_op2;
+    a.c1 = fused->conv_c1;
+    a.c2 = fused->conv_c2;
+    a.mv_grib = fused->mv_grib;
+    a.cut_off = fused->cut_off_negative;
+  }
   if (corr) {
     if (!corr->gem || !corr->dem_term || !corr->valid) return set_error(G2P_ERR_INVALID, "g2p_apply_planned_corrected: null correction arrays");
     a.corr_gem = corr->gem;
@@ -823,12 +954,14 @@ static int apply_planned(const g2p_plan* p, const double* coef, const double* sr
     a.corr_mv = corr->mv;
   }
   cudaStream_t st = as_stream(stream);
+  int rc;
   if (p->k == 1) {
-    if (mask_policy == G2P_MASK_PROPAGATE) return launch_window<1, 1>(p, a, st);
-    return mask ? launch_window<1, 2>(p, a, st) : launch_window<1, 0>(p, a, st);
+    rc = mask_policy == G2P_MASK_PROPAGATE ? launch_window<1, 1>(p, a, st) : mask ? launch_window<1, 2>(p, a, st) : launch_window<1, 0>(p, a, st);
+  } else {
+    rc = mask_policy == G2P_MASK_PROPAGATE ? launch_window<4, 1>(p, a, st) : mask ? launch_window<4, 2>(p, a, st) : launch_window<4, 0>(p, a, st);
   }
-  if (mask_policy == G2P_MASK_PROPAGATE) return launch_window<4, 1>(p, a, st);
-  return mask ? launch_window<4, 2>(p, a, st) : launch_window<4, 0>(p, a, st);
+  if (d_items) cudaFreeAsync(d_items, st);
+  return rc;
 }
 
 int g2p_apply_planned(const g2p_plan* p, const double* coef, const double* src, const uint8_t* src_mask, int b,
@@ -842,6 +975,16 @@ int g2p_apply_planned_corrected(const g2p_plan* p, const double* coef, const dou
                                 const g2p_correction* corr, double* out, uint8_t* out_mask, void* stream) {
   if (!corr) return set_error(G2P_ERR_INVALID, "g2p_apply_planned_corrected: corr is null");
   return apply_planned(p, coef, src, src_mask, b, src_stride, out_stride, mv_out, mask_policy, corr, out, out_mask, stream);
+}
+
+int g2p_apply_planned_fused(const g2p_plan* p, const double* coef, const g2p_manip_desc* desc, const double* src,
+                            const uint8_t* src_mask, int b_in, int64_t src_stride, int64_t out_stride, double mv_out,
+                            int mask_policy, const g2p_correction* corr, double* out, uint8_t* out_mask, void* stream) {
+  if (!desc) return set_error(G2P_ERR_INVALID, "g2p_apply_planned_fused: desc is null");
+  for (int op : {desc->conv_op1, desc->conv_op2})
+    if (op < G2P_OP_NONE || op > G2P_OP_DIV) return set_error(G2P_ERR_INVALID, "g2p_apply_planned_fused: unknown conversion op %d", op);
+  return apply_planned(p, coef, src, src_mask, desc->n_out, src_stride, out_stride, mv_out, mask_policy, corr, out, out_mask,
+                       stream, desc, b_in);
 }
 
 }  // extern "C"

@@ -466,10 +466,15 @@ class FusedPipeline:
         self.compact, self.touched = table.compact()
 
     def run(self, src, src_mask, plan, converter=None, cut_off=False, mv_out=NC_FILL_F64,
-            mask_policy=L.MASK_AS_REFERENCE, corrector=None, members=1):
+            mask_policy=L.MASK_AS_REFERENCE, corrector=None, members=1, fused=None):
         """src: device [b, n] float64 (messages in `plan.slots` order; with `members` > 1 the rows are
         member-major: all steps of member 0, then member 1, ... and the plan is applied to each member),
-        src_mask: device uint8 [b, n] or None.  -> out [members * n_out, m] device (+ out_mask under PROPAGATE)."""
+        src_mask: device uint8 [b, n] or None.  -> out [members * n_out, m] device (+ out_mask under PROPAGATE).
+
+        `fused=None` picks the single-launch kernel (g2p_apply_planned_fused) whenever every output combines at
+        most two inputs (accumulation, instantaneous, 1-2 step averages) and the buffers are aligned for the
+        windowed kernel; otherwise - or with `fused=False` - g2p_manip writes compact fields that the apply
+        kernel reads (two launches).  Both give identical bytes."""
         if members == 1:
             src, src_mask = synthesise_steps(plan, src, src_mask)
             items = [it for _, it in plan.outputs]
@@ -480,7 +485,52 @@ class FusedPipeline:
             items = [ManipItem(it.kind, [i + mb * per if i >= 0 else i for i in it.inputs], it.unit_time, it.divisor,
                                it.mask_all) for mb in range(members) for _, it in plan.outputs]
         use_mask = src_mask is not None and mask_policy != L.MASK_AS_REFERENCE
+        policy = mask_policy if use_mask else L.MASK_AS_REFERENCE
+        can_fuse = self._can_fuse(src, src_mask if use_mask else None, items, use_mask)
+        if fused is True and not can_fuse:
+            raise ApplicationException.get_exc(NOT_IMPLEMENTED, 'this plan / these buffers cannot use the fused kernel')
+        self.last_path = 'fused' if (can_fuse and fused is not False) else 'two-kernel'
+        if self.last_path == 'fused':
+            return self._run_fused(src, src_mask if use_mask else None, items, converter, cut_off, mv_out, policy,
+                                   corrector)
         vals, vmask = manip_device(src, src_mask if use_mask else None, items,
                                    converter=converter, cut_off=cut_off, touched=self.touched)
-        return self.compact.apply(vals, float(mv_out), src_mask=vmask, mask_policy=mask_policy if use_mask else
-                                  L.MASK_AS_REFERENCE, correction=corrector)
+        return self.compact.apply(vals, float(mv_out), src_mask=vmask, mask_policy=policy, correction=corrector)
+
+    def _can_fuse(self, src, src_mask, items, use_mask):
+        t = self.table
+        if t.k not in (1, 4) or t.plan() is None or t.plan_info()['max_window'] > 2048:
+            return False
+        n_pad = -(-t.n_src // 16) * 16
+        if src.data_ptr() % 16 or src.stride(0) % 2 or src.stride(0) < n_pad or src.stride(1) != 1:
+            return False
+        if use_mask and (src_mask.data_ptr() % 16 or src.stride(0) % 16 or src_mask.stride(0) != src.stride(0)):
+            return False
+        for it in items:
+            if len(it.inputs) > 2 or (use_mask and it.mask_all):
+                return False
+        return True
+
+    def _run_fused(self, src, src_mask, items, converter, cut_off, mv_out, policy, corrector):
+        lib = device.require_cuda()
+        t = self.table
+        n_out = len(items)
+        carr = (L.ManipItem * max(n_out, 1))(*[it.to_c() for it in items])
+        desc = L.ManipDesc()
+        fields = converter.desc_fields() if converter is not None and not converter.identity else dict(
+            conv_op1=L.OP_NONE, conv_c1=0.0, conv_op2=L.OP_NONE, conv_c2=0.0, mv_grib=0.0)
+        for k, v in fields.items():
+            setattr(desc, k, v)
+        desc.cut_off_negative = 1 if cut_off else 0
+        desc.n_out = n_out
+        desc.items = C.cast(carr, C.POINTER(L.ManipItem))
+        out = torch.empty((n_out, t.m), dtype=torch.float64, device=src.device)
+        omask = torch.empty((n_out, t.m), dtype=torch.uint8, device=src.device) if policy == L.MASK_PROPAGATE else None
+        L.check(lib.g2p_set_device(src.device.index))
+        L.check(lib.g2p_apply_planned_fused(
+            t.plan(), C.c_void_p(t.coef.data_ptr()) if t.k > 1 else None, C.byref(desc), C.c_void_p(src.data_ptr()),
+            C.c_void_p(src_mask.data_ptr()) if src_mask is not None else None, src.shape[0], src.stride(0), out.stride(0),
+            float(mv_out), int(policy), C.byref(corrector.c_struct()) if corrector is not None else None,
+            C.c_void_p(out.data_ptr()), C.c_void_p(omask.data_ptr()) if omask is not None else None,
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return (out, omask) if policy == L.MASK_PROPAGATE else out

@@ -139,9 +139,15 @@ def test_fused_pipeline_matches_oracle_chain(M, kind):
     corr = M.Corrector.from_geopotential(table, z, synth.GRIB_MV, mv_out, dem, float(synth.PCR_MV_F32))
     pipe = M.FusedPipeline(table)
     assert pipe.compact.n_src == pipe.touched.numel() < n
-    src = torch.from_numpy(fields).cuda()
+    n_pad = -(-n // 16) * 16                      # rows padded to 16 values, as the windowed kernels need
+    src = torch.zeros((len(steps), n_pad), dtype=torch.float64, device='cuda')[:, :n]
+    src.copy_(torch.from_numpy(fields))
     got = pipe.run(src, None, plan, converter=conv, cut_off=cut, mv_out=mv_out, corrector=corr).cpu().numpy()
-    assert pipe.compact.last_path == 'window'
+    # accumulation (2 inputs per output) and instantaneous (1) run as ONE launch; the 24-add average needs g2p_manip
+    assert pipe.last_path == ('two-kernel' if kind == 'average' else 'fused')
+    two = pipe.run(src, None, plan, converter=conv, cut_off=cut, mv_out=mv_out, corrector=corr, fused=False).cpu().numpy()
+    assert pipe.last_path == 'two-kernel' and pipe.compact.last_path == 'window'
+    np.testing.assert_array_equal(got, two)
     # ---- oracle chain
     converted = {s: MR.convert(fields[i].copy(), func, synth.GRIB_MV) for i, s in enumerate(steps)}
     if kind == 'accumulation':
@@ -164,8 +170,16 @@ def test_fused_pipeline_matches_oracle_chain(M, kind):
             want = MR.correct(p, dem.ravel(), gem, float(synth.PCR_MV_F32), synth.GRIB_MV)
         np.testing.assert_array_equal(got[o], np.asarray(ma.filled(want)))
     # ---- the same without correction, masks propagated (fill): masked wherever a used input is masked
-    msk = torch.from_numpy(np.broadcast_to(mask, fields.shape).copy().view(np.uint8)).cuda()
+    msk = torch.zeros((len(steps), n_pad), dtype=torch.uint8, device='cuda')[:, :n]
+    msk.copy_(torch.from_numpy(np.broadcast_to(mask, fields.shape).copy().view(np.uint8)))
     got2 = pipe.run(src, msk, plan, converter=conv, cut_off=cut, mv_out=mv_out, mask_policy=L.MASK_FILL).cpu().numpy()
+    two2 = pipe.run(src, msk, plan, converter=conv, cut_off=cut, mv_out=mv_out, mask_policy=L.MASK_FILL, fused=False)
+    np.testing.assert_array_equal(got2, two2.cpu().numpy())
+    p3, m3 = pipe.run(src, msk, plan, converter=conv, cut_off=cut, mv_out=mv_out, mask_policy=L.MASK_PROPAGATE, corrector=corr)
+    q3, n3 = pipe.run(src, msk, plan, converter=conv, cut_off=cut, mv_out=mv_out, mask_policy=L.MASK_PROPAGATE, corrector=corr,
+                      fused=False)
+    np.testing.assert_array_equal(p3.cpu().numpy(), q3.cpu().numpy())
+    np.testing.assert_array_equal(m3.cpu().numpy(), n3.cpu().numpy())
     masked_in = {s: ma.masked_where(mask, converted[s]) for s in steps}
     if kind == 'accumulation':
         refm = MR.accumulation(masked_in, 0, 72, 24, 24)
