@@ -542,9 +542,12 @@ def run_b200(args):
         pms = parallel.max_over_ranks(pms, dev)
         # algorithmic bytes: 2 input steps x 8 B per touched point + 8 B per target and output, + gem/dem/table once
         pbytes = n_out * (2 * 8 * n_touched + 8 * m) + m * (K_INVDIST * 12 + 17)
+        ms_single = timed(lambda: fused.run(psrc, None, plan, converter=conv, cut_off=True, mv_out=synth.NC_FILL_F64,
+                                            corrector=corr, members=members, fused=True), reps=3)
         pipeline = {'metric': 'fused pipeline output messages/s', 'value': n_out * ws / (pms * 1e-3), 'unit': 'messages/s',
                     'ms_per_pass': pms, 'outputs_per_gpu': n_out, 'inputs_per_gpu': int(psrc.shape[0]),
                     'members_per_gpu': members, 'gpu_launches_per_pass': pl,
+                    'ms_per_pass_single_launch_variant': ms_single,
                     'algorithmic_GBps_per_gpu': pbytes / (pms * 1e-3) / 1e9,
                     'frac_of_hbm_peak': pbytes / (pms * 1e-3) / 1e9 / hbm_peak,
                     'workload': 'BASELINE configs[4]: x*1000 -> 24 h accumulation (steps 0..360 by 6 h) -> cut-off -> '

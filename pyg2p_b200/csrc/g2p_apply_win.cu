@@ -59,6 +59,8 @@ struct g2p_plan {
   uint16_t* lidx;      // [k][m]
   g2p::Range* ranges;  // [n_tiles][kMaxRanges]
   int32_t* tile_info;  // [n_tiles][4] = {n_ranges, value window (skewed), mask window (dense), 0}
+  mutable void* item_scratch;       // device copy of the fused pipeline's item list (grown on demand)
+  mutable size_t item_scratch_bytes;
   int max_mwindow;     // largest dense (mask) window
 };
 
@@ -850,6 +852,7 @@ int g2p_plan_destroy(g2p_plan* p) {
   if (p->lidx) cudaFree(p->lidx);
   if (p->ranges) cudaFree(p->ranges);
   if (p->tile_info) cudaFree(p->tile_info);
+  if (p->item_scratch) cudaFree(p->item_scratch);
   delete p;
   return G2P_OK;
 }
@@ -931,13 +934,17 @@ static int apply_planned(const g2p_plan* p, const double* coef, const double* sr
       if (d.in0 >= b_in || d.in1 >= b_in || (d.in0 < 0 && it.kind != G2P_AGG_PICK) || (d.in1 < 0 && it.kind == G2P_AGG_AVERAGE && it.n_in > 1))
         return set_error(G2P_ERR_INVALID, "g2p_apply_planned_fused: item %d references a message outside 0..%d", o, b_in - 1);
     }
-    G2P_CUDA(cudaMallocAsync(&d_items, items.size() * sizeof(AggItem), as_stream(stream)));
-    // pageable source: the copy is staged before the call returns, `items` may go out of scope
-    cudaError_t e = cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(AggItem), cudaMemcpyHostToDevice, as_stream(stream));
-    if (e != cudaSuccess) {
-      cudaFreeAsync(d_items, as_stream(stream));
-      return cuda_fail(e, "g2p_apply_planned_fused: item upload", __FILE__, __LINE__);
+    const size_t need = items.size() * sizeof(AggItem);
+    if (p->item_scratch_bytes < need) {   // one plan is used from one stream at a time (as its table is)
+      if (p->item_scratch) cudaFree(p->item_scratch);
+      p->item_scratch = nullptr;
+      p->item_scratch_bytes = 0;
+      G2P_CUDA(cudaMalloc(&p->item_scratch, need * 2));
+      p->item_scratch_bytes = need * 2;
     }
+    d_items = reinterpret_cast<AggItem*>(p->item_scratch);
+    // pageable source: the copy is staged before the call returns, `items` may go out of scope
+    G2P_CUDA(cudaMemcpyAsync(d_items, items.data(), need, cudaMemcpyHostToDevice, as_stream(stream)));
     a.agg_items = d_items;
     a.op1 = fused->conv_op1;
     a.op2 = fused->conv_op2;
@@ -960,7 +967,6 @@ static int apply_planned(const g2p_plan* p, const double* coef, const double* sr
   } else {
     rc = mask_policy == G2P_MASK_PROPAGATE ? launch_window<4, 1>(p, a, st) : mask ? launch_window<4, 2>(p, a, st) : launch_window<4, 0>(p, a, st);
   }
-  if (d_items) cudaFreeAsync(d_items, st);
   return rc;
 }
 

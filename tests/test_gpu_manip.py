@@ -142,12 +142,15 @@ def test_fused_pipeline_matches_oracle_chain(M, kind):
     n_pad = -(-n // 16) * 16                      # rows padded to 16 values, as the windowed kernels need
     src = torch.zeros((len(steps), n_pad), dtype=torch.float64, device='cuda')[:, :n]
     src.copy_(torch.from_numpy(fields))
-    got = pipe.run(src, None, plan, converter=conv, cut_off=cut, mv_out=mv_out, corrector=corr).cpu().numpy()
-    # accumulation (2 inputs per output) and instantaneous (1) run as ONE launch; the 24-add average needs g2p_manip
-    assert pipe.last_path == ('two-kernel' if kind == 'average' else 'fused')
-    two = pipe.run(src, None, plan, converter=conv, cut_off=cut, mv_out=mv_out, corrector=corr, fused=False).cpu().numpy()
+    F = kind != 'average'      # accumulation (2 inputs per output) and instantaneous (1) can run as ONE launch
+    got = pipe.run(src, None, plan, converter=conv, cut_off=cut, mv_out=mv_out, corrector=corr, fused=F).cpu().numpy()
+    assert pipe.last_path == ('fused' if F else 'two-kernel')
+    two = pipe.run(src, None, plan, converter=conv, cut_off=cut, mv_out=mv_out, corrector=corr).cpu().numpy()
     assert pipe.last_path == 'two-kernel' and pipe.compact.last_path == 'window'
     np.testing.assert_array_equal(got, two)
+    if not F:
+        with pytest.raises(Exception):
+            pipe.run(src, None, plan, converter=conv, cut_off=cut, mv_out=mv_out, corrector=corr, fused=True)
     # ---- oracle chain
     converted = {s: MR.convert(fields[i].copy(), func, synth.GRIB_MV) for i, s in enumerate(steps)}
     if kind == 'accumulation':
@@ -172,10 +175,11 @@ def test_fused_pipeline_matches_oracle_chain(M, kind):
     # ---- the same without correction, masks propagated (fill): masked wherever a used input is masked
     msk = torch.zeros((len(steps), n_pad), dtype=torch.uint8, device='cuda')[:, :n]
     msk.copy_(torch.from_numpy(np.broadcast_to(mask, fields.shape).copy().view(np.uint8)))
-    got2 = pipe.run(src, msk, plan, converter=conv, cut_off=cut, mv_out=mv_out, mask_policy=L.MASK_FILL).cpu().numpy()
+    got2 = pipe.run(src, msk, plan, converter=conv, cut_off=cut, mv_out=mv_out, mask_policy=L.MASK_FILL, fused=F).cpu().numpy()
     two2 = pipe.run(src, msk, plan, converter=conv, cut_off=cut, mv_out=mv_out, mask_policy=L.MASK_FILL, fused=False)
     np.testing.assert_array_equal(got2, two2.cpu().numpy())
-    p3, m3 = pipe.run(src, msk, plan, converter=conv, cut_off=cut, mv_out=mv_out, mask_policy=L.MASK_PROPAGATE, corrector=corr)
+    p3, m3 = pipe.run(src, msk, plan, converter=conv, cut_off=cut, mv_out=mv_out, mask_policy=L.MASK_PROPAGATE, corrector=corr,
+                      fused=F)
     q3, n3 = pipe.run(src, msk, plan, converter=conv, cut_off=cut, mv_out=mv_out, mask_policy=L.MASK_PROPAGATE, corrector=corr,
                       fused=False)
     np.testing.assert_array_equal(p3.cpu().numpy(), q3.cpu().numpy())
