@@ -139,6 +139,13 @@ int g2p_table_pack_rec(const int32_t* idx, const double* coef, int64_t m, int k,
 int g2p_table_unpack_rec(const void* rec, int64_t m, int k, int coeff_dtype, int32_t* idx_out,
                          double* coef_out, void* stream);
 
+/* The source points a table references ("touched"), sorted, and the table renumbered onto them: only those
+ * values of a message are needed downstream (4 % of an O1280 field for the EFAS grid), so g2p_manip gathers
+ * exactly them - also straight out of pinned host memory - and the apply kernels read compact fields.
+ *   touched_out: int32, capacity min(n, m*k); cidx_out: int32 [k][m] (sentinel = nc); nc_out: host.  Synchronises. */
+int g2p_table_compact(const int32_t* idx, int64_t m, int k, int64_t n, int32_t* touched_out, int32_t* cidx_out,
+                      int64_t* nc_out /* host */, void* stream);
+
 /* K7  batched intertable apply.  Replaces Interpolator._interpolate_scipy_append_mv
  * (interpolation/__init__.py:142-162) for `b` messages in one launch.
  *   idx, coef  : SoA table, int32 [k][m], float64 [k][m] (coef may be NULL when k == 1)

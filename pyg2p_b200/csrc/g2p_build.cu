@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_add_kernel(uint32_t* __rest
     if (base + i < n) {
       const uint32_t v = out[base + i] + add;
       out[base + i] = v;
-      cursor[base + i] = v;
+      if (cursor) cursor[base + i] = v;
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = total;
@@ -1035,6 +1035,26 @@ static IndexView view_of(const g2p_index* ix) {
   return v;
 }
 
+// ------------------------------------------------------------------ table compaction (touched source points)
+__global__ void mark_touched_kernel(const int32_t* __restrict__ idx, int64_t total, int64_t n, uint32_t* __restrict__ used) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t v = idx[i];
+    if (v >= 0 && v < n) used[v] = 1u;  // benign race: every writer stores the same value
+  }
+}
+__global__ void list_touched_kernel(const uint32_t* __restrict__ used, const uint32_t* __restrict__ pos, int64_t n,
+                                    int32_t* __restrict__ touched) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
+    if (used[v]) touched[pos[v]] = (int32_t)v;
+}
+__global__ void renumber_kernel(const int32_t* __restrict__ idx, int64_t total, int64_t n, const uint32_t* __restrict__ pos,
+                                int32_t nc, int32_t* __restrict__ cidx) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t v = idx[i];
+    cidx[i] = (v >= 0 && v < n) ? (int32_t)pos[v] : nc;
+  }
+}
+
 }  // namespace g2p
 
 using namespace g2p;
@@ -1205,6 +1225,47 @@ int g2p_weights(int mode, int k, int64_t m, int64_t n_src, double mub, int dtype
   else
     weights_kernel<false><<<grid_for(m, 256), 256, 0, st>>>(mode, k, m, (int32_t)n_src, mub, idx, coef);
   G2P_LAUNCHED();
+  return G2P_OK;
+}
+
+int g2p_table_compact(const int32_t* idx, int64_t m, int k, int64_t n, int32_t* touched_out, int32_t* cidx_out,
+                      int64_t* nc_out, void* stream) {
+  if (!idx || !touched_out || !cidx_out || !nc_out) return set_error(G2P_ERR_INVALID, "g2p_table_compact: null pointer");
+  if (m < 0 || k < 1 || k > 16 || n < 1 || n > 0x7ffffff0LL) return set_error(G2P_ERR_INVALID, "g2p_table_compact: bad sizes");
+  cudaStream_t st = as_stream(stream);
+  const int64_t total = m * k;
+  const int nb = (int)ceil_div(n, kScanBlock);
+  uint32_t *d_used = nullptr, *d_pos = nullptr, *d_bsums = nullptr;
+  G2P_CUDA(pool_alloc(&d_used, (size_t)n * 4, st));
+  G2P_CUDA(pool_alloc(&d_pos, (size_t)(n + 1) * 4, st));
+  G2P_CUDA(pool_alloc(&d_bsums, (size_t)nb * 4, st));
+  G2P_CUDA(cudaMemsetAsync(d_used, 0, (size_t)n * 4, st));
+  if (total > 0) {
+    mark_touched_kernel<<<grid_for(total, 256), 256, 0, st>>>(idx, total, n, d_used);
+    G2P_LAUNCHED();
+  }
+  scan_blocks_kernel<<<nb, kScanThreads, 0, st>>>(d_used, d_pos, n, d_bsums);
+  G2P_LAUNCHED();
+  scan_sums_kernel<<<1, 1024, 0, st>>>(d_bsums, nb);
+  G2P_LAUNCHED();
+  scan_add_kernel<<<nb, kScanThreads, 0, st>>>(d_pos, n, d_bsums, nullptr, 0u);
+  G2P_LAUNCHED();
+  uint32_t last_pos = 0, last_used = 0;
+  G2P_CUDA(cudaMemcpyAsync(&last_pos, d_pos + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+  G2P_CUDA(cudaMemcpyAsync(&last_used, d_used + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+  G2P_CUDA(cudaStreamSynchronize(st));
+  const int64_t nc = (int64_t)last_pos + last_used;
+  list_touched_kernel<<<grid_for(n, 256), 256, 0, st>>>(d_used, d_pos, n, touched_out);
+  G2P_LAUNCHED();
+  if (total > 0) {
+    renumber_kernel<<<grid_for(total, 256), 256, 0, st>>>(idx, total, n, d_pos, (int32_t)nc, cidx_out);
+    G2P_LAUNCHED();
+  }
+  G2P_CUDA(cudaStreamSynchronize(st));
+  pool_free(d_used, (size_t)n * 4);
+  pool_free(d_pos, (size_t)(n + 1) * 4);
+  pool_free(d_bsums, (size_t)nb * 4);
+  *nc_out = nc;
   return G2P_OK;
 }
 

@@ -347,14 +347,17 @@ class DeviceTable:
         Only the source values an intertable references are needed downstream (4 % of an O1280 field for the
         EFAS grid); `g2p_manip` gathers exactly those, and this table reads them back by compact index."""
         if getattr(self, '_compact', None) is None:
-            flat = self.idx.reshape(-1)
-            touched = torch.unique(flat[(flat >= 0) & (flat < self.n_src)])
-            nc = int(touched.numel())
-            pos = torch.searchsorted(touched, self.idx.to(torch.int64).reshape(-1)).reshape(self.idx.shape)
-            inside = (self.idx >= 0) & (self.idx < self.n_src)
-            cidx = torch.where(inside, pos, torch.full_like(pos, nc)).to(torch.int32).contiguous()
+            lib = require_cuda()
+            _bind_device(self.device)
+            with torch.cuda.device(self.device):
+                touched = torch.empty((min(self.n_src, self.k * self.m),), dtype=torch.int32, device=self.device)
+                cidx = torch.empty_like(self.idx)
+                nc = C.c_int64()
+                L.check(lib.g2p_table_compact(_ptr(self.idx), self.m, self.k, self.n_src, _ptr(touched), _ptr(cidx),
+                                              C.byref(nc), _stream()))
+            nc = int(nc.value)
             self._compact = (DeviceTable(cidx, self.coef, nc, coef_f32=self.coef_f32, shape_1d=self.shape_1d,
-                                         grid_shape=self.grid_shape), touched.to(torch.int32).contiguous())
+                                         grid_shape=self.grid_shape), touched[:nc].contiguous())
         return self._compact
 
     def apply(self, src, mv_out, src_mask=None, mask_policy=L.MASK_AS_REFERENCE, out=None, out_mask=None,
