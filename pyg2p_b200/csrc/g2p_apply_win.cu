@@ -723,6 +723,9 @@ int g2p_plan_create(const int32_t* idx, int64_t m, int k, int64_t n, int64_t row
     cols = m;
   }
   if (rows * cols != m) return set_error(G2P_ERR_INVALID, "g2p_plan_create: rows*cols != m");
+  // the windowed kernel keeps byte offsets of source rows (8*n) in int32 and of output rows (8*m) in uint32
+  if (n >= (1LL << 28) || m >= (1LL << 29))
+    return set_error(G2P_ERR_UNSUPPORTED, "g2p_plan_create: grids beyond 2^28 source / 2^29 target points use g2p_apply");
   cudaStream_t st = as_stream(stream);
   g2p_plan* p = new g2p_plan();
   p->m = m;
