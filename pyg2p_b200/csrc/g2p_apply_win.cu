@@ -13,11 +13,17 @@
 //     per range from one warp: the ranges are ~32 values long, 44 bulk copies per tile and message,
 //     and UBLKCP takes its operands from uniform registers, so the issuing warp serialised them at
 //     ~20 instructions each and every other warp waited at the barrier - see profiles/.)
-//   * all threads gather their k neighbours from shared memory (bank-conflict-light because
-//     neighbouring lanes own neighbouring targets), do the no-FMA weighted sum and write the
-//     outputs with 128-bit streaming stores.
+//   * one message ahead of the gathers, a fold pass writes a NaN marker over every staged value
+//     whose mask byte is set, so the inner loop has no mask gathers (a NaN result takes a rare path
+//     that looks for the marker among its operands);
+//   * all threads gather their k neighbours from shared memory - neighbouring lanes own neighbouring
+//     targets, and the plan places the ranges (latitude rings) at offsets skewed by their measured
+//     longitude alignment so that neighbouring rings fall into disjoint bank groups -, do the no-FMA
+//     weighted sum (and optionally the Corrector formula) and write the outputs with streaming stores,
+//     128 contiguous bytes per half-warp.
 // Every source value is read from L2/HBM once per tile instead of once per referencing target, and
-// index/weight registers are loaded once per (tile, message chunk).
+// index/weight registers are loaded once per (tile, message chunk).  Variants by template flag: mask
+// policy, Corrector epilogue (CORR), source-grid stages fused into the fold pass (AGG).
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
