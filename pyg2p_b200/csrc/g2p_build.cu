@@ -4,18 +4,21 @@
 // Replaces ScipyInterpolation.__init__ / interpolate_split / to_3d / _build_nn /
 // _build_weights_invdist (reference src/pyg2p/main/interpolation/scipy_interpolation_lib.py
 // :523-570, :615-663, :665-696, :698-727, :774-812 + :1018-1026) and the scipy cKDTree they
-// call.  Design (DESIGN.md §3):
+// call.  Design (DESIGN.md §4):
 //   * source points are binned into an equi-angular cube-sphere grid (6 faces x G x G cells),
 //     counting-sorted by cell key into 32-byte records {x, y, z, id} so one candidate is one
 //     32-byte sector and one row of cells is one contiguous range of records;
 //   * a query is a cap search: for a radius D the cap {p : |p-q| <= D} is bounded, on each
 //     face it can reach, by an (alpha, beta) rectangle computed from the tangent planes through
-//     the face axes; all cells of the rectangles are scanned by a group of LANES threads with
-//     a register-resident sorted top-(k+1) per lane, merged with group shuffles;
+//     the face axes; all cells of the rectangles are scanned by a group of LANES threads (2 by
+//     default) with a register-resident sorted top-k per lane plus the best distance behind it
+//     (for the tie flags), merged with group shuffles;
 //   * the search ends when the k-th best distance is <= D, so every point that could tie or
 //     beat it has been examined; otherwise D is set to the k-th best (or doubled);
 //   * squared distances are ((dx*dx + dy*dy) + dz*dz) in float64 with separate IEEE ops - the
-//     cKDTree arithmetic - and ordered by (d2, source id).
+//     cKDTree arithmetic - and ordered by (d2, source id);
+//   * lat/lon -> xyz uses double-double sin/cos so that the coordinates equal libm's bit for bit in
+//     99.7 % of the points.
 #include <cfloat>
 #include <climits>
 #include <cmath>
