@@ -179,6 +179,8 @@ typedef struct g2p_plan_info {
   int32_t max_ranges;   /* largest number of index ranges of one tile */
   double mean_window;   /* mean per-tile window, in source values */
   int64_t bytes;        /* device memory held by the plan */
+  int32_t block_rows, block_cols; /* targets owned by one half-warp (1x16, 2x8 or 4x4), chosen per table */
+  double gather_wavefronts;       /* mean shared-memory wavefronts per half-warp gather (1 = conflict-free) */
 } g2p_plan_info;
 
 /* idx: int32 [k][m] device (the SoA table indexes; values >= n are "no value").  Synchronises `stream`. */

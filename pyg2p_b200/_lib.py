@@ -36,7 +36,8 @@ class IndexInfo(C.Structure):
 class PlanInfo(C.Structure):
     _fields_ = [('m', C.c_int64), ('n', C.c_int64), ('k', C.c_int32), ('tile_rows', C.c_int32),
                 ('tile_cols', C.c_int32), ('n_tiles', C.c_int32), ('max_window', C.c_int32),
-                ('max_ranges', C.c_int32), ('mean_window', C.c_double), ('bytes', C.c_int64)]
+                ('max_ranges', C.c_int32), ('mean_window', C.c_double), ('bytes', C.c_int64),
+                ('block_rows', C.c_int32), ('block_cols', C.c_int32), ('gather_wavefronts', C.c_double)]
 
 
 MANIP_MAX_IN = 32

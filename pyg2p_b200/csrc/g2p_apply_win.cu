@@ -7,7 +7,7 @@
 // Here the targets are cut into 2-D tiles of 1024; the source points a tile references form a few
 // contiguous index ranges (pieces of neighbouring latitude rings).  A plan, built once per table,
 // lists those ranges per tile (16-element aligned) and rewrites the table's int32 indexes as
-// uint16 offsets into the tile's window.  The apply kernel then, per (tile, message):
+// uint16 byte offsets into the tile's window.  The apply kernel then, per (tile, message):
 //   * all threads copy the ranges - values and mask bytes - into a shared-memory stage with 16-byte
 //     cp.async (LDGSTS, L2-only), 2-4 stages in flight.  (A first version issued one cp.async.bulk
 //     per range from one warp: the ranges are ~32 values long, 44 bulk copies per tile and message,
@@ -41,7 +41,7 @@ constexpr int kMaxRanges = 96;                           // source index ranges 
 constexpr int kMaxStages = 4;
 constexpr int kBlockElems = 16;                          // range granularity: 16 values = 128 B, 16 mask bytes
 constexpr int kPlanSpanBlocks = 1 << 17;                 // bitmap span per tile: 2 M source elements
-constexpr int kMaxWindowElems = 8192;                    // 16 x 16-byte value chunks per thread and message
+constexpr int kMaxWindowElems = 8176;                    // 16 x 16-byte value chunks per thread and message; byte offsets fit uint16
 constexpr uint16_t kLocalSentinel = 0xffff;
 
 struct __align__(16) Range {
@@ -62,12 +62,15 @@ struct g2p_plan {
   int max_window;      // elements, over tiles
   int max_ranges;
   double mean_window;
-  uint16_t* lidx;      // [k][m]
+  uint16_t* lidx;      // [k][m] byte offsets into the tile's value window (0xffff: no value)
   g2p::Range* ranges;  // [n_tiles][kMaxRanges]
   int32_t* tile_info;  // [n_tiles][4] = {n_ranges, value window (skewed), mask window (dense), 0}
   mutable void* item_scratch;       // device copy of the fused pipeline's item list (grown on demand)
   mutable size_t item_scratch_bytes;
   int max_mwindow;     // largest dense (mask) window
+  int block_cols_log2; // half-warp block shape (TileGeom)
+  int skew_mod, skew_step;
+  double gather_wavefronts;  // mean shared-memory wavefronts per half-warp gather (1 = conflict-free)
 };
 
 namespace g2p {
@@ -76,14 +79,21 @@ namespace g2p {
 struct TileGeom {
   int64_t rows, cols;
   int tile_rows, tile_cols, tiles_c, threads_per_row;
+  int block_cols_log2;  // a half-warp owns a block of (16 >> block_cols_log2) rows x (1 << block_cols_log2) columns
 };
 
-// target columns owned by thread x of a tile row: x, x + T, x + 2T, x + 3T with T = threads per row, so that
-// neighbouring lanes own neighbouring targets: their k-th neighbours are the same or adjacent source points
-// (broadcast / distinct banks in shared memory) and a half-warp stores 128 contiguous bytes
+// The threads of a tile form a grid of tile_rows x T (T = threads per row); thread (tr, x) owns the target
+// columns x, x + T, x + 2T, x + 3T of tile row tr.  A half-warp (the unit a 64-bit shared-memory load is served
+// in) owns a compact block of that grid - 1x16, 2x8 or 4x4 - so that its k-th neighbours are the same or
+// adjacent source points of at most a few rings (broadcast / distinct banks in shared memory); the two
+// half-warps of a warp sit side by side, so a warp stores 2 x 128 (2x8 blocks) contiguous bytes per target slot.
 __device__ __forceinline__ void thread_targets(const TileGeom& g, int tile, int tid, int64_t& r, int64_t (&c)[kWinTPT]) {
   const int ty = tile / g.tiles_c, tx = tile - ty * g.tiles_c;
-  const int tr = tid / g.threads_per_row, x = tid - tr * g.threads_per_row;
+  const int hw = tid >> 4, l = tid & 15;
+  const int bpr = g.threads_per_row >> g.block_cols_log2;  // blocks per row of blocks
+  const int by = hw / bpr, bx = hw - by * bpr;
+  const int tr = by * (16 >> g.block_cols_log2) + (l >> g.block_cols_log2);
+  const int x = (bx << g.block_cols_log2) + (l & ((1 << g.block_cols_log2) - 1));
   r = (int64_t)ty * g.tile_rows + tr;
   const int64_t c0 = (int64_t)tx * g.tile_cols + x;
 #pragma unroll
@@ -101,7 +111,9 @@ struct PlanArgs {
   int32_t* tile_info;
   int32_t* status;  // [0] = first failing reason (0 ok), [1] = max value window, [2] = max ranges, [3] = max mask window
   unsigned long long* total_window;
+  unsigned long long* total_wavefronts;  // shared-memory wavefronts of all half-warp gathers of one message
   int dry;          // only measure (no lidx / ranges written): used to choose the tile shape
+  int skew_mod, skew_step;  // range i goes to bank group skew_step * (i % skew_mod)
 };
 
 __global__ void __launch_bounds__(kWinThreads) plan_kernel(const PlanArgs a) {
@@ -234,9 +246,11 @@ __global__ void __launch_bounds__(kWinThreads) plan_kernel(const PlanArgs a) {
   }
   __syncthreads();
   // ---- skewed shared-memory offsets: with u(r) the position of range r that lines up with position 0 of
-  // range 0, a value at "longitude" x = p - u(r) of ring r goes to bank (x + 8*(r & 1)) mod 16 (8-byte banks):
-  // lanes of a half-warp that read neighbouring rings then hit disjoint bank groups (measured on
-  // O1280 -> EFAS: 1.67 wavefronts per half-warp gather instead of 2.34 with dense offsets).
+  // range 0, a value at "longitude" x = p - u(r) of ring r goes to bank (x + step*(r % mod)) mod 16 (8-byte banks):
+  // lanes of a half-warp that read neighbouring rings then hit disjoint bank groups.  (mod, step) = (2, 8) for
+  // half-warps that own 16 targets of one row (they see 8-9 points of each of two rings), (4, 4) for 2x8 and 4x4
+  // blocks (3-5 points of up to four rings).  O1280 -> EFAS, wavefronts per half-warp gather (tools/bank_sim.py,
+  // the first two confirmed by ncu): dense offsets 2.34, 1x16 + (2, 8) 1.62, 2x8 + (4, 4) 1.41, 4x4 + (4, 4) 1.17.
   if (tid == 0) {
     int u = 0, cur = 0;
     for (int i = 0; i < nr; ++i) {
@@ -249,7 +263,7 @@ __global__ void __launch_bounds__(kWinThreads) plan_kernel(const PlanArgs a) {
         }
         u -= d;
       }
-      int want = ((8 * (i & 1) - u) % 16 + 16) % 16;
+      int want = ((a.skew_step * (i % a.skew_mod) - u) % 16 + 16) % 16;
       want &= ~1;                                   // 16-byte cp.async chunks: even element offsets
       const int off = cur + (((want - cur) % 16) + 16) % 16;
       s_ranges[i].smem_off = off;
@@ -273,20 +287,39 @@ __global__ void __launch_bounds__(kWinThreads) plan_kernel(const PlanArgs a) {
     }
   }
   __syncthreads();
-  if (s_fail || a.dry) return;
-  for (int i = tid; i < nr; i += kWinThreads) a.ranges[(int64_t)tile * kMaxRanges + i] = s_ranges[i];
-  // ---- local offsets
+  if (s_fail) return;
+  if (!a.dry)
+    for (int i = tid; i < nr; i += kWinThreads) a.ranges[(int64_t)tile * kMaxRanges + i] = s_ranges[i];
+  // ---- local offsets; and what the gathers of this layout cost: a 64-bit shared-memory load is served per
+  // half-warp, one wavefront per distinct word on the busiest of the 16 8-byte banks (lanes reading the same
+  // word share it).  The sum over the tile is what the host compares between half-warp block shapes.
+  const int lane = tid & 31, hw_base = lane & 16, hl = lane & 15;
+  unsigned wave_sum = 0;
 #pragma unroll
   for (int t = 0; t < kWinTPT; ++t) {
     const bool ok = r < a.g.rows && c[t] < a.g.cols;
-    if (!ok) continue;
     const int64_t j = r * a.g.cols + c[t];
     for (int kk = 0; kk < a.k; ++kk) {
-      uint16_t l = kLocalSentinel;
-      if (rr[t][kk] >= 0) l = (uint16_t)(s_ranges[rr[t][kk]].smem_off + (my[t][kk] - s_ranges[rr[t][kk]].src_start));
-      a.lidx[(int64_t)kk * a.m + j] = l;
+      uint16_t l = kLocalSentinel;   // the sentinel slot is the last element of a stage: bank 15, like 0xffff
+      if (rr[t][kk] >= 0) l = (uint16_t)(8 * (s_ranges[rr[t][kk]].smem_off + (my[t][kk] - s_ranges[rr[t][kk]].src_start)));
+      if (ok && !a.dry) a.lidx[(int64_t)kk * a.m + j] = l;
+      const unsigned mine = l >> 3;  // the 8-byte word
+      bool first = true;  // no lower lane of the half-warp reads the same word
+      for (int q = 0; q < 16; ++q) {
+        const unsigned other = __shfl_sync(0xffffffffu, mine, hw_base + q);
+        if (q < hl && other == mine) first = false;
+      }
+      int cnt = 0;        // distinct words on this lane's bank
+      for (int q = 0; q < 16; ++q) {
+        const unsigned other = __shfl_sync(0xffffffffu, mine, hw_base + q);
+        const int f = __shfl_sync(0xffffffffu, (int)first, hw_base + q);
+        if (f && ((other ^ mine) & 15u) == 0) ++cnt;
+      }
+      for (int o = 8; o > 0; o >>= 1) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, o));
+      wave_sum += (unsigned)cnt;
     }
   }
+  if (hl == 0) atomicAdd(a.total_wavefronts, (unsigned long long)wave_sum);
 }
 
 // ------------------------------------------------------------------ PTX helpers: cp.async (LDGSTS)
@@ -586,7 +619,7 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
 #pragma unroll
       for (int kk = 0; kk < K; ++kk) {
         const uint16_t l = ok[t] ? __ldg(a.lidx + (int64_t)kk * a.m + j) : kLocalSentinel;
-        li[t][kk] = 8u * ((l == kLocalSentinel) ? (uint32_t)sent : (uint32_t)l);
+        li[t][kk] = (l == kLocalSentinel) ? 8u * (uint32_t)sent : (uint32_t)l;  // byte offsets as the plan stores them
         w[t][kk] = (K > 1 && ok[t]) ? __ldg(a.coef + (int64_t)kk * a.m + j) : 1.0;
       }
       if (CORR) {
@@ -759,20 +792,20 @@ int g2p_plan_create(const int32_t* idx, int64_t m, int k, int64_t n, int64_t row
   int32_t* d_status = nullptr;
   unsigned long long* d_total = nullptr;
   cudaError_t e = cudaMalloc(&p->lidx, (size_t)k * m * sizeof(uint16_t));
-  if (e == cudaSuccess) e = cudaMalloc(&d_status, 4 * sizeof(int32_t) + sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&d_status, 4 * sizeof(int32_t) + 2 * sizeof(unsigned long long));
   if (e != cudaSuccess) {
     g2p_plan_destroy(p);
     return cuda_fail(e, "g2p_plan_create: cudaMalloc", __FILE__, __LINE__);
   }
   d_total = reinterpret_cast<unsigned long long*>(d_status + 4);
-  int32_t status[6] = {0, 0, 0, 0, 0, 0};
-  auto run = [&](Shape sh, int dry) -> cudaError_t {
+  int32_t status[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // + total window (u64) + total gather wavefronts (u64)
+  auto run = [&](Shape sh, int want_rows, int dry) -> cudaError_t {
     p->tile_rows = sh.tr;
     p->tile_cols = sh.tc;
     p->tiles_c = (int)ceil_div(cols, sh.tc);
     p->tiles_r = (int)ceil_div(rows, sh.tr);
     p->n_tiles = p->tiles_c * p->tiles_r;
-    cudaError_t err = cudaMemsetAsync(d_status, 0, 4 * sizeof(int32_t) + sizeof(unsigned long long), st);
+    cudaError_t err = cudaMemsetAsync(d_status, 0, 4 * sizeof(int32_t) + 2 * sizeof(unsigned long long), st);
     if (err != cudaSuccess) return err;
     if (!dry) {
       if (p->ranges) cudaFree(p->ranges);
@@ -796,11 +829,30 @@ int g2p_plan_create(const int32_t* idx, int64_t m, int k, int64_t n, int64_t row
     a.g.tile_cols = sh.tc;
     a.g.tiles_c = p->tiles_c;
     a.g.threads_per_row = sh.tc / kWinTPT;
+    {
+      // half-warp block: `want_rows` rows when the tile has them, the rest of the 16 lanes along the row
+      int br = std::min(want_rows, sh.tr);
+      int bc = std::min(16 / br, a.g.threads_per_row);
+      br = 16 / bc;
+      int lg = 0;
+      while ((1 << lg) < bc) ++lg;
+      p->block_cols_log2 = lg;
+      p->skew_mod = br == 1 ? 2 : 4;
+      p->skew_step = br == 1 ? 8 : 4;
+      if (const char* e = getenv("G2P_WIN_SKEW_MOD")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4) { p->skew_mod = v; p->skew_step = v == 1 ? 0 : 16 / v; }
+      }
+    }
+    a.g.block_cols_log2 = p->block_cols_log2;
+    a.skew_mod = p->skew_mod;
+    a.skew_step = p->skew_step;
     a.lidx = p->lidx;
     a.ranges = p->ranges;
     a.tile_info = p->tile_info;
     a.status = d_status;
     a.total_window = d_total;
+    a.total_wavefronts = d_total + 1;
     a.dry = dry;
     plan_kernel<<<p->n_tiles, kWinThreads, kPlanSpanBlocks / 8, st>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -814,7 +866,7 @@ int g2p_plan_create(const int32_t* idx, int64_t m, int k, int64_t n, int64_t row
   unsigned long long best_total = ~0ull;
   if ((int64_t)ceil_div(cols, 4) * rows > 0x7fffffffLL) e = cudaErrorInvalidValue;
   for (size_t i = 0; e == cudaSuccess && cand.size() > 1 && i < cand.size(); ++i) {
-    e = run(cand[i], 1);
+    e = run(cand[i], 1, 1);
     if (e != cudaSuccess) break;
     unsigned long long total;
     memcpy(&total, &status[4], sizeof(total));
@@ -830,14 +882,38 @@ int g2p_plan_create(const int32_t* idx, int64_t m, int k, int64_t n, int64_t row
     if (best < 0) {
       status[0] = last_fail ? last_fail : 1;
     } else {
-      e = run(cand[best], 0);
+      // half-warp block shape: the one whose gathers take the fewest shared-memory wavefronts on this table
+      // (O1280 -> EFAS: 2x8 blocks 1.41 per half-warp load against 1.62 for 1x16, 0.80 ms against 0.89 ms per 383
+      // messages; on global lat/lon targets, whose rows run along the source rings, 1x16 wins).  4x4 blocks
+      // have still fewer conflicts on projected grids but their stores touch 4 rows per request - measured equal
+      // to 2x8 at best, so they are only used on request (G2P_WIN_BLOCK_ROWS=4).
+      int want_rows = 0;
+      if (const char* ev = getenv("G2P_WIN_BLOCK_ROWS")) want_rows = atoi(ev);
+      if (want_rows != 1 && want_rows != 2 && want_rows != 4) {
+        unsigned long long best_waves = ~0ull;
+        for (int cand_rows : {1, 2}) {
+          if (cand_rows > cand[best].tr) continue;
+          e = run(cand[best], cand_rows, 1);
+          if (e != cudaSuccess) break;
+          unsigned long long waves;
+          memcpy(&waves, &status[6], sizeof(waves));
+          // a 2-row block splits a warp's store over more rows: it must save 10 % of the wavefronts to pay
+          // (GloFAS 0.05 deg: 1.41 against 1.48 per load, yet 0.90 ms against 0.87 ms for 16 messages)
+          if (status[0] == 0 && (double)waves < (cand_rows == 1 ? 1.0 : 0.9) * (double)best_waves) {
+            best_waves = waves;
+            want_rows = cand_rows;
+          }
+        }
+        if (want_rows == 0) want_rows = 1;
+      }
+      if (e == cudaSuccess) e = run(cand[best], want_rows, 0);
     }
   }
   cudaFree(d_status);
   if (e != cudaSuccess) rc = cuda_fail(e, "g2p_plan_create", __FILE__, __LINE__);
   else if (status[0] != 0) {
     static const char* why[] = {"", "a tile's indexes span more than 2 M source points", "a tile needs more than 96 index ranges",
-                                "a tile's window exceeds 8192 source values"};
+                                "a tile's window exceeds 8176 source values"};
     rc = set_error(G2P_ERR_UNSUPPORTED, "g2p_plan_create: table is not windowable (%s); use g2p_apply", why[status[0] & 3]);
   }
   if (rc != G2P_OK) {
@@ -852,6 +928,11 @@ int g2p_plan_create(const int32_t* idx, int64_t m, int k, int64_t n, int64_t row
   p->max_window = status[1];
   p->max_mwindow = status[3];
   p->max_ranges = status[2];
+  {
+    unsigned long long waves;
+    memcpy(&waves, &status[6], sizeof(waves));
+    p->gather_wavefronts = (double)waves / ((double)p->n_tiles * (kWinThreads / 16) * kWinTPT * k);
+  }
   *out = p;
   return G2P_OK;
 }
@@ -877,6 +958,9 @@ int g2p_plan_get_info(const g2p_plan* p, g2p_plan_info* info) {
   info->max_window = p->max_window;
   info->max_ranges = p->max_ranges;
   info->mean_window = p->mean_window;
+  info->block_rows = 16 >> p->block_cols_log2;
+  info->block_cols = 1 << p->block_cols_log2;
+  info->gather_wavefronts = p->gather_wavefronts;
   info->bytes = (int64_t)p->k * p->m * 2 + (int64_t)p->n_tiles * (kMaxRanges * (int64_t)sizeof(Range) + 16);
   return G2P_OK;
 }
@@ -918,6 +1002,7 @@ static int apply_planned(const g2p_plan* p, const double* coef, const double* sr
   a.g.tile_cols = p->tile_cols;
   a.g.tiles_c = p->tiles_c;
   a.g.threads_per_row = p->tile_cols / kWinTPT;
+  a.g.block_cols_log2 = p->block_cols_log2;
   a.b = b;
   a.n_tiles = p->n_tiles;
   a.mv_out = mv_out;
