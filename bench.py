@@ -579,7 +579,7 @@ def run_b200(args):
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': workload_config(B),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                         'frac': achieved / hbm_peak, 'traffic': traffic, 'kernel': 'g2p::apply_window_kernel<4, true>' if table.last_path == 'window'
+                         'frac': achieved / hbm_peak, 'traffic': traffic, 'kernel': 'g2p::apply_window_kernel<4, 1, CV, 4, false, false>' if table.last_path == 'window'
                          else 'g2p::apply_kernel<4, true>', 'plan': table.plan_info() or table.plan_error,
                          'algorithmic_bytes_per_launch': bytes_launch, 'avg_launch_ms': avg_kernel_ms,
                          'launch_ms_min_median_max': [float(np.min(kern_ms)), float(np.median(kern_ms)), float(np.max(kern_ms))],
