@@ -206,24 +206,32 @@ int g2p_apply_planned(const g2p_plan* plan, const double* coef, const double* sr
  *   PICK     out = 0.0 + c(V[in0])                         (instantaneous; in0 < 0: zeros)
  *   ACCUM    out = ((0.0 + c(V[in0])) - c(V[in1])) * unit_time / divisor      (in1 < 0: zeros at step 0)
  *   AVERAGE  out = (0.0 + c(V[in0]) + c(V[in1]) + ...) / divisor              (one add per hourly iterator)
+ *   WAVERAGE out = (0.0 + c(V[in0])*w0 + c(V[in1])*w1 + ...) / divisor        (`@halfweights` average, aggregator.py:
+ *            186-207: w = w_edge for the first / last input when edge_mask bit 0 / 1 is set, else unit_time (the
+ *            mid weight); a masked input value is added unweighted, as numpy.ma's multiply leaves it; n_in = 0 and
+ *            divisor = 0 give the reference's 0/0 = NaN field when fewer than two steps fall in the window)
  *   COPY     out = c(V[in0]), mask = mask(V[in0])   (no aggregation: the plain compaction of a message;
  *            `src` / `src_mask` may then be PINNED HOST memory - the kernel reads the touched values
  *            over PCIe and nothing else of the field ever crosses the bus)
  * out_mask follows the reference literally: ACCUM keeps only the mask of V[in1] (the current step loses its
- * mask in `v_iter_ma += V[t]`, aggregator.py:142-148), AVERAGE the OR of its inputs - of ALL b_in messages
- * when mask_all is set, which is what _average does (:232) -, PICK none (:264-276).  With `touched` (device, int32[nc], sorted source indexes) the
+ * mask in `v_iter_ma += V[t]`, aggregator.py:142-148), PICK none (:264-276); AVERAGE / WAVERAGE by mask_all:
+ * -1 none - what _average really returns, because `numeric.get_masks(v_ord.values())` (:232) passes the dict view
+ * as ONE argument and gets no mask -, 0 the OR of the item's inputs, 1 the OR of ALL b_in messages (what :231
+ * says it intends).  With `touched` (device, int32[nc], sorted source indexes) the
  * outputs are compact fields out[o][c] = manip(V[..][touched[c]]); NULL = whole grid (nc = n). */
 #define G2P_MANIP_MAX_IN 32
 enum { G2P_OP_NONE = 0, G2P_OP_MUL = 1, G2P_OP_ADD = 2, G2P_OP_DIV = 3 };
-enum { G2P_AGG_PICK = 0, G2P_AGG_ACCUM = 1, G2P_AGG_AVERAGE = 2, G2P_AGG_COPY = 3 };
+enum { G2P_AGG_PICK = 0, G2P_AGG_ACCUM = 1, G2P_AGG_AVERAGE = 2, G2P_AGG_COPY = 3, G2P_AGG_WAVERAGE = 4 };
 
 typedef struct g2p_manip_item {
   int32_t kind;                     /* G2P_AGG_* */
-  int32_t n_in;                     /* PICK / COPY 1, ACCUM 2, AVERAGE 1..G2P_MANIP_MAX_IN */
+  int32_t n_in;                     /* PICK / COPY 1, ACCUM 2, AVERAGE 1..G2P_MANIP_MAX_IN, WAVERAGE 0..G2P_MANIP_MAX_IN */
   int32_t in[G2P_MANIP_MAX_IN];     /* input message numbers, in the order they are added */
   int32_t mask_all;
-  double unit_time;                 /* ACCUM */
-  double divisor;                   /* ACCUM: aggregation step; AVERAGE: count */
+  int32_t edge_mask;                /* WAVERAGE: bit 0 / 1 = the first / last input carries w_edge */
+  double unit_time;                 /* ACCUM: unit time; WAVERAGE: the mid weight dt1 */
+  double divisor;                   /* ACCUM: aggregation step; AVERAGE: count; WAVERAGE: sum of the weights */
+  double w_edge;                    /* WAVERAGE: the half weight dt1/2 */
 } g2p_manip_item;
 
 typedef struct g2p_manip_desc {

@@ -103,7 +103,7 @@ def accumulation(values, start, end, aggr_step, unit_time, force_zero=False):
 
 def average(values, start, end, aggr_step, second_t_res=False):
     """aggregator.py:155-236 (no half weights): one add per hourly iterator, next available
-    step when an hour is absent, divide by the count, mask = OR of ALL inputs (:232)."""
+    step when an hour is absent, divide by the count; the result is NOT masked (see the note at the end)."""
     v_ord = dict(sorted(values.items()))
     shape = next(iter(v_ord.values())).shape
     if start == 0 or second_t_res:
@@ -123,7 +123,46 @@ def average(values, start, end, aggr_step, second_t_res=False):
             cnt += 1
             acc = acc + ma.getdata(v)
         res = acc / cnt
-        out[(t, t + aggr_step)] = ma.masked_where(_masks(*v_ord.values()), res, copy=False)
+        # `numeric.get_masks(v_ord.values())` (:232): ONE argument, the dict view, no MaskedArray -> mask None
+        out[(t, t + aggr_step)] = ma.masked_where(None, res, copy=False)
+    return out
+
+
+def average_halfweights(values, start, end, aggr_step, second_t_res=False):
+    """aggregator.py:155-236 with `aggr_halfweights` (:176-207): window [t, t+D] inclusive, only the steps present
+    in the input, weights dt1 = D / (present - 1), dt1 / 2 for the window's first and last hour; `v * dt` on a
+    MaskedArray leaves masked elements unmultiplied (numpy.ma binary operations copy the first operand's data back
+    under the mask); sum / sum of the weights (0/0 = NaN when fewer than two steps are present); not masked."""
+    v_ord = dict(sorted(values.items()))
+    shape = next(iter(v_ord.values())).shape
+    if start == 0 or second_t_res:
+        it0, it1 = start, end - aggr_step + 2
+    else:
+        it0, it1 = start - aggr_step, end - aggr_step + 1
+    out = {}
+    keys = list(v_ord.keys())
+    for t in range(it0, it1, aggr_step):
+        iter_from, iter_to = t, t + aggr_step + 1
+        acc = np.zeros(shape)
+        cnt = 0.0
+        count_steps = sum(1 for h in range(iter_from, iter_to) if h in keys) - 1
+        if count_steps > 0:
+            dt1 = aggr_step / count_steps
+            dt2 = dt1 / 2
+            for h in range(iter_from, iter_to):
+                if h not in keys:
+                    continue
+                w = dt2 if (h == iter_from or h == iter_to - 1) else dt1
+                v = v_ord[h]
+                data = np.asarray(ma.getdata(v), dtype=np.float64)
+                vm = data * w
+                if isinstance(v, ma.MaskedArray) and v.mask is not ma.nomask:
+                    vm = np.where(ma.getmaskarray(v), data, vm)
+                cnt += w
+                acc = acc + vm
+        with np.errstate(all='ignore'):
+            res = acc / cnt if cnt != 0.0 else acc / np.float64(0.0)
+        out[(t, t + aggr_step)] = ma.masked_where(None, res, copy=False)   # unmasked, see average()
     return out
 
 

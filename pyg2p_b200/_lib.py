@@ -42,12 +42,12 @@ class PlanInfo(C.Structure):
 
 MANIP_MAX_IN = 32
 OP_NONE, OP_MUL, OP_ADD, OP_DIV = 0, 1, 2, 3
-AGG_PICK, AGG_ACCUM, AGG_AVERAGE, AGG_COPY = 0, 1, 2, 3
+AGG_PICK, AGG_ACCUM, AGG_AVERAGE, AGG_COPY, AGG_WAVERAGE = 0, 1, 2, 3, 4
 
 
 class ManipItem(C.Structure):
     _fields_ = [('kind', C.c_int32), ('n_in', C.c_int32), ('inputs', C.c_int32 * MANIP_MAX_IN), ('mask_all', C.c_int32),
-                ('unit_time', C.c_double), ('divisor', C.c_double)]
+                ('edge_mask', C.c_int32), ('unit_time', C.c_double), ('divisor', C.c_double), ('w_edge', C.c_double)]
 
 
 class ManipDesc(C.Structure):

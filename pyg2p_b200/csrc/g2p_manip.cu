@@ -4,7 +4,8 @@
 // Replaces, for all output messages of a run in one launch,
 //   Converter.convert           where(x != mv, f(x), mv)              (manipulation/conversion.py:21,33-42)
 //   Aggregator._accumulation    ((0.0 + V[t]) - V[t-D]) * unit / D    (manipulation/aggregator.py:72-153)
-//   Aggregator._average         (0.0 + V[i1] + V[i2] + ...) / count   (:155-236), one add per hourly iterator
+//   Aggregator._average         (0.0 + V[i1] + V[i2] + ...) / count   (:155-236), one add per hourly iterator;
+//                               with `@halfweights` (0.0 + V[i1]*dt/2 + V[i2]*dt + ... + V[ik]*dt/2) / sum(dt)
 //   Aggregator._instantaneous   0.0 + V[t]                            (:244-279)
 //   Converter.cut_off_negative  where(v < 0, 0, v)                    (conversion.py:44-52)
 // in the reference's evaluation order (numexpr evaluates left to right in float64; every operation below
@@ -24,9 +25,9 @@ namespace g2p {
 constexpr int kManipMaxIn = G2P_MANIP_MAX_IN;
 
 struct ManipItem {       // device copy of g2p_manip_item
-  int kind, n_in, mask_all, pad;
+  int kind, n_in, mask_all, edge_mask;
   int in[kManipMaxIn];
-  double unit_time, divisor;
+  double unit_time, divisor, w_edge;
 };
 
 struct ManipArgs {
@@ -72,6 +73,18 @@ __device__ __forceinline__ double manip_point(const ManipArgs& a, const ManipIte
     double s = 0.0;
     for (int q = 0; q < it.n_in; ++q) s = __dadd_rn(s, convert(a, __ldg(a.src + (int64_t)it.in[q] * a.src_stride + i)));
     res = __ddiv_rn(s, it.divisor);
+  } else if (it.kind == G2P_AGG_WAVERAGE) {
+    // `@halfweights`: v_ma = V[h] * dt (dt/2 for the first and last hour of the window); temp_sum += v_ma;
+    // / sum of the weights (:186-207, :230).  V[h] * dt on a MaskedArray leaves the masked elements unmultiplied.
+    double s = 0.0;
+    for (int q = 0; q < it.n_in; ++q) {
+      const int64_t at = (int64_t)it.in[q] * a.src_stride + i;
+      const double x = convert(a, __ldg(a.src + at));
+      const bool edge = (q == 0 && (it.edge_mask & 1)) || (q == it.n_in - 1 && (it.edge_mask & 2));
+      const bool masked = a.src_mask && __ldg(a.src_mask + at) != 0;
+      s = __dadd_rn(s, masked ? x : __dmul_rn(x, edge ? it.w_edge : it.unit_time));
+    }
+    res = __ddiv_rn(s, it.divisor);
   } else if (it.kind == G2P_AGG_COPY) {
     res = convert(a, a.src[(int64_t)it.in[0] * a.src_stride + i]);
   } else {
@@ -81,13 +94,16 @@ __device__ __forceinline__ double manip_point(const ManipArgs& a, const ManipIte
   if (a.cut_off && res < 0.0) res = 0.0;  // where(v < 0, 0, v): NaN stays NaN
   mk = 0;
   if (a.src_mask) {
-    if (it.mask_all == 1) {  // _average masks with the OR of ALL inputs of the run (aggregator.py:232)
+    if (it.mask_all < 0) {
+      // what _average really returns: `numeric.get_masks(v_ord.values())` (aggregator.py:232) hands get_masks ONE
+      // argument, the dict view, which is no MaskedArray - the mask is None and the averages come out unmasked
+    } else if (it.mask_all == 1) {  // the OR of ALL inputs of the run (what the comment at aggregator.py:231 intends)
       for (int q = 0; q < a.b_in; ++q) mk |= __ldg(a.src_mask + (int64_t)q * a.src_stride + i);
     } else if (it.kind == G2P_AGG_ACCUM) {
       // the current step is copied into a fresh ndarray (`v_iter_ma += V[t]`, :142-143) and loses its
       // mask there: only the mask of V[t-D] survives (:148)
       if (it.in[1] >= 0) mk = __ldg(a.src_mask + (int64_t)it.in[1] * a.src_stride + i);
-    } else if (it.kind == G2P_AGG_AVERAGE) {
+    } else if (it.kind == G2P_AGG_AVERAGE || it.kind == G2P_AGG_WAVERAGE) {
       for (int q = 0; q < it.n_in; ++q) mk |= __ldg(a.src_mask + (int64_t)it.in[q] * a.src_stride + i);
     } else if (it.kind == G2P_AGG_COPY) {
       mk = a.src_mask[(int64_t)it.in[0] * a.src_stride + i];
@@ -189,14 +205,15 @@ int g2p_manip(const g2p_manip_desc* desc, const double* src, const uint8_t* src_
   std::vector<ManipItem> items(desc->n_out);
   for (int o = 0; o < desc->n_out; ++o) {
     const g2p_manip_item& s = desc->items[o];
-    if (s.kind < G2P_AGG_PICK || s.kind > G2P_AGG_COPY) return set_error(G2P_ERR_INVALID, "g2p_manip: item %d: unknown kind %d", o, s.kind);
+    if (s.kind < G2P_AGG_PICK || s.kind > G2P_AGG_WAVERAGE) return set_error(G2P_ERR_INVALID, "g2p_manip: item %d: unknown kind %d", o, s.kind);
     const int need = s.kind == G2P_AGG_ACCUM ? 2 : ((s.kind == G2P_AGG_PICK || s.kind == G2P_AGG_COPY) ? 1 : s.n_in);
-    if (s.n_in != need || need < 1 || need > kManipMaxIn) return set_error(G2P_ERR_INVALID, "g2p_manip: item %d: n_in = %d", o, s.n_in);
+    if (s.n_in != need || need < (s.kind == G2P_AGG_WAVERAGE ? 0 : 1) || need > kManipMaxIn) return set_error(G2P_ERR_INVALID, "g2p_manip: item %d: n_in = %d", o, s.n_in);
     ManipItem& d = items[o];
     d.kind = s.kind;
     d.n_in = s.n_in;
     d.mask_all = s.mask_all;
-    d.pad = 0;
+    d.edge_mask = s.edge_mask;
+    d.w_edge = s.w_edge;
     for (int q = 0; q < kManipMaxIn; ++q) {
       d.in[q] = q < s.n_in ? s.in[q] : -1;
       if (q < s.n_in && (s.in[q] >= b_in || (s.in[q] < 0 && !(s.kind == G2P_AGG_ACCUM && q == 1) && s.kind != G2P_AGG_PICK)))

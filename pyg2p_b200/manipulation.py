@@ -144,8 +144,9 @@ class Converter:
 class ManipItem:
     """one output message of g2p_manip."""
 
-    def __init__(self, kind, inputs, unit_time=0.0, divisor=1.0, mask_all=0):
+    def __init__(self, kind, inputs, unit_time=0.0, divisor=1.0, mask_all=0, w_edge=0.0, edge_mask=0):
         self.kind, self.inputs, self.unit_time, self.divisor, self.mask_all = kind, list(inputs), unit_time, divisor, mask_all
+        self.w_edge, self.edge_mask = w_edge, edge_mask
 
     @classmethod
     def pick(cls, i):
@@ -160,6 +161,7 @@ class ManipItem:
         for q, v in enumerate(self.inputs):
             it.inputs[q] = v
         it.unit_time, it.divisor = float(self.unit_time), float(self.divisor)
+        it.w_edge, it.edge_mask = float(self.w_edge), int(self.edge_mask)
         return it
 
 
@@ -222,9 +224,11 @@ def plan_accumulation(steps, start, end, aggr_step, unit_time, force_zero=False)
     return plan
 
 
-def plan_average(steps, start, end, aggr_step, second_t_res=False):
+def plan_average(steps, start, end, aggr_step, second_t_res=False, mask_all=-1):
     """aggregator.py:155-236 without half weights: one add per hourly iterator, the next available step when an
-    hour is absent, divided by the count; masked with the OR of all inputs."""
+    hour is absent, divided by the count.  `mask_all` = -1: unmasked, as the reference's averages are (its
+    `get_masks(v_ord.values())`, :232, receives the dict view as one argument and returns None); 1: the OR of all
+    inputs that line intends."""
     keys = sorted(steps)
     plan = AggregationPlan(keys)
     if start == 0 or second_t_res:
@@ -235,7 +239,36 @@ def plan_average(steps, start, end, aggr_step, second_t_res=False):
         ins = []
         for h in range(t + 1, t + aggr_step + 1):
             ins.append(plan.slot(h if h in keys else keys[bisect.bisect_left(keys, h)]))
-        plan.outputs.append(((t, t + aggr_step), ManipItem(L.AGG_AVERAGE, ins, divisor=float(len(ins)), mask_all=1)))
+        plan.outputs.append(((t, t + aggr_step), ManipItem(L.AGG_AVERAGE, ins, divisor=float(len(ins)), mask_all=mask_all)))
+    return plan
+
+
+def plan_average_halfweights(steps, start, end, aggr_step, second_t_res=False, mask_all=-1):
+    """aggregator.py:155-236 with `@halfweights` (:176-207): the window includes its first hour, only the steps
+    PRESENT in the input are added (no next-available substitution), each weighted dt1 = aggr_step / (present - 1),
+    the window's first and last hour dt1 / 2; divided by the sum of the weights; mask as in plan_average.
+    Fewer than two present steps: nothing is added and the reference's 0/0 gives a NaN field."""
+    keys = sorted(steps)
+    plan = AggregationPlan(keys)
+    if start == 0 or second_t_res:
+        it0, it1 = start, end - aggr_step + 2
+    else:
+        it0, it1 = start - aggr_step, end - aggr_step + 1
+    for t in range(it0, it1, aggr_step):
+        iter_from, iter_to = t, t + aggr_step + 1
+        present = [h for h in range(iter_from, iter_to) if h in keys]
+        count_steps = len(present) - 1
+        ins, dt1, dt2, edge, sum_counter = [], 0.0, 0.0, 0, 0.0
+        if count_steps > 0:
+            dt1 = aggr_step / count_steps
+            dt2 = dt1 / 2
+            for h in present:
+                is_edge = h == iter_from or h == iter_to - 1
+                sum_counter += dt2 if is_edge else dt1
+                ins.append(plan.slot(h))
+            edge = (1 if present[0] == iter_from else 0) | (2 if present[-1] == iter_to - 1 else 0)
+        item = ManipItem(L.AGG_WAVERAGE, ins, unit_time=dt1, divisor=sum_counter, mask_all=mask_all, w_edge=dt2, edge_mask=edge)
+        plan.outputs.append(((t, t + aggr_step), item))
     return plan
 
 
@@ -290,7 +323,8 @@ class Aggregator:
                 NOT_IMPLEMENTED, details=f'Manipulation {self._aggregation} for parameter type: {self._step_type}')
         if self._aggregation == AVERAGE:
             if self._aggregation_halfweights:
-                raise ApplicationException.get_exc(NOT_IMPLEMENTED, 'average with half weights on the GPU path')
+                return plan_average_halfweights(end_steps, self._start, self._end, self._aggregation_step,
+                                                bool(self._second_t_res))
             return plan_average(end_steps, self._start, self._end, self._aggregation_step, bool(self._second_t_res))
         return plan_instantaneous(end_steps, self._start, self._end, self._aggregation_step, self._input_step,
                                   self._step_type)
@@ -487,7 +521,7 @@ class FusedPipeline:
                 raise ApplicationException.get_exc(NOT_IMPLEMENTED, 'synthesised steps with members > 1')
             per = len(plan.slots)
             items = [ManipItem(it.kind, [i + mb * per if i >= 0 else i for i in it.inputs], it.unit_time, it.divisor,
-                               it.mask_all) for mb in range(members) for _, it in plan.outputs]
+                               it.mask_all, it.w_edge, it.edge_mask) for mb in range(members) for _, it in plan.outputs]
         use_mask = src_mask is not None and mask_policy != L.MASK_AS_REFERENCE
         policy = mask_policy if use_mask else L.MASK_AS_REFERENCE
         can_fuse = self._can_fuse(src, src_mask if use_mask else None, items, use_mask)
@@ -511,7 +545,7 @@ class FusedPipeline:
         if use_mask and (src_mask.data_ptr() % 16 or src.stride(0) % 16 or src_mask.stride(0) != src.stride(0)):
             return False
         for it in items:
-            if len(it.inputs) > 2 or (use_mask and it.mask_all):
+            if len(it.inputs) > 2 or it.kind == L.AGG_WAVERAGE or (use_mask and it.mask_all):
                 return False
         return True
 

@@ -274,6 +274,18 @@ def make_manip_cases():
 
     run('avg_full', ivals(steps), aggr_type='average', step_type='instant', start_step=0, end_step=72)
     run('avg_start24', ivals(steps), aggr_type='average', step_type='instant', start_step=24, end_step=72)
+    # `@halfweights` averages (reference tests/test_aggregator.py:57): full, later start, a missing step, masked inputs
+    half = dict(aggr_type='average', step_type='instant', aggr_halfweights=True)
+
+    def mvals(stepset):
+        return {Step(s, s, res, 6, 0): ma.masked_where(mask, inst[steps.index(s)].copy(), copy=True) for s in stepset}
+
+    run('avgh_full', ivals(steps), start_step=0, end_step=72, **half)
+    run('avgh_start24', ivals(steps), start_step=24, end_step=72, **half)
+    run('avgh_gap', ivals([s for s in steps if s not in (24, 54)]), start_step=0, end_step=72, **half)
+    run('avgh_masked', mvals(steps), start_step=0, end_step=72, **half)
+    run('avgh_step12', ivals(steps), start_step=12, end_step=72, aggr_step=12, **half)
+    run('avg_masked', mvals(steps), aggr_type='average', step_type='instant', start_step=0, end_step=72)
     run('inst_full', ivals(steps), aggr_type='instantaneous', step_type='instant', start_step=0, end_step=72,
         aggr_step=12)
     run('inst_gap', ivals([s for s in steps if s not in (0, 36)]), aggr_type='instantaneous',

@@ -83,6 +83,17 @@ def test_aggregator_matches_reference(M, g):
     iv = dict(aggr_type='average', step_type='instant')
     _check(g, 'avg_full', agg(**iv).do_manipulation(vals(steps, inst, start_is_end=True)))
     _check(g, 'avg_start24', agg(start_step=24, **iv).do_manipulation(vals(steps, inst, start_is_end=True)))
+    _check(g, 'avg_masked', agg(**iv).do_manipulation(vals(steps, inst, masked=True, start_is_end=True)))
+    # `@halfweights` (reference tests/test_aggregator.py:57-77): window incl. its first hour, half weights at both ends
+    ih = dict(aggr_halfweights=True, **iv)
+    _check(g, 'avgh_full', agg(**ih).do_manipulation(vals(steps, inst, start_is_end=True)))
+    _check(g, 'avgh_start24', agg(start_step=24, **ih).do_manipulation(vals(steps, inst, start_is_end=True)))
+    _check(g, 'avgh_gap', agg(**ih).do_manipulation(vals([s for s in steps if s not in (24, 54)], inst, start_is_end=True)))
+    _check(g, 'avgh_masked', agg(**ih).do_manipulation(vals(steps, inst, masked=True, start_is_end=True)))
+    _check(g, 'avgh_step12', agg(aggr_step=12, start_step=12, **ih).do_manipulation(vals(steps, inst, start_is_end=True)))
+    # fewer than two steps inside a window: the reference divides 0 by 0
+    lone = agg(aggr_step=3, start_step=3, end_step=6, **ih).do_manipulation(vals(steps, inst, start_is_end=True))
+    assert all(np.isnan(np.asarray(v)).all() for v in lone.values()) and len(lone) == 2
     ii = dict(aggr_type='instantaneous', step_type='instant', aggr_step=12)
     _check(g, 'inst_full', agg(**ii).do_manipulation(vals(steps, inst, start_is_end=True)))
     _check(g, 'inst_gap', agg(**ii).do_manipulation(vals([s for s in steps if s not in (0, 36)], inst, start_is_end=True)))

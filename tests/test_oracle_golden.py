@@ -132,6 +132,13 @@ def test_manipulation_matches_reference(golden_dir):
     check('acc_step12_unit6', MR.accumulation(vals(steps), 12, 72, 12, 6))
     check('avg_full', MR.average(vals(steps, inst), 0, 72, 24))
     check('avg_start24', MR.average(vals(steps, inst), 24, 72, 24))
+    check('avg_masked', MR.average(vals(steps, inst, masked=True), 0, 72, 24))      # the reference's averages carry no mask
+    # `@halfweights` (reference tests/test_aggregator.py:57-77)
+    check('avgh_full', MR.average_halfweights(vals(steps, inst), 0, 72, 24))
+    check('avgh_start24', MR.average_halfweights(vals(steps, inst), 24, 72, 24))
+    check('avgh_gap', MR.average_halfweights(vals([s for s in steps if s not in (24, 54)], inst), 0, 72, 24))
+    check('avgh_masked', MR.average_halfweights(vals(steps, inst, masked=True), 0, 72, 24))
+    check('avgh_step12', MR.average_halfweights(vals(steps, inst), 12, 72, 12))
     check('inst_full', MR.instantaneous(vals(steps, inst), 0, 72, 12, input_step=6))
     check('inst_gap', MR.instantaneous(vals([s for s in steps if s not in (0, 36)], inst), 0, 72, 12, input_step=6))
     out = MR.correct(g['corr_p'].copy(), g['corr_dem'], g['corr_gem'], float(g['corr_dem_mv']), float(g['corr_gem_mv']))
