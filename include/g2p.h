@@ -273,6 +273,30 @@ int g2p_apply_planned_corrected(const g2p_plan* plan, const double* coef, const 
                                 const g2p_correction* corr /* host struct of device pointers */, double* out,
                                 uint8_t* out_mask, void* stream);
 
+/* What the writers do to an interpolated (and corrected) field before it reaches the file, per target
+ * (writers/__init__.py:66 `out_v[out_v == mv_output] = nan`; writers/netcdf.py:149-151,170-183 and writers/pcr.py:
+ * 32-34,44-50 `_mask_values` + `values[isnan(values)] = mv`):
+ *   out = (clone_mask | value mask | isnan(v) | (use_match & v == mv_match)) ? mv_write : v
+ * clone_mask = missing cells of the clone map (nullable), mv_match = the Interpolator's mv_output (netCDF path
+ * only: use_match), mv_write = missing value of the file (netCDF: fill value * scale_factor + offset; PCRaster:
+ * nodata of the clone map).  g2p_writer_post_apply runs it in place on [b][m] fields (mask nullable = the
+ * PROPAGATE out_mask); g2p_apply_planned_post runs it - after the optional correction - in the epilogue of the
+ * windowed apply kernel, so the fields leave the device ready for the writer and no mask array has to follow them. */
+typedef struct g2p_writer_post {
+  const uint8_t* clone_mask;  /* device, m; nullable */
+  double mv_match;
+  int32_t use_match;
+  double mv_write;
+} g2p_writer_post;
+
+int g2p_writer_post_apply(double* values, const uint8_t* mask, int64_t m, int b, int64_t stride,
+                          const g2p_writer_post* post /* host struct */, void* stream);
+/* as g2p_apply_planned_corrected; corr and post are both optional (NULL) */
+int g2p_apply_planned_post(const g2p_plan* plan, const double* coef, const double* src, const uint8_t* src_mask, int b,
+                           int64_t src_stride, int64_t out_stride, double mv_out, int mask_policy,
+                           const g2p_correction* corr, const g2p_writer_post* post, double* out, uint8_t* out_mask,
+                           void* stream);
+
 /* The whole pipeline in ONE launch: convert -> aggregate -> cut-off (in the staging step of the windowed
  * apply kernel, on exactly the source values the tile gathers) -> interpolate -> correct.  `desc` as for
  * g2p_manip, with at most two inputs per output item (PICK, COPY, ACCUM, AVERAGE of <= 2) and no mask_all items

@@ -275,3 +275,21 @@ def apply_grib_invdist(v, rec, shape, mv_out):
     res = v[ind[2]] * cf[0] + v[ind[3]] * cf[1] + v[ind[4]] * cf[2] + v[ind[5]] * cf[3]
     result[ind[0], ind[1]] = _result_masked(res, mv_out)
     return result
+
+
+def writer_post(values, clone_mask, mv_write, mv_output=None, value_mask=None):
+    """What the writers do to an interpolated field before it reaches the file:
+    writers/__init__.py:66 `out_v[out_v == mv_output] = nan` (netCDF path only: pass mv_output);
+    writers/netcdf.py:149-151 + :170-183 / writers/pcr.py:33 + :44-50: `_mask_values` fills the clone-map mask
+    (OR the value mask when the values are a MaskedArray) with the file's missing value, NaNs become it too.
+    values: [..., rows, cols]; clone_mask: [rows, cols] bool."""
+    v = np.array(values, dtype=np.float64, copy=True)
+    bad = np.broadcast_to(np.asarray(clone_mask, dtype=bool), v.shape).copy()
+    if value_mask is not None:
+        bad |= np.asarray(value_mask, dtype=bool)
+    if mv_output is not None:
+        bad |= v == mv_output
+    bad |= np.isnan(v)
+    v[bad] = mv_write
+    return v
+

@@ -60,6 +60,10 @@ class Correction(C.Structure):
     _fields_ = [('gem', C.c_void_p), ('dem_term', C.c_void_p), ('valid', C.c_void_p), ('mv', C.c_double)]
 
 
+class WriterPost(C.Structure):
+    _fields_ = [('clone_mask', C.c_void_p), ('mv_match', C.c_double), ('use_match', C.c_int32), ('mv_write', C.c_double)]
+
+
 _vp, _i64, _i32, _f64 = C.c_void_p, C.c_int64, C.c_int, C.c_double
 _rotp = C.POINTER(Rotation)
 
@@ -94,6 +98,9 @@ PROTOTYPES = {
     'g2p_correct': (C.c_int, [_vp, _vp, _i64, _i32, _i64, C.POINTER(Correction), _vp]),
     'g2p_apply_planned_corrected': (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f64, _i32, C.POINTER(Correction),
                                               _vp, _vp, _vp]),
+    'g2p_writer_post_apply': (C.c_int, [_vp, _vp, _i64, _i32, _i64, C.POINTER(WriterPost), _vp]),
+    'g2p_apply_planned_post': (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _f64, _i32, C.POINTER(Correction),
+                                         C.POINTER(WriterPost), _vp, _vp, _vp]),
     'g2p_apply_planned_fused': (C.c_int, [_vp, _vp, C.POINTER(ManipDesc), _vp, _vp, _i32, _i64, _i64, _f64, _i32,
                                           C.POINTER(Correction), _vp, _vp, _vp]),
 }

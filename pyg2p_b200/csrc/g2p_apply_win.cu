@@ -370,6 +370,10 @@ struct WinArgs {
   const double* corr_dem_term;
   const uint8_t* corr_valid;
   double corr_mv;
+  // writers' post-processing (g2p_writer_post), after the correction
+  int post_on, post_use_match;
+  const uint8_t* post_clone;
+  double post_mv_match, post_mv_write;
   // AGG: the source-grid stages fused into the staging step (see apply_window_kernel)
   const AggItem* agg_items;   // device, one per output message
   int op1, op2, cut_off;
@@ -424,7 +428,9 @@ __device__ __forceinline__ double agg_convert(const WinArgs& a, double x) {
   return y;
 }
 
-// CORR: Corrector epilogue `where(valid & (p != mv), (p + gem) - dem_term, mv)` (manipulation/correction.py:46,74-81)
+// CORR: epilogue variant: the Corrector formula `where(valid & (p != mv), (p + gem) - dem_term, mv)`
+//       (manipulation/correction.py:46,74-81) when corr_gem is set, then the writers' post-processing
+//       (clone mask | value mask | NaN | == mv_output -> the file's missing value) when post_on is set
 // AGG : the source-grid stages run inside the staging step: an output message stages the windows of its (<= 2)
 //       input messages, and the fold pass - one message ahead of the gathers, where the mask bytes are folded
 //       anyway - evaluates conversion, aggregation (PICK / ACCUM / AVERAGE of <= 2 / COPY, g2p_manip's arithmetic)
@@ -610,7 +616,7 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
     const int64_t j0 = r * a.g.cols + c[0];
     uint32_t ob[kWinTPT];  // byte offset of the target in an output row
     double cgem[CORR ? kWinTPT : 1], cdt[CORR ? kWinTPT : 1];
-    bool cvalid[CORR ? kWinTPT : 1];
+    bool cvalid[CORR ? kWinTPT : 1], pclone[CORR ? kWinTPT : 1];
 #pragma unroll
     for (int t = 0; t < kWinTPT; ++t) {
       ok[t] = r < a.g.rows && c[t] < a.g.cols;
@@ -623,9 +629,11 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
         w[t][kk] = (K > 1 && ok[t]) ? __ldg(a.coef + (int64_t)kk * a.m + j) : 1.0;
       }
       if (CORR) {
-        cgem[t] = ok[t] ? __ldg(a.corr_gem + j) : 0.0;
-        cdt[t] = ok[t] ? __ldg(a.corr_dem_term + j) : 0.0;
-        cvalid[t] = ok[t] ? __ldg(a.corr_valid + j) != 0 : false;
+        const bool cr = ok[t] && a.corr_gem != nullptr;
+        cgem[t] = cr ? __ldg(a.corr_gem + j) : 0.0;
+        cdt[t] = cr ? __ldg(a.corr_dem_term + j) : 0.0;
+        cvalid[t] = cr ? __ldg(a.corr_valid + j) != 0 : false;
+        pclone[t] = (ok[t] && a.post_clone) ? __ldg(a.post_clone + j) != 0 : false;
       }
     }
     char* o = reinterpret_cast<char*>(a.out) + (int64_t)msg_begin * a.out_stride * 8;       // block-uniform
@@ -662,8 +670,11 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
           for (int kk = 0; kk < K; ++kk) mk |= (uint32_t)(__double_as_longlong(v[kk]) == (long long)kMaskMarker);
           if (mk) res = a.mv_out;
         }
-        if (CORR && !mk)  // a masked output stays the missing value; p = NaN passes the guards and stays NaN
-          res = (cvalid[t] && res != a.corr_mv) ? __dsub_rn(__dadd_rn(res, cgem[t]), cdt[t]) : a.corr_mv;
+        if (CORR) {
+          if (a.corr_gem && !mk)  // a masked output stays the missing value; p = NaN passes the guards and stays NaN
+            res = (cvalid[t] && res != a.corr_mv) ? __dsub_rn(__dadd_rn(res, cgem[t]), cdt[t]) : a.corr_mv;
+          if (a.post_on && (pclone[t] || mk || res != res || (a.post_use_match && res == a.post_mv_match))) res = a.post_mv_write;
+        }
         if (ok[t]) {
           __stcs(reinterpret_cast<double*>(o + ob[t]), res);
           if (MP == 1) *reinterpret_cast<uint8_t*>(om + (ob[t] >> 3)) = (uint8_t)mk;
@@ -713,10 +724,11 @@ static int launch_window_s(const g2p_plan* p, WinArgs a, cudaStream_t st) {
     // the fused pipeline is instantiated for the window sizes it is used with (CV <= 4: windows up to 2048 values)
     if (CV > 4) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned_fused: window of %d values is too large; use g2p_manip + g2p_apply_planned", p->max_window);
     if (CV <= 4)
-      return a.corr_gem ? launch_window_c<K, MP, (CV <= 4 ? CV : 2), S, true, true>(p, a, st)
-                        : launch_window_c<K, MP, (CV <= 4 ? CV : 2), S, false, true>(p, a, st);
+      return (a.corr_gem || a.post_on) ? launch_window_c<K, MP, (CV <= 4 ? CV : 2), S, true, true>(p, a, st)
+                                       : launch_window_c<K, MP, (CV <= 4 ? CV : 2), S, false, true>(p, a, st);
   }
-  return a.corr_gem ? launch_window_c<K, MP, CV, S, true, false>(p, a, st) : launch_window_c<K, MP, CV, S, false, false>(p, a, st);
+  return (a.corr_gem || a.post_on) ? launch_window_c<K, MP, CV, S, true, false>(p, a, st)
+                                   : launch_window_c<K, MP, CV, S, false, false>(p, a, st);
 }
 
 template <int K, int MP, int CV>
@@ -967,7 +979,8 @@ int g2p_plan_get_info(const g2p_plan* p, g2p_plan_info* info) {
 
 static int apply_planned(const g2p_plan* p, const double* coef, const double* src, const uint8_t* src_mask, int b,
                          int64_t src_stride, int64_t out_stride, double mv_out, int mask_policy, const g2p_correction* corr,
-                         double* out, uint8_t* out_mask, void* stream, const g2p_manip_desc* fused = nullptr, int b_in = 0) {
+                         double* out, uint8_t* out_mask, void* stream, const g2p_manip_desc* fused = nullptr, int b_in = 0,
+                         const g2p_writer_post* post = nullptr) {
   if (!p || !src || !out) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: null plan/src/out");
   if (p->k > 1 && !coef) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: coef is required for k > 1");
   if (p->k != 1 && p->k != 4) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: k=%d (1 and 4 are planned; use g2p_apply)", p->k);
@@ -1054,6 +1067,13 @@ static int apply_planned(const g2p_plan* p, const double* coef, const double* sr
     a.corr_valid = corr->valid;
     a.corr_mv = corr->mv;
   }
+  if (post) {
+    a.post_on = 1;
+    a.post_clone = post->clone_mask;
+    a.post_use_match = post->use_match;
+    a.post_mv_match = post->mv_match;
+    a.post_mv_write = post->mv_write;
+  }
   cudaStream_t st = as_stream(stream);
   int rc;
   if (p->k == 1) {
@@ -1085,6 +1105,13 @@ int g2p_apply_planned_fused(const g2p_plan* p, const double* coef, const g2p_man
     if (op < G2P_OP_NONE || op > G2P_OP_DIV) return set_error(G2P_ERR_INVALID, "g2p_apply_planned_fused: unknown conversion op %d", op);
   return apply_planned(p, coef, src, src_mask, desc->n_out, src_stride, out_stride, mv_out, mask_policy, corr, out, out_mask,
                        stream, desc, b_in);
+}
+
+int g2p_apply_planned_post(const g2p_plan* p, const double* coef, const double* src, const uint8_t* src_mask, int b,
+                           int64_t src_stride, int64_t out_stride, double mv_out, int mask_policy, const g2p_correction* corr,
+                           const g2p_writer_post* post, double* out, uint8_t* out_mask, void* stream) {
+  return apply_planned(p, coef, src, src_mask, b, src_stride, out_stride, mv_out, mask_policy, corr, out, out_mask, stream,
+                       nullptr, 0, post);
 }
 
 }  // extern "C"

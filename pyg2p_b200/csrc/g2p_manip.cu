@@ -183,6 +183,19 @@ __global__ void correct_kernel(double* __restrict__ v, const uint8_t* __restrict
   }
 }
 
+// writers' post-processing in place (see g2p_writer_post in g2p.h)
+__global__ void writer_post_kernel(double* __restrict__ v, const uint8_t* __restrict__ mask, int64_t m, int b, int64_t stride,
+                                   const uint8_t* __restrict__ clone, double mv_match, int use_match, double mv_write) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (int64_t)gridDim.x * blockDim.x) {
+    const bool out_of_clone = clone && clone[j] != 0;
+    for (int q = 0; q < b; ++q) {
+      const int64_t at = (int64_t)q * stride + j;
+      const double p = v[at];
+      if (out_of_clone || (mask && mask[at]) || p != p || (use_match && p == mv_match)) v[at] = mv_write;
+    }
+  }
+}
+
 }  // namespace g2p
 
 using namespace g2p;
@@ -290,6 +303,17 @@ int g2p_correct(double* values, const uint8_t* mask, int64_t m, int b, int64_t s
   int64_t blocks = std::min<int64_t>(ceil_div(m, 256), (int64_t)num_sms() * 16);
   correct_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(values, mask, m, b, stride, corr->gem, corr->dem_term,
                                                                  corr->valid, corr->mv);
+  G2P_LAUNCHED();
+  return G2P_OK;
+}
+
+int g2p_writer_post_apply(double* values, const uint8_t* mask, int64_t m, int b, int64_t stride, const g2p_writer_post* post,
+                          void* stream) {
+  if (!values || !post || m < 0 || b < 0 || stride < m) return set_error(G2P_ERR_INVALID, "g2p_writer_post_apply: bad arguments");
+  if (m == 0 || b == 0) return G2P_OK;
+  int64_t blocks = std::min<int64_t>(ceil_div(m, 256), (int64_t)num_sms() * 16);
+  writer_post_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(values, mask, m, b, stride, post->clone_mask,
+                                                                     post->mv_match, post->use_match, post->mv_write);
   G2P_LAUNCHED();
   return G2P_OK;
 }

@@ -361,12 +361,13 @@ class DeviceTable:
         return self._compact
 
     def apply(self, src, mv_out, src_mask=None, mask_policy=L.MASK_AS_REFERENCE, out=None, out_mask=None,
-              correction=None):
+              correction=None, post=None):
         """Batched K7 on device-resident messages.  src: float64 [b, n] (or [n]); returns out [b, m]
         (and out_mask uint8 [b, m] under PROPAGATE; masked outputs hold mv_out under PROPAGATE and FILL).
         Asynchronous on the current stream.
         Uses the windowed kernel (g2p_apply_planned) when the table and the buffers allow it, else the
-        generic gather kernel (g2p_apply); both are bit-identical."""
+        generic gather kernel (g2p_apply); both are bit-identical.  `correction` (a Corrector) and `post` (a
+        WriterPost) run in the epilogue of the windowed kernel, or as their own passes after the generic one."""
         lib = require_cuda()
         _bind_device(self.device)
         squeeze = src.dim() == 1
@@ -397,11 +398,12 @@ class DeviceTable:
                     out_mask = torch.empty((b, self.m), dtype=torch.uint8, device=self.device)
             if b > 0 and self.m > 0 and self._window_ok(src, src_mask, propagate):
                 self.last_path = 'window'
-                if correction is not None:
-                    L.check(lib.g2p_apply_planned_corrected(
+                if correction is not None or post is not None:
+                    L.check(lib.g2p_apply_planned_post(
                         self.plan(), _ptr(self.coef) if self.k > 1 else None, _ptr(src),
                         _ptr(src_mask) if propagate else None, b, src.stride(0), out.stride(0), float(mv_out),
-                        int(mask_policy), C.byref(correction.c_struct()), _ptr(out),
+                        int(mask_policy), C.byref(correction.c_struct()) if correction is not None else None,
+                        C.byref(post.c_struct()) if post is not None else None, _ptr(out),
                         _ptr(out_mask) if mask_policy == L.MASK_PROPAGATE else None, _stream()))
                 else:
                     L.check(lib.g2p_apply_planned(self.plan(), _ptr(self.coef) if self.k > 1 else None, _ptr(src),
@@ -411,17 +413,62 @@ class DeviceTable:
                                                   _stream()))
             elif b > 0 and self.m > 0:
                 self.last_path = 'generic'
+                # no plan for this table: the Corrector and the writers' post-processing run as their own passes.
+                # Both leave masked cells alone / turn them into the file's missing value, so under FILL (masked
+                # outputs hold mv_out, no mask array for the caller) a scratch mask array carries them across.
+                g_policy, g_mask = mask_policy, (out_mask if mask_policy == L.MASK_PROPAGATE else None)
+                if mask_policy == L.MASK_FILL and (correction is not None or post is not None):
+                    g_policy = L.MASK_PROPAGATE                  # one row stride for values and masks in the C ABI
+                    g_mask = torch.empty((b, out.stride(0)), dtype=torch.uint8, device=self.device)[:, :self.m]
                 L.check(lib.g2p_apply(_ptr(self.idx), _ptr(self.coef) if self.k > 1 else None, self.m, self.k, _ptr(src),
                                       _ptr(src_mask) if propagate else None, n, b, src.stride(0), out.stride(0),
-                                      float(mv_out), int(mask_policy), _ptr(out),
-                                      _ptr(out_mask) if mask_policy == L.MASK_PROPAGATE else None, _stream()))
-                if correction is not None:   # no plan for this table: the Corrector runs as its own pass
-                    L.check(lib.g2p_correct(_ptr(out), _ptr(out_mask) if mask_policy == L.MASK_PROPAGATE else None,
+                                      float(mv_out), int(g_policy), _ptr(out),
+                                      _ptr(g_mask) if g_mask is not None else None, _stream()))
+                if correction is not None:
+                    L.check(lib.g2p_correct(_ptr(out), _ptr(g_mask) if g_mask is not None else None,
                                             self.m, b, out.stride(0), C.byref(correction.c_struct()), _stream()))
+                if post is not None:
+                    L.check(lib.g2p_writer_post_apply(_ptr(out), _ptr(g_mask) if g_mask is not None else None, self.m, b,
+                                                      out.stride(0), C.byref(post.c_struct()), _stream()))
         if squeeze:
             out = out[0]
             out_mask = out_mask[0] if out_mask is not None else None
         return (out, out_mask) if mask_policy == L.MASK_PROPAGATE else out
+
+
+class WriterPost:
+    """What the reference's writers do to a field before it reaches the file (writers/__init__.py:66,
+    writers/netcdf.py:149-151,170-183, writers/pcr.py:32-34,44-50), as a per-target epilogue of the apply:
+    `out = (clone_mask | value mask | isnan(v) | v == match) ? mv_write : v`.
+    clone_mask: bool/uint8 array over the target grid (missing cells of the clone map) or None; mv_write: the
+    missing value of the file (netCDF: fill value * scale_factor + offset; PCRaster: nodata of the clone map);
+    match: the Interpolator's mv_output on the netCDF path (`out_v[out_v == mv_output] = nan`), None on the
+    PCRaster path."""
+
+    def __init__(self, clone_mask, mv_write, match=None, device='cuda'):
+        require_cuda()
+        self.clone = None
+        if clone_mask is not None:
+            cm = np.ascontiguousarray(np.asarray(clone_mask)).astype(np.uint8).ravel()
+            self.clone = torch.from_numpy(cm).to(device)
+        self.mv_write = float(mv_write)
+        self.match = None if match is None else float(match)
+        self._c = L.WriterPost(self.clone.data_ptr() if self.clone is not None else None,
+                               self.match if self.match is not None else 0.0, 0 if self.match is None else 1, self.mv_write)
+
+    def c_struct(self):
+        return self._c
+
+    def apply_(self, values, mask=None):
+        """in place on a device tensor [b, m] (mask: the PROPAGATE out_mask or None)."""
+        lib = require_cuda()
+        v2 = values if values.dim() == 2 else values.unsqueeze(0)
+        m2 = mask if mask is None or mask.dim() == 2 else mask.unsqueeze(0)
+        if self.clone is not None and self.clone.numel() != v2.shape[1]:
+            raise ValueError('clone mask and fields differ in size')
+        L.check(lib.g2p_writer_post_apply(_ptr(v2), _ptr(m2) if m2 is not None else None, v2.shape[1], v2.shape[0],
+                                          v2.stride(0), C.byref(self._c), _stream()))
+        return values
 
 
 def launch_count():
@@ -473,12 +520,16 @@ class HostApplyPipeline:
         view.numpy()[...] = host[lo:hi]
         return view
 
-    def run(self, src, mv_out, src_mask=None, mask_policy=L.MASK_AS_REFERENCE, out=None, out_mask=None):
+    def run(self, src, mv_out, src_mask=None, mask_policy=L.MASK_AS_REFERENCE, out=None, out_mask=None,
+            correction=None, post=None):
         """src: [b, n] float64 pinned tensor (or ndarray); src_mask: [b, n] uint8/bool or None.
-        Returns (out [b, m] pinned tensor, out_mask [b, m] pinned uint8 tensor or None)."""
+        Returns (out [b, m] pinned tensor, out_mask [b, m] pinned uint8 tensor or None).  With `post` (a WriterPost)
+        the fields arrive ready for the writer - masked cells already hold its missing value - and no mask array
+        is copied back."""
         t = self.t
         propagate = mask_policy in (L.MASK_PROPAGATE, L.MASK_FILL)   # masks go in
-        want_omask = mask_policy == L.MASK_PROPAGATE                # ... and a mask array comes out
+        dev_omask = mask_policy == L.MASK_PROPAGATE                  # ... the kernel writes a mask array
+        want_omask = dev_omask and post is None                      # ... and it comes back to the host
         if propagate and not self.with_mask:
             raise ValueError('pipeline was created without mask buffers')
         b = src.shape[0]
@@ -523,9 +574,10 @@ class HostApplyPipeline:
                 cur.wait_event(ev_out[s])                  # slot's previous output has left the device
             if propagate:
                 t.apply(self.d_src[s][:nb], mv_out, src_mask=self.d_msk[s][:nb], mask_policy=mask_policy,
-                        out=self.d_out[s][:nb], out_mask=self.d_omk[s][:nb] if want_omask else None)
+                        out=self.d_out[s][:nb], out_mask=self.d_omk[s][:nb] if dev_omask else None,
+                        correction=correction, post=post)
             else:
-                t.apply(self.d_src[s][:nb], mv_out, out=self.d_out[s][:nb])
+                t.apply(self.d_src[s][:nb], mv_out, out=self.d_out[s][:nb], correction=correction, post=post)
             ev_k[s] = torch.cuda.Event()
             ev_k[s].record(cur)
             with torch.cuda.stream(self.s_out):
@@ -585,11 +637,14 @@ class CompactHostPipeline:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
-    def run(self, src, mv_out, src_mask=None, mask_policy=L.MASK_AS_REFERENCE, out=None, out_mask=None):
-        """src: [b, n] float64 PINNED tensor; src_mask: [b, n] uint8 pinned tensor or None -> (out, out_mask) pinned."""
+    def run(self, src, mv_out, src_mask=None, mask_policy=L.MASK_AS_REFERENCE, out=None, out_mask=None,
+            correction=None, post=None):
+        """src: [b, n] float64 PINNED tensor; src_mask: [b, n] uint8 pinned tensor or None -> (out, out_mask) pinned.
+        `correction` / `post` as in HostApplyPipeline.run (with `post` no mask array is copied back)."""
         t = self.t
         masks_in = mask_policy in (L.MASK_PROPAGATE, L.MASK_FILL)
-        want_omask = mask_policy == L.MASK_PROPAGATE
+        dev_omask = mask_policy == L.MASK_PROPAGATE
+        want_omask = dev_omask and post is None
         if masks_in and not self.with_mask:
             raise ValueError('pipeline was created without mask buffers')
         if not (isinstance(src, torch.Tensor) and src.is_pinned() and src.dtype == torch.float64 and src.stride(1) == 1):
@@ -619,7 +674,7 @@ class CompactHostPipeline:
                 self.h2d_bytes += nb * nc * (9 if masks_in else 8)     # what the gather pulls over PCIe (touched values)
                 self.ct.apply(self.d_c[s][:nb, :nc], mv_out, src_mask=self.d_cm[s][:nb, :nc] if masks_in else None,
                               mask_policy=mask_policy, out=self.d_out[s][:nb],
-                              out_mask=self.d_omk[s][:nb] if want_omask else None)
+                              out_mask=self.d_omk[s][:nb] if dev_omask else None, correction=correction, post=post)
                 ev_k = torch.cuda.Event()
                 ev_k.record(cur)
                 with torch.cuda.stream(self.s_out):

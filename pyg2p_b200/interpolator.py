@@ -142,14 +142,19 @@ class Interpolator:
         return out[0]
 
     def interpolate_batch(self, latgrib, longrib, values, grid_id, grid_details=None, masks=None, out=None,
-                          out_mask=None):
+                          out_mask=None, corrector=None, writer_post=None):
         """`values`: sequence of source fields [n] (ndarray / MaskedArray) or a 2-D array [b, n] - all messages
         of the run that share `grid_id`.  Returns an array [b, rows, cols] (MaskedArray under 'propagate').
 
         Fast path for decoders: `values` = the tensor from `pinned_source_buffer(b, n)` (and `masks` = a pinned
         uint8 tensor of the same shape, 1 = missing, when `mask_policy == 'propagate'`); `out` / `out_mask` =
         pinned tensors [b, rows*cols] from `pinned_output_buffer` to reuse between calls (the returned arrays
-        are views of them)."""
+        are views of them).
+
+        `corrector` (manipulation.Corrector) and `writer_post` (from `self.writer_post(...)`) hoist the rest of the
+        writers' per-step loop (writers/__init__.py:62-67, 103-106) into the same kernel: correction, then
+        `== mv_output -> NaN`, clone-map mask, value mask and NaN -> the file's missing value.  With `writer_post`
+        the result is a plain ndarray ready for `values_nc[t] = ...` / `WriteArray`."""
         pinned = isinstance(values, torch.Tensor)
         first = values[0].numpy() if pinned else values[0]
         table = self._table_for(latgrib, longrib, first, grid_id, grid_details)
@@ -177,15 +182,24 @@ class Interpolator:
                     h_msk.numpy()[i] = np.broadcast_to(ma.getmaskarray(x).ravel(), (n,)) if masked_in[i] else 0
         out, omask = pipe.run(h_src, float(self.mv_output), src_mask=h_msk,
                               mask_policy=L.MASK_PROPAGATE if propagate else L.MASK_AS_REFERENCE, out=out,
-                              out_mask=out_mask)
+                              out_mask=out_mask, correction=corrector, post=writer_post)
         torch.cuda.current_stream(table.device).synchronize()
         res = out.numpy().reshape((b,) + shape)
+        if writer_post is not None:
+            return res
         if propagate:
             return ma.masked_array(res, mask=omask.numpy().view(np.bool_).reshape((b,) + shape), fill_value=self.mv_output,
                                    copy=False)
         if table.k == 1 and not pinned and any(isinstance(x, ma.MaskedArray) for x in values):
             return ma.masked_array(res)          # `v[indexes]` of a MaskedArray stays one, with no mask (:153)
         return res
+
+    def writer_post(self, clone_mask, mv_write, netcdf=True):
+        """the writers' post-processing as an epilogue for `interpolate_batch`: `clone_mask` = missing cells of
+        the clone map (`Writer._mask`), `mv_write` = the file's missing value (netCDF: `default_fillvals[fmt] *
+        scale_factor + offset`, writers/netcdf.py:149; PCRaster: nodata of the clone map, writers/pcr.py:29);
+        `netcdf` adds the `out_v[out_v == mv_output] = nan` of writers/__init__.py:66."""
+        return device.WriterPost(clone_mask, mv_write, match=self.mv_output if netcdf else None)
 
     @staticmethod
     def pinned_source_buffer(b, n):

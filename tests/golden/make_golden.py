@@ -316,6 +316,63 @@ def make_manip_cases():
     print('manip cases written:', sorted(k for k in out if k.endswith('_keys')))
 
 
+# ----------------------------------------------------------------------------- writer post-processing cases
+def make_writer_cases():
+    """The writers' treatment of an interpolated field, by the reference's own `_mask_values` methods
+    (writers/netcdf.py:170-183, writers/pcr.py:44-50) around the inline statements of writers/__init__.py:66,
+    writers/netcdf.py:149-151 and writers/pcr.py:33 (copied here as they are not callable on their own)."""
+    from pyg2p.main.writers.netcdf import NetCDFWriter
+    from pyg2p.main.writers.pcr import PCRasterWriter
+    rng = np.random.default_rng(21)
+    t, rows, cols = 3, 7, 9
+    mv_output = float(synth.PCR_MV_F32)
+    clone = rng.random((rows, cols)) < 0.25
+    v = 280.0 + rng.standard_normal((t, rows, cols))
+    v[rng.random(v.shape) < 0.1] = np.nan          # invdist rows beyond min_upper_bound
+    v[rng.random(v.shape) < 0.1] = mv_output       # nearest rows beyond min_upper_bound / masked under FILL
+    vmask = rng.random(v.shape) < 0.15
+    out = dict(values=v, vmask=vmask, clone=clone, mv_output=np.float64(mv_output))
+    # netCDF: per step `out_v[out_v == mv_output] = nan`; np.array(list) drops masks; scaled missing value
+    for tag, scale, offset in (('nc', 1.0, 0.0), ('nc_scaled', 0.01, 273.15)):
+        w = object.__new__(NetCDFWriter)
+        w._mask = clone
+        steps = []
+        for i in range(t):
+            out_v = v[i].copy()
+            out_v[out_v == mv_output] = np.nan
+            steps.append(out_v)
+        values = np.array(steps, dtype=np.float64)
+        mv_scaled = np.float64(netCDF4.default_fillvals['f8']) * np.float64(scale) + np.float64(offset)
+        values = w._mask_values(values, mv_scaled)
+        values[np.isnan(values)] = mv_scaled
+        out[f'{tag}_out'] = np.asarray(values)
+        out[f'{tag}_mv'] = np.float64(mv_scaled)
+    # the same with MaskedArray steps kept masked (what a mask-propagating caller hands to `_mask_values`)
+    w = object.__new__(NetCDFWriter)
+    w._mask = clone
+    mvals = ma.masked_array(np.where(v == mv_output, np.nan, v), mask=vmask)
+    mv_scaled = np.float64(netCDF4.default_fillvals['f8'])
+    values = w._mask_values(mvals, mv_scaled)
+    values[np.isnan(values)] = mv_scaled
+    out['nc_masked_out'] = np.asarray(values)
+    # PCRaster: one map at a time, `values[isnan(values)] = mv` then `_mask_values`
+    pw = object.__new__(PCRasterWriter)
+    pw._mask = clone
+    pw.mv = mv_output
+    res_plain, res_masked = [], []
+    for i in range(t):
+        a = v[i].copy()
+        a[np.isnan(a)] = pw.mv
+        res_plain.append(np.asarray(pw._mask_values(a)))
+        b = ma.masked_array(v[i].copy(), mask=vmask[i])
+        b[np.isnan(b)] = pw.mv
+        res_masked.append(np.asarray(pw._mask_values(b)))
+    out['pcr_out'] = np.array(res_plain)
+    out['pcr_masked_out'] = np.array(res_masked)
+    np.savez_compressed(os.path.join(HERE, 'writer_post.npz'), **out)
+    print('writer cases written')
+
+
 def make_reference_fixture_copies():
     """Inputs of the reference's own golden intertable (tests/data/tbl_pf10slhf_550800_scipy_nearest.npy.gz):
     the EFAS lat/lon PCRaster maps (as float32 arrays, MV cells = -3.4028235e38 as GDAL delivers them) and the
@@ -336,3 +393,4 @@ if __name__ == '__main__':
     make_build_cases()
     make_apply_cases()
     make_manip_cases()
+    make_writer_cases()

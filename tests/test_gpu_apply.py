@@ -291,3 +291,74 @@ def test_full_size_glofas_tables_window_equals_generic(dev, monkeypatch, res, k)
         assert torch.equal(ar.view(torch.int64), br.view(torch.int64))
     const = tbl.apply(torch.full((1, lat.size), 7.25, device='cuda', dtype=torch.float64), 0.0)
     assert torch.allclose(const, torch.full_like(const, 7.25), rtol=2e-15, atol=0)
+
+
+def test_writer_post_matches_reference_golden(dev, golden_dir):
+    """g2p_writer_post_apply against the outputs of the reference writers' own `_mask_values` (netCDF with and
+    without scale/offset, PCRaster, plain and masked values)."""
+    g = np.load(os.path.join(golden_dir, 'writer_post.npz'))
+    v, vmask, clone, mvo = g['values'], g['vmask'], g['clone'], float(g['mv_output'])
+    t = v.shape[0]
+
+    def run(post, masked):
+        d = torch.from_numpy(v.reshape(t, -1).copy()).cuda()
+        dm = torch.from_numpy(vmask.reshape(t, -1).astype(np.uint8)).cuda() if masked else None
+        return post.apply_(d, dm).cpu().numpy().reshape(v.shape)
+
+    np.testing.assert_array_equal(run(dev.WriterPost(clone, float(g['nc_mv']), match=mvo), False), g['nc_out'])
+    np.testing.assert_array_equal(run(dev.WriterPost(clone, float(g['nc_scaled_mv']), match=mvo), False), g['nc_scaled_out'])
+    np.testing.assert_array_equal(run(dev.WriterPost(clone, float(g['nc_mv']), match=mvo), True), g['nc_masked_out'])
+    np.testing.assert_array_equal(run(dev.WriterPost(clone, mvo), False), g['pcr_out'])
+    np.testing.assert_array_equal(run(dev.WriterPost(clone, mvo), True), g['pcr_masked_out'])
+    # no clone map: only NaN / == mv_output / masked cells change
+    np.testing.assert_array_equal(run(dev.WriterPost(None, 7.0, match=mvo), True),
+                                  R.writer_post(v, np.zeros_like(clone), 7.0, mv_output=mvo, value_mask=vmask))
+
+
+def test_apply_with_writer_post_epilogue(dev, monkeypatch):
+    """interpolate (+ correct) + the writers' post-processing in ONE windowed launch == generic apply, then the
+    Corrector pass, then the oracle's restatement of the writers; O320 -> EFAS invdist and nearest."""
+    from pyg2p_b200 import manipulation as M
+    from pyg2p_b200 import synth
+    lat, lon, det = synth.octahedral_grid(320)
+    tl, tlo = synth.efas_target()
+    ix = dev.SourceIndex(lon, lat, det['radius'])
+    mub = ix.min_upper_bound(det['Nj'])
+    rng = np.random.default_rng(3)
+    clone = rng.random(tl.shape) < 0.3
+    mv_out = float(synth.PCR_MV_F32)
+    dem = (500.0 + 300 * rng.random(tl.shape)).astype(np.float32)
+    dem[rng.random(tl.shape) < 0.1] = synth.PCR_MV_F32
+    gem = 3.0 * rng.random(tl.shape)
+    gem[rng.random(tl.shape) < 0.05] = synth.GRIB_MV
+    corr = M.Corrector(dem, float(synth.PCR_MV_F32), gem, synth.GRIB_MV)
+    g = torch.Generator(device='cuda').manual_seed(4)
+    src = 280.0 + torch.randn((9, lat.size), generator=g, device='cuda', dtype=torch.float64)
+    msk = (torch.rand((9, lat.size), generator=g, device='cuda') < 0.05).to(torch.uint8)
+    for k, mode in ((4, L.MODE_INVDIST), (1, L.MODE_NEAREST)):
+        # a regional source subset would leave rows beyond mub; shrink mub instead so that both NaN rows (invdist)
+        # and mv_out rows (nearest) occur
+        out = ix.knn(tlo, tl, k=k, mode=mode, mub=0.6 * mub, want_flags=False)
+        tbl = dev.DeviceTable(out['idx'], out['coef'], lat.size, grid_shape=tl.shape)
+        for post, mvw, match in ((dev.WriterPost(clone, 9.969209968386869e36 * 0.01 + 273.15, match=mv_out), None, mv_out),
+                                 (dev.WriterPost(clone, mv_out), None, None)):
+            for policy in (L.MASK_AS_REFERENCE, L.MASK_PROPAGATE, L.MASK_FILL):
+                for c in (None, corr):
+                    kw = dict(src_mask=msk if policy != L.MASK_AS_REFERENCE else None, mask_policy=policy)
+                    monkeypatch.setenv('G2P_APPLY_PATH', 'window')
+                    got = tbl.apply(src, mv_out, correction=c, post=post, **kw)
+                    assert tbl.last_path == 'window'
+                    got = got[0] if policy == L.MASK_PROPAGATE else got
+                    monkeypatch.setenv('G2P_APPLY_PATH', 'generic')
+                    two = tbl.apply(src, mv_out, correction=c, post=post, **kw)
+                    two = two[0] if policy == L.MASK_PROPAGATE else two
+                    ref = tbl.apply(src, mv_out, correction=c, **kw)
+                    assert tbl.last_path == 'generic'
+                    ref, rmask = (ref if policy == L.MASK_PROPAGATE else (ref, None))
+                    want = R.writer_post(ref.cpu().numpy().reshape((-1,) + tl.shape), clone, post.mv_write,
+                                         mv_output=post.match,
+                                         value_mask=rmask.cpu().numpy().reshape((-1,) + tl.shape) if rmask is not None else None)
+                    np.testing.assert_array_equal(got.cpu().numpy().reshape(want.shape), want)
+                    np.testing.assert_array_equal(two.cpu().numpy().reshape(want.shape), want)
+        assert np.isnan(ref.cpu().numpy()).any() or (ref == mv_out).any()
+

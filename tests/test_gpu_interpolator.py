@@ -157,6 +157,17 @@ def test_batch_equals_per_message_and_mask_policies(api, tmp_path):
         data, mk = R.apply_propagate(masked[3], coef, idx, 4, it.mv_output, mask)
     np.testing.assert_array_equal(ma.getmaskarray(prop[3]).ravel(), mk)
     np.testing.assert_array_equal(ma.getdata(prop[3]).ravel(), data)
+    # the writers' per-step post-processing hoisted into the batch: fields arrive as the writer would store them
+    clone = rng.random(prop.shape[1:]) < 0.2
+    mv_nc = 9.969209968386869e36 * 0.1 + 5.0
+    post = it.writer_post(clone, mv_nc, netcdf=True)
+    ready = it.interpolate_batch(lat, lon, masked, 'g$3', det, writer_post=post)
+    assert isinstance(ready, np.ndarray) and not isinstance(ready, ma.MaskedArray)
+    np.testing.assert_array_equal(ready, R.writer_post(ma.getdata(prop), clone, mv_nc, mv_output=it.mv_output,
+                                                       value_mask=ma.getmaskarray(prop)))
+    it.mask_policy = 'as_reference'
+    ready = it.interpolate_batch(lat, lon, masked, 'g$3', det, writer_post=it.writer_post(clone, it.mv_output, netcdf=False))
+    np.testing.assert_array_equal(ready, R.writer_post(ref, clone, it.mv_output))
 
 
 def test_scipy_interpolation_signature_and_outputs(api):

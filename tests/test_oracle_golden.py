@@ -181,3 +181,15 @@ def test_oracle_reproduces_the_reference_golden_table(golden_dir):
     np.testing.assert_array_equal(idx == n, tbl['indexes'] == n)
     assert (idx != tbl['indexes']).sum() <= 10
     assert np.max(np.abs(np.asarray(w, dtype=np.float64) - tbl['coeffs'])) < 1.0
+
+
+def test_writer_post_matches_reference(golden_dir):
+    """oracle restatement of the writers' post-processing against the reference's own `_mask_values` outputs."""
+    g = np.load(os.path.join(golden_dir, 'writer_post.npz'))
+    v, vmask, clone, mvo = g['values'], g['vmask'], g['clone'], float(g['mv_output'])
+    np.testing.assert_array_equal(R.writer_post(v, clone, float(g['nc_mv']), mv_output=mvo), g['nc_out'])
+    np.testing.assert_array_equal(R.writer_post(v, clone, float(g['nc_scaled_mv']), mv_output=mvo), g['nc_scaled_out'])
+    np.testing.assert_array_equal(R.writer_post(v, clone, float(g['nc_mv']), mv_output=mvo, value_mask=vmask), g['nc_masked_out'])
+    np.testing.assert_array_equal(R.writer_post(v, clone, mvo), g['pcr_out'])
+    np.testing.assert_array_equal(R.writer_post(v, clone, mvo, value_mask=vmask), g['pcr_masked_out'])
+
