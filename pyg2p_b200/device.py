@@ -662,9 +662,14 @@ class CompactHostPipeline:
         nc = self.ct.n_src
         cur = torch.cuda.current_stream(t.device)
         ev_out = [None, None]
+        # chunk bounds: a short first chunk, so that the D2H engine - the bottleneck - starts early
+        bounds, lo = [], 0
+        while lo < b:
+            hi = min(b, lo + (max(1, self.c // 4) if lo == 0 and b > self.c else self.c))
+            bounds.append((lo, hi))
+            lo = hi
         with torch.cuda.device(t.device):
-            for ci, lo in enumerate(range(0, b, self.c)):
-                hi = min(b, lo + self.c)
+            for ci, (lo, hi) in enumerate(bounds):
                 s, nb = ci % 2, hi - lo
                 if ev_out[s] is not None:
                     cur.wait_event(ev_out[s])                  # the slot's previous results have left the device
