@@ -261,6 +261,9 @@ typedef struct g2p_correction {
   const double* dem_term;   /* device, m */
   const uint8_t* valid;     /* device, m */
   double mv;                /* 9.969209968386869e36 */
+  int32_t mode;             /* 0: (p + gem) - dem_term   [`p+gem-dem*c`, dem_term = dem*c]
+                               1: (p / gem) * dem_term   [`p/gem*(10**((c)*dem/d))`, dem_term = 10**((c*dem)/d), which the
+                                  host evaluates once per target grid with the libm `pow` the reference's numexpr calls] */
 } g2p_correction;
 
 int g2p_correction_prepare(const void* dem, int dem_dtype, double dem_mv, const double* gem, double gem_mv, double coeff,

@@ -57,7 +57,8 @@ class ManipDesc(C.Structure):
 
 
 class Correction(C.Structure):
-    _fields_ = [('gem', C.c_void_p), ('dem_term', C.c_void_p), ('valid', C.c_void_p), ('mv', C.c_double)]
+    _fields_ = [('gem', C.c_void_p), ('dem_term', C.c_void_p), ('valid', C.c_void_p), ('mv', C.c_double),
+                ('mode', C.c_int32)]
 
 
 class WriterPost(C.Structure):

@@ -370,6 +370,7 @@ struct WinArgs {
   const double* corr_dem_term;
   const uint8_t* corr_valid;
   double corr_mv;
+  int corr_mode;  // g2p_correction.mode
   // writers' post-processing (g2p_writer_post), after the correction
   int post_on, post_use_match;
   const uint8_t* post_clone;
@@ -672,7 +673,8 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
         }
         if (CORR) {
           if (a.corr_gem && !mk)  // a masked output stays the missing value; p = NaN passes the guards and stays NaN
-            res = (cvalid[t] && res != a.corr_mv) ? __dsub_rn(__dadd_rn(res, cgem[t]), cdt[t]) : a.corr_mv;
+            res = !(cvalid[t] && res != a.corr_mv) ? a.corr_mv
+                  : a.corr_mode == 0 ? __dsub_rn(__dadd_rn(res, cgem[t]), cdt[t]) : __dmul_rn(__ddiv_rn(res, cgem[t]), cdt[t]);
           if (a.post_on && (pclone[t] || mk || res != res || (a.post_use_match && res == a.post_mv_match))) res = a.post_mv_write;
         }
         if (ok[t]) {
@@ -1062,10 +1064,12 @@ static int apply_planned(const g2p_plan* p, const double* coef, const double* sr
   }
   if (corr) {
     if (!corr->gem || !corr->dem_term || !corr->valid) return set_error(G2P_ERR_INVALID, "g2p_apply_planned_corrected: null correction arrays");
+    if (corr->mode != 0 && corr->mode != 1) return set_error(G2P_ERR_INVALID, "g2p_apply_planned_corrected: unknown correction mode %d", corr->mode);
     a.corr_gem = corr->gem;
     a.corr_dem_term = corr->dem_term;
     a.corr_valid = corr->valid;
     a.corr_mv = corr->mv;
+    a.corr_mode = corr->mode;
   }
   if (post) {
     a.post_on = 1;

@@ -170,7 +170,7 @@ __global__ void correction_prepare_kernel(const void* __restrict__ dem, int dem_
 // standalone Corrector.correct on [b][m] outputs (used after the generic apply kernel); masked outputs stay as they are
 __global__ void correct_kernel(double* __restrict__ v, const uint8_t* __restrict__ mask, int64_t m, int b, int64_t stride,
                                const double* __restrict__ gem, const double* __restrict__ dem_term,
-                               const uint8_t* __restrict__ valid, double mv) {
+                               const uint8_t* __restrict__ valid, double mv, int mode) {
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (int64_t)gridDim.x * blockDim.x) {
     const double g = gem[j], dt = dem_term[j];
     const bool ok = valid[j] != 0;
@@ -178,7 +178,7 @@ __global__ void correct_kernel(double* __restrict__ v, const uint8_t* __restrict
       const int64_t at = (int64_t)q * stride + j;
       if (mask && mask[at]) continue;
       const double p = v[at];
-      v[at] = (ok && p != mv) ? __dsub_rn(__dadd_rn(p, g), dt) : mv;
+      v[at] = !(ok && p != mv) ? mv : mode == 0 ? __dsub_rn(__dadd_rn(p, g), dt) : __dmul_rn(__ddiv_rn(p, g), dt);
     }
   }
 }
@@ -299,10 +299,11 @@ int g2p_correct(double* values, const uint8_t* mask, int64_t m, int b, int64_t s
                 void* stream) {
   if (!values || !corr || !corr->gem || !corr->dem_term || !corr->valid || m < 0 || b < 0 || stride < m)
     return set_error(G2P_ERR_INVALID, "g2p_correct: bad arguments");
+  if (corr->mode != 0 && corr->mode != 1) return set_error(G2P_ERR_INVALID, "g2p_correct: unknown correction mode %d", corr->mode);
   if (m == 0 || b == 0) return G2P_OK;
   int64_t blocks = std::min<int64_t>(ceil_div(m, 256), (int64_t)num_sms() * 16);
   correct_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(values, mask, m, b, stride, corr->gem, corr->dem_term,
-                                                                 corr->valid, corr->mv);
+                                                                 corr->valid, corr->mv, corr->mode);
   G2P_LAUNCHED();
   return G2P_OK;
 }

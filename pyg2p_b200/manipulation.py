@@ -7,6 +7,7 @@ the arithmetic runs on the GPU in the reference's evaluation order.  No CPU fall
 import ast
 import bisect
 import ctypes as C
+import re
 
 import numpy as np
 import numpy.ma as ma
@@ -437,37 +438,69 @@ class Corrector:
     intertable, after `gem_formula` was applied on the source grid (correction.py:84-108) - use
     `Corrector.from_geopotential` to do both steps."""
 
+    # the two formula families of the reference's templates and README (README.md:958-978)
+    _NUM = r'\(?\s*(-?[0-9.]+(?:[eE][-+]?[0-9]+)?)\s*\)?'
+    _LINEAR = re.compile(r'^p\+gem-dem\*' + _NUM + r'$')
+    _PRESSURE = re.compile(r'^p/gem\*\(10\*\*\(' + _NUM + r'\*dem/' + _NUM + r'\)\)$')
+    _GEM_PRESSURE = re.compile(r'^\(?10\*\*\(' + _NUM + r'\*\(z/' + _NUM + r'\)/' + _NUM + r'\)\)?$')
+
     def __init__(self, dem_values, dem_mv, gem_values, gem_mv, formula='p+gem-dem*0.0065'):
         compact = formula.replace(' ', '')
-        if not (compact.startswith('p+gem-dem*')):
-            raise ApplicationException.get_exc(NOT_IMPLEMENTED, f'correction formula {formula!r} (only p+gem-dem*c)')
-        self.coeff = float(compact[len('p+gem-dem*'):])
         lib = device.require_cuda()
         dem = np.ascontiguousarray(dem_values)
         if dem.dtype not in (np.float32, np.float64):
             dem = dem.astype(np.float64)
         self.shape = dem.shape
         m = dem.size
-        d_dem = torch.from_numpy(dem.ravel()).cuda()
         self.gem = device.to_device(np.asarray(ma.getdata(gem_values), dtype=np.float64).ravel(), torch.float64, 'cuda')
         self.dem_term = torch.empty(m, dtype=torch.float64, device='cuda')
         self.valid = torch.empty(m, dtype=torch.uint8, device='cuda')
-        L.check(lib.g2p_correction_prepare(C.c_void_p(d_dem.data_ptr()), L.F32 if dem.dtype == np.float32 else L.F64,
-                                           float(dem_mv), C.c_void_p(self.gem.data_ptr()), float(gem_mv), self.coeff, m,
-                                           C.c_void_p(self.dem_term.data_ptr()), C.c_void_p(self.valid.data_ptr()),
-                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        lin, prs = self._LINEAR.match(compact), self._PRESSURE.match(compact)
+        if lin:
+            # `p+gem-dem*c`: dem_term = dem*c and the guards, per target, on the device
+            self.mode, self.coeff = 0, float(lin.group(1))
+            d_dem = torch.from_numpy(dem.ravel()).cuda()
+            L.check(lib.g2p_correction_prepare(C.c_void_p(d_dem.data_ptr()), L.F32 if dem.dtype == np.float32 else L.F64,
+                                               float(dem_mv), C.c_void_p(self.gem.data_ptr()), float(gem_mv), self.coeff, m,
+                                               C.c_void_p(self.dem_term.data_ptr()), C.c_void_p(self.valid.data_ptr()),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        elif prs:
+            # `p/gem*(10**((c)*dem/d))`: the per-target factor 10**((c*dem)/d) is a constant of the target grid; it is
+            # evaluated once, here, with numpy's float64 power - the libm `pow` numexpr calls in the reference - so that
+            # it carries the reference's bits; (p/gem)*factor runs per message in the kernel epilogue
+            self.mode, self.coeff = 1, float(prs.group(1))
+            dem64 = dem.ravel().astype(np.float64)          # numexpr promotes a float32 dem before `c*dem`
+            with np.errstate(all='ignore'):
+                term = np.power(10.0, (self.coeff * dem64) / float(prs.group(2)))
+            gem_h = np.asarray(ma.getdata(gem_values), dtype=np.float64).ravel()
+            valid = (dem64 != float(dem_mv)) & (gem_h != gem_mv)    # numexpr compares a float32 dem in double
+            self.dem_term.copy_(torch.from_numpy(term))
+            self.valid.copy_(torch.from_numpy(valid.astype(np.uint8)))
+        else:
+            raise ApplicationException.get_exc(NOT_IMPLEMENTED, f'correction formula {formula!r} (p+gem-dem*c and '
+                                                                f'p/gem*(10**((c)*dem/d)) are built)')
         self.mv = NC_FILL_F64
-        self._c = L.Correction(self.gem.data_ptr(), self.dem_term.data_ptr(), self.valid.data_ptr(), self.mv)
+        self._c = L.Correction(self.gem.data_ptr(), self.dem_term.data_ptr(), self.valid.data_ptr(), self.mv, self.mode)
 
     @classmethod
     def from_geopotential(cls, table, z_values, z_mv, mv_out, dem_values, dem_mv, formula='p+gem-dem*0.0065',
                           gem_formula='(z/9.81)*0.0065'):
         """`_read_geo` (correction.py:84-108): gem = interpolate(where(z != mv, gem_formula(z), mv))."""
-        conv = Converter.__new__(Converter)
-        conv._mv, conv._do_cut_off, conv.identity = z_mv, False, False
-        conv.ops = parse_function(gem_formula, var='z')
-        src, _ = _upload([z_values])
-        g_src, _ = manip_device(src, None, [ManipItem.pick(0)], converter=conv)
+        prs = cls._GEM_PRESSURE.match(gem_formula.replace(' ', ''))
+        if prs:
+            # `10**((c)*(z/g)/d)`: one field per run, evaluated on the host with the reference's libm `pow`
+            # (see __init__), then interpolated on the device like any message
+            c_, g_, d_ = (float(prs.group(i)) for i in (1, 2, 3))
+            z = np.asarray(ma.getdata(z_values), dtype=np.float64).ravel()
+            with np.errstate(all='ignore'):
+                gz = np.where(z != z_mv, np.power(10.0, (c_ * (z / g_)) / d_), z_mv)
+            g_src = torch.from_numpy(gz).cuda().unsqueeze(0)
+        else:
+            conv = Converter.__new__(Converter)
+            conv._mv, conv._do_cut_off, conv.identity = z_mv, False, False
+            conv.ops = parse_function(gem_formula, var='z')
+            src, _ = _upload([z_values])
+            g_src, _ = manip_device(src, None, [ManipItem.pick(0)], converter=conv)
         # `0.0 + x` of PICK is exact except for -0.0, which the formula cannot produce from a geopotential
         n_pad = -(-table.n_src // 16) * 16
         buf = torch.zeros((1, n_pad), dtype=torch.float64, device='cuda')

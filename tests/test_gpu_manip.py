@@ -110,8 +110,50 @@ def test_corrector_matches_reference(M, g):
     want = MR.correct(g['corr_p'].copy(), g['corr_dem'].astype(np.float32).astype(np.float64), g['corr_gem'],
                       float(g['corr_dem_mv']), float(g['corr_gem_mv']))
     np.testing.assert_array_equal(c32.correct(g['corr_p'].copy()), np.asarray(ma.filled(want)))
+    # the README's pressure formula (README.md:968-978), against the vector the reference's own Corrector.correct made
+    prs = 'p/gem*(10**((-0.159)*dem/1000))'
+    cp = M.Corrector(g['corr_dem'], float(g['corr_dem_mv']), g['corr_gem'], float(g['corr_gem_mv']), formula=prs)
+    np.testing.assert_array_equal(cp.correct(g['corr_p'].copy()), g['corr_out_pressure'])
+    cp32 = M.Corrector(g['corr_dem'].astype(np.float32), float(g['corr_dem_mv']), g['corr_gem'], float(g['corr_gem_mv']),
+                       formula=prs)
+    want = MR.correct(g['corr_p'].copy(), g['corr_dem'].astype(np.float32), g['corr_gem'], float(g['corr_dem_mv']),
+                      float(g['corr_gem_mv']), formula=prs)
+    np.testing.assert_array_equal(cp32.correct(g['corr_p'].copy()), np.asarray(ma.filled(want)))
     with pytest.raises(Exception):
-        M.Corrector(g['corr_dem'], 0.0, g['corr_gem'], 0.0, formula='p/gem*(10**((-0.159)*dem/1000))')
+        M.Corrector(g['corr_dem'], 0.0, g['corr_gem'], 0.0, formula='p*gem+sqrt(dem)')
+
+
+def test_pressure_correction_in_the_apply_epilogue(M):
+    """`p/gem*(10**((-0.159)*dem/1000))` with gem = interpolate(`10**((-0.159)*(z/9.81)/1000)`): Corrector.from_geopotential
+    + the windowed apply epilogue == the oracle's chain (gem formula on the source grid, apply, correct)."""
+    from pyg2p_b200 import device
+    lat, lon, det = synth.regular_ll_grid(62.0, 38.0, 97, -8.0, 32.0, 161)
+    n = lat.size
+    tl, tlo = synth.efas_target(rows=96, cols=70, cell=20000.0, x_ul=3500000.0, y_ul=4000000.0)
+    ix = device.SourceIndex(lon, lat, det['radius'])
+    out = ix.knn(tlo, tl, k=4, mode=L.MODE_INVDIST, mub=ix.min_upper_bound(det['Nj']), want_flags=False)
+    table = device.DeviceTable(out['idx'], out['coef'], n, grid_shape=tl.shape)
+    idx, w = table.indexes_coeffs()
+    rng = np.random.default_rng(8)
+    z = synth.field_geopotential(lat, lon)
+    z[rng.random(n) < 0.01] = synth.GRIB_MV
+    dem = synth.field_dem(tl, tlo, float(synth.PCR_MV_F32)).astype(np.float32)
+    gem_f, prs = '(10**((-0.159)*(z/9.81)/1000))', 'p/gem*(10**((-0.159)*dem/1000))'
+    corr = M.Corrector.from_geopotential(table, z, synth.GRIB_MV, synth.NC_FILL_F64, dem, float(synth.PCR_MV_F32),
+                                         formula=prs, gem_formula=gem_f)
+    fields = 1000.0 + 20 * rng.standard_normal((5, n))
+    n_pad = -(-n // 16) * 16
+    src = torch.zeros((5, n_pad), dtype=torch.float64, device='cuda')
+    src[:, :n] = torch.from_numpy(fields).cuda()
+    got = table.apply(src[:, :n], synth.NC_FILL_F64, correction=corr)
+    assert table.last_path == 'window'
+    with np.errstate(all='ignore'):
+        gem_src = MR.gem_from_geopotential(z.copy(), synth.GRIB_MV, gem_f)
+        gem_t = R.apply_sequential(gem_src, w, idx, 4, synth.NC_FILL_F64)
+        for i in range(5):
+            p = R.apply_sequential(fields[i], w, idx, 4, synth.NC_FILL_F64)
+            want = MR.correct(p, dem.ravel(), gem_t, float(synth.PCR_MV_F32), synth.GRIB_MV, formula=prs)
+            np.testing.assert_array_equal(got[i].cpu().numpy(), np.asarray(ma.filled(want)))
 
 
 @pytest.mark.parametrize('kind', ['accumulation', 'average', 'instantaneous'])
