@@ -708,7 +708,11 @@ static int launch_window_c(const g2p_plan* p, WinArgs a, cudaStream_t st) {
   a.stages = S;
   // message chunks: long enough to amortise the per-item index/weight loads, short enough to
   // give every CTA several items
-  int64_t want_chunks = ceil_div(8 * grid_cap, p->n_tiles);
+  // (measured on O1280 -> EFAS, tools/chunk_sweep.py: 6 items per CTA against 8 is 1 % faster at 383 messages and
+  // 5-8 % faster at 32-128 messages; 4 and fewer lose at 383 to the uneven last round)
+  int per_cta = 6;
+  if (const char* ev = getenv("G2P_WIN_ITEMS_PER_CTA")) per_cta = std::max(1, atoi(ev));
+  int64_t want_chunks = ceil_div(per_cta * grid_cap, p->n_tiles);
   int64_t max_chunks = ceil_div(a.b, 8);
   int64_t n_chunks = std::max<int64_t>(1, std::min(want_chunks, max_chunks));
   a.msgs_per_chunk = (int)ceil_div(a.b, n_chunks);
