@@ -805,6 +805,13 @@ int g2p_plan_create(const int32_t* idx, int64_t m, int k, int64_t n, int64_t row
       cand.push_back({tr, tc});
     }
     if (cand.empty()) cand.push_back({1, kTileTargets});
+    if (const char* ev = getenv("G2P_WIN_TILE_COLS")) {  // experiments: force one tile shape
+      const int tc = atoi(ev);
+      if (tc >= 4 && tc <= kTileTargets && (tc & (tc - 1)) == 0) {
+        cand.clear();
+        cand.push_back({kTileTargets / tc, tc});
+      }
+    }
   }
   cudaGetDevice(&p->device);
   int32_t* d_status = nullptr;
