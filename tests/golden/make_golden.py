@@ -12,8 +12,9 @@ from /root/reference/src and calls, on small synthetic inputs:
 
   * `ScipyInterpolation(...).interpolate(...)`           (modes nearest, invdist; f64 and f32 targets)
   * `Interpolator._interpolate_scipy_append_mv(...)`     (k=1, k=4, plain and masked input)
-  * `Converter.convert / cut_off_negative`, `Aggregator.do_manipulation` (3 modes),
-    `Corrector.correct`
+  * `Converter.convert / cut_off_negative`, `Aggregator.do_manipulation` (3 modes, `@halfweights`
+    averages, masked inputs), `Corrector.correct` (both formulas of the README)
+  * `NetCDFWriter._mask_values`, `PCRasterWriter._mask_values` around the writers' inline statements
 
 The only arithmetic not executed by reference code is inside the `numexpr.evaluate` shim,
 which evaluates the reference's expression strings with numpy under numexpr's typing rules
