@@ -332,16 +332,24 @@ class DeviceTable:
         path = os.environ.get('G2P_APPLY_PATH', 'auto')
         if self.k not in (1, 4) or path == 'generic':
             return False
-        if self.k == 1 and path != 'window':
-            # one gather per target: staging the window costs more than it saves (measured on O1280 -> 0.1 deg,
-            # profiles/r01_apply_sweep.md: generic 67-77 % of HBM peak, windowed 49-80 %)
-            return False
+        k1_needs_compact_tiles = self.k == 1 and path != 'window'
         n_pad = -(-self.n_src // 16) * 16
         if src.data_ptr() % 16 or src.stride(0) % 2 or src.stride(0) < n_pad:
             return False
         if propagate and (src_mask.data_ptr() % 16 or src.stride(0) % 16):
             return False
-        return self.plan() is not None
+        if self.plan() is None:
+            return False
+        if k1_needs_compact_tiles:
+            # one gather per target.  Where the target rows run along the source rings (global lat/lon targets: the plan
+            # picks 1 x 1024 tiles) the generic kernel's gathers are nearly coalesced and staging does not pay
+            # (O1280 -> 0.1 deg: generic 67-77 % of HBM peak, windowed 49-80 %); where they cut across the rings (projected
+            # regional targets: compact 16 x 64 tiles) the window wins (O1280 -> EFAS nearest, 383 messages:
+            # 0.81 / 0.88 ms without / with masks against 1.05 / 1.68 ms), profiles/r01_apply_sweep.md
+            if getattr(self, '_k1_window', None) is None:
+                self._k1_window = self.plan_info()['tile_rows'] >= 4
+            return self._k1_window
+        return True
 
     def compact(self):
         """(table over the compact numbering of the touched source points, touched int32 [nc] sorted).
