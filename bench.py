@@ -436,6 +436,18 @@ def run_b200(args):
                                    'what': 'interpolate_batch(..., writer_post=...): clone mask / value mask / NaN / '
                                            'mv_output -> fill value in the apply epilogue, no mask array copied back'}
     del ready, want, post
+    # the reference's own call pattern: one `interpolate_scipy(lat, lon, v, grid_id, details)` per message, v a
+    # pageable numpy MaskedArray as ecCodes hands it over (informational)
+    pm_fields = [np.ma.masked_array(src[i].cpu().numpy(), mask=src_mask[i].cpu().numpy().astype(bool)) for i in range(4)]
+    one = interp.interpolate_scipy(lat, lon, pm_fields[0], grid_id, det)
+    assert torch.equal(torch.from_numpy(np.ma.getdata(one).reshape(-1)).to(dev), out_t[0])
+    t0 = time.perf_counter()
+    for i in range(20):
+        interp.interpolate_scipy(lat, lon, pm_fields[i % 4], grid_id, det)
+    e2e['per_message_call'] = {'ms': (time.perf_counter() - t0) / 20 * 1e3,
+                               'what': 'Interpolator.interpolate_scipy on one pageable numpy MaskedArray per call '
+                                       '(host picks the touched values into a pinned buffer, H2D, apply, D2H, numpy out)'}
+    del pm_fields, one
     import shutil
     shutil.rmtree(tmpdir, ignore_errors=True)
     del interp, first

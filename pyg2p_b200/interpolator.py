@@ -173,6 +173,25 @@ class Interpolator:
             masked_in = [isinstance(x, ma.MaskedArray) and x.mask is not ma.nomask for x in values]
             propagate = self.mask_policy == 'propagate' and any(masked_in)
             pipe = self._pipeline(table, propagate)
+            if isinstance(pipe, device.CompactHostPipeline):
+                # pageable fields and a regional table: pick the touched values of every message straight into a
+                # small pinned buffer (2.2 MB of a 52.8 MB O1280 field for EFAS) instead of staging whole fields
+                th = pipe.touched_host()
+                nc = th.size
+                h_c = device.pinned_empty((b, nc))
+                h_cm = device.pinned_empty((b, nc), torch.uint8) if propagate else None
+                for i, x in enumerate(values):
+                    np.take(np.asarray(ma.getdata(x), dtype=np.float64).reshape(-1), th, out=h_c.numpy()[i])
+                    if propagate:
+                        if masked_in[i]:
+                            np.take(np.broadcast_to(ma.getmaskarray(x).reshape(-1), (n,)).view(np.uint8), th,
+                                    out=h_cm.numpy()[i])
+                        else:
+                            h_cm.numpy()[i] = 0
+                out, omask = pipe.run_compact(h_c, float(self.mv_output), h_cm=h_cm,
+                                              mask_policy=L.MASK_PROPAGATE if propagate else L.MASK_AS_REFERENCE, out=out,
+                                              out_mask=out_mask, correction=corrector, post=writer_post)
+                return self._batch_result(table, out, omask, b, shape, propagate, pinned, values, writer_post)
             h_src = device.pinned_empty((b, n))
             h_np = h_src.numpy()
             h_msk = device.pinned_empty((b, n), torch.uint8) if propagate else None
@@ -183,6 +202,9 @@ class Interpolator:
         out, omask = pipe.run(h_src, float(self.mv_output), src_mask=h_msk,
                               mask_policy=L.MASK_PROPAGATE if propagate else L.MASK_AS_REFERENCE, out=out,
                               out_mask=out_mask, correction=corrector, post=writer_post)
+        return self._batch_result(table, out, omask, b, shape, propagate, pinned, values, writer_post)
+
+    def _batch_result(self, table, out, omask, b, shape, propagate, pinned, values, writer_post):
         torch.cuda.current_stream(table.device).synchronize()
         res = out.numpy().reshape((b,) + shape)
         if writer_post is not None:
