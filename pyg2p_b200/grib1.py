@@ -1,9 +1,10 @@
-"""Minimal GRIB edition 1 grid reader: the Grid Description Section of `regular_ll` (type 0) and `rotated_ll`
+"""Minimal GRIB edition 1 reader: the Grid Description Section of `regular_ll` (type 0) and `rotated_ll`
 (type 10) messages -> 1-D latitude / longitude arrays in scanning order plus the geodetic keys the
 interpolation reads (`radius`, `Nj`, `gridType`, south pole of rotation) - what the reference obtains from
-ecCodes through `GribGridDetails` (src/pyg2p/__init__.py:60-144).  ecCodes stays the decoder of the data
-section; this module exists so that intertables can be (re)built and checked where ecCodes is not installed,
-e.g. to regenerate the reference's golden table from its own `tests/data/input.grib`.
+ecCodes through `GribGridDetails` (src/pyg2p/__init__.py:60-144) - and the values of simply packed grid-point
+data (`read_values`).  ecCodes stays the decoder in production; this module exists so that intertables can be
+(re)built and checked where ecCodes is not installed, e.g. to regenerate the reference's golden table from its own
+`tests/data/input.grib` and to run the reference's own test scenarios on its own messages.
 
 Rotated grids are unrotated the way ecCodes' lat/lon iterator does since 1.14.3 (pole rotation on the unit
 sphere, result rounded to 6 decimals in single precision).
@@ -79,3 +80,72 @@ def read_grid(source):
     # (src/pyg2p/__init__.py:104-111), e.g. '-15.75$16.125$511$415$212065$rotated_ll'
     details['grid_id'] = f"{lo1}${_s3(g[20:23]) / 1e3}${ni}${nj}${ni * nj}${details['gridType']}"
     return lats, lons, details
+
+
+def _ibm32(b):
+    """IBM System/360 single precision (GRIB1 reference value): sign, 7-bit base-16 exponent, 24-bit fraction."""
+    v = int.from_bytes(b, 'big')
+    sign = -1.0 if v & 0x80000000 else 1.0
+    return sign * (v & 0xffffff) / 16777216.0 * 16.0 ** (((v >> 24) & 0x7f) - 64)
+
+
+def split_messages(raw):
+    """byte strings of the GRIB1 messages in `raw` (a whole file)."""
+    out, i = [], 0
+    while True:
+        i = raw.find(b'GRIB', i)
+        if i < 0 or i + 8 > len(raw):
+            return out
+        n = int.from_bytes(raw[i + 4:i + 7], 'big')
+        if raw[i + 7] == 1 and raw[i + n - 4:i + n] == b'7777':
+            out.append(raw[i:i + n])
+            i += n
+        else:
+            i += 4
+
+
+def read_values(message, missing_value=9999.0):
+    """values of one GRIB1 message with simple packing of grid-point data (BDS flag 0), as ecCodes' `values` key:
+    (reference + X * 2**E) * 10**-D, points cleared in the bitmap section get `missing_value`.
+    -> (values float64 [n], meta dict with the product-definition keys the reference selects messages by)."""
+    raw = bytes(message)
+    if raw[:4] != b'GRIB' or raw[7] != 1:
+        raise ValueError('not a GRIB edition 1 message')
+    pds = raw[8:]
+    pds_len = int.from_bytes(pds[0:3], 'big')
+    flag = pds[7]
+    meta = dict(table2Version=pds[3], centre=pds[4], indicatorOfParameter=pds[8], indicatorOfTypeOfLevel=pds[9],
+                level=int.from_bytes(pds[10:12], 'big'), unitOfTimeRange=pds[17], P1=pds[18], P2=pds[19],
+                timeRangeIndicator=pds[20], decimalScaleFactor=_s2(pds[26:28]))
+    at = 8 + pds_len
+    if flag & 0x80:
+        at += int.from_bytes(raw[at:at + 3], 'big')             # grid description section
+    bitmap = None
+    if flag & 0x40:
+        bms_len = int.from_bytes(raw[at:at + 3], 'big')
+        if int.from_bytes(raw[at + 4:at + 6], 'big') != 0:
+            raise ValueError('predefined bitmaps are not supported')
+        bits = np.unpackbits(np.frombuffer(raw, dtype=np.uint8, count=bms_len - 6, offset=at + 6))
+        bitmap = bits[:bits.size - raw[at + 3]].astype(bool)
+        at += bms_len
+    bds_len = int.from_bytes(raw[at:at + 3], 'big')
+    bflag, unused = raw[at + 3] >> 4, raw[at + 3] & 0x0f
+    if bflag & 0b1100:
+        raise ValueError('only simple packing of grid-point data is supported')
+    e_scale = _s2(raw[at + 4:at + 6])
+    ref = _ibm32(raw[at + 6:at + 10])
+    nbits = raw[at + 10]
+    n_packed = ((bds_len - 11) * 8 - unused) // nbits if nbits else (int(bitmap.sum()) if bitmap is not None else 0)
+    if nbits:
+        bits = np.unpackbits(np.frombuffer(raw, dtype=np.uint8, count=bds_len - 11, offset=at + 11))[:n_packed * nbits]
+        weights = (1 << np.arange(nbits - 1, -1, -1)).astype(np.uint64)
+        x = bits.reshape(n_packed, nbits).astype(np.uint64) @ weights
+    else:
+        x = np.zeros(n_packed, dtype=np.uint64)
+    packed = (ref + x.astype(np.float64) * 2.0 ** e_scale) * 10.0 ** (-meta['decimalScaleFactor'])
+    if bitmap is None:
+        return packed, meta
+    values = np.full(bitmap.size, float(missing_value))
+    values[bitmap] = packed[:int(bitmap.sum())]
+    return values, meta
+

@@ -386,6 +386,20 @@ def make_reference_fixture_copies():
         head = f.read(400)
     with open(os.path.join(HERE, 'ref_input_grib_header.bin'), 'wb') as f:
         f.write(head)
+    # inputs of the reference's own test scenarios (tests/test_interpolation.py, tests/test_correction.py): the first
+    # 2t message of tests/data/input.grib (step 0 = `first_step_range`), tests/data/geopotential.grib, tests/data/dem.map
+    from pyg2p_b200 import grib1
+    from pyg2p_b200.maps import Dem
+    with open('/root/reference/tests/data/input.grib', 'rb') as f:
+        first = grib1.split_messages(f.read())[0]
+    with open(os.path.join(HERE, 'ref_input_2t_step0.grib'), 'wb') as f:
+        f.write(first)
+    with open('/root/reference/tests/data/geopotential.grib', 'rb') as f:
+        geo = grib1.split_messages(f.read())[0]
+    with open(os.path.join(HERE, 'ref_geopotential.grib'), 'wb') as f:
+        f.write(geo)
+    dem = Dem('/root/reference/tests/data/dem.map')
+    np.savez_compressed(os.path.join(HERE, 'ref_efas_dem_map.npz'), dem=dem.values, mv=np.float64(dem.mv))
     print('reference fixture copies written:', ll.identifier)
 
 
