@@ -139,3 +139,53 @@ def test_correction(Interpolator, data, tmp_path):
     np.testing.assert_array_equal(np.asarray(ma.getdata(values_out)), exact)
     corrected = (dem != dem_mv) & (values_resampled != interpolator.mv_output)
     assert corrected.mean() > 0.2 and 230.0 < np.asarray(values_out)[corrected].mean() < 300.0
+
+
+# ----------------------------------------------------------------------------- reference tests/test_aggregator.py
+def _aggregator_case(data, **kw):
+    """`messages.first_resolution_values()` of the five 2t messages of tests/data/input.grib (steps 0..24 by 6 h,
+    instantaneous, Nj = 415, level 2).  The fixture holds the first message; the later steps are derived from it
+    (the reference's assertions are on the keys)."""
+    from pyg2p_b200 import manipulation as M
+    values_orig = {M.Step(s, s, 415, 6, 2): data['values'] + 0.25 * s for s in (0, 6, 12, 18, 24)}
+    base = dict(aggr_halfweights=False, input_step=6, step_type='instant', start_step=0, mv_grib=data['missing'], end_step=24,
+                unit_time=24, force_zero_array=False)
+    base.update(kw)
+    return M, values_orig, M.Aggregator(**base).do_manipulation(values_orig)
+
+
+def test_aggregator_instant(data):
+    M, values_orig, values = _aggregator_case(data, aggr_step=6, aggr_type='instantaneous')
+    assert len(values_orig) == len(values)                                      # the reference's assertions (:29-33)
+    keys_orig, keys_res = list(values_orig.keys()), list(values.keys())
+    assert keys_orig[0] == keys_res[0] and keys_orig[-1] == keys_res[-1]
+    for k in keys_orig:
+        np.testing.assert_array_equal(values[k], 0.0 + values_orig[k])
+
+
+def test_aggregator_average(data):
+    M, values_orig, values = _aggregator_case(data, aggr_step=24, aggr_type='average')
+    assert len(values) == 1 and list(values.keys())[0] == M.Step(0, 24, 415, 24, 2)   # (:52-54)
+    # hours 1..24, each taking the next available step: 6 x (6, 12, 18, 24)
+    acc = np.zeros_like(data['values'])
+    for h in range(1, 25):
+        acc = acc + values_orig[M.Step(-(-h // 6) * 6, -(-h // 6) * 6, 415, 6, 2)]
+    np.testing.assert_array_equal(np.asarray(list(values.values())[0]), acc / 24.0)
+
+
+def test_aggregator_average_halfweights(data):
+    M, values_orig, values = _aggregator_case(data, aggr_step=24, aggr_type='average', aggr_halfweights=True, start_step=24)
+    assert len(values) == 1 and list(values.keys())[0] == M.Step(0, 24, 415, 24, 2)   # (:75-77)
+    acc = np.zeros_like(data['values'])
+    for s, w in ((0, 3.0), (6, 6.0), (12, 6.0), (18, 6.0), (24, 3.0)):
+        acc = acc + values_orig[M.Step(s, s, 415, 6, 2)] * w
+    np.testing.assert_array_equal(np.asarray(list(values.values())[0]), acc / 24.0)
+
+
+def test_aggregator_accumulation(data):
+    M, values_orig, values = _aggregator_case(data, aggr_step=6, aggr_type='accumulation')
+    keys_res = list(values.keys())
+    assert len(values) == 4 and keys_res[0] == M.Step(0, 6, 415, 6, 2) and keys_res[-1] == M.Step(18, 24, 415, 6, 2)   # (:98-101)
+    for k in keys_res:
+        cur, prev = values_orig[M.Step(k.end_step, k.end_step, 415, 6, 2)], values_orig[M.Step(k.start_step, k.start_step, 415, 6, 2)]
+        np.testing.assert_array_equal(np.asarray(values[k]), ((0.0 + cur) - prev) * 24 / 6)
