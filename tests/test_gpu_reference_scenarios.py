@@ -189,3 +189,33 @@ def test_aggregator_accumulation(data):
     for k in keys_res:
         cur, prev = values_orig[M.Step(k.end_step, k.end_step, 415, 6, 2)], values_orig[M.Step(k.start_step, k.start_step, 415, 6, 2)]
         np.testing.assert_array_equal(np.asarray(values[k]), ((0.0 + cur) - prev) * 24 / 6)
+
+
+# ----------------------------------------------------------------------------- reference tests/test_conversion.py
+class TestConversion:
+    data = np.random.default_rng(0).uniform(low=-100.0, high=100.0, size=(100, 100))
+
+    def test_identity(self):
+        from pyg2p_b200.manipulation import Converter
+        converter = Converter('x=x')
+        data = self.data.copy()
+        res = converter.convert(data)
+        assert np.allclose(data, res)
+
+    def test_conversion(self):
+        from pyg2p_b200.manipulation import Converter
+        converter = Converter('x=x-273.15')
+        data = self.data.copy()
+        res = converter.convert(data)
+        assert np.allclose(data - 273.15, res)
+        np.testing.assert_array_equal(res, data - 273.15)
+
+    def test_cutoff(self):
+        from pyg2p_b200.manipulation import Converter
+        assert self.data[self.data < 0].size > 0
+        converter = Converter('x=x', cut_off=True)
+        data = self.data.copy()
+        res = converter.convert(data)
+        res = converter.cut_off_negative(res)
+        assert res[res < 0].size == 0
+        assert np.allclose(res[res > 0], data[data > 0])
