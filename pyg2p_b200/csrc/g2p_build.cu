@@ -641,6 +641,7 @@ struct KnnArgs {
   double* dmax2_out;         // SELF mode: max over queries of d2[1]
   int64_t q0;                // SELF mode: first source record of this call (sharded self query)
   unsigned long long* stats; // [0] extra passes, [1] candidates examined (debug counters; nullable)
+  double r0_scale;           // scales the initial search radius (experiments: G2P_KNN_R0)
 };
 
 __device__ __forceinline__ bool lex_lt(double da, int ia, double db, int ib) {
@@ -793,14 +794,17 @@ __device__ __forceinline__ void merge_group(TopK<KK>& top, unsigned gmask) {
 
 // initial search radius in units of the mean spacing h, by k
 __device__ __forceinline__ double initial_radius_factor(int k) {
-  return k <= 1 ? 0.85 : (k == 2 ? 1.25 : (k <= 4 ? 1.6 : 0.62 * sqrt((double)k) + 0.5));
+  // (measured on O1280 -> 0.05 deg, k = 4: 1.44 h -> 8.00 ms per build, 1.6 h -> 8.24 ms, 1.28 h -> 8.44 ms, 1.76 h -> 8.56 ms:
+  // a smaller cap scans fewer cells but more queries need a second pass)
+  return 0.9 * (k <= 1 ? 0.85 : (k == 2 ? 1.25 : (k <= 4 ? 1.6 : 0.62 * sqrt((double)k) + 0.5)));
 }
 
 template <int KK, int LANES>
 __device__ __forceinline__ void knn_search(const IndexView& ix, int k, double qx, double qy, double qz, int lane,
-                                           unsigned gmask, TopK<KK>& top, unsigned& passes, unsigned& examined) {
+                                           unsigned gmask, TopK<KK>& top, unsigned& passes, unsigned& examined,
+                                           double r0_scale) {
   const double qnorm = sqrt(qx * qx + qy * qy + qz * qz);
-  double D = ix.h * initial_radius_factor(k);
+  double D = ix.h * initial_radius_factor(k) * r0_scale;
   const double Dmax = 2.0 * (ix.radius + qnorm) + ix.radius;
   passes = 0;
   examined = 0;
@@ -889,7 +893,7 @@ __global__ void __launch_bounds__(256, (KK >= 4 && KK < 11) ? 3 : 1) knn_kernel(
     }
     TopK<KK> top;
     unsigned passes, examined;
-    knn_search<KK, LANES>(a.ix, k, qx, qy, qz, lane, gmask, top, passes, examined);
+    knn_search<KK, LANES>(a.ix, k, qx, qy, qz, lane, gmask, top, passes, examined, a.r0_scale);
     extra_passes += passes - 1;
     cand += examined;
     if (QSRC == QUERY_SELF) {
@@ -1166,6 +1170,7 @@ int g2p_index_max_nn_dist_part(g2p_index* ix, int64_t first, int64_t last, doubl
   G2P_CUDA(pool_alloc(&d_max, sizeof(double), st));
   G2P_CUDA(cudaMemsetAsync(d_max, 0, sizeof(double), st));
   KnnArgs a{};
+  a.r0_scale = env_double("G2P_KNN_R0", 1.0);
   a.ix = view_of(ix);
   a.m = last - first;
   a.q0 = first;
@@ -1198,6 +1203,7 @@ int g2p_knn(const g2p_index* ix, const void* tlon, const void* tlat, const doubl
   if (m < 0) return set_error(G2P_ERR_INVALID, "g2p_knn: m < 0");
   if (m == 0) return G2P_OK;
   KnnArgs a{};
+  a.r0_scale = env_double("G2P_KNN_R0", 1.0);
   a.ix = view_of(ix);
   a.tlon = tlon;
   a.tlat = tlat;
