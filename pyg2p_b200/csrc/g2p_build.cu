@@ -1219,6 +1219,20 @@ int g2p_knn(const g2p_index* ix, const void* tlon, const void* tlat, const doubl
   a.flags_out = flags_out;
   a.xyz_out = xyz_out;
   int qsrc = txyz ? QUERY_XYZ : (dtype == G2P_F32 ? QUERY_LATLON_F32 : QUERY_LATLON_F64);
+  if (getenv("G2P_KNN_STATS")) {  // diagnostics: search passes and candidates per query, on stderr (synchronises)
+    unsigned long long* d_stats = nullptr;
+    G2P_CUDA(cudaMalloc(&d_stats, 16));
+    G2P_CUDA(cudaMemsetAsync(d_stats, 0, 16, as_stream(stream)));
+    a.stats = d_stats;
+    const int rc = launch_knn(a, qsrc, as_stream(stream));
+    unsigned long long h[2] = {0, 0};
+    cudaMemcpyAsync(h, d_stats, 16, cudaMemcpyDeviceToHost, as_stream(stream));
+    cudaStreamSynchronize(as_stream(stream));
+    cudaFree(d_stats);
+    fprintf(stderr, "g2p_knn: %lld queries k=%d: %.3f extra passes and %.1f candidates per query\n", (long long)m, k,
+            (double)h[0] / (double)m, (double)h[1] / (double)m);
+    return rc;
+  }
   return launch_knn(a, qsrc, as_stream(stream));
 }
 
