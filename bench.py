@@ -543,6 +543,16 @@ def run_b200(args):
                             'h2d_bytes': int(lon.nbytes + lat.nbytes + gl.nbytes + glo.nbytes), 'd2h_bytes': int(rec.nbytes),
                             'api': 'ScipyInterpolation(...).build_table(lon, lat).to_record(): pageable numpy lat/lon in, '
                                    'numpy record array {int64 indexes, f8 coeffs} (m, 4) out'}
+            # writing the table as the Interpolator does (`.npy.gz`, readable by the reference's loader): every host
+            # core compresses a slice (the reference's single-threaded level-9 write takes ~41 s per million k=4 rows)
+            import tempfile as _tf
+            from pyg2p_b200.interpolator import save_npy_gz_parallel
+            with _tf.TemporaryDirectory(prefix='g2p_tbl_') as td:
+                tpath = os.path.join(td, 'tbl.npy.gz')
+                t0 = time.perf_counter()
+                save_npy_gz_parallel(tpath, rec)
+                build['e2e']['table_write_seconds'] = time.perf_counter() - t0
+                build['e2e']['table_file_bytes'] = os.path.getsize(tpath)
             del si, rec
 
     # ---- fused pipeline (BASELINE configs[4], eue_r24-style): members x (steps 0..360 by 6 h) of one GPU's share
