@@ -553,6 +553,12 @@ def run_b200(args):
                 save_npy_gz_parallel(tpath, rec)
                 build['e2e']['table_write_seconds'] = time.perf_counter() - t0
                 build['e2e']['table_file_bytes'] = os.path.getsize(tpath)
+                from pyg2p_b200.interpolator import load_npy_gz_parallel
+                t0 = time.perf_counter()
+                back = load_npy_gz_parallel(tpath)
+                build['e2e']['table_read_seconds'] = time.perf_counter() - t0
+                assert back.shape == rec.shape and back[-1].tobytes() == rec[-1].tobytes()
+                del back
             del si, rec
 
     # ---- fused pipeline (BASELINE configs[4], eue_r24-style): members x (steps 0..360 by 6 h) of one GPU's share

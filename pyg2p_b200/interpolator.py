@@ -21,13 +21,19 @@ from .maps import LatLong
 from .scipy_interpolation import ScipyInterpolation
 
 
+_GZ_SUBFIELD = b'G2'            # gzip FEXTRA subfield of our members: uint64 length of the deflate payload
+
+
 def save_npy_gz_parallel(path, array, level=1, chunk_bytes=16 << 20, threads=None):
     """`np.save` through gzip, compressed by all host cores: the `.npy` byte stream is cut into chunks, every
     chunk becomes one gzip member (zlib releases the GIL), the members are concatenated.  A multi-member file
     is a valid gzip stream - `gzip.GzipFile(path).read()` / `np.load` in the reference read it unchanged
     (interpolation/__init__.py:107-120) - and decompresses to exactly the bytes `np.save` writes.  The
-    reference's single-threaded level-9 write costs ~40 s per million k=4 rows."""
+    reference's single-threaded level-9 write costs ~40 s per million k=4 rows.
+    Every member carries, in a gzip FEXTRA subfield (ignored by other readers, the way BGZF does it), the length of
+    its deflate payload, so that `load_npy_gz_parallel` can find the members without inflating them."""
     import io
+    import struct
     import zlib
     from concurrent.futures import ThreadPoolExecutor
     buf = io.BytesIO()
@@ -35,12 +41,72 @@ def save_npy_gz_parallel(path, array, level=1, chunk_bytes=16 << 20, threads=Non
     data = buf.getbuffer()
 
     def member(lo):
-        c = zlib.compressobj(level, zlib.DEFLATED, 31)          # wbits 31 = gzip container
-        return c.compress(data[lo:lo + chunk_bytes]) + c.flush()
+        raw = data[lo:lo + chunk_bytes]
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)         # raw deflate: header and trailer are written here
+        payload = c.compress(raw) + c.flush()
+        extra = _GZ_SUBFIELD + struct.pack('<HQ', 8, len(payload))
+        head = b'\x1f\x8b\x08\x04' + b'\x00\x00\x00\x00' + b'\x00\xff' + struct.pack('<H', len(extra)) + extra
+        return head + payload + struct.pack('<II', zlib.crc32(raw) & 0xffffffff, len(raw) & 0xffffffff)
 
     with ThreadPoolExecutor(max_workers=threads or os.cpu_count() or 1) as pool, open(path, 'wb') as f:
         for part in pool.map(member, range(0, max(len(data), 1), chunk_bytes)):
             f.write(part)
+
+
+def load_npy_gz_parallel(path, threads=None):
+    """`np.load(gzip.GzipFile(path))` for files written by `save_npy_gz_parallel`, inflated by all host cores: the
+    members are found by hopping over their payloads (length in the FEXTRA subfield, size of the content in the
+    gzip trailer), every member is inflated straight into its slice of the result.  Any other gzip file (the
+    reference's own single-member tables) is read the plain way (interpolation/__init__.py:107-120)."""
+    import struct
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    with open(path, 'rb') as f:
+        blob = f.read()
+    members, at, total = [], 0, 0
+    while at < len(blob):
+        ok = (blob[at:at + 4] == b'\x1f\x8b\x08\x04' and len(blob) >= at + 24 and blob[at + 12:at + 14] == _GZ_SUBFIELD
+              and struct.unpack_from('<HH', blob, at + 10)[0] == 12 and struct.unpack_from('<H', blob, at + 14)[0] == 8)
+        if not ok:
+            members = None
+            break
+        n_payload = struct.unpack_from('<Q', blob, at + 16)[0]
+        start = at + 24
+        end = start + n_payload
+        if end + 8 > len(blob):
+            members = None
+            break
+        crc, size = struct.unpack_from('<II', blob, end)
+        members.append((start, end, total, size, crc))
+        total += size
+        at = end + 8
+    if not members:
+        with gzip.GzipFile(path, 'r') as f:
+            return np.load(f)
+    out = np.empty(total, dtype=np.uint8)       # not zero-filled: the pages are first touched by the inflating threads
+    view = memoryview(out)
+
+    def inflate(m):
+        start, end, lo, size, crc = m
+        raw = zlib.decompressobj(-15).decompress(memoryview(blob)[start:end])
+        if len(raw) != size or (zlib.crc32(raw) & 0xffffffff) != crc:
+            raise OSError(f'{path}: corrupt gzip member at byte {start}')
+        view[lo:lo + size] = raw
+
+    with ThreadPoolExecutor(max_workers=threads or os.cpu_count() or 1) as pool:
+        list(pool.map(inflate, members))
+    return _npy_from_buffer(out)
+
+
+def _npy_from_buffer(buf):
+    """np.load of an in-memory `.npy` image without another copy of the data."""
+    import io
+    from numpy.lib import format as npf
+    f = io.BytesIO(bytes(memoryview(buf)[:4096]))
+    version = npf.read_magic(f)
+    shape, fortran, dtype = npf.read_array_header_1_0(f) if version == (1, 0) else npf.read_array_header_2_0(f)
+    arr = np.frombuffer(buf, dtype=dtype, offset=f.tell(), count=int(np.prod(shape, dtype=np.int64)))
+    return arr.reshape(shape, order='F' if fortran else 'C')
 
 
 def _normalize_filename(name):
@@ -131,8 +197,7 @@ class Interpolator:
         if tbl_fullpath not in self._LOADED_INTERTABLES:
             path = tbl_fullpath if os.path.exists(tbl_fullpath) else tbl_fullpath + '.gz'
             if path.endswith('.gz'):
-                with gzip.GzipFile(path, 'r') as f:
-                    self._LOADED_INTERTABLES[tbl_fullpath] = np.load(f)
+                self._LOADED_INTERTABLES[tbl_fullpath] = load_npy_gz_parallel(path)
             else:
                 self._LOADED_INTERTABLES[tbl_fullpath] = np.load(path)
         return self._LOADED_INTERTABLES[tbl_fullpath]
@@ -286,8 +351,7 @@ class Interpolator:
                     raise ApplicationException.get_exc(
                         NO_INTERTABLE_CREATED, details=f'Tried to read both {tbl_fullpath} and {path} but none was found')
             if path.endswith('.gz'):
-                with gzip.GzipFile(path, 'r') as f:
-                    rec = np.load(f)
+                rec = load_npy_gz_parallel(path)
             else:
                 rec = np.load(path)
             self._LOADED_INTERTABLES[tbl_fullpath] = rec

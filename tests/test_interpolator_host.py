@@ -122,3 +122,35 @@ def test_parallel_gzip_table_is_read_by_the_reference_loader(tmp_path):
     save_npy_gz_parallel(str(tmp_path / 'empty.npy.gz'), rec[:0])
     with gzip.GzipFile(tmp_path / 'empty.npy.gz', 'r') as f:
         assert np.load(f).shape == (0, 4)
+
+
+def test_parallel_gzip_loader(tmp_path):
+    """`load_npy_gz_parallel` inflates the members of our own files side by side (their lengths travel in a gzip FEXTRA
+    subfield) and falls back to the plain reader for any other gzip file - e.g. the reference's own tables."""
+    import zlib
+    from pyg2p_b200.interpolator import load_npy_gz_parallel, save_npy_gz_parallel
+    rng = np.random.default_rng(1)
+    for shape in ((200_000, 4), (70_001,), (0, 4), (3, 4)):
+        rec = np.zeros(shape, dtype=[('indexes', '<i8'), ('coeffs', '<f8' if len(shape) == 2 else '<f4')])
+        rec['indexes'] = rng.integers(0, 6_599_681, shape)
+        rec['coeffs'] = rng.random(shape)
+        path = str(tmp_path / 'tbl.npy.gz')
+        save_npy_gz_parallel(path, rec, chunk_bytes=1 << 19)
+        back = load_npy_gz_parallel(path)
+        assert back.dtype == rec.dtype and back.shape == rec.shape and back.tobytes() == rec.tobytes()
+        with gzip.GzipFile(path, 'r') as f:                     # the reference's reader sees the same array
+            assert np.load(f).tobytes() == rec.tobytes()
+        plain = str(tmp_path / 'plain.npy.gz')                  # single member, no subfield: what the reference writes
+        with gzip.GzipFile(plain, 'w', compresslevel=1) as f:
+            np.save(f, rec)
+        assert load_npy_gz_parallel(plain).tobytes() == rec.tobytes()
+    # the reference's golden table goes through the fallback
+    golden = os.path.join(os.path.dirname(__file__), 'golden', 'ref_tbl_pf10slhf_550800_scipy_nearest.npy.gz')
+    assert load_npy_gz_parallel(golden).shape == (550800,)
+    # a damaged member is noticed (CRC of the inflated bytes)
+    blob = bytearray(open(path, 'rb').read())
+    blob[len(blob) // 2] ^= 0x55
+    bad = str(tmp_path / 'bad.npy.gz')
+    open(bad, 'wb').write(bytes(blob))
+    with pytest.raises((OSError, zlib.error, ValueError)):
+        load_npy_gz_parallel(bad)
