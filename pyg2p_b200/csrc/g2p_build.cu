@@ -902,6 +902,71 @@ __global__ void __launch_bounds__(256, KK < 11 ? 3 : 1) knn_kernel(const KnnArgs
       if (lane == 0 && d2 > self_max) self_max = d2;
       continue;
     }
+    if (LANES == 2 && KK == 4 && k == 4 && a.mode == G2P_MODE_INVDIST) {
+      // invdist epilogue on BOTH lanes of the query (each holds the same merged list): lane l takes the square roots,
+      // reciprocals and divisions of neighbours 2l and 2l+1; only the running sum ((w0 + w1) + w2) + w3 crosses lanes
+      const double e2a = lane ? top.d[2] : top.d[0], e2b = lane ? top.d[3] : top.d[1];
+      const int ida = lane ? top.id[2] : top.id[0], idb = lane ? top.id[3] : top.id[1];
+      double da = __dsqrt_rn(e2a), db = __dsqrt_rn(e2b);
+      if (F32) {
+        da = (double)(float)da;
+        db = (double)(float)db;
+      }
+      const int lead = (threadIdx.x & 31) & ~1;                 // lane 0 of this pair within the warp
+      const double d0 = __shfl_sync(gmask, da, lead);
+      const double nan = __longlong_as_double(0x7ff8000000000000LL);
+      double wa, wb;
+      bool inside;
+      if (F32 ? ((float)d0 <= 1e-10f) : (d0 <= 1e-10)) {        // the target coincides with a source point
+        wa = lane ? 0.0 : 1.0;
+        wb = 0.0;
+        inside = true;
+      } else if (d0 <= a.mub) {   // (both lanes of a pair see the same d0: they take the same branch, shuffles included)
+        if (F32) {
+          const float fa = (float)da, fb = (float)db;
+          const float ra = __fdiv_rn(1.0f, __fmul_rn(fa, fa)), rb = __fdiv_rn(1.0f, __fmul_rn(fb, fb));
+          const float p01 = __shfl_sync(gmask, __fadd_rn(ra, rb), lead);      // w0 + w1 (from lane 0)
+          const float sum = __shfl_sync(gmask, __fadd_rn(__fadd_rn(p01, ra), rb), lead + 1);   // (+ w2) + w3 (on lane 1)
+          wa = (double)__fdiv_rn(ra, sum);
+          wb = (double)__fdiv_rn(rb, sum);
+        } else {
+          const double ra = __ddiv_rn(1.0, __dmul_rn(da, da)), rb = __ddiv_rn(1.0, __dmul_rn(db, db));
+          const double p01 = __shfl_sync(gmask, __dadd_rn(ra, rb), lead);
+          const double sum = __shfl_sync(gmask, __dadd_rn(__dadd_rn(p01, ra), rb), lead + 1);
+          wa = __ddiv_rn(ra, sum);
+          wb = __ddiv_rn(rb, sum);
+        }
+        inside = true;
+      } else {
+        wa = wb = nan;
+        inside = false;
+      }
+      const int32_t nsrc2 = (int32_t)a.ix.n;
+      const int64_t sa = (int64_t)(2 * lane) * a.m + q;
+      a.idx_out[sa] = (inside && ida != INT_MAX) ? ida : nsrc2;
+      a.coef_out[sa] = wa;
+      a.idx_out[sa + a.m] = (inside && idb != INT_MAX) ? idb : nsrc2;
+      a.coef_out[sa + a.m] = wb;
+      if (lane == 0) {
+        if (a.xyz_out) {
+          a.xyz_out[3 * q] = qx; a.xyz_out[3 * q + 1] = qy; a.xyz_out[3 * q + 2] = qz;
+        }
+        if (a.flags_out) {
+          uint8_t flag = 0;
+#pragma unroll
+          for (int s = 0; s < KK; ++s) {
+            if (top.id[s] == INT_MAX) flag |= G2P_FLAG_SHORT;
+            const double after = (s + 1 < KK) ? top.d[(s + 1 < KK) ? s + 1 : s] : top.nxt;
+            if (after < inf) {
+              if (top.d[s] == after) flag |= G2P_FLAG_TIE;
+              else if (after - top.d[s] <= after * 5.7e-14) flag |= G2P_FLAG_NEAR_TIE;
+            }
+          }
+          a.flags_out[q] = flag;
+        }
+      }
+      continue;
+    }
     if (lane != 0) continue;
     if (a.xyz_out) {
       a.xyz_out[3 * q] = qx; a.xyz_out[3 * q + 1] = qy; a.xyz_out[3 * q + 2] = qz;
