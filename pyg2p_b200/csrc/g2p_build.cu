@@ -752,8 +752,24 @@ __device__ __forceinline__ void scan_cap(const IndexView& ix, double qx, double 
     // the face lies within 54.74 deg of its axis: unreachable if angle(q, axis) > gamma + 54.74 deg
     if ((float)cf < cosf(fminf(gam + 0.9554f, 3.1415926f)) - 1e-5f) continue;
     int alo, ahi, blo, bhi;
-    if (!axis_range((float)a, (float)cf, s, G, alo, ahi)) continue;
-    if (!axis_range((float)b, (float)cf, s, G, blo, bhi)) continue;
+    if (LANES == 2) {
+      // the two lanes of a query hold the same q: each works out one axis of the rectangle and they swap the results
+      const unsigned pair = 3u << ((threadIdx.x & 31) & ~1);
+      int lo, hi;
+      if (!axis_range((float)(lane ? b : a), (float)cf, s, G, lo, hi)) {
+        lo = 1;
+        hi = 0;
+      }
+      const int olo = __shfl_xor_sync(pair, lo, 1), ohi = __shfl_xor_sync(pair, hi, 1);
+      alo = lane ? olo : lo;
+      ahi = lane ? ohi : hi;
+      blo = lane ? lo : olo;
+      bhi = lane ? hi : ohi;
+      if (alo > ahi || blo > bhi) continue;
+    } else {
+      if (!axis_range((float)a, (float)cf, s, G, alo, ahi)) continue;
+      if (!axis_range((float)b, (float)cf, s, G, blo, bhi)) continue;
+    }
     for (int ib = blo; ib <= bhi; ++ib) {
       const int64_t row = ((int64_t)f * G + ib) * G;
       const uint32_t p0 = __ldg(ix.cell_start + row + alo);
