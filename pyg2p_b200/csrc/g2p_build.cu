@@ -1062,16 +1062,18 @@ __global__ void weights_kernel(int mode, int k, int64_t m, int32_t nsrc, double 
   }
 }
 
-static int knn_lanes() {
-  static int lanes = 0;
-  if (lanes == 0) {
-    // threads per query.  Measured on B200, O1280 -> 0.05 deg k=4 (21.6 M queries): 1 lane 17.8 ms, 2 lanes 7.5 ms,
-    // 4 lanes 12.8 ms, 8 lanes 23.4 ms - with ~30 candidates per query the shuffle merge of wider groups
-    // costs more than the scan it parallelises (profiles/r01_build.md)
-    int v = (int)env_double("G2P_KNN_LANES", 2);
-    lanes = (v == 1 || v == 2 || v == 4 || v == 8 || v == 32) ? v : 2;
+static int knn_lanes(int kk) {
+  static int forced = -1;
+  if (forced < 0) {
+    const int v = (int)env_double("G2P_KNN_LANES", 0);
+    forced = (v == 1 || v == 2 || v == 4 || v == 8 || v == 32) ? v : 0;
   }
-  return lanes;
+  if (forced) return forced;
+  // threads per query.  Measured on B200, O1280 -> 0.05 deg k=4 (21.6 M queries): 1 lane 17.8 ms, 2 lanes 7.5 ms,
+  // 4 lanes 12.8 ms, 8 lanes 23.4 ms - with ~20 candidates per query the shuffle merge of wider groups costs more
+  // than the scan it parallelises; for one or two neighbours a lane of its own per query is best (k=1, 5.4 M
+  // queries: 0.65 ms against 0.82 ms; the k=2 self query of 6.6 M points: 0.71 ms against 0.87 ms), profiles/r01_build.md
+  return kk <= 2 ? 1 : 2;
 }
 
 template <int KK, int LANES>
@@ -1093,7 +1095,7 @@ static int launch_knn_q(const KnnArgs& a, int qsrc, cudaStream_t st) {
 
 template <int KK>
 static int launch_knn_l(const KnnArgs& a, int qsrc, cudaStream_t st) {
-  switch (knn_lanes()) {
+  switch (knn_lanes(KK)) {
     case 1: return launch_knn_q<KK, 1>(a, qsrc, st);
     case 2: return launch_knn_q<KK, 2>(a, qsrc, st);
     case 4: return launch_knn_q<KK, 4>(a, qsrc, st);
