@@ -887,7 +887,7 @@ __device__ __forceinline__ void invdist_weights(const double* d, int k, double m
 enum { QUERY_LATLON_F64 = 0, QUERY_LATLON_F32 = 1, QUERY_XYZ = 2, QUERY_SELF = 3 };
 
 template <int KK, int LANES, int QSRC>
-__global__ void __launch_bounds__(256, KK < 11 ? 3 : 1) knn_kernel(const KnnArgs a) {
+__global__ void __launch_bounds__(256, KK <= 2 ? 5 : (KK <= 4 ? 4 : (KK < 11 ? 3 : 1))) knn_kernel(const KnnArgs a) {
   constexpr bool F32 = (QSRC == QUERY_LATLON_F32);
   const int lane = threadIdx.x % LANES;
   const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31) / LANES * LANES));
