@@ -46,7 +46,25 @@ enum {
 
 enum { G2P_F64 = 0, G2P_F32 = 1 };                 /* dtype of lat/lon maps, distances, coeffs */
 enum { G2P_MODE_RAW = 0, G2P_MODE_NEAREST = 1, G2P_MODE_INVDIST = 2 };
-enum { G2P_MASK_AS_REFERENCE = 0, G2P_MASK_PROPAGATE = 1, G2P_MASK_FILL = 2 };
+enum {
+  G2P_MASK_AS_REFERENCE = 0,
+  G2P_MASK_PROPAGATE = 1,
+  G2P_MASK_FILL = 2,
+  G2P_MASK_PROPAGATE_BITS = 3, /* PROPAGATE with bit-packed masks, in and out (see g2p_apply) */
+  G2P_MASK_MARKED = 4          /* masked source values carry G2P_MASK_MARKER; out_mask (nullable) is bit-packed */
+};
+
+/* Bit-packed masks (G2P_MASK_PROPAGATE_BITS / G2P_MASK_MARKED): bit j of a row is bit (j & 7) of byte (j >> 3),
+ * i.e. numpy.packbits(mask, bitorder='little') - one bit per point, as the GRIB bitmap section itself stores
+ * missing points.  A source row of `src_stride` values has src_stride / 8 mask bytes (src_stride % 8 == 0); an
+ * output row of `out_stride` values has G2P_BITS_ROW_BYTES(out_stride) mask bytes (whole 32-bit words). */
+#define G2P_BITS_ROW_BYTES(stride) ((((stride) + 31) / 32) * 4)
+
+/* The float64 quiet NaN that stands for "masked" inside a source field under G2P_MASK_MARKED (and inside the
+ * shared-memory windows of the apply kernels under every mask policy).  Producers that touch every value anyway -
+ * g2p_manip, g2p_mark_masked - write it where the mask is set, so that the apply kernel needs no mask input.
+ * Consumers test the upper 32 bits only (sign ignored): any NaN whose upper word is 0x7ff86d61 is masked. */
+#define G2P_MASK_MARKER 0x7ff86d61736b0001ull
 
 /* per-target flags written by g2p_knn */
 enum {
@@ -158,10 +176,20 @@ int g2p_table_compact(const int32_t* idx, int64_t m, int k, int64_t n, int32_t* 
  *   mask_policy: AS_REFERENCE ignores src_mask (the reference drops it);
  *                PROPAGATE is the intended semantics of :148-161: out_mask = OR of the k source masks and
  *                the masked outputs hold mv_out (`ma.filled(result, mv_out)`, what the writers do with a
- *                masked result: util/numeric.py:21-27); FILL is PROPAGATE without the out_mask array */
+ *                masked result: util/numeric.py:21-27); FILL is PROPAGATE without the out_mask array;
+ *                PROPAGATE_BITS is PROPAGATE with src_mask and out_mask bit-packed (layout above; 8x less mask
+ *                traffic, and out_mask costs one memset plus a store per MASKED output only);
+ *                MARKED takes no src_mask: a source value equal to G2P_MASK_MARKER is masked; out_mask is
+ *                bit-packed and may be NULL (then it is FILL for marked fields) */
 int g2p_apply(const int32_t* idx, const double* coef, int64_t m, int k, const double* src,
               const uint8_t* src_mask, int64_t n, int b, int64_t src_stride, int64_t out_stride,
               double mv_out, int mask_policy, double* out, uint8_t* out_mask, void* stream);
+
+/* In place on b rows of n values: v = mask ? G2P_MASK_MARKER : v (src_mask uint8, or bit-packed when
+ * mask_bits != 0; strides as in g2p_apply).  The producer-side half of G2P_MASK_MARKED for fields that reach the
+ * device with a separate mask. */
+int g2p_mark_masked(double* src, const uint8_t* src_mask, int mask_bits, int64_t n, int b, int64_t src_stride,
+                    void* stream);
 
 /* K7w  windowed apply: the same operation as g2p_apply with the source values staged through shared
  * memory by TMA bulk copies (see pyg2p_b200/csrc/g2p_apply_win.cu).  It needs a plan, built once per
@@ -190,7 +218,8 @@ int g2p_plan_destroy(g2p_plan* plan);
 int g2p_plan_get_info(const g2p_plan* plan, g2p_plan_info* info /* host */);
 /* arguments as g2p_apply; the indexes come from the plan.  Requirements (else G2P_ERR_UNSUPPORTED):
  * k in {1, 4}; src 16-byte aligned with src_stride a multiple of 2 and >= n rounded up to 16;
- * under PROPAGATE also src_mask 16-byte aligned and src_stride a multiple of 16. */
+ * under PROPAGATE / FILL also src_mask 16-byte aligned and src_stride a multiple of 16; under PROPAGATE_BITS
+ * src_stride a multiple of 8 and out_mask 4-byte aligned. */
 int g2p_apply_planned(const g2p_plan* plan, const double* coef, const double* src, const uint8_t* src_mask, int b,
                       int64_t src_stride, int64_t out_stride, double mv_out, int mask_policy, double* out,
                       uint8_t* out_mask, void* stream);

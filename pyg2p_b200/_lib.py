@@ -14,7 +14,8 @@ OK = 0
 ERR_UNSUPPORTED = -5
 F64, F32 = 0, 1
 MODE_RAW, MODE_NEAREST, MODE_INVDIST = 0, 1, 2
-MASK_AS_REFERENCE, MASK_PROPAGATE, MASK_FILL = 0, 1, 2
+MASK_AS_REFERENCE, MASK_PROPAGATE, MASK_FILL, MASK_PROPAGATE_BITS, MASK_MARKED = 0, 1, 2, 3, 4
+MASK_MARKER = 0x7ff86d61736b0001          # G2P_MASK_MARKER: the float64 NaN that stands for 'masked' in a source field
 FLAG_TIE, FLAG_NEAR_TIE, FLAG_SHORT = 1, 2, 4
 
 
@@ -89,6 +90,7 @@ PROTOTYPES = {
     'g2p_table_unpack_rec': (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     'g2p_table_compact': (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp, C.POINTER(C.c_int64), _vp]),
     'g2p_apply': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _i32, _i64, _i64, _f64, _i32, _vp, _vp, _vp]),
+    'g2p_mark_masked': (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i64, _vp]),
     'g2p_plan_create': (C.c_int, [_vp, _i64, _i32, _i64, _i64, _i64, C.POINTER(_vp), _vp]),
     'g2p_plan_destroy': (C.c_int, [_vp]),
     'g2p_plan_get_info': (C.c_int, [_vp, C.POINTER(PlanInfo)]),

@@ -28,6 +28,7 @@ struct ApplyArgs {
   double* out;
   uint8_t* out_mask;
   int64_t m, n, src_stride, out_stride;
+  int64_t sbits_stride, obits_stride;  // bit-packed mask rows: bytes per source row, uint32 words per output row
   int b, k;
   int msgs_per_chunk, n_target_tiles;
   int64_t n_tiles;
@@ -44,12 +45,32 @@ __device__ __forceinline__ double weighted(const double (&w)[K], const double (&
   return acc;
 }
 
-template <int K, bool MASK, int U>
+constexpr unsigned long long kMarker = G2P_MASK_MARKER;
+
+// MP: 0 no masks, 1 byte masks (PROPAGATE / FILL), 3 bit-packed masks (PROPAGATE_BITS), 4 MARKED source values
+template <int MP>
+__device__ __forceinline__ uint32_t src_masked(const ApplyArgs& a, int msg, int32_t i, double v) {
+  if (MP == 1) return __ldg(a.src_mask + (int64_t)msg * a.src_stride + i) != 0;
+  if (MP == 3) return (__ldg(a.src_mask + (int64_t)msg * a.sbits_stride + (i >> 3)) >> (i & 7)) & 1u;
+  if (MP == 4) return ((uint32_t)__double2hiint(v) & 0x7fffffffu) == (uint32_t)(kMarker >> 32);  // upper word, as the windowed kernel
+  return 0u;
+}
+
+template <int MP>
+__device__ __forceinline__ void store_mask(const ApplyArgs& a, int msg, int64_t j, uint32_t mk) {
+  if (!a.out_mask) return;
+  if (MP == 1) a.out_mask[(int64_t)msg * a.out_stride + j] = (uint8_t)mk;
+  if (MP >= 3 && mk)   // the launcher cleared the bit rows
+    atomicOr(reinterpret_cast<uint32_t*>(a.out_mask) + (int64_t)msg * a.obits_stride + (j >> 5), 1u << (j & 31));
+}
+
+template <int K, int MP, int U>
 __device__ __forceinline__ void apply_messages(const ApplyArgs& a, int msg, int64_t j0, bool has1,
                                                const int32_t (&i0)[K], const int32_t (&i1)[K],
                                                const double (&w0)[K], const double (&w1)[K]) {
+  constexpr bool MASK = MP != 0;
   double v0[U][K], v1[U][K];
-  uint8_t mk0[U], mk1[U];
+  uint32_t mk0[U], mk1[U];
   const uint32_t n = (uint32_t)a.n;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
@@ -60,15 +81,14 @@ __device__ __forceinline__ void apply_messages(const ApplyArgs& a, int msg, int6
       v1[u][kk] = ((uint32_t)i1[kk] < n) ? __ldg(s + i1[kk]) : a.mv_out;
     }
     if (MASK) {
-      const uint8_t* __restrict__ sm = a.src_mask + (int64_t)(msg + u) * a.src_stride;
-      uint8_t m0 = 0, m1 = 0;
+      uint32_t m0 = 0, m1 = 0;
 #pragma unroll
       for (int kk = 0; kk < K; ++kk) {
-        if ((uint32_t)i0[kk] < n) m0 |= __ldg(sm + i0[kk]);
-        if ((uint32_t)i1[kk] < n) m1 |= __ldg(sm + i1[kk]);
+        if ((uint32_t)i0[kk] < n) m0 |= src_masked<MP>(a, msg + u, i0[kk], v0[u][kk]);
+        if ((uint32_t)i1[kk] < n) m1 |= src_masked<MP>(a, msg + u, i1[kk], v1[u][kk]);
       }
-      mk0[u] = m0 ? 1 : 0;
-      mk1[u] = m1 ? 1 : 0;
+      mk0[u] = m0;
+      mk1[u] = m1;
     }
   }
 #pragma unroll
@@ -86,15 +106,31 @@ __device__ __forceinline__ void apply_messages(const ApplyArgs& a, int msg, int6
       __stcs(o, r0);
       if (has1) __stcs(o + 1, r1);
     }
-    if (MASK && a.out_mask) {
-      uint8_t* om = a.out_mask + (int64_t)(msg + u) * a.out_stride + j0;
-      om[0] = mk0[u];
-      if (has1) om[1] = mk1[u];
+    if (MP >= 3) {
+      // bit-packed out_mask: a warp owns 64 neighbouring targets starting at a multiple of 64; lanes 0, 4, .. 28
+      // assemble one byte each from the two ballots (threads past the end of the table have left: they are not in
+      // `act` and contribute zero bits)
+      if (a.out_mask) {
+        const unsigned act = __activemask();
+        const uint32_t b0 = __ballot_sync(act, mk0[u] != 0), b1 = __ballot_sync(act, has1 && mk1[u] != 0);
+        const int lane = threadIdx.x & 31;
+        if ((lane & 3) == 0) {
+          uint32_t n0 = (b0 >> lane) & 0xfu, n1 = (b1 >> lane) & 0xfu;
+          n0 = (n0 | (n0 << 2)) & 0x33u;
+          n0 = (n0 | (n0 << 1)) & 0x55u;
+          n1 = (n1 | (n1 << 2)) & 0x33u;
+          n1 = (n1 | (n1 << 1)) & 0x55u;
+          a.out_mask[(int64_t)(msg + u) * a.obits_stride * 4 + (j0 >> 3)] = (uint8_t)(n0 | (n1 << 1));
+        }
+      }
+    } else if (MASK) {
+      store_mask<MP>(a, msg + u, j0, mk0[u]);
+      if (has1) store_mask<MP>(a, msg + u, j0 + 1, mk1[u]);
     }
   }
 }
 
-template <int K, bool MASK>
+template <int K, int MP>
 __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const ApplyArgs a) {
   for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int tt = (int)(tile % a.n_target_tiles);
@@ -121,13 +157,13 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const ApplyArgs a)
     const int msg_end = min(a.b, msg_begin + a.msgs_per_chunk);
     int msg = msg_begin;
     for (; msg + kMsgUnroll <= msg_end; msg += kMsgUnroll)
-      apply_messages<K, MASK, kMsgUnroll>(a, msg, j0, has1, i0, i1, w0, w1);
-    for (; msg < msg_end; ++msg) apply_messages<K, MASK, 1>(a, msg, j0, has1, i0, i1, w0, w1);
+      apply_messages<K, MP, kMsgUnroll>(a, msg, j0, has1, i0, i1, w0, w1);
+    for (; msg < msg_end; ++msg) apply_messages<K, MP, 1>(a, msg, j0, has1, i0, i1, w0, w1);
   }
 }
 
 // generic k (2..16 other than 4): one target per thread, runtime loop; used for k=3/11 tables
-template <bool MASK>
+template <int MP>
 __global__ void __launch_bounds__(kApplyThreads) apply_kernel_anyk(const ApplyArgs a) {
   const int64_t total = a.m * (int64_t)a.b;
   const uint32_t n = (uint32_t)a.n;
@@ -136,7 +172,7 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel_anyk(const ApplyAr
     const int64_t j = t - (int64_t)msg * a.m;
     const double* __restrict__ s = a.src + (int64_t)msg * a.src_stride;
     double acc = 0.0;
-    uint8_t mk = 0;
+    uint32_t mk = 0;
     for (int kk = 0; kk < a.k; ++kk) {
       const int32_t i = __ldg(a.idx + (int64_t)kk * a.m + j);
       const double w = __ldg(a.coef + (int64_t)kk * a.m + j);
@@ -144,11 +180,25 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel_anyk(const ApplyAr
       const double v = in ? __ldg(s + i) : a.mv_out;
       const double p = __dmul_rn(w, v);
       acc = (kk == 0) ? p : __dadd_rn(acc, p);
-      if (MASK && in) mk |= __ldg(a.src_mask + (int64_t)msg * a.src_stride + i);
+      if (MP != 0 && in) mk |= src_masked<MP>(a, msg, i, v);
     }
-    if (MASK && mk) acc = a.mv_out;
+    if (MP != 0 && mk) acc = a.mv_out;
     __stcs(a.out + (int64_t)msg * a.out_stride + j, acc);
-    if (MASK && a.out_mask) a.out_mask[(int64_t)msg * a.out_stride + j] = mk ? 1 : 0;
+    if (MP != 0) store_mask<MP>(a, msg, j, mk);
+  }
+}
+
+// v = mask ? marker : v, in place (g2p_mark_masked)
+template <bool BITS>
+__global__ void mark_masked_kernel(double* __restrict__ src, const uint8_t* __restrict__ mask, int64_t n, int b,
+                                   int64_t src_stride) {
+  const int64_t total = n * (int64_t)b;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int msg = (int)(t / n);
+    const int64_t i = t - (int64_t)msg * n;
+    const uint32_t mk = BITS ? (mask[(int64_t)msg * (src_stride / 8) + (i >> 3)] >> (i & 7)) & 1u
+                             : mask[(int64_t)msg * src_stride + i];
+    if (mk) reinterpret_cast<unsigned long long*>(src)[(int64_t)msg * src_stride + i] = kMarker;
   }
 }
 
@@ -160,10 +210,10 @@ static int resident_ctas(Kern kern) {
   return per_sm * num_sms();
 }
 
-template <int K, bool MASK>
+template <int K, int MP>
 static int launch_apply(ApplyArgs a, cudaStream_t st) {
-  static int grid_cap = 0;  // per (K, MASK) instantiation
-  if (grid_cap == 0) grid_cap = resident_ctas(apply_kernel<K, MASK>);
+  static int grid_cap = 0;  // per (K, MP) instantiation
+  if (grid_cap == 0) grid_cap = resident_ctas(apply_kernel<K, MP>);
   a.n_target_tiles = (int)ceil_div(a.m, (int64_t)kApplyThreads * kTargetsPerThread);
   // enough (target tile x message chunk) tiles for an even spread over the persistent grid,
   // but chunks as long as possible so the table is re-read (from L2) rarely
@@ -176,18 +226,18 @@ static int launch_apply(ApplyArgs a, cudaStream_t st) {
   n_chunks = ceil_div(a.b, per);
   a.n_tiles = (int64_t)a.n_target_tiles * n_chunks;
   int grid = (int)(a.n_tiles < grid_cap ? a.n_tiles : grid_cap);
-  apply_kernel<K, MASK><<<grid, kApplyThreads, 0, st>>>(a);
+  apply_kernel<K, MP><<<grid, kApplyThreads, 0, st>>>(a);
   G2P_LAUNCHED();
   return G2P_OK;
 }
 
-template <bool MASK>
+template <int MP>
 static int launch_apply_anyk(ApplyArgs a, cudaStream_t st) {
   static int grid_cap = 0;
-  if (grid_cap == 0) grid_cap = resident_ctas(apply_kernel_anyk<MASK>);
+  if (grid_cap == 0) grid_cap = resident_ctas(apply_kernel_anyk<MP>);
   int64_t blocks = ceil_div(a.m * (int64_t)a.b, kApplyThreads);
   int grid = (int)(blocks < (int64_t)grid_cap * 4 ? blocks : (int64_t)grid_cap * 4);
-  apply_kernel_anyk<MASK><<<grid, kApplyThreads, 0, st>>>(a);
+  apply_kernel_anyk<MP><<<grid, kApplyThreads, 0, st>>>(a);
   G2P_LAUNCHED();
   return G2P_OK;
 }
@@ -257,12 +307,16 @@ int g2p_apply(const int32_t* idx, const double* coef, int64_t m, int k, const do
   if (k > 1 && !coef) return set_error(G2P_ERR_INVALID, "g2p_apply: coef is required for k > 1");
   if (m < 0 || n < 0 || n > 0x7fffffffLL || b < 0) return set_error(G2P_ERR_INVALID, "g2p_apply: bad sizes");
   if (src_stride < n || out_stride < m) return set_error(G2P_ERR_INVALID, "g2p_apply: strides shorter than rows");
-  const bool mask = (mask_policy == G2P_MASK_PROPAGATE || mask_policy == G2P_MASK_FILL);
-  if (!mask && mask_policy != G2P_MASK_AS_REFERENCE)
+  const bool mask = (mask_policy == G2P_MASK_PROPAGATE || mask_policy == G2P_MASK_FILL);   // byte masks
+  const bool bits = mask_policy == G2P_MASK_PROPAGATE_BITS, marked = mask_policy == G2P_MASK_MARKED;
+  if (!mask && !bits && !marked && mask_policy != G2P_MASK_AS_REFERENCE)
     return set_error(G2P_ERR_INVALID, "g2p_apply: unknown mask_policy %d", mask_policy);
-  if (mask && !src_mask) return set_error(G2P_ERR_INVALID, "g2p_apply: PROPAGATE / FILL need src_mask");
-  if (mask_policy == G2P_MASK_PROPAGATE && !out_mask)
+  if ((mask || bits) && !src_mask) return set_error(G2P_ERR_INVALID, "g2p_apply: PROPAGATE / FILL need src_mask");
+  if ((mask_policy == G2P_MASK_PROPAGATE || bits) && !out_mask)
     return set_error(G2P_ERR_INVALID, "g2p_apply: PROPAGATE needs out_mask");
+  if (bits && (src_stride % 8) != 0) return set_error(G2P_ERR_INVALID, "g2p_apply: bit-packed masks need src_stride %% 8 == 0");
+  if ((bits || marked) && out_mask && (reinterpret_cast<uintptr_t>(out_mask) & 3))
+    return set_error(G2P_ERR_INVALID, "g2p_apply: a bit-packed out_mask must be 4-byte aligned");
   if (mask_policy == G2P_MASK_FILL) out_mask = nullptr;
   if (m == 0 || b == 0) return G2P_OK;
   ApplyArgs a{};
@@ -276,14 +330,39 @@ int g2p_apply(const int32_t* idx, const double* coef, int64_t m, int k, const do
   a.n = n;
   a.src_stride = src_stride;
   a.out_stride = out_stride;
+  a.sbits_stride = src_stride / 8;
+  a.obits_stride = G2P_BITS_ROW_BYTES(out_stride) / 4;
   a.b = b;
   a.k = k;
   a.mv_out = mv_out;
   a.vec_store = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (out_stride % 2 == 0);
   cudaStream_t st = as_stream(stream);
-  if (k == 1) return mask ? launch_apply<1, true>(a, st) : launch_apply<1, false>(a, st);
-  if (k == 4) return mask ? launch_apply<4, true>(a, st) : launch_apply<4, false>(a, st);
-  return mask ? launch_apply_anyk<true>(a, st) : launch_apply_anyk<false>(a, st);
+  if ((bits || marked) && out_mask) {
+    // k = 1 / 4: whole mask bytes come from warp ballots, only the padding bytes of the rows are cleared here;
+    // other k: only masked outputs touch the rows (atomicOr) and everything else is this memset
+    const size_t row_bytes = (size_t)a.obits_stride * 4, used = (size_t)((m + 7) / 8);
+    if (k != 1 && k != 4) G2P_CUDA(cudaMemsetAsync(out_mask, 0, (size_t)b * row_bytes, st));
+    else if (row_bytes > used) G2P_CUDA(cudaMemset2DAsync(out_mask + used, row_bytes, 0, row_bytes - used, (size_t)b, st));
+  }
+  const int mp = bits ? 3 : marked ? 4 : mask ? 1 : 0;
+  if (k == 1)
+    return mp == 3 ? launch_apply<1, 3>(a, st) : mp == 4 ? launch_apply<1, 4>(a, st) : mp == 1 ? launch_apply<1, 1>(a, st) : launch_apply<1, 0>(a, st);
+  if (k == 4)
+    return mp == 3 ? launch_apply<4, 3>(a, st) : mp == 4 ? launch_apply<4, 4>(a, st) : mp == 1 ? launch_apply<4, 1>(a, st) : launch_apply<4, 0>(a, st);
+  return mp == 3 ? launch_apply_anyk<3>(a, st) : mp == 4 ? launch_apply_anyk<4>(a, st) : mp == 1 ? launch_apply_anyk<1>(a, st) : launch_apply_anyk<0>(a, st);
+}
+
+int g2p_mark_masked(double* src, const uint8_t* src_mask, int mask_bits, int64_t n, int b, int64_t src_stride, void* stream) {
+  if (!src || !src_mask) return set_error(G2P_ERR_INVALID, "g2p_mark_masked: null src / src_mask");
+  if (n < 0 || b < 0 || src_stride < n) return set_error(G2P_ERR_INVALID, "g2p_mark_masked: bad sizes");
+  if (mask_bits && (src_stride % 8) != 0) return set_error(G2P_ERR_INVALID, "g2p_mark_masked: bit-packed masks need src_stride %% 8 == 0");
+  if (n == 0 || b == 0) return G2P_OK;
+  const int64_t blocks = ceil_div(n * (int64_t)b, 256);
+  const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? blocks : (int64_t)num_sms() * 16);
+  if (mask_bits) mark_masked_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(src, src_mask, n, b, src_stride);
+  else mark_masked_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(src, src_mask, n, b, src_stride);
+  G2P_LAUNCHED();
+  return G2P_OK;
 }
 
 int g2p_table_pack_rec(const int32_t* idx, const double* coef, int64_t m, int k, int coeff_dtype, void* rec_out,

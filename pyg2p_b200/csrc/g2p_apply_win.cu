@@ -339,6 +339,18 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
   return v;
 }
+// the same with the window offset taken from the low / high half of a packed pair; the unpacking sits inside the
+// volatile asm so that it stays in the message loop (hoisted, it would cost the registers the packing saves)
+__device__ __forceinline__ double lds_f64_lo16(uint32_t base, uint32_t packed) {
+  double v;
+  asm volatile("{\n\t.reg .u32 t;\n\tand.b32 t, %2, 0xffff;\n\tadd.u32 t, t, %1;\n\tld.shared.f64 %0, [t];\n\t}" : "=d"(v) : "r"(base), "r"(packed));
+  return v;
+}
+__device__ __forceinline__ double lds_f64_hi16(uint32_t base, uint32_t packed) {
+  double v;
+  asm volatile("{\n\t.reg .u32 t;\n\tshr.u32 t, %2, 16;\n\tadd.u32 t, t, %1;\n\tld.shared.f64 %0, [t];\n\t}" : "=d"(v) : "r"(base), "r"(packed));
+  return v;
+}
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -362,6 +374,9 @@ struct WinArgs {
   double* out;
   uint8_t* out_mask;
   int64_t m, src_stride, out_stride;
+  int64_t sbits_stride;   // MP == 3: bytes per source mask row (src_stride / 8)
+  int64_t obits_stride;   // MP >= 3: uint32 words per output mask row
+  int obits_ballot;       // MP >= 3: mask bytes assembled from warp ballots (else atomicOr into cleared rows)
   TileGeom g;
   int b, n_tiles, msgs_per_chunk, stages, stage_elems, stage_melems;
   int64_t n_items;
@@ -414,9 +429,28 @@ __device__ __forceinline__ int mask_window_range(const Range* ranges, int nr, in
 // A masked source value is replaced, in shared memory, by this quiet NaN: the weighted sum of a target
 // with a masked neighbour is then NaN and the (rare) slow path looks for the marker among its operands,
 // so the k mask-byte gathers per target disappear from the inner loop.
-constexpr unsigned long long kMaskMarker = 0x7ff86d61736b0001ull;
+constexpr unsigned long long kMaskMarker = G2P_MASK_MARKER;
+// The test for "masked" looks at the upper word only (sign ignored): quiet-NaN payloads pass through float64
+// multiplies and adds on sm_100a, so the weighted sum of a target with a marked neighbour carries the marker's upper
+// word itself and ONE integer compare per target finds it - no branch, although with scattered missing points nearly
+// every warp holds a masked target.  A NaN result without the marker (NaN weights, NaN inputs, or a NaN weight
+// whose payload won against the marker's) takes the rare path that inspects the operands.  The fold passes only
+// write the upper word over a masked value.
+constexpr uint32_t kMarkerHi = (uint32_t)(G2P_MASK_MARKER >> 32);
+__device__ __forceinline__ bool is_marked_hi(uint32_t hi) { return (hi & 0x7fffffffu) == kMarkerHi; }
+__device__ __forceinline__ void sts_marker(uint32_t value_addr) {
+  asm volatile("st.shared.u32 [%0+4], %1;" ::"r"(value_addr), "r"(kMarkerHi) : "memory");
+}
 
-// MP: 0 = no masks (AS_REFERENCE), 1 = PROPAGATE (out_mask written), 2 = FILL
+// MP: 0 = no masks (AS_REFERENCE), 1 = PROPAGATE (byte masks in and out), 2 = FILL (byte masks in),
+//     3 = PROPAGATE_BITS: the source mask is one bit per point.  Nothing of it is staged: the ranges are 16-element
+//         blocks, so every block's mask is one aligned uint16 of the message's bit row; the thread that owns a block
+//         loads it into a register one message ahead (a plain read-only load, its latency hidden behind a whole
+//         message of gathers) and the fold pass writes markers for its set bits.  The output mask is bit-packed
+//         too: the launcher clears it and only MASKED outputs touch it (atomicOr in the rare NaN path), so the hot
+//         loop has no mask stores at all.
+//     4 = MARKED: the source values already carry the marker: no mask input, no fold pass; out_mask as for 3
+//         (or none).
 // CV: 16-byte value chunks copied per thread and message (value window <= 512*CV elements)
 // S : stages
 // where(x != mv, op2(op1(x)), mv)  (manipulation/conversion.py:21); op1 == NONE is the identity 'x=x'
@@ -442,11 +476,16 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ Range s_ranges[kMaxRanges];
   __shared__ int s_tile_info[4];
-  constexpr bool MASK = MP != 0;
-  constexpr bool FOLD = MASK || AGG;
+  constexpr bool MASK = MP == 1 || MP == 2;  // byte masks staged through shared memory
+  constexpr bool BITS = MP == 3;             // bit masks read into registers
+  constexpr bool ANYMASK = MP != 0;          // a result can be masked
+  constexpr bool OBITS = MP >= 3;            // bit-packed output mask
+  constexpr bool FOLD = MASK || BITS || AGG;
   constexpr int NIN = AGG ? 2 : 1;  // staged input windows per message
   constexpr int CM = (CV + 7) / 8;  // 16-byte mask chunks per thread; also 4-element fold groups per thread / 4
   constexpr int CF = (CV + 1) / 2;  // fold groups (4 mask bytes) per thread
+  constexpr int CB = (CV + 3) / 4;  // 8-element groups (one byte of mask bits) per thread
+  static_assert(!(AGG && MP >= 3), "the fused kernel takes byte masks");
   const int tid = threadIdx.x;
   const uint32_t val_base = smem_u32(s_raw);                                             // [S][NIN][stage_elems] f64
   const uint32_t msk_base = val_base + (uint32_t)S * NIN * a.stage_elems * 8u;           // [S][NIN][stage_melems] u8
@@ -493,11 +532,39 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
 #pragma unroll
     for (int i = 0; i < CF; ++i) {
       fdst[i] = -1;
-      if (FOLD) {
+      if (MASK || AGG) {
         const int e = 4 * (tid + kWinThreads * i);
         const int rg = mask_window_range(s_ranges, nr, mwindow, e);
         if (rg >= 0) fdst[i] = 8 * (s_ranges[rg].smem_off + (e - s_ranges[rg].mask_off));
       }
+    }
+    //   bsrc[i]: byte index, in a message's bit row, of the mask bits of the 8 values staged at stage bytes bdst[i]
+    //   (the ranges are 16-element blocks, so every aligned group of 8 staged values is one byte of the bit row; the
+    //   work is spread like the byte-mask fold: one group per thread, no loops)
+    int bsrc[BITS ? CB : 1], bdst[BITS ? CB : 1];
+    if (BITS) {
+#pragma unroll
+      for (int i = 0; i < CB; ++i) {
+        bsrc[i] = -1;
+        bdst[i] = 0;
+        const int e = 8 * (tid + kWinThreads * i);
+        const int rg = mask_window_range(s_ranges, nr, mwindow, e);
+        if (rg >= 0) {
+          bsrc[i] = (s_ranges[rg].src_start + (e - s_ranges[rg].mask_off)) >> 3;
+          bdst[i] = 8 * (s_ranges[rg].smem_off + (e - s_ranges[rg].mask_off));
+        }
+      }
+    }
+    const uint8_t* brow = BITS ? a.src_mask + (int64_t)msg_begin * a.sbits_stride : nullptr;
+    uint32_t bcur[BITS ? CB : 1], bnxt[BITS ? CB : 1];
+    auto load_bits = [&](uint32_t (&dst)[BITS ? CB : 1], int msg) {   // message `msg` of the chunk (zeros past its end)
+#pragma unroll
+      for (int i = 0; i < (BITS ? CB : 1); ++i)
+        dst[i] = (BITS && bsrc[i] >= 0 && msg < n_msg) ? (uint32_t)__ldg(brow + (int64_t)msg * a.sbits_stride + bsrc[i]) : 0u;
+    };
+    if (BITS) {
+      load_bits(bcur, 0);
+      load_bits(bnxt, 1);
     }
     const char* grow_v = reinterpret_cast<const char*>(a.src) + (int64_t)msg_begin * vrow;        // block-uniform
     const char* grow_m = MASK ? reinterpret_cast<const char*>(a.src_mask) + (int64_t)msg_begin * mrow : nullptr;
@@ -543,6 +610,19 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
     // into the values the targets will gather, then fold the mask bytes into them
     int fold_it = 0;  // message of the chunk the next fold works on
     auto fold = [&](uint32_t sv, uint32_t sm) {
+      if (BITS) {
+#pragma unroll
+        for (int i = 0; i < CB; ++i) {
+          const uint32_t bits = bcur[i];
+          if (bits) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if ((bits >> q) & 1u)
+                sts_marker(sv + (uint32_t)bdst[i] + 8u * q);
+          }
+        }
+        return;
+      }
       AggItem it{};
       if (AGG) it = a.agg_items[msg_begin + fold_it];
       ++fold_it;
@@ -587,7 +667,7 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               if ((m4 >> (8 * q)) & 0xffu)
-                asm volatile("st.shared.u64 [%0], %1;" ::"r"(sv + (uint32_t)fdst[i] + 8u * q), "l"(kMaskMarker) : "memory");
+                sts_marker(sv + (uint32_t)fdst[i] + 8u * q);
           }
         }
       }
@@ -612,7 +692,10 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
     int64_t r, c[kWinTPT];
     thread_targets(a.g, tile, tid, r, c);
     bool ok[kWinTPT];
-    uint32_t li[kWinTPT][K];
+    // window byte offsets of the neighbours, two uint16 per register (K = 4): the kernel lives at the 80-register
+    // line of three CTAs per SM, and eight registers saved here are what the bit-mask paths need
+    constexpr int KP = K > 1 ? K / 2 : 1;
+    uint32_t li[kWinTPT][KP];
     double w[kWinTPT][K];
     const int64_t j0 = r * a.g.cols + c[0];
     uint32_t ob[kWinTPT];  // byte offset of the target in an output row
@@ -626,7 +709,10 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
 #pragma unroll
       for (int kk = 0; kk < K; ++kk) {
         const uint16_t l = ok[t] ? __ldg(a.lidx + (int64_t)kk * a.m + j) : kLocalSentinel;
-        li[t][kk] = (l == kLocalSentinel) ? 8u * (uint32_t)sent : (uint32_t)l;  // byte offsets as the plan stores them
+        const uint32_t lb = (l == kLocalSentinel) ? 8u * (uint32_t)sent : (uint32_t)l;  // byte offsets as the plan stores them
+        if (K == 1) li[t][0] = lb;
+        else if ((kk & 1) == 0) li[t][kk >> 1] = lb;
+        else li[t][kk >> 1] |= lb << 16;
         w[t][kk] = (K > 1 && ok[t]) ? __ldg(a.coef + (int64_t)kk * a.m + j) : 1.0;
       }
       if (CORR) {
@@ -639,6 +725,35 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
     }
     char* o = reinterpret_cast<char*>(a.out) + (int64_t)msg_begin * a.out_stride * 8;       // block-uniform
     char* om = (MP == 1) ? reinterpret_cast<char*>(a.out_mask) + (int64_t)msg_begin * a.out_stride : nullptr;
+    uint32_t* ob_row = (OBITS && a.out_mask) ? reinterpret_cast<uint32_t*>(a.out_mask) + (int64_t)msg_begin * a.obits_stride : nullptr;
+    // Bit-packed output mask from ballots: per target slot a warp owns whole bytes of the mask rows (8 neighbouring
+    // columns of one row sit in 8 neighbouring lanes - two nibbles for 4x4 blocks), 4 bytes per slot, 16 per
+    // message.  Lane q < 16 writes byte (slot q >> 2, byte q & 3): its row offset and the position of its bits in
+    // the slot's ballot are fixed for the whole chunk.
+    if (OBITS && ob_row && a.obits_ballot && tile == a.n_tiles - 1) {   // the padding bytes of the chunk's mask rows
+      const int used = (int)((a.m + 7) >> 3), tail = (int)(a.obits_stride * 4) - used;
+      for (int i = tid; i < tail * n_msg; i += kWinThreads)
+        reinterpret_cast<uint8_t*>(ob_row)[(int64_t)(i / tail) * a.obits_stride * 4 + used + (i % tail)] = 0;
+    }
+    int ob_byte = -1;        // byte offset in a mask row (-1: nothing to write)
+    uint32_t ob_shift = 0;   // lane of the byte's first bit
+    if (OBITS && ob_row && a.obits_ballot) {
+      const int lane = tid & 31;
+      const int bc_small = a.g.block_cols_log2 == 2;
+#pragma unroll
+      for (int t = 0; t < kWinTPT; ++t) {
+        const int mine = ok[t] ? (int)(ob[t] >> 6) : -1;   // byte of this lane's target
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int leader = bc_small ? 4 * i : 8 * i;
+          const int v = __shfl_sync(0xffffffffu, mine, leader);
+          if (lane == 4 * t + i) {
+            ob_byte = v;
+            ob_shift = (uint32_t)leader;
+          }
+        }
+      }
+    }
 
     uint32_t gv_s = val_base;                   // stage of the message being gathered
     uint32_t fv_s = val_base, fm_s = msk_base;  // stage of the message being folded (one ahead)
@@ -647,6 +762,11 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
       __syncthreads();
       fold(fv_s, fm_s);
       advance(fv_s, fm_s);
+      if (BITS) {
+#pragma unroll
+        for (int i = 0; i < CB; ++i) bcur[i] = bnxt[i];  // bits of message 1
+        load_bits(bnxt, 2);
+      }
     }
     // ---- messages
     for (int it = 0; it < n_msg; ++it) {
@@ -659,18 +779,34 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
         if (it + 1 < n_msg) fold(fv_s, fm_s);
         advance(fv_s, fm_s);
       }
+      if (BITS) {
+        // rotate: the load issued one message ago is consumed here, the next one has a whole message to land
+#pragma unroll
+        for (int i = 0; i < CB; ++i) bcur[i] = bnxt[i];
+        load_bits(bnxt, it + 3);
+      }
+      uint32_t mkbits = 0;   // OBITS: bit t = slot t's output is masked
 #pragma unroll
       for (int t = 0; t < kWinTPT; ++t) {
         double v[K];
 #pragma unroll
-        for (int kk = 0; kk < K; ++kk) v[kk] = lds_f64(gv_s + li[t][kk]);
+        for (int kk = 0; kk < K; ++kk)
+          v[kk] = K == 1 ? lds_f64(gv_s + li[t][0]) : (kk & 1) ? lds_f64_hi16(gv_s, li[t][kk >> 1]) : lds_f64_lo16(gv_s, li[t][kk >> 1]);
         double res = weighted_sum<K>(w[t], v);
         uint32_t mk = 0;
-        if (MASK && res != res) {  // NaN: a masked neighbour, or NaN weights / inputs (then it stays NaN)
+        if (ANYMASK) {
+          const uint32_t hi = (uint32_t)__double2hiint(res) & 0x7fffffffu;
+          mk = hi == kMarkerHi;
+          if (hi >= 0x7ff00000u && !mk) {   // rare: NaN / Inf without the marker's payload - look at the operands
 #pragma unroll
-          for (int kk = 0; kk < K; ++kk) mk |= (uint32_t)(__double_as_longlong(v[kk]) == (long long)kMaskMarker);
-          if (mk) res = a.mv_out;
+            for (int kk = 0; kk < K; ++kk) mk |= (uint32_t)is_marked_hi((uint32_t)__double2hiint(v[kk]));
+          }
+          if (mk) {
+            res = a.mv_out;
+            if (OBITS && ob_row && !a.obits_ballot && ok[t]) atomicOr(ob_row + (ob[t] >> 8), 1u << ((ob[t] >> 3) & 31u));
+          }
         }
+        if (OBITS) mkbits |= (mk != 0 && ok[t]) ? (1u << t) : 0u;
         if (CORR) {
           if (a.corr_gem && !mk)  // a masked output stays the missing value; p = NaN passes the guards and stays NaN
             res = !(cvalid[t] && res != a.corr_mv) ? a.corr_mv
@@ -682,10 +818,23 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
           if (MP == 1) *reinterpret_cast<uint8_t*>(om + (ob[t] >> 3)) = (uint8_t)mk;
         }
       }
+      if (OBITS && ob_row && a.obits_ballot) {   // block-uniform; the votes come after the four slots' arithmetic
+        const int slot = (tid & 31) >> 2;
+        uint32_t bt = 0;
+#pragma unroll
+        for (int t = 0; t < kWinTPT; ++t) {
+          const uint32_t v = __ballot_sync(0xffffffffu, (mkbits >> t) & 1u);
+          if (slot == t) bt = v;
+        }
+        const uint32_t byte = a.g.block_cols_log2 == 2 ? (((bt >> ob_shift) & 0xfu) | (((bt >> (ob_shift + 16)) & 0xfu) << 4))
+                                                       : ((bt >> ob_shift) & 0xffu);
+        if (ob_byte >= 0) reinterpret_cast<uint8_t*>(ob_row)[ob_byte] = (uint8_t)byte;
+      }
       gv_s += stage_vbytes;
       if (gv_s == val_end) gv_s = val_base;
       o += a.out_stride * 8;
       if (MP == 1) om += a.out_stride;
+      if (OBITS && ob_row) ob_row += a.obits_stride;
     }
     cp_async_wait<0>();
   }
@@ -697,7 +846,7 @@ static size_t win_smem_bytes(int stages, int stage_elems, int stage_melems, bool
 
 template <int K, int MP, int CV, int S, bool CORR, bool AGG>
 static int launch_window_c(const g2p_plan* p, WinArgs a, cudaStream_t st) {
-  constexpr bool MASK = MP != 0;
+  constexpr bool MASK = MP == 1 || MP == 2;  // byte masks are the only ones staged
   const size_t smem = win_smem_bytes(S, a.stage_elems, a.stage_melems, MASK, AGG ? 2 : 1);
   auto kern = apply_window_kernel<K, MP, CV, S, CORR, AGG>;
   G2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -727,11 +876,12 @@ static int launch_window_c(const g2p_plan* p, WinArgs a, cudaStream_t st) {
 template <int K, int MP, int CV, int S>
 static int launch_window_s(const g2p_plan* p, WinArgs a, cudaStream_t st) {
   if (a.agg_items) {
+    if (MP >= 3) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned_fused: byte masks only (PROPAGATE / FILL)");
     // the fused pipeline is instantiated for the window sizes it is used with (CV <= 4: windows up to 2048 values)
     if (CV > 4) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned_fused: window of %d values is too large; use g2p_manip + g2p_apply_planned", p->max_window);
-    if (CV <= 4)
-      return (a.corr_gem || a.post_on) ? launch_window_c<K, MP, (CV <= 4 ? CV : 2), S, true, true>(p, a, st)
-                                       : launch_window_c<K, MP, (CV <= 4 ? CV : 2), S, false, true>(p, a, st);
+    if constexpr (CV <= 4 && MP < 3)
+      return (a.corr_gem || a.post_on) ? launch_window_c<K, MP, CV, S, true, true>(p, a, st)
+                                       : launch_window_c<K, MP, CV, S, false, true>(p, a, st);
   }
   return (a.corr_gem || a.post_on) ? launch_window_c<K, MP, CV, S, true, false>(p, a, st)
                                    : launch_window_c<K, MP, CV, S, false, false>(p, a, st);
@@ -744,9 +894,10 @@ static int launch_window_cv(const g2p_plan* p, WinArgs a, cudaStream_t st) {
   // (measured on O1280 -> EFAS, masks: 3 stages 1.25 ms, 4 stages 1.11 ms, 5 stages 1.16 ms, 6 stages 1.25 ms - more
   // shared memory per CTA leaves less L1 for the table and output traffic)
   const int nin = a.agg_items ? 2 : 1;
-  if (win_smem_bytes(4, a.stage_elems, a.stage_melems, MP != 0, nin) <= (size_t)(nin == 2 ? 100 : 72) * 1024)
+  constexpr bool staged_mask = MP == 1 || MP == 2;
+  if (win_smem_bytes(4, a.stage_elems, a.stage_melems, staged_mask, nin) <= (size_t)(nin == 2 ? 100 : 72) * 1024)
     return launch_window_s<K, MP, CV, 4>(p, a, st);
-  if (win_smem_bytes(3, a.stage_elems, a.stage_melems, MP != 0, nin) > 220 * 1024)
+  if (win_smem_bytes(3, a.stage_elems, a.stage_melems, staged_mask, nin) > 220 * 1024)
     return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: window of %d elements does not fit in shared memory", p->max_window);
   return launch_window_s<K, MP, CV, 3>(p, a, st);
 }
@@ -756,6 +907,10 @@ static int launch_window(const g2p_plan* p, WinArgs a, cudaStream_t st) {
   a.stage_elems = ((p->max_window + 1 + 15) / 16) * 16;  // +1: the sentinel slot
   a.stage_melems = ((p->max_mwindow + 15) / 16) * 16;
   const int chunks = (p->max_window / 2 + kWinThreads - 1) / kWinThreads;  // 16-byte value chunks per thread
+#ifdef G2P_DEV_BUILD   // `make dev`: kernel experiments on the O1280 -> EFAS table only (compiles in a fifth of the time)
+  if (chunks != 3) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: dev build, CV = 3 only");
+  return launch_window_cv<K, MP, 3>(p, a, st);
+#endif
   if (chunks <= 2) return launch_window_cv<K, MP, 2>(p, a, st);
   if (chunks <= 3) return launch_window_cv<K, MP, 3>(p, a, st);
   if (chunks <= 4) return launch_window_cv<K, MP, 4>(p, a, st);
@@ -998,11 +1153,17 @@ static int apply_planned(const g2p_plan* p, const double* coef, const double* sr
   if (p->k > 1 && !coef) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: coef is required for k > 1");
   if (p->k != 1 && p->k != 4) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: k=%d (1 and 4 are planned; use g2p_apply)", p->k);
   if (b < 0) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: b < 0");
-  const bool mask = (mask_policy == G2P_MASK_PROPAGATE || mask_policy == G2P_MASK_FILL);
-  if (!mask && mask_policy != G2P_MASK_AS_REFERENCE)
+  const bool mask = (mask_policy == G2P_MASK_PROPAGATE || mask_policy == G2P_MASK_FILL);   // byte masks
+  const bool bits = mask_policy == G2P_MASK_PROPAGATE_BITS, marked = mask_policy == G2P_MASK_MARKED;
+  if (!mask && !bits && !marked && mask_policy != G2P_MASK_AS_REFERENCE)
     return set_error(G2P_ERR_INVALID, "g2p_apply_planned: unknown mask_policy %d", mask_policy);
-  if (mask && !src_mask) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: PROPAGATE / FILL need src_mask");
-  if (mask_policy == G2P_MASK_PROPAGATE && !out_mask) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: PROPAGATE needs out_mask");
+  if ((mask || bits) && !src_mask) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: PROPAGATE / FILL need src_mask");
+  if ((mask_policy == G2P_MASK_PROPAGATE || bits) && !out_mask) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: PROPAGATE needs out_mask");
+  if (bits && (src_stride % 8) != 0)
+    return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: bit-packed masks need src_stride %% 8 == 0; use g2p_apply");
+  if ((bits || marked) && out_mask && (reinterpret_cast<uintptr_t>(out_mask) & 3))
+    return set_error(G2P_ERR_INVALID, "g2p_apply_planned: a bit-packed out_mask must be 4-byte aligned");
+  if ((bits || marked) && fused) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned_fused: byte masks only (PROPAGATE / FILL)");
   if (src_stride < p->n_pad || out_stride < p->m) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: strides shorter than rows (src rows must be padded to a multiple of 16)");
   // bulk copies need 16-byte aligned sources: value rows at 16 B, mask rows at 16 B
   if ((reinterpret_cast<uintptr_t>(src) & 15) || (src_stride % 2) != 0)
@@ -1022,6 +1183,17 @@ static int apply_planned(const g2p_plan* p, const double* coef, const double* sr
   a.m = p->m;
   a.src_stride = src_stride;
   a.out_stride = out_stride;
+  a.sbits_stride = src_stride / 8;
+  a.obits_stride = G2P_BITS_ROW_BYTES(out_stride) / 4;
+  if ((bits || marked) && out_mask) {
+    // whole mask bytes come from warp ballots when every byte of a mask row belongs to one warp and slot: rows start
+    // on a byte (one row, or cols % 8 == 0) and a slot's warp footprint is whole 8-column groups
+    const int tpr = p->tile_cols / kWinTPT;
+    a.obits_ballot = (p->rows == 1 || p->cols % 8 == 0) && tpr % 8 == 0 && p->block_cols_log2 >= 2;
+    if (const char* ev = getenv("G2P_WIN_OBITS_ATOMIC")) if (atoi(ev)) a.obits_ballot = 0;
+    if (!a.obits_ballot)   // only masked outputs touch the bit rows (atomicOr), everything else is this memset
+      G2P_CUDA(cudaMemsetAsync(out_mask, 0, (size_t)b * a.obits_stride * 4, as_stream(stream)));
+  }
   a.g.rows = p->rows;
   a.g.cols = p->cols;
   a.g.tile_rows = p->tile_rows;
@@ -1092,9 +1264,11 @@ static int apply_planned(const g2p_plan* p, const double* coef, const double* sr
   cudaStream_t st = as_stream(stream);
   int rc;
   if (p->k == 1) {
-    rc = mask_policy == G2P_MASK_PROPAGATE ? launch_window<1, 1>(p, a, st) : mask ? launch_window<1, 2>(p, a, st) : launch_window<1, 0>(p, a, st);
+    rc = bits ? launch_window<1, 3>(p, a, st) : marked ? launch_window<1, 4>(p, a, st)
+         : mask_policy == G2P_MASK_PROPAGATE ? launch_window<1, 1>(p, a, st) : mask ? launch_window<1, 2>(p, a, st) : launch_window<1, 0>(p, a, st);
   } else {
-    rc = mask_policy == G2P_MASK_PROPAGATE ? launch_window<4, 1>(p, a, st) : mask ? launch_window<4, 2>(p, a, st) : launch_window<4, 0>(p, a, st);
+    rc = bits ? launch_window<4, 3>(p, a, st) : marked ? launch_window<4, 4>(p, a, st)
+         : mask_policy == G2P_MASK_PROPAGATE ? launch_window<4, 1>(p, a, st) : mask ? launch_window<4, 2>(p, a, st) : launch_window<4, 0>(p, a, st);
   }
   return rc;
 }

@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "g2p_common.cuh"
+#include "g2p_sincosf.h"
 
 namespace g2p {
 
@@ -51,11 +52,15 @@ __device__ __forceinline__ void load_pt(const Pt* p, double& x, double& y, doubl
 
 struct Rot {
   int on;
+  int libm_fma;  // float32 maps: which glibc build of sinf / cosf is restated (g2p_sincosf.h); 1 = the FMA build
   double xx, xy, xz, yx, yy, yz, zx, zz;  // x = (xx*ux + xy*uy) + xz*uz ; y = (yx*ux + yy*uy) - yz*uz ; z = zx*ux + zz*uz
 };
 
 static Rot make_rot(const g2p_rotation* r) {
   Rot o{};
+  // G2P_LIBM_FMA=0: hosts whose glibc resolves sinf / cosf to the non-FMA (sse2) build
+  o.libm_fma = 1;
+  if (const char* ev = getenv("G2P_LIBM_FMA")) o.libm_fma = atoi(ev) != 0;
   if (!r) return o;
   // teta = -radians(90 + latSP), fi = -radians(lonSP)  (scipy_interpolation_lib.py:674-675)
   const double deg = kPi / 180.0;
@@ -166,10 +171,21 @@ __device__ __noinline__ void sincos_cr(double x, double* sn, double* cs) {
   *cs = (n == 0) ? c.h : (n == 1) ? -s.h : (n == 2) ? -c.h : s.h;
 }
 
+// float32 sin / cos exactly as glibc's sinf / cosf return them (what numexpr's float32 opcodes call), widened
+__device__ __forceinline__ void sincosf_libm(float ang, int fma_build, double& s, double& c) {
+  if (fma_build) {
+    s = (double)g2p_scf::sincosf_glibc<true, false>(ang);
+    c = (double)g2p_scf::sincosf_glibc<true, true>(ang);
+  } else {
+    s = (double)g2p_scf::sincosf_glibc<false, false>(ang);
+    c = (double)g2p_scf::sincosf_glibc<false, true>(ang);
+  }
+}
+
 // ------------------------------------------------------------------ K1  lat/lon -> xyz
 // f64: radians = deg * (pi/180) in double (numpy deg2rad), libdevice sin/cos, products
 // (r*cos(lon))*cos(lat) left to right with separate multiplies.
-// f32: radians in float32, sin/cos rounded to float32 (see below), promoted to double for the products with the double
+// f32: radians in float32, sin/cos = glibc's sinf/cosf bit for bit, promoted to double for the products with the double
 // radius, result rounded to float32 (reference :691-694) and widened again for the search.
 // PAIRED: the two lanes of a lane pair (same query) share the trigonometry - the even lane evaluates the
 // longitude, the odd lane the latitude, and they swap results with one shuffle - which halves the cost of the
@@ -184,10 +200,7 @@ __device__ __forceinline__ void latlon_to_xyz(const void* lon, const void* lat, 
     if (F32) {
       const float dr = 0.017453292519943295f;
       const float ang = __fmul_rn(reinterpret_cast<const float*>(odd ? lat : lon)[i], dr);
-      double s, c;
-      sincos((double)ang, &s, &c);
-      s1 = (double)(float)s;
-      c1 = (double)(float)c;
+      sincosf_libm(ang, rot.libm_fma, s1, c1);
     } else {
       const double ang = __dmul_rn(reinterpret_cast<const double*>(odd ? lat : lon)[i], 0.017453292519943295);
       sincos_cr(ang, &s1, &c1);
@@ -201,15 +214,9 @@ __device__ __forceinline__ void latlon_to_xyz(const void* lon, const void* lat, 
     const float dr = 0.017453292519943295f;  // float32(pi/180): numpy's deg2radf constant
     float lo = __fmul_rn(reinterpret_cast<const float*>(lon)[i], dr);
     float la = __fmul_rn(reinterpret_cast<const float*>(lat)[i], dr);
-    // numexpr evaluates float32 sin/cos with libm's sinf/cosf, which are correctly rounded in ~98.7 % of
-    // the cases; rounding the float64 result reproduces that (libdevice sinf/cosf are 1-2 ulp off)
-    double s, c;
-    sincos((double)lo, &s, &c);
-    cx = (double)(float)c;
-    sx = (double)(float)s;
-    sincos((double)la, &s, &c);
-    cy = (double)(float)c;
-    sy = (double)(float)s;
+    // numexpr evaluates float32 sin/cos with libm's sinf/cosf: restated bit for bit (g2p_sincosf.h)
+    sincosf_libm(lo, rot.libm_fma, sx, cx);
+    sincosf_libm(la, rot.libm_fma, sy, cy);
   } else {
     const double dr = 0.017453292519943295;
     double lo = __dmul_rn(reinterpret_cast<const double*>(lon)[i], dr);

@@ -327,16 +327,18 @@ class DeviceTable:
         return np.ascontiguousarray(rec['indexes']), np.ascontiguousarray(rec['coeffs'])
 
     # ---- apply
-    def _window_ok(self, src, src_mask, propagate):
-        """alignment rules of g2p_apply_planned (TMA bulk copies need 16-byte aligned rows)."""
+    def _window_ok(self, src, src_mask, propagate, bits=False):
+        """alignment rules of g2p_apply_planned (16-byte cp.async chunks need 16-byte aligned rows)."""
         path = os.environ.get('G2P_APPLY_PATH', 'auto')
-        if self.k not in (1, 4) or path == 'generic':
+        if self.k not in (1, 4) or path == 'generic' or getattr(self, '_window_refused', False):
             return False
         k1_needs_compact_tiles = self.k == 1 and path != 'window'
         n_pad = -(-self.n_src // 16) * 16
         if src.data_ptr() % 16 or src.stride(0) % 2 or src.stride(0) < n_pad:
             return False
         if propagate and (src_mask.data_ptr() % 16 or src.stride(0) % 16):
+            return False
+        if bits and src.stride(0) % 8:
             return False
         if self.plan() is None:
             return False
@@ -390,7 +392,9 @@ class DeviceTable:
             raise ValueError(f'source field has {n} values, intertable was built for {self.n_src}')
         if src.stride(1) != 1:
             src = src.contiguous()
-        propagate = mask_policy in (L.MASK_PROPAGATE, L.MASK_FILL)
+        propagate = mask_policy in (L.MASK_PROPAGATE, L.MASK_FILL)        # byte masks in
+        bits = mask_policy == L.MASK_PROPAGATE_BITS                       # bit-packed masks in and out
+        marked = mask_policy == L.MASK_MARKED                             # no mask in; bit-packed mask out (optional)
         with torch.cuda.device(self.device):
             if out is None:
                 out = torch.empty((b, self.m), dtype=torch.float64, device=self.device)
@@ -405,32 +409,57 @@ class DeviceTable:
                     src_mask = src_mask.contiguous()
                 if out_mask is None and mask_policy == L.MASK_PROPAGATE:
                     out_mask = torch.empty((b, self.m), dtype=torch.uint8, device=self.device)
-            if b > 0 and self.m > 0 and self._window_ok(src, src_mask, propagate):
-                self.last_path = 'window'
+            if bits:
+                if src_mask is None or src_mask.dtype != torch.uint8:
+                    raise ValueError('PROPAGATE_BITS needs a bit-packed uint8 src_mask (pack_mask_bits)')
+                if src.stride(0) % 8 or src_mask.stride(1) != 1 or src_mask.stride(0) != src.stride(0) // 8:
+                    raise ValueError('bit-packed src_mask rows must hold src.stride(0) / 8 bytes '
+                                     '(pad the source rows to a multiple of 16 values)')
+            if bits or (marked and out_mask is not False):
+                if out_mask is None:
+                    out_mask = torch.empty((b, bits_row_bytes(out.stride(0))), dtype=torch.uint8, device=self.device)
+                elif out_mask.stride(0) != bits_row_bytes(out.stride(0)) or out_mask.data_ptr() % 4:
+                    raise ValueError('bit-packed out_mask rows must hold bits_row_bytes(out.stride(0)) bytes')
+            if marked and out_mask is False:
+                out_mask = None
+            takes_mask = propagate or bits
+            gives_mask = mask_policy == L.MASK_PROPAGATE or bits or (marked and out_mask is not None)
+            done = False
+            if b > 0 and self.m > 0 and self._window_ok(src, src_mask, propagate, bits):
                 if correction is not None or post is not None:
-                    L.check(lib.g2p_apply_planned_post(
+                    rc = lib.g2p_apply_planned_post(
                         self.plan(), _ptr(self.coef) if self.k > 1 else None, _ptr(src),
-                        _ptr(src_mask) if propagate else None, b, src.stride(0), out.stride(0), float(mv_out),
+                        _ptr(src_mask) if takes_mask else None, b, src.stride(0), out.stride(0), float(mv_out),
                         int(mask_policy), C.byref(correction.c_struct()) if correction is not None else None,
                         C.byref(post.c_struct()) if post is not None else None, _ptr(out),
-                        _ptr(out_mask) if mask_policy == L.MASK_PROPAGATE else None, _stream()))
+                        _ptr(out_mask) if gives_mask else None, _stream())
                 else:
-                    L.check(lib.g2p_apply_planned(self.plan(), _ptr(self.coef) if self.k > 1 else None, _ptr(src),
-                                                  _ptr(src_mask) if propagate else None, b, src.stride(0),
-                                                  out.stride(0), float(mv_out), int(mask_policy), _ptr(out),
-                                                  _ptr(out_mask) if mask_policy == L.MASK_PROPAGATE else None,
-                                                  _stream()))
-            elif b > 0 and self.m > 0:
+                    rc = lib.g2p_apply_planned(self.plan(), _ptr(self.coef) if self.k > 1 else None, _ptr(src),
+                                               _ptr(src_mask) if takes_mask else None, b, src.stride(0),
+                                               out.stride(0), float(mv_out), int(mask_policy), _ptr(out),
+                                               _ptr(out_mask) if gives_mask else None, _stream())
+                if rc == L.ERR_UNSUPPORTED:
+                    # e.g. the window does not fit in shared memory: remembered, the generic kernel serves the table
+                    self._window_refused = True
+                    self.plan_error = lib.g2p_last_error().decode('utf-8', 'replace')
+                else:
+                    L.check(rc)
+                    self.last_path = 'window'
+                    done = True
+            if not done and b > 0 and self.m > 0:
                 self.last_path = 'generic'
                 # no plan for this table: the Corrector and the writers' post-processing run as their own passes.
                 # Both leave masked cells alone / turn them into the file's missing value, so under FILL (masked
                 # outputs hold mv_out, no mask array for the caller) a scratch mask array carries them across.
-                g_policy, g_mask = mask_policy, (out_mask if mask_policy == L.MASK_PROPAGATE else None)
+                g_policy, g_mask = mask_policy, (out_mask if gives_mask else None)
+                if (correction is not None or post is not None) and (bits or marked):
+                    raise NotImplementedError('Corrector / writer post-processing after the generic kernel take byte '
+                                              'masks: use PROPAGATE / FILL for tables without a window plan')
                 if mask_policy == L.MASK_FILL and (correction is not None or post is not None):
                     g_policy = L.MASK_PROPAGATE                  # one row stride for values and masks in the C ABI
                     g_mask = torch.empty((b, out.stride(0)), dtype=torch.uint8, device=self.device)[:, :self.m]
                 L.check(lib.g2p_apply(_ptr(self.idx), _ptr(self.coef) if self.k > 1 else None, self.m, self.k, _ptr(src),
-                                      _ptr(src_mask) if propagate else None, n, b, src.stride(0), out.stride(0),
+                                      _ptr(src_mask) if takes_mask else None, n, b, src.stride(0), out.stride(0),
                                       float(mv_out), int(g_policy), _ptr(out),
                                       _ptr(g_mask) if g_mask is not None else None, _stream()))
                 if correction is not None:
@@ -442,7 +471,55 @@ class DeviceTable:
         if squeeze:
             out = out[0]
             out_mask = out_mask[0] if out_mask is not None else None
-        return (out, out_mask) if mask_policy == L.MASK_PROPAGATE else out
+        return (out, out_mask) if gives_mask else out
+
+
+def bits_row_bytes(stride):
+    """G2P_BITS_ROW_BYTES: bytes of one bit-packed output mask row (whole 32-bit words)."""
+    return ((int(stride) + 31) // 32) * 4
+
+
+def pack_mask_bits(mask, row_values=None):
+    """bool / uint8 mask [b, n] (numpy or tensor, host or device) -> bit-packed uint8 [b, row_values / 8] in the
+    layout of G2P_MASK_PROPAGATE_BITS: bit j of a row = bit (j & 7) of byte (j >> 3), i.e.
+    `numpy.packbits(mask, axis=1, bitorder='little')` - the GRIB bitmap section holds the same information, one bit
+    per point.  `row_values`: the padded row length of the source buffer (multiple of 16; default n rounded up)."""
+    if isinstance(mask, np.ndarray):
+        b, n = mask.shape
+        rv = -(-n // 16) * 16 if row_values is None else int(row_values)
+        out = np.zeros((b, rv // 8), dtype=np.uint8)
+        out[:, :(n + 7) // 8] = np.packbits(mask.astype(bool), axis=1, bitorder='little')
+        return out
+    b, n = mask.shape
+    rv = -(-n // 16) * 16 if row_values is None else int(row_values)
+    full = torch.zeros((b, rv), dtype=torch.uint8, device=mask.device)
+    full[:, :n] = mask.to(torch.uint8) != 0
+    wts = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.uint8, device=mask.device)
+    return (full.view(b, rv // 8, 8) * wts).sum(dim=2, dtype=torch.uint8)
+
+
+def unpack_mask_bits(bits, m):
+    """bit-packed rows [b, bytes] -> bool [b, m] (numpy)"""
+    a = bits.cpu().numpy() if isinstance(bits, torch.Tensor) else np.asarray(bits)
+    return np.unpackbits(a, axis=1, bitorder='little')[:, :m].astype(bool)
+
+
+def mark_masked(src, src_mask, bits=False):
+    """In place on device fields [b, n]: v = mask ? G2P_MASK_MARKER : v (g2p_mark_masked) - the producer-side half of
+    the MARKED mask policy for fields that reach the device with a separate mask."""
+    lib = require_cuda()
+    _bind_device(src.device)
+    if src.dim() == 1:
+        src, src_mask = src.unsqueeze(0), src_mask.unsqueeze(0)
+    if src_mask.dtype == torch.bool:
+        src_mask = src_mask.view(torch.uint8)
+    b, n = src.shape
+    want = src.stride(0) // 8 if bits else src.stride(0)
+    if src.stride(1) != 1 or src_mask.stride(1) != 1 or src_mask.stride(0) != want:
+        raise ValueError('values and masks must share the row stride (bit-packed: stride / 8 bytes per row)')
+    with torch.cuda.device(src.device):
+        L.check(lib.g2p_mark_masked(_ptr(src), _ptr(src_mask), 1 if bits else 0, n, b, src.stride(0), _stream()))
+    return src
 
 
 class WriterPost:

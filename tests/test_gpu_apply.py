@@ -66,7 +66,7 @@ def test_record_roundtrip_and_reference_golden_table(dev, golden_dir):
 
 @pytest.mark.parametrize('k', [1, 2, 3, 4, 11])
 @pytest.mark.parametrize('m,b', [(1, 1), (2, 3), (1001, 7), (65537, 9), (300000, 2)])
-def test_apply_random_tables(dev, k, m, b):
+def test_apply_random_tables(dev, k, m, b, monkeypatch):
     """ragged sizes (odd m -> unaligned rows), sentinels, NaN weights, all k the reference uses."""
     rng = np.random.default_rng(100 * k + m % 97 + b)
     n = 5000
@@ -91,6 +91,36 @@ def test_apply_random_tables(dev, k, m, b):
             data, mk = R.apply_propagate(v[i], rec['coeffs'], rec['indexes'], k, mv, mask[i])
         _eq(o2[i].cpu().numpy(), data)
         _eq(m2[i].cpu().numpy().astype(bool), mk)
+    monkeypatch.setenv('G2P_APPLY_PATH', 'generic')
+    _check_bits_and_marked(dev, tbl, v, mask, mv, rec, k, 'generic')
+
+
+def _check_bits_and_marked(dev, tbl, v, mask, mv, rec, k, path):
+    """PROPAGATE_BITS (bit-packed masks in and out) and MARKED (masked values carry the marker NaN) against the
+    oracle's PROPAGATE result."""
+    b, n = v.shape
+    src = _padded(v)
+    n_pad = src.stride(0)
+    bits = dev.pack_mask_bits(mask, n_pad)
+    assert bits.tobytes() == dev.pack_mask_bits(torch.from_numpy(mask).cuda(), n_pad).cpu().numpy().tobytes()
+    o4, m4 = tbl.apply(src, mv, src_mask=torch.from_numpy(bits).cuda(), mask_policy=L.MASK_PROPAGATE_BITS)
+    assert tbl.last_path == path, tbl.plan_error
+    marked = src.clone() if src.is_contiguous() else _padded(v)
+    dev.mark_masked(marked, _padded(mask.view(np.uint8)))
+    marked2 = _padded(v)
+    dev.mark_masked(marked2, torch.from_numpy(bits).cuda(), bits=True)
+    assert torch.equal(marked.view(torch.int64), marked2.view(torch.int64))
+    assert int((marked.view(torch.int64) == L.MASK_MARKER).sum()) == int(mask.sum())
+    o5, m5 = tbl.apply(marked, mv, mask_policy=L.MASK_MARKED)
+    o6 = tbl.apply(marked, mv, mask_policy=L.MASK_MARKED, out_mask=False)
+    m4, m5 = dev.unpack_mask_bits(m4, tbl.m), dev.unpack_mask_bits(m5, tbl.m)
+    for i in range(b):
+        with np.errstate(all='ignore'):
+            data, mk = R.apply_propagate(v[i], rec['coeffs'], rec['indexes'], k, mv, mask[i])
+        for o, mm in ((o4, m4), (o5, m5), (o6, None)):
+            _eq(o[i].cpu().numpy(), data)
+            if mm is not None:
+                _eq(mm[i], mk)
 
 
 def test_apply_f32_coeff_table(dev):
@@ -217,6 +247,7 @@ def test_window_path_random_tables(dev, k, shape, b, monkeypatch):
             _eq(o2[i].cpu().numpy(), data)
             _eq(m2[i].cpu().numpy().astype(bool), mk)
             _eq(o3[i].cpu().numpy(), data)
+        _check_bits_and_marked(dev, tbl, v, mask, mv, rec, k, 'window')
 
 
 def test_scattered_table_falls_back_to_generic_gpu_kernel(dev):
