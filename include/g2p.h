@@ -63,7 +63,7 @@ enum {
 /* The float64 quiet NaN that stands for "masked" inside a source field under G2P_MASK_MARKED (and inside the
  * shared-memory windows of the apply kernels under every mask policy).  Producers that touch every value anyway -
  * g2p_manip, g2p_mark_masked - write it where the mask is set, so that the apply kernel needs no mask input.
- * Consumers test the upper 32 bits only (sign ignored): any NaN whose upper word is 0x7ff86d61 is masked. */
+ * Consumers test the upper 32 bits only: any NaN whose upper word is 0x7ff86d61 is masked. */
 #define G2P_MASK_MARKER 0x7ff86d61736b0001ull
 
 /* per-target flags written by g2p_knn */

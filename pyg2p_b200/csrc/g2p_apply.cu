@@ -52,7 +52,7 @@ template <int MP>
 __device__ __forceinline__ uint32_t src_masked(const ApplyArgs& a, int msg, int32_t i, double v) {
   if (MP == 1) return __ldg(a.src_mask + (int64_t)msg * a.src_stride + i) != 0;
   if (MP == 3) return (__ldg(a.src_mask + (int64_t)msg * a.sbits_stride + (i >> 3)) >> (i & 7)) & 1u;
-  if (MP == 4) return ((uint32_t)__double2hiint(v) & 0x7fffffffu) == (uint32_t)(kMarker >> 32);  // upper word, as the windowed kernel
+  if (MP == 4) return (uint32_t)__double2hiint(v) == (uint32_t)(kMarker >> 32);  // upper word, as the windowed kernel
   return 0u;
 }
 

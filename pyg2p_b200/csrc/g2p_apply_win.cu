@@ -430,14 +430,11 @@ __device__ __forceinline__ int mask_window_range(const Range* ranges, int nr, in
 // with a masked neighbour is then NaN and the (rare) slow path looks for the marker among its operands,
 // so the k mask-byte gathers per target disappear from the inner loop.
 constexpr unsigned long long kMaskMarker = G2P_MASK_MARKER;
-// The test for "masked" looks at the upper word only (sign ignored): quiet-NaN payloads pass through float64
-// multiplies and adds on sm_100a, so the weighted sum of a target with a marked neighbour carries the marker's upper
-// word itself and ONE integer compare per target finds it - no branch, although with scattered missing points nearly
-// every warp holds a masked target.  A NaN result without the marker (NaN weights, NaN inputs, or a NaN weight
-// whose payload won against the marker's) takes the rare path that inspects the operands.  The fold passes only
-// write the upper word over a masked value.
+// The test for "masked" looks at the upper word only: one integer compare per gathered operand, no branch (with
+// scattered missing points nearly every warp holds a masked target, so a "rare path" is not rare).  The fold passes
+// only write the upper word over a masked value.  (Deriving the mask from the NaN payload of the weighted sum does
+// not work: sm_100a's DADD does not reliably pass the payload on - measured, 57 % of the warps fell through.)
 constexpr uint32_t kMarkerHi = (uint32_t)(G2P_MASK_MARKER >> 32);
-__device__ __forceinline__ bool is_marked_hi(uint32_t hi) { return (hi & 0x7fffffffu) == kMarkerHi; }
 __device__ __forceinline__ void sts_marker(uint32_t value_addr) {
   asm volatile("st.shared.u32 [%0+4], %1;" ::"r"(value_addr), "r"(kMarkerHi) : "memory");
 }
@@ -795,16 +792,11 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
         double res = weighted_sum<K>(w[t], v);
         uint32_t mk = 0;
         if (ANYMASK) {
-          const uint32_t hi = (uint32_t)__double2hiint(res) & 0x7fffffffu;
-          mk = hi == kMarkerHi;
-          if (hi >= 0x7ff00000u && !mk) {   // rare: NaN / Inf without the marker's payload - look at the operands
+          // branch-free: with scattered missing points nearly every warp holds a masked target
 #pragma unroll
-            for (int kk = 0; kk < K; ++kk) mk |= (uint32_t)is_marked_hi((uint32_t)__double2hiint(v[kk]));
-          }
-          if (mk) {
-            res = a.mv_out;
-            if (OBITS && ob_row && !a.obits_ballot && ok[t]) atomicOr(ob_row + (ob[t] >> 8), 1u << ((ob[t] >> 3) & 31u));
-          }
+          for (int kk = 0; kk < K; ++kk) mk |= (uint32_t)((uint32_t)__double2hiint(v[kk]) == kMarkerHi);
+          if (mk) res = a.mv_out;
+          if (OBITS && ob_row && !a.obits_ballot && mk && ok[t]) atomicOr(ob_row + (ob[t] >> 8), 1u << ((ob[t] >> 3) & 31u));
         }
         if (OBITS) mkbits |= (mk != 0 && ok[t]) ? (1u << t) : 0u;
         if (CORR) {
