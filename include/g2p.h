@@ -54,6 +54,14 @@ enum {
   G2P_MASK_MARKED = 4          /* masked source values carry G2P_MASK_MARKER; out_mask (nullable) is bit-packed */
 };
 
+/* Summation order of the k = 4 weighted sum, OR-ed into the `mask_policy` argument of the apply entry points.
+ * Default: ((w0*v0 + w1*v1) + w2*v2) + w3*v3 - what numpy's einsum does on the strided float64 field views of a table
+ * loaded from file (reference interpolation/__init__.py:156).  G2P_SUM_PAIRWISE:
+ * (w0*v0 + w2*v2) + (w1*v1 + w3*v3) - what the same einsum does when it buffers its operands: tables with float32
+ * coefficients (PCRaster REAL4 target maps) and freshly built contiguous tables.  Separate multiplies and adds in
+ * both; other k are not affected. */
+#define G2P_SUM_PAIRWISE 0x100
+
 /* Bit-packed masks (G2P_MASK_PROPAGATE_BITS / G2P_MASK_MARKED): bit j of a row is bit (j & 7) of byte (j >> 3),
  * i.e. numpy.packbits(mask, bitorder='little') - one bit per point, as the GRIB bitmap section itself stores
  * missing points.  A source row of `src_stride` values has src_stride / 8 mask bytes (src_stride % 8 == 0); an

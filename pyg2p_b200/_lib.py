@@ -15,6 +15,7 @@ ERR_UNSUPPORTED = -5
 F64, F32 = 0, 1
 MODE_RAW, MODE_NEAREST, MODE_INVDIST = 0, 1, 2
 MASK_AS_REFERENCE, MASK_PROPAGATE, MASK_FILL, MASK_PROPAGATE_BITS, MASK_MARKED = 0, 1, 2, 3, 4
+SUM_PAIRWISE = 0x100                     # G2P_SUM_PAIRWISE, OR-ed into mask_policy
 MASK_MARKER = 0x7ff86d61736b0001          # G2P_MASK_MARKER: the float64 NaN that stands for 'masked' in a source field
 FLAG_TIE, FLAG_NEAR_TIE, FLAG_SHORT = 1, 2, 4
 

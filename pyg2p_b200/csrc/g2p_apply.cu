@@ -29,7 +29,7 @@ struct ApplyArgs {
   uint8_t* out_mask;
   int64_t m, n, src_stride, out_stride;
   int64_t sbits_stride, obits_stride;  // bit-packed mask rows: bytes per source row, uint32 words per output row
-  int b, k;
+  int b, k, pairwise;
   int msgs_per_chunk, n_target_tiles;
   int64_t n_tiles;
   double mv_out;
@@ -37,8 +37,11 @@ struct ApplyArgs {
 };
 
 template <int K>
-__device__ __forceinline__ double weighted(const double (&w)[K], const double (&v)[K]) {
+__device__ __forceinline__ double weighted(const double (&w)[K], const double (&v)[K], int pairwise) {
   if (K == 1) return v[0];
+  if (K == 4 && pairwise)   // G2P_SUM_PAIRWISE
+    return __dadd_rn(__dadd_rn(__dmul_rn(w[0], v[0]), __dmul_rn(w[K > 2 ? 2 : 0], v[K > 2 ? 2 : 0])),
+                     __dadd_rn(__dmul_rn(w[1], v[1]), __dmul_rn(w[K > 3 ? 3 : 0], v[K > 3 ? 3 : 0])));
   double acc = __dmul_rn(w[0], v[0]);
 #pragma unroll
   for (int kk = 1; kk < K; ++kk) acc = __dadd_rn(acc, __dmul_rn(w[kk], v[kk]));
@@ -93,8 +96,8 @@ __device__ __forceinline__ void apply_messages(const ApplyArgs& a, int msg, int6
   }
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    double r0 = weighted<K>(w0, v0[u]);
-    double r1 = weighted<K>(w1, v1[u]);
+    double r0 = weighted<K>(w0, v0[u], a.pairwise);
+    double r1 = weighted<K>(w1, v1[u], a.pairwise);
     if (MASK) {  // masked outputs carry the target missing value (`ma.filled(result, mv_out)`)
       if (mk0[u]) r0 = a.mv_out;
       if (mk1[u]) r1 = a.mv_out;
@@ -307,6 +310,8 @@ int g2p_apply(const int32_t* idx, const double* coef, int64_t m, int k, const do
   if (k > 1 && !coef) return set_error(G2P_ERR_INVALID, "g2p_apply: coef is required for k > 1");
   if (m < 0 || n < 0 || n > 0x7fffffffLL || b < 0) return set_error(G2P_ERR_INVALID, "g2p_apply: bad sizes");
   if (src_stride < n || out_stride < m) return set_error(G2P_ERR_INVALID, "g2p_apply: strides shorter than rows");
+  const int pairwise = (mask_policy & G2P_SUM_PAIRWISE) != 0;
+  mask_policy &= ~G2P_SUM_PAIRWISE;
   const bool mask = (mask_policy == G2P_MASK_PROPAGATE || mask_policy == G2P_MASK_FILL);   // byte masks
   const bool bits = mask_policy == G2P_MASK_PROPAGATE_BITS, marked = mask_policy == G2P_MASK_MARKED;
   if (!mask && !bits && !marked && mask_policy != G2P_MASK_AS_REFERENCE)
@@ -334,6 +339,7 @@ int g2p_apply(const int32_t* idx, const double* coef, int64_t m, int k, const do
   a.obits_stride = G2P_BITS_ROW_BYTES(out_stride) / 4;
   a.b = b;
   a.k = k;
+  a.pairwise = pairwise;
   a.mv_out = mv_out;
   a.vec_store = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (out_stride % 2 == 0);
   cudaStream_t st = as_stream(stream);

@@ -376,6 +376,7 @@ struct WinArgs {
   int64_t m, src_stride, out_stride;
   int64_t sbits_stride;   // MP == 3: bytes per source mask row (src_stride / 8)
   int64_t obits_stride;   // MP >= 3: uint32 words per output mask row
+  int pairwise;           // G2P_SUM_PAIRWISE
   int obits_ballot;       // MP >= 3: mask bytes assembled from warp ballots (else atomicOr into cleared rows)
   TileGeom g;
   int b, n_tiles, msgs_per_chunk, stages, stage_elems, stage_melems;
@@ -396,9 +397,13 @@ struct WinArgs {
   double c1, c2, mv_grib;
 };
 
+// pairwise (block-uniform, K = 4): (w0*v0 + w2*v2) + (w1*v1 + w3*v3), see G2P_SUM_PAIRWISE
 template <int K>
-__device__ __forceinline__ double weighted_sum(const double (&w)[K], const double (&v)[K]) {
+__device__ __forceinline__ double weighted_sum(const double (&w)[K], const double (&v)[K], int pairwise) {
   if (K == 1) return v[0];
+  if (K == 4 && pairwise)
+    return __dadd_rn(__dadd_rn(__dmul_rn(w[0], v[0]), __dmul_rn(w[K > 2 ? 2 : 0], v[K > 2 ? 2 : 0])),
+                     __dadd_rn(__dmul_rn(w[1], v[1]), __dmul_rn(w[K > 3 ? 3 : 0], v[K > 3 ? 3 : 0])));
   double acc = __dmul_rn(w[0], v[0]);
 #pragma unroll
   for (int kk = 1; kk < K; ++kk) acc = __dadd_rn(acc, __dmul_rn(w[kk], v[kk]));
@@ -789,7 +794,7 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
 #pragma unroll
         for (int kk = 0; kk < K; ++kk)
           v[kk] = K == 1 ? lds_f64(gv_s + li[t][0]) : (kk & 1) ? lds_f64_hi16(gv_s, li[t][kk >> 1]) : lds_f64_lo16(gv_s, li[t][kk >> 1]);
-        double res = weighted_sum<K>(w[t], v);
+        double res = weighted_sum<K>(w[t], v, a.pairwise);
         uint32_t mk = 0;
         if (ANYMASK) {
           // branch-free: with scattered missing points nearly every warp holds a masked target
@@ -1145,6 +1150,8 @@ static int apply_planned(const g2p_plan* p, const double* coef, const double* sr
   if (p->k > 1 && !coef) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: coef is required for k > 1");
   if (p->k != 1 && p->k != 4) return set_error(G2P_ERR_UNSUPPORTED, "g2p_apply_planned: k=%d (1 and 4 are planned; use g2p_apply)", p->k);
   if (b < 0) return set_error(G2P_ERR_INVALID, "g2p_apply_planned: b < 0");
+  const int pairwise = (mask_policy & G2P_SUM_PAIRWISE) != 0;
+  mask_policy &= ~G2P_SUM_PAIRWISE;
   const bool mask = (mask_policy == G2P_MASK_PROPAGATE || mask_policy == G2P_MASK_FILL);   // byte masks
   const bool bits = mask_policy == G2P_MASK_PROPAGATE_BITS, marked = mask_policy == G2P_MASK_MARKED;
   if (!mask && !bits && !marked && mask_policy != G2P_MASK_AS_REFERENCE)
@@ -1194,6 +1201,7 @@ static int apply_planned(const g2p_plan* p, const double* coef, const double* sr
   a.g.threads_per_row = p->tile_cols / kWinTPT;
   a.g.block_cols_log2 = p->block_cols_log2;
   a.b = b;
+  a.pairwise = pairwise;
   a.n_tiles = p->n_tiles;
   a.mv_out = mv_out;
   AggItem* d_items = nullptr;

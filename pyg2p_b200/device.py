@@ -208,6 +208,9 @@ class DeviceTable:
         self.grid_shape = tuple(int(x) for x in grid_shape) if grid_shape is not None else None
         if self.grid_shape is not None and self.grid_shape[0] * self.grid_shape[1] != self.m:
             raise ValueError(f'grid_shape {self.grid_shape} does not hold {self.m} targets')
+        # k = 4 summation order (G2P_SUM_PAIRWISE): numpy's einsum adds ((p0 + p1) + p2) + p3 on the strided float64
+        # views of a loaded table and (p0 + p2) + (p1 + p3) when it buffers - which it does for float32 coefficients
+        self.sum_pairwise = self.coef_f32
         self._plan = None            # C.c_void_p of a g2p_plan, False once found not windowable
         self.plan_error = None
 
@@ -423,6 +426,7 @@ class DeviceTable:
             if marked and out_mask is False:
                 out_mask = None
             takes_mask = propagate or bits
+            policy_arg = int(mask_policy) | (L.SUM_PAIRWISE if self.sum_pairwise else 0)
             gives_mask = mask_policy == L.MASK_PROPAGATE or bits or (marked and out_mask is not None)
             done = False
             if b > 0 and self.m > 0 and self._window_ok(src, src_mask, propagate, bits):
@@ -430,13 +434,13 @@ class DeviceTable:
                     rc = lib.g2p_apply_planned_post(
                         self.plan(), _ptr(self.coef) if self.k > 1 else None, _ptr(src),
                         _ptr(src_mask) if takes_mask else None, b, src.stride(0), out.stride(0), float(mv_out),
-                        int(mask_policy), C.byref(correction.c_struct()) if correction is not None else None,
+                        policy_arg, C.byref(correction.c_struct()) if correction is not None else None,
                         C.byref(post.c_struct()) if post is not None else None, _ptr(out),
                         _ptr(out_mask) if gives_mask else None, _stream())
                 else:
                     rc = lib.g2p_apply_planned(self.plan(), _ptr(self.coef) if self.k > 1 else None, _ptr(src),
                                                _ptr(src_mask) if takes_mask else None, b, src.stride(0),
-                                               out.stride(0), float(mv_out), int(mask_policy), _ptr(out),
+                                               out.stride(0), float(mv_out), policy_arg, _ptr(out),
                                                _ptr(out_mask) if gives_mask else None, _stream())
                 if rc == L.ERR_UNSUPPORTED:
                     # e.g. the window does not fit in shared memory: remembered, the generic kernel serves the table
@@ -460,7 +464,7 @@ class DeviceTable:
                     g_mask = torch.empty((b, out.stride(0)), dtype=torch.uint8, device=self.device)[:, :self.m]
                 L.check(lib.g2p_apply(_ptr(self.idx), _ptr(self.coef) if self.k > 1 else None, self.m, self.k, _ptr(src),
                                       _ptr(src_mask) if takes_mask else None, n, b, src.stride(0), out.stride(0),
-                                      float(mv_out), int(g_policy), _ptr(out),
+                                      float(mv_out), int(g_policy) | (policy_arg & L.SUM_PAIRWISE), _ptr(out),
                                       _ptr(g_mask) if g_mask is not None else None, _stream()))
                 if correction is not None:
                     L.check(lib.g2p_correct(_ptr(out), _ptr(g_mask) if g_mask is not None else None,

@@ -601,7 +601,8 @@ class FusedPipeline:
         L.check(lib.g2p_apply_planned_fused(
             t.plan(), C.c_void_p(t.coef.data_ptr()) if t.k > 1 else None, C.byref(desc), C.c_void_p(src.data_ptr()),
             C.c_void_p(src_mask.data_ptr()) if src_mask is not None else None, src.shape[0], src.stride(0), out.stride(0),
-            float(mv_out), int(policy), C.byref(corrector.c_struct()) if corrector is not None else None,
+            float(mv_out), int(policy) | (L.SUM_PAIRWISE if t.sum_pairwise else 0),
+            C.byref(corrector.c_struct()) if corrector is not None else None,
             C.c_void_p(out.data_ptr()), C.c_void_p(omask.data_ptr()) if omask is not None else None,
             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return (out, omask) if policy == L.MASK_PROPAGATE else out

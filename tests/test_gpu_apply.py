@@ -134,6 +134,35 @@ def test_apply_f32_coeff_table(dev):
     assert tbl.coef_f32 and tbl.to_record().tobytes() == np.ascontiguousarray(rec).tobytes()
 
 
+@pytest.mark.parametrize('path', ['generic', 'window'])
+def test_apply_f32_coeff_k4_matches_einsum_order(dev, path, monkeypatch):
+    """float32 coefficients (tables built for PCRaster REAL4 maps): numpy's einsum buffers the operands and adds
+    (w0*v0 + w2*v2) + (w1*v1 + w3*v3); float64 record views are summed left to right.  Both kernels follow the table's
+    dtype and match `_interpolate_scipy_append_mv` (np.einsum on the record's field views) bit for bit."""
+    monkeypatch.setenv('G2P_APPLY_PATH', path)
+    rng = np.random.default_rng(21)
+    rows, cols, n, k, b = 40, 130, 3000, 4, 5
+    m = rows * cols
+    centre = rng.integers(0, n, size=m)
+    idx = np.clip(centre[:, None] + rng.integers(-30, 31, size=(m, k)), 0, n)
+    w = rng.random((m, k))
+    w /= w.sum(axis=1, keepdims=True)
+    v = 280.0 + 20 * rng.standard_normal((b, n))
+    mask = rng.random((b, n)) < 0.05
+    for dt in (np.float32, np.float64):
+        rec = R.to_record(idx, w.astype(dt))
+        tbl = dev.DeviceTable.from_record(rec, n, grid_shape=(rows, cols))
+        assert tbl.sum_pairwise == (dt == np.float32)
+        out = tbl.apply(_padded(v), 1e20).cpu().numpy()
+        assert tbl.last_path == path
+        o2, m2 = tbl.apply(_padded(v), 1e20, src_mask=_padded(mask.view(np.uint8)), mask_policy=L.MASK_PROPAGATE)
+        for i in range(b):
+            _eq(out[i], R.apply_as_reference(v[i], rec['coeffs'], rec['indexes'], k, 1e20))      # the reference's own einsum
+            data, mk = R.apply_propagate(v[i], rec['coeffs'], rec['indexes'], k, 1e20, mask[i])
+            _eq(o2[i].cpu().numpy(), data)
+            _eq(m2[i].cpu().numpy().astype(bool), mk)
+
+
 def test_apply_strided_batch_and_empty(dev):
     rng = np.random.default_rng(9)
     m, n, k = 1000, 400, 4
