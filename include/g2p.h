@@ -250,6 +250,7 @@ int g2p_apply_planned(const g2p_plan* plan, const double* coef, const double* sr
  *   COPY     out = c(V[in0]), mask = mask(V[in0])   (no aggregation: the plain compaction of a message;
  *            `src` / `src_mask` may then be PINNED HOST memory - the kernel reads the touched values
  *            over PCIe and nothing else of the field ever crosses the bus)
+ * With src_mask and NO out_mask, a masked output holds G2P_MASK_MARKER instead (input for G2P_MASK_MARKED).
  * out_mask follows the reference literally: ACCUM keeps only the mask of V[in1] (the current step loses its
  * mask in `v_iter_ma += V[t]`, aggregator.py:142-148), PICK none (:264-276); AVERAGE / WAVERAGE by mask_all:
  * -1 none - what _average really returns, because `numeric.get_masks(v_ord.values())` (:232) passes the dict view

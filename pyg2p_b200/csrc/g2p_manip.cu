@@ -132,13 +132,16 @@ __device__ __forceinline__ void manip_body(const ManipArgs& a, const ManipItem& 
 #pragma unroll
     for (int u = 0; u < kManipPerThread; ++u) {
       if (c0 + u >= a.nc) break;
+      // no out_mask: a masked output carries the marker NaN instead (the MARKED input form of the apply kernels)
+      if (a.src_mask && !a.out_mask && mk[u]) res[u] = __longlong_as_double((long long)G2P_MASK_MARKER);
       a.out[(int64_t)o * a.out_stride + c0 + u] = res[u];
-      if (a.src_mask) a.out_mask[(int64_t)o * a.out_stride + c0 + u] = mk[u] ? 1 : 0;
+      if (a.out_mask) a.out_mask[(int64_t)o * a.out_stride + c0 + u] = mk[u] ? 1 : 0;
     }
   }
 }
 
-constexpr int kManipInline = 16;   // items passed by value in the kernel parameters (no upload, no sync)
+constexpr int kManipInline = 128;  // items passed by value in the kernel parameters (no upload, no sync; 21 KB of the 32 KB
+                                   // parameter space): the 90 outputs of the eue_r24-style pipeline are one launch
 struct ManipInline {
   ManipItem items[kManipInline];
 };
@@ -210,7 +213,6 @@ int g2p_manip(const g2p_manip_desc* desc, const double* src, const uint8_t* src_
   if (n < 0 || b_in < 1 || src_stride < n) return set_error(G2P_ERR_INVALID, "g2p_manip: bad sizes");
   if (!touched) nc = n;
   if (nc < 0 || out_stride < nc) return set_error(G2P_ERR_INVALID, "g2p_manip: out_stride shorter than the output rows");
-  if (src_mask && !out_mask) return set_error(G2P_ERR_INVALID, "g2p_manip: src_mask without out_mask");
   for (int op : {desc->conv_op1, desc->conv_op2})
     if (op < G2P_OP_NONE || op > G2P_OP_DIV) return set_error(G2P_ERR_INVALID, "g2p_manip: unknown conversion op %d", op);
   if (desc->n_out == 0 || nc == 0) return G2P_OK;

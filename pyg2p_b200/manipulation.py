@@ -356,10 +356,18 @@ def _upload(fields):
     return src, msk
 
 
-def manip_device(src, src_mask, items, converter=None, cut_off=False, touched=None):
-    """g2p_manip on device tensors: src [b, n] -> out [n_out, nc] (+ mask).  `touched`: int32 device tensor."""
+def manip_device(src, src_mask, items, converter=None, cut_off=False, touched=None, marked=False, src_ptrs=None):
+    """g2p_manip on device tensors: src [b, n] -> out [n_out, nc] (+ mask).  `touched`: int32 device tensor.
+    `marked`: no mask array comes out, masked outputs hold G2P_MASK_MARKER instead (the input form of the apply
+    kernels' MARKED policy).  `src_ptrs` = (values address, mask address or 0, b_in, n, row stride, device): raw
+    addresses instead of tensors - PINNED HOST memory works, the kernel then reads the touched values over PCIe."""
     lib = device.require_cuda()
-    b_in, n = src.shape
+    if src_ptrs is not None:
+        v_ptr, m_ptr, b_in, n, stride, dev = src_ptrs
+    else:
+        b_in, n = src.shape
+        v_ptr, m_ptr, stride, dev = src.data_ptr(), (src_mask.data_ptr() if src_mask is not None else 0), src.stride(0), src.device
+    has_mask = bool(m_ptr)
     nc = n if touched is None else touched.numel()
     n_out = len(items)
     carr = (L.ManipItem * max(n_out, 1))(*[it.to_c() for it in items])
@@ -372,15 +380,14 @@ def manip_device(src, src_mask, items, converter=None, cut_off=False, touched=No
     desc.n_out = n_out
     desc.items = C.cast(carr, C.POINTER(L.ManipItem))
     nc_pad = -(-nc // 16) * 16                       # rows padded to 16 values: what the windowed apply needs
-    out = torch.empty((n_out, nc_pad), dtype=torch.float64, device=src.device)
-    omask = torch.empty((n_out, nc_pad), dtype=torch.uint8, device=src.device) if src_mask is not None else None
+    out = torch.empty((n_out, nc_pad), dtype=torch.float64, device=dev)
+    omask = torch.empty((n_out, nc_pad), dtype=torch.uint8, device=dev) if has_mask and not marked else None
     if nc_pad != nc:
         out[:, nc:] = 0.0
         if omask is not None:
             omask[:, nc:] = 0
-    L.check(lib.g2p_set_device(src.device.index))
-    L.check(lib.g2p_manip(C.byref(desc), C.c_void_p(src.data_ptr()),
-                          C.c_void_p(src_mask.data_ptr()) if src_mask is not None else None, n, b_in, src.stride(0),
+    L.check(lib.g2p_set_device(dev.index))
+    L.check(lib.g2p_manip(C.byref(desc), C.c_void_p(v_ptr), C.c_void_p(m_ptr) if has_mask else None, n, b_in, stride,
                           C.c_void_p(touched.data_ptr()) if touched is not None else None, nc, out.stride(0),
                           C.c_void_p(out.data_ptr()), C.c_void_p(omask.data_ptr()) if omask is not None else None,
                           C.c_void_p(torch.cuda.current_stream().cuda_stream)))
@@ -564,9 +571,84 @@ class FusedPipeline:
         if self.last_path == 'fused':
             return self._run_fused(src, src_mask if use_mask else None, items, converter, cut_off, mv_out, policy,
                                    corrector)
+        if policy == L.MASK_MARKED:
+            # masks in (bytes), markers between the two kernels, bit-packed mask out: the apply kernel stages no mask
+            vals, _ = manip_device(src, src_mask, items, converter=converter, cut_off=cut_off, touched=self.touched,
+                                   marked=True)
+            return self.compact.apply(vals, float(mv_out), mask_policy=L.MASK_MARKED, correction=corrector)
         vals, vmask = manip_device(src, src_mask if use_mask else None, items,
                                    converter=converter, cut_off=cut_off, touched=self.touched)
         return self.compact.apply(vals, float(mv_out), src_mask=vmask, mask_policy=policy, correction=corrector)
+
+    def run_host(self, h_src, h_mask, plan, converter=None, cut_off=False, mv_out=NC_FILL_F64, corrector=None,
+                 members=1, out=None, out_mask=None, post=None):
+        """The same chain from messages that lie in PINNED HOST memory, one member at a time: h_src [members * steps, n]
+        float64 pinned tensor (rows member-major, `plan.slots` order), h_mask uint8 [., n] pinned or None ->
+        (out [members * n_out, m] pinned float64, out_mask bit-packed pinned uint8 or None).
+        Per member: g2p_manip reads exactly the touched values of the member's messages out of the host buffers over PCIe
+        (zero-copy) and evaluates convert / aggregate / cut-off on them (masked values -> markers), the windowed apply with
+        the Corrector / writer epilogue follows, and the results go back by D2H while the next member computes.  With
+        `post` (a WriterPost) masked cells already hold the file's missing value and no mask is returned."""
+        if plan.synth:
+            raise ApplicationException.get_exc(NOT_IMPLEMENTED, 'synthesised steps in the host pipeline')
+        t = self.table
+        per, n_out = len(plan.slots), len(plan.outputs)
+        if h_src.shape[0] != members * per or not h_src.is_pinned() or h_src.dtype != torch.float64:
+            raise ValueError('h_src must be a pinned float64 tensor [members * steps, n]')
+        if h_mask is not None and (not h_mask.is_pinned() or h_mask.stride(0) != h_src.stride(0)):
+            raise ValueError('h_mask must be a pinned uint8 tensor with the row stride of h_src')
+        items = [it for _, it in plan.outputs]
+        want_mask = h_mask is not None and post is None
+        if out is None:
+            out = device.pinned_empty((members * n_out, t.m))
+        brow = device.bits_row_bytes(t.m)
+        if want_mask and out_mask is None:
+            out_mask = device.pinned_empty((members * n_out, brow), torch.uint8)
+        dev = t.device
+        cur = torch.cuda.current_stream(dev)
+        if getattr(self, '_s_out', None) is None:
+            self._s_out = torch.cuda.Stream(device=dev)
+            self._slots = [(torch.empty((n_out, t.m), dtype=torch.float64, device=dev),
+                            torch.empty((n_out, brow), dtype=torch.uint8, device=dev)) for _ in range(2)]
+        if self._slots[0][0].shape[0] != n_out:
+            self._slots = [(torch.empty((n_out, t.m), dtype=torch.float64, device=dev),
+                            torch.empty((n_out, brow), dtype=torch.uint8, device=dev)) for _ in range(2)]
+        ev_out = [None, None]
+        self.h2d_bytes = self.d2h_bytes = 0
+        nc = self.compact.n_src
+        with torch.cuda.device(dev):
+            for mb in range(members):
+                s = mb % 2
+                d_out, d_bits = self._slots[s]
+                if ev_out[s] is not None:
+                    cur.wait_event(ev_out[s])
+                ptrs = (h_src.data_ptr() + mb * per * h_src.stride(0) * 8,
+                        (h_mask.data_ptr() + mb * per * h_src.stride(0)) if h_mask is not None else 0,
+                        per, t.n_src, h_src.stride(0), dev)
+                vals, _ = manip_device(None, None, items, converter=converter, cut_off=cut_off, touched=self.touched,
+                                       marked=True, src_ptrs=ptrs)
+                # every output reads its inputs' touched values (an accumulation: two steps), masks as bytes
+                self.h2d_bytes += sum(len([i for i in it.inputs if i >= 0]) for it in items) * nc * (9 if h_mask is not None else 8)
+                if h_mask is not None:
+                    self.compact.apply(vals, float(mv_out), mask_policy=L.MASK_MARKED, out=d_out,
+                                       out_mask=d_bits if want_mask else False, correction=corrector, post=post)
+                else:
+                    self.compact.apply(vals, float(mv_out), out=d_out, correction=corrector, post=post)
+                ev_k = torch.cuda.Event()
+                ev_k.record(cur)
+                with torch.cuda.stream(self._s_out):
+                    self._s_out.wait_event(ev_k)
+                    out[mb * n_out:(mb + 1) * n_out].copy_(d_out, non_blocking=True)
+                    self.d2h_bytes += n_out * t.m * 8
+                    if want_mask:
+                        out_mask[mb * n_out:(mb + 1) * n_out].copy_(d_bits, non_blocking=True)
+                        self.d2h_bytes += n_out * brow
+                    ev_out[s] = torch.cuda.Event()
+                    ev_out[s].record(self._s_out)
+            for e in ev_out:
+                if e is not None:
+                    cur.wait_event(e)
+        return out, (out_mask if want_mask else None)
 
     def _can_fuse(self, src, src_mask, items, use_mask):
         t = self.table

@@ -254,3 +254,77 @@ def test_fused_pipeline_matches_oracle_chain(M, kind):
         with np.errstate(all='ignore'):
             data, _ = R.apply_propagate(v, w, idx, 4, mv_out, np.broadcast_to(mk, (n,)))
         np.testing.assert_array_equal(got2[o], data)
+
+
+def test_pipeline_marked_and_host_buffers(M):
+    """The marker form of the two-launch pipeline (byte masks in, marker NaNs between the kernels, bit-packed mask out)
+    and the host-buffer form (`run_host`: the gather kernel reads the touched values out of pinned host memory, one member
+    per pass, results back by D2H) give the bytes of the byte-mask pipeline that the oracle chain pins above."""
+    from pyg2p_b200 import device
+    lat, lon, det = synth.regular_ll_grid(62.0, 38.0, 97, -8.0, 32.0, 161)
+    n = lat.size
+    tl, tlo = synth.efas_target(rows=96, cols=70, cell=20000.0, x_ul=3500000.0, y_ul=4000000.0)
+    m = tl.size
+    ix = device.SourceIndex(lon, lat, det['radius'])
+    out = ix.knn(tlo, tl, k=4, mode=L.MODE_INVDIST, mub=ix.min_upper_bound(det['Nj']), want_flags=False)
+    table = device.DeviceTable(out['idx'], out['coef'], n, grid_shape=tl.shape)
+    steps = list(range(0, 73, 6))
+    members = 3
+    rng = np.random.default_rng(11)
+    fields = np.cumsum(np.maximum(0, rng.standard_normal((members, len(steps), n))) * 2e-3 - 2e-4, axis=1)
+    masks = rng.random((members, len(steps), n)) < 0.01
+    fields[masks] = synth.GRIB_MV
+    fields = fields.reshape(members * len(steps), n)
+    masks = masks.reshape(members * len(steps), n)
+    conv = M.Converter(func='x=x*1000', cut_off=True)
+    conv.set_missing_value(synth.GRIB_MV)
+    a = M.Aggregator(input_step=6, start_step=0, end_step=72, mv_grib=synth.GRIB_MV, force_zero_array=False,
+                     aggr_halfweights=False, aggr_type='accumulation', step_type='accum', aggr_step=24, unit_time=24)
+    plan = a.plan(steps)
+    dem = synth.field_dem(tl, tlo, synth.PCR_MV_F32).astype(np.float32)
+    z = synth.field_geopotential(lat, lon)
+    z[::97] = synth.GRIB_MV
+    mv_out = synth.NC_FILL_F64
+    corr = M.Corrector.from_geopotential(table, z, synth.GRIB_MV, mv_out, dem, float(synth.PCR_MV_F32))
+    pipe = M.FusedPipeline(table)
+    n_pad = -(-n // 16) * 16
+    h_src = device.pinned_empty((fields.shape[0], n_pad))[:, :n]
+    h_msk = device.pinned_empty((fields.shape[0], n_pad), torch.uint8)[:, :n]
+    h_src.copy_(torch.from_numpy(fields))
+    h_msk.copy_(torch.from_numpy(masks.view(np.uint8)))
+    src, msk = h_src.cuda(), h_msk.cuda()
+    src = torch.zeros((fields.shape[0], n_pad), dtype=torch.float64, device='cuda')[:, :n].copy_(src)
+    msk = torch.zeros((fields.shape[0], n_pad), dtype=torch.uint8, device='cuda')[:, :n].copy_(msk)
+    pipe.run(src, msk, plan, converter=conv, cut_off=True, mv_out=mv_out, mask_policy=L.MASK_PROPAGATE, corrector=corr,
+             members=members)                         # first call: table compaction and window plan
+    l0 = device.launch_count()
+    want, want_mask = pipe.run(src, msk, plan, converter=conv, cut_off=True, mv_out=mv_out, mask_policy=L.MASK_PROPAGATE,
+                               corrector=corr, members=members)
+    assert device.launch_count() - l0 == 2            # one g2p_manip launch for all outputs + one apply
+    want, want_mask = want.cpu().numpy(), want_mask.cpu().numpy().astype(bool)
+    assert 0.005 < want_mask.mean() < 0.5
+    got, bits = pipe.run(src, msk, plan, converter=conv, cut_off=True, mv_out=mv_out, mask_policy=L.MASK_MARKED,
+                         corrector=corr, members=members)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    np.testing.assert_array_equal(device.unpack_mask_bits(bits, m), want_mask)
+    h_out, h_bits = pipe.run_host(h_src, h_msk, plan, converter=conv, cut_off=True, mv_out=mv_out, corrector=corr,
+                                  members=members)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(h_out.numpy(), want)
+    np.testing.assert_array_equal(device.unpack_mask_bits(h_bits, m), want_mask)
+    assert pipe.h2d_bytes > 0 and pipe.d2h_bytes == want.size * 8 + h_bits.numel()
+    # writer-ready variant: masked / NaN / clone-masked cells hold the file's missing value, no mask comes back
+    clone = rng.random(tl.shape) < 0.2
+    post = device.WriterPost(clone, 1e20, match=mv_out)
+    h_out2, none = pipe.run_host(h_src, h_msk, plan, converter=conv, cut_off=True, mv_out=mv_out, corrector=corr,
+                                 members=members, post=post)
+    torch.cuda.synchronize()
+    ready = want.copy()
+    ready[want_mask | np.isnan(want) | (want == mv_out) | clone.ravel()[None, :]] = 1e20
+    assert none is None
+    np.testing.assert_array_equal(h_out2.numpy(), ready)
+    # without masks
+    plain = pipe.run(src, None, plan, converter=conv, cut_off=True, mv_out=mv_out, corrector=corr, members=members)
+    h_out3, _ = pipe.run_host(h_src, None, plan, converter=conv, cut_off=True, mv_out=mv_out, corrector=corr, members=members)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(h_out3.numpy(), plain.cpu().numpy())
