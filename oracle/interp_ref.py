@@ -160,8 +160,74 @@ def build_weights_invdist(distances, indexes, z, mub, mv_target, nnear):
     return result, weights, idxs
 
 
+def adw_cutoff_weights(distances, ref_radius=None):
+    """`adw_compute_weights_from_cutoff_distances` (:322-381), Shepard 1968 cut-off radii.
+
+    r_ref = mean of the 7th distances (or the caller's global value, :579-585); r' = d(5) where d(4) > r_ref, r_ref
+    where d(4) <= r_ref < d(10), else d(11); s = 1/d for d <= r'/3, (27/(4r'))*(d/r' - 1)^2 for r'/3 < d <= r', else 0;
+    w = s^2.  The reference runs this under numba with parallel=True: its mean is a parallel reduction whose rounding
+    depends on the number of threads (r_ref moves by a few ulp between machines, and weights of stations near the cut-off
+    radius - d/r' - 1 cancels - move by up to ~1e-11 relative with it).  At NUMBA_NUM_THREADS=1 the mean is the sequential
+    float64 sum restated here; the golden vectors were generated that way.  float32 maps: distances, r', s and w are
+    float32 arrays, the arithmetic between them follows numba's typing (see the comments below)."""
+    f32 = distances.dtype == np.float32
+    # numba at one thread: a sequential float64 sum (float32 distances included); the global value otherwise
+    r_ref = np.cumsum(distances[:, 6], dtype=np.float64)[-1] / len(distances) if ref_radius is None else ref_radius
+    r = distances[:, 10].copy()
+    f1 = distances[:, 3] > r_ref
+    r[f1] = distances[f1, 4]
+    f2 = np.logical_and(~f1, distances[:, 9] > r_ref)
+    r[f2] = r_ref
+    rb = r.reshape(-1, 1)
+    rb64 = rb.astype(np.float64)            # numba typing: float32 array (op) int64 literal -> float64
+    s = np.zeros_like(distances)
+    near = distances <= rb64 / 3
+    with np.errstate(all='ignore'):
+        s[near] = (1. / distances.astype(np.float64))[near]
+        mid = np.logical_and(~near, distances <= rb)
+        # `distances / r` stays float32 for float32 maps (array / array), `- 1` and `** 2` are float64
+        s[mid] = ((27 / (4 * rb64)) * (((distances / rb).astype(np.float64) - 1) ** 2))[mid]
+    return s ** 2, s, r_ref
+
+
+def adw_directional(s, indexes, tlat, tlon, slat, slon):
+    """the non-broadcasting loop of `_build_weights_invdist` (:953-973): angular term on the lat/lon plane,
+    `sum_j (1 - cos(theta_ij)) s_j / sum_j s_j` over j != i; NaN (no other station in range) -> 1 (:988)."""
+    k = indexes.shape[1]
+    wd = np.zeros_like(s)
+    with np.errstate(all='ignore'):
+        for i in range(k):
+            xj = tlat[:, np.newaxis] - slat[indexes]
+            yj = tlon[:, np.newaxis] - slon[indexes]
+            dj = np.sqrt(xj ** 2 + yj ** 2)
+            cos_theta = (xj[:, i, np.newaxis] * xj + yj[:, i, np.newaxis] * yj) / (dj[:, i, np.newaxis] * dj)
+            others = np.concatenate([np.arange(i), np.arange(i + 1, k)])
+            cos_theta = cos_theta[:, others]
+            sj = s[:, others]
+            wd[:, i] = np.sum((1 - cos_theta) * sj, axis=1) / np.sum(sj, axis=1)
+    return np.nan_to_num(wd, nan=1)
+
+
+def build_weights_adw(distances, indexes, z, tlat, tlon, slat, slon, nnear=11, ref_radius=None):
+    """`_build_weights_invdist(adw_type='Shepard')` (:817-838, :953-1001, :1019-1021, :1036-1052): no
+    min_upper_bound, no sentinel rows; w = s^2 (1 + directional), normalised; d0 <= 1e-10 -> [1, 0, ...]."""
+    w, s, r_ref = adw_cutoff_weights(distances, ref_radius)
+    wd = adw_directional(s, indexes, np.asarray(tlat).ravel(), np.asarray(tlon).ravel(), np.asarray(slat).ravel(),
+                         np.asarray(slon).ravel())
+    w = np.multiply(w, 1 + wd)
+    with np.errstate(all='ignore'):
+        weights = w / np.sum(w, axis=1, keepdims=True)
+        result = np.einsum('ij,ij->i', weights, z[indexes])
+    exact = distances[:, 0] <= 1e-10
+    first = np.zeros(nnear, dtype=weights.dtype)
+    first[0] = 1
+    weights[exact] = first
+    result[exact] = z[indexes[exact][:, 0]]
+    return result, weights, indexes
+
+
 class BuildOracle:
-    """`ScipyInterpolation.__init__` + `interpolate` for modes nearest / invdist
+    """`ScipyInterpolation.__init__` + `interpolate` for modes nearest / invdist / adw
     (:523-570, :572-663) with cKDTree as the neighbour search."""
 
     def __init__(self, longrib, latgrib, grid_details, source_values, nnear, mv_target, mv_source,
@@ -176,9 +242,12 @@ class BuildOracle:
         x, y, zz = to_3d(longrib, latgrib, self.radius, rotation=source_rotation)
         self.source_xyz = stack_xyz(x, y, zz)
         self.tree = build_tree(self.source_xyz)
-        self.min_upper_bound = min_upper_bound(self.tree, self.source_xyz, grid_details.get('Nj'), self.workers)
+        self.longrib, self.latgrib = longrib, latgrib
+        # "not used in adw (Shepard) algorithm" (:561-562)
+        self.min_upper_bound = None if mode == 'adw' else min_upper_bound(self.tree, self.source_xyz,
+                                                                          grid_details.get('Nj'), self.workers)
 
-    def interpolate(self, lonefas, latefas, python_loop=False):
+    def interpolate(self, lonefas, latefas, python_loop=False, num_of_splits=None):
         x, y, z = to_3d(lonefas, latefas, self.radius, rotation=self.target_rotation)
         self.target_xyz = stack_xyz(x, y, z)
         distances, indexes = query(self.tree, self.target_xyz, self.nnear, self.workers)
@@ -189,7 +258,16 @@ class BuildOracle:
             return result, distances, idxs
         if self.mode == 'invdist':
             return build_weights_invdist(distances, indexes, self.z, self.min_upper_bound, self.mv_target, self.nnear)
-        raise ValueError(f'oracle covers nearest/invdist only, got {self.mode}')
+        if self.mode == 'adw' and self.nnear == 11:
+            ref_radius = None
+            if num_of_splits is not None:
+                # :576-585 - the reference radius of a split build is numpy's mean over a k=7 query of ALL targets; the
+                # row blocks (:597-607) are then independent, so they are evaluated in one piece here
+                d7, _ = query(self.tree, self.target_xyz, 7, self.workers)
+                ref_radius = np.mean(d7[:, 6])
+            return build_weights_adw(distances, indexes, self.z, latefas, lonefas, self.latgrib, self.longrib, self.nnear,
+                                     ref_radius=ref_radius)
+        raise ValueError(f'oracle covers nearest / invdist / adw only, got {self.mode}')
 
 
 # --------------------------------------------------------------------------- table record

@@ -10,7 +10,7 @@ dask, ujson are absent and `np.NaN` is gone from numpy 2.  This script installs 
 shims for exactly those third-party names, then imports the UNMODIFIED reference modules
 from /root/reference/src and calls, on small synthetic inputs:
 
-  * `ScipyInterpolation(...).interpolate(...)`           (modes nearest, invdist; f64 and f32 targets)
+  * `ScipyInterpolation(...).interpolate(...)`           (modes nearest, invdist, adw; f64 and f32 targets)
   * `Interpolator._interpolate_scipy_append_mv(...)`     (k=1, k=4, plain and masked input)
   * `Converter.convert / cut_off_negative`, `Aggregator.do_manipulation` (3 modes, `@halfweights`
     averages, masked inputs), `Corrector.correct` (both formulas of the README)
@@ -35,6 +35,9 @@ import numpy as np
 import numpy.ma as ma
 
 sys.dont_write_bytecode = True
+# numba's parallel reductions (the ADW reference radius, a mean) round differently for every thread count: one thread
+# = a sequential sum, which the oracle restates
+os.environ.setdefault('NUMBA_NUM_THREADS', '1')
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, REPO)
@@ -185,6 +188,42 @@ def make_build_cases():
     tlat = np.concatenate([slat[sel], slat[sel] + 0.123]).reshape(2, -1)
     tlon = np.concatenate([slon[sel], slon[sel] - 0.321]).reshape(2, -1)
     build_case('o24_coincident_f64', slat, slon, det, tlat, tlon, synth.NC_FILL_F64)
+
+
+def adw_case(name, slat, slon, details, tlat, tlon, mv_target, num_of_splits=None):
+    """mode adw (Shepard, k = 11): `_build_weights_invdist(adw_type='Shepard')` incl. the numba kernel
+    `adw_compute_weights_from_cutoff_distances`, run by the reference itself (numba is importable here)."""
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    z = 280.0 + 10.0 * rng.standard_normal(slat.shape)
+    si = quiet(ScipyInterpolation, slon, slat, details, z, 11, mv_target, synth.GRIB_MV, parallel=False, mode='adw',
+               num_of_splits=num_of_splits)
+    assert si.min_upper_bound is None
+    result, weights, indexes = quiet(si.interpolate, tlon, tlat)
+    out = dict(src_lat=slat, src_lon=slon, tgt_lat=tlat, tgt_lon=tlon, z=z, radius=np.float64(details.get('radius')),
+               nj=np.int64(details.get('Nj')), mv_target=np.float64(mv_target), adw_result=filled(result),
+               adw_weights=np.asarray(weights), adw_indexes=np.asarray(indexes),
+               num_of_splits=np.int64(num_of_splits or 0))
+    np.savez_compressed(os.path.join(HERE, f'build_adw_{name}.npz'), **out)
+    print('adw', name, 'N', slat.size, 'M', tlat.size, 'weights', out['adw_weights'].dtype, 'exact rows',
+          int((out['adw_weights'][:, 0] == 1).sum()), 'NaN rows', int(np.isnan(out['adw_weights']).any(axis=1).sum()))
+
+
+def make_adw_cases():
+    slat, slon, det = synth.octahedral_grid(24)
+    lon = np.arange(-30.0, 40.0, 1.0) + 0.5
+    lat = np.arange(70.0, 20.0, -1.0) - 0.5
+    tlon, tlat = np.meshgrid(lon, lat)
+    adw_case('o24_box_f64', slat, slon, det, tlat, tlon, synth.NC_FILL_F64)
+    # the same target in 5 row blocks: the reference radius comes from a separate k=7 query over all targets (:576-585)
+    adw_case('o24_box_f64_splits', slat, slon, det, tlat, tlon, synth.NC_FILL_F64, num_of_splits=5)
+    tlat, tlon = synth.efas_target(rows=48, cols=50, cell=100000.0, dtype=np.float32)
+    tlat, tlon = synth.with_mv_region(tlat, tlon)
+    adw_case('o24_laea_f32mv', slat, slon, det, tlat, tlon, float(synth.PCR_MV_F32))
+    # targets on source points (d0 <= 1e-10 -> [1, 0, ...]; the angular term of such a row is 0/0) mixed with offsets
+    sel = np.arange(0, slat.size, 7)
+    tlat = np.concatenate([slat[sel], slat[sel] + 0.123]).reshape(2, -1)
+    tlon = np.concatenate([np.where(slon[sel] > 180, slon[sel] - 360, slon[sel]), slon[sel] - 0.321]).reshape(2, -1)
+    adw_case('o24_coincident_f64', slat, slon, det, tlat, tlon, synth.NC_FILL_F64)
 
 
 # ----------------------------------------------------------------------------- apply cases
@@ -404,8 +443,8 @@ def make_reference_fixture_copies():
 
 
 if __name__ == '__main__':
-    make_reference_fixture_copies()
-    make_build_cases()
-    make_apply_cases()
-    make_manip_cases()
-    make_writer_cases()
+    only = set(sys.argv[1:])            # e.g. `make_golden.py adw`: regenerate one group
+    for tag, fn in (('fixtures', make_reference_fixture_copies), ('build', make_build_cases), ('adw', make_adw_cases),
+                    ('apply', make_apply_cases), ('manip', make_manip_cases), ('writer', make_writer_cases)):
+        if not only or tag in only:
+            fn()

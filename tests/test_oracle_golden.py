@@ -36,6 +36,28 @@ def test_build_matches_reference(golden_dir, case, mode, k):
     np.testing.assert_array_equal(np.asarray(ma.filled(res))[ok], g[f'{mode}_result'][ok])
 
 
+ADW_CASES = ['o24_box_f64', 'o24_box_f64_splits', 'o24_laea_f32mv', 'o24_coincident_f64']
+
+
+@pytest.mark.parametrize('case', ADW_CASES)
+def test_adw_build_matches_reference(golden_dir, case):
+    """mode adw (Shepard, k = 11): vectors from the reference's own `_build_weights_invdist(adw_type='Shepard')` and its
+    numba kernel (scipy_interpolation_lib.py:322-381, :817-838, :953-1052), bit for bit, float64 and float32 maps."""
+    g = np.load(os.path.join(golden_dir, f'build_adw_{case}.npz'))
+    o = R.BuildOracle(g['src_lon'], g['src_lat'], _details(g), g['z'], 11, float(g['mv_target']), synth.GRIB_MV, mode='adw')
+    assert o.min_upper_bound is None
+    res, w, idx = o.interpolate(g['tgt_lon'], g['tgt_lat'], num_of_splits=int(g['num_of_splits']) or None)
+    np.testing.assert_array_equal(idx, g['adw_indexes'])
+    assert w.dtype == g['adw_weights'].dtype
+    np.testing.assert_array_equal(w, g['adw_weights'])
+    np.testing.assert_array_equal(np.asarray(res, dtype=g['adw_result'].dtype), g['adw_result'])
+    assert idx.max() < g['z'].size                      # no sentinel rows: adw has no min_upper_bound
+    if case == 'o24_coincident_f64':
+        exact = o.raw_distances[:, 0] <= 1e-10
+        # (targets written with longitudes in -180..180 land ~1e-9 m from their source point: not `exact`, 1/d ~ 1e9)
+        assert 100 < exact.sum() <= len(idx) // 2 and (w[exact, 0] == 1).all() and (w[exact, 1:] == 0).all()
+
+
 def test_build_nn_loop_equals_vectorised(golden_dir):
     g = np.load(os.path.join(golden_dir, 'build_regional_global_f64.npz'))
     o = R.BuildOracle(g['src_lon'], g['src_lat'], _details(g), g['z'], 1, float(g['mv_target']), synth.GRIB_MV)
