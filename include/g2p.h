@@ -158,6 +158,26 @@ int g2p_knn(const g2p_index* index, const void* tlon, const void* tlat, const do
 int g2p_weights(int mode, int k, int64_t m, int64_t n_src, double mub, int dtype,
                 int32_t* idx_inout, double* coef_inout, void* stream);
 
+/* K5b  Angular-distance weighting, mode `adw` (Shepard 1968) with k = 11.  Replaces the Shepard branch of
+ * `_build_weights_invdist` (scipy_interpolation_lib.py:817-838, :953-1001, :1019-1021, :1036-1052) and its numba kernel
+ * `adw_compute_weights_from_cutoff_distances` (:322-381).  Input is the RAW result of g2p_knn (k = 11).
+ *
+ * g2p_adw_distance_sum: the reference radius is the mean of the 7th distances over ALL targets (`np.mean(distances[:, 6])`,
+ * :339, or the k=7 query of a split build, :576-585).  Returns the sum of dist[column][0..m) as an unevaluated
+ * double-double {hi, lo} in sum_out (HOST, 2 doubles), accumulated exactly enough that hi does not depend on the launch
+ * shape; with the targets split over ranks the partial sums are added before dividing by the global m.  Synchronises.
+ * (The reference's own value comes from a numba parallel reduction and moves by a few ulp with the thread count.)
+ *
+ * g2p_weights_adw: in place on coef (distances [k][m] in -> normalised weights out; float32-representable values when
+ * dtype == G2P_F32, as the reference computes them in float32 arrays for float32 target maps).  tlat / tlon are the m
+ * ORIGINAL target coordinates (`dtype`), slat / slon the float64 source coordinates: the angular term is evaluated on the
+ * lat/lon plane (:955-966).  No min_upper_bound, no sentinel rows (:561-562); d(1) <= 1e-10 -> [1, 0, ..., 0]. */
+int g2p_adw_distance_sum(const double* dist, int64_t m, int k, int column, int dtype, double* sum_out /* host[2] */,
+                         void* stream);
+int g2p_weights_adw(int64_t m, int k, int dtype, double ref_radius, const void* tlat, const void* tlon,
+                    const double* slat, const double* slon, int64_t n_src, const int32_t* idx, double* coef_inout,
+                    void* stream);
+
 /* K6  SoA table <-> the reference's record layout.  rec: m*k records of
  * {int64 indexes; float64 coeffs} (16 B) or, coeff_dtype F32, {int64; float32} (12 B, packed). */
 int g2p_table_pack_rec(const int32_t* idx, const double* coef, int64_t m, int k, int coeff_dtype,

@@ -211,6 +211,8 @@ def adw_directional(s, indexes, tlat, tlon, slat, slon):
 def build_weights_adw(distances, indexes, z, tlat, tlon, slat, slon, nnear=11, ref_radius=None):
     """`_build_weights_invdist(adw_type='Shepard')` (:817-838, :953-1001, :1019-1021, :1036-1052): no
     min_upper_bound, no sentinel rows; w = s^2 (1 + directional), normalised; d0 <= 1e-10 -> [1, 0, ...]."""
+    # cKDTree hands over C-contiguous arrays; numpy's summation order below depends on the memory layout
+    distances, indexes = np.ascontiguousarray(distances), np.ascontiguousarray(indexes)
     w, s, r_ref = adw_cutoff_weights(distances, ref_radius)
     wd = adw_directional(s, indexes, np.asarray(tlat).ravel(), np.asarray(tlon).ravel(), np.asarray(slat).ravel(),
                          np.asarray(slon).ravel())

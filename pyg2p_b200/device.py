@@ -170,6 +170,46 @@ def weights(mode, idx, coef, n_src, mub, dtype_code=L.F64):
     return idx, coef
 
 
+def adw_reference_radius(dist, dtype_code=L.F64, m_total=None):
+    """`np.mean(distances[:, 6])` (reference scipy_interpolation_lib.py:339, :585) from the raw k = 11 (or k = 7) distances
+    [k, m] of this rank's targets: an exact (double-double) column sum on the device; under an initialised process group the
+    partial sums of the ranks are added (all-gather of two doubles per rank) before dividing by the global target count."""
+    from . import parallel
+    lib = require_cuda()
+    _bind_device(dist.device)
+    k, m = dist.shape
+    pair = (C.c_double * 2)()
+    with torch.cuda.device(dist.device):
+        L.check(lib.g2p_adw_distance_sum(_ptr(dist), int(m), int(k), 6, int(dtype_code), pair, _stream()))
+    parts = parallel.gather_pairs((pair[0], pair[1]), dist.device)
+    total = parallel.sum_over_ranks(m, dist.device) if m_total is None else m_total
+    hi = lo = 0.0
+    for a, b in parts:                      # two-sum merge: the result does not depend on the rank partition
+        t = hi + a
+        bb = t - hi
+        lo += (hi - (t - bb)) + (a - bb)
+        lo += b
+        hi = t
+    return (hi + lo) / int(round(total))
+
+
+def weights_adw(idx, dist, tlat, tlon, slat, slon, ref_radius, dtype_code=L.F64):
+    """Standalone K5b (in place on dist -> weights): raw k = 11 (idx, dist) -> Shepard angular-distance weights.
+    tlat / tlon: the targets' ORIGINAL coordinates (device, float64 or float32 = dtype_code), slat / slon: float64 device."""
+    lib = require_cuda()
+    _bind_device(idx.device)
+    k, m = idx.shape
+    want = torch.float32 if dtype_code == L.F32 else torch.float64
+    if tlat.dtype != want or tlon.dtype != want or slat.dtype != torch.float64 or slon.dtype != torch.float64:
+        raise ValueError('weights_adw: target coordinates in the map dtype, source coordinates in float64')
+    if tlat.numel() != m or tlon.numel() != m or slat.numel() != slon.numel():
+        raise ValueError('weights_adw: coordinate arrays do not match the table')
+    with torch.cuda.device(idx.device):
+        L.check(lib.g2p_weights_adw(int(m), int(k), int(dtype_code), float(ref_radius), _ptr(tlat), _ptr(tlon), _ptr(slat),
+                                    _ptr(slon), int(slat.numel()), _ptr(idx), _ptr(dist), _stream()))
+    return idx, dist
+
+
 def latlon_to_xyz(lon, lat, radius, rotation=None, device=None):
     """K1: `to_3d` (reference scipy_interpolation_lib.py:665-696) on the device; (n,3) float64."""
     lib = require_cuda()

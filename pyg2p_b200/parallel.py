@@ -81,3 +81,15 @@ def sum_over_ranks(value, device):
     if ws > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def gather_pairs(pair, device):
+    """(hi, lo) of every rank, in rank order (the partial double-double sums of the ADW reference radius)."""
+    rank, ws = world()
+    if ws == 1:
+        return [tuple(pair)]
+    mine = torch.tensor([float(pair[0]), float(pair[1])], dtype=torch.float64, device=device)
+    full = torch.empty((ws * 2,), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(full, mine)
+    h = full.cpu().tolist()
+    return [(h[2 * r], h[2 * r + 1]) for r in range(ws)]

@@ -1,9 +1,9 @@
 """Drop-in for the reference's `ScipyInterpolation` (main/interpolation/scipy_interpolation_lib.py:516-727,
-:774-812, :1018-1076) for the modes `nearest` and `invdist`: same constructor signature, same
+:774-812, :1018-1076) for the modes `nearest`, `invdist` and `adw` (Shepard, k = 11): same constructor signature, same
 `interpolate(lonefas, latefas) -> (result, weights, indexes)` with the same shapes and dtypes, computed by
 the CUDA library (cube-sphere index + k-NN + weights) instead of scipy's cKDTree and numpy.
 
-No CPU fallback: the other modes (adw, cdd, bilinear, triangulation, bilinear_delaunay) are outside this
+No CPU fallback: the other modes (cdd, bilinear, triangulation, bilinear_delaunay) are outside this
 package's scope and raise INVALID_INTERPOL_METHOD, as the reference does for unknown modes (:655).
 """
 import numpy as np
@@ -14,7 +14,7 @@ from . import _lib as L
 from . import device, parallel
 from .exceptions import INVALID_INTERPOL_METHOD, WEIRD_STUFF, ApplicationException
 
-_MODES = {'nearest': (L.MODE_NEAREST, 1), 'invdist': (L.MODE_INVDIST, None)}
+_MODES = {'nearest': (L.MODE_NEAREST, 1), 'invdist': (L.MODE_INVDIST, None), 'adw': (L.MODE_RAW, 11)}
 
 
 class ScipyInterpolation:
@@ -24,7 +24,7 @@ class ScipyInterpolation:
     def __init__(self, longrib, latgrib, grid_details, source_values, nnear, mv_target, mv_source,
                  target_is_rotated=False, parallel=False, mode='nearest', cdd_map='', cdd_mode='', cdd_options=None,
                  use_broadcasting=False, num_of_splits=None, device_index=None):
-        if mode not in _MODES or (mode == 'nearest' and nnear != 1):
+        if mode not in _MODES or (_MODES[mode][1] is not None and nnear != _MODES[mode][1]):
             raise ApplicationException.get_exc(
                 INVALID_INTERPOL_METHOD, f'interpolation method not supported (mode = {mode}, nnear = {nnear})')
         self.geodetic_info = grid_details
@@ -44,8 +44,9 @@ class ScipyInterpolation:
         rot = None if self.rotated_bugfix_gribapi else self._south_pole()
         self.index = device.SourceIndex(np.asarray(longrib, dtype=np.float64), np.asarray(latgrib, dtype=np.float64),
                                         grid_details.get('radius'), rotation=rot, device=dev)
-        # self query k=2 -> max -> dmax + dmax*4/Nj (:568-570); not used by adw (out of scope)
-        self.min_upper_bound = self.index.min_upper_bound(grid_details.get('Nj'))
+        # self query k=2 -> max -> dmax + dmax*4/Nj (:568-570); "not used in adw (Shepard) algorithm" (:561-562)
+        self.min_upper_bound = None if mode == 'adw' else self.index.min_upper_bound(grid_details.get('Nj'))
+        self.ref_radius = None
         self.table = None
         self.flags = None
 
@@ -75,13 +76,27 @@ class ScipyInterpolation:
         rank, ws = parallel.world()
         lo, hi = parallel.shard_bounds(m, rank, ws, align=cols) if ws > 1 else (0, m)
         flat_lon, flat_lat = lonefas.reshape(-1)[lo:hi], latefas.reshape(-1)[lo:hi]
-        out = self.index.knn(flat_lon, flat_lat, k=self.nnear, mode=mode_code, mub=self.min_upper_bound,
+        out = self.index.knn(flat_lon, flat_lat, k=self.nnear, mode=mode_code, mub=self.min_upper_bound or 0.0,
                              radius=self.geodetic_info.get('radius'), rotation=rot, want_flags=True)
         idx, coef = out['idx'], out['coef']
         self.flags = out['flags']
+        if self.mode == 'adw':
+            # Shepard weights from the raw neighbours (:817-838, :953-1052).  The reference radius is the mean 7th distance
+            # over ALL targets - of this build (:339), or of the k=7 query a split build runs first (:576-585): the same
+            # numbers, so one global value serves both (the ranks add their partial sums)
+            code = out['coef_dtype']
+            dev = idx.device
+            self.ref_radius = device.adw_reference_radius(coef, code, m_total=m)
+            t_lat = device.to_device(flat_lat, torch.float32 if code == L.F32 else torch.float64, dev)
+            t_lon = device.to_device(flat_lon, torch.float32 if code == L.F32 else torch.float64, dev)
+            s_lat = device.to_device(np.asarray(self.latgrib, dtype=np.float64).ravel(), torch.float64, dev)
+            s_lon = device.to_device(np.asarray(self.longrib, dtype=np.float64).ravel(), torch.float64, dev)
+            device.weights_adw(idx, coef, t_lat, t_lon, s_lat, s_lon, self.ref_radius, code)
         if ws > 1:
             idx, coef = parallel.all_gather_table(idx, coef, m, align=cols)
-        f32 = lonefas.dtype == np.float32 and self.mode == 'nearest'     # coeffs = float32 distances (:627-635)
+        # float32 maps: nearest stores float32 distances (:627-635), adw float32 weights (`w / sums` of float32 arrays,
+        # :1019-1021); invdist stores float32-valued weights into z.dtype = float64 arrays (:787)
+        f32 = lonefas.dtype == np.float32 and self.mode in ('nearest', 'adw')
         shape = lonefas.shape if lonefas.ndim == 2 else None
         self.table = device.DeviceTable(idx, coef, self.z.size, coef_f32=f32, grid_shape=shape)
         return self.table
