@@ -153,6 +153,22 @@ int g2p_knn(const g2p_index* index, const void* tlon, const void* tlat, const do
             double mub, int32_t* idx_out, double* coef_out, uint8_t* flags_out, double* xyz_out,
             void* stream);
 
+/* g2p_knn writing a BLOCK of a larger table: the m targets of this call are columns [out_offset, out_offset + m) of
+ * idx_out / coef_out rows of `out_stride` values (flags_out / xyz_out stay per call, m entries).  This is how a rank
+ * of a multi-GPU build writes its target block straight into its copy of the full table. */
+int g2p_knn_block(const g2p_index* index, const void* tlon, const void* tlat, const double* txyz,
+                  int64_t m, int dtype, double radius, const g2p_rotation* rot /* host, nullable */, int k, int mode,
+                  double mub, int32_t* idx_out, double* coef_out, int64_t out_stride, int64_t out_offset,
+                  uint8_t* flags_out, double* xyz_out, void* stream);
+
+/* Multi-GPU table assembly over NVLink peer memory (replaces the NCCL all-gather of table shards): the
+ * byte range [col_off, col_off + seg_bytes) of each of n_rows rows (pitch row_bytes) of the local buffer is stored
+ * at the same place in n_peers peer buffers.  peer_bases: HOST array of device pointers of the peers' buffers as mapped
+ * into this process (CUDA IPC / torch symmetric memory); all sizes multiples of 4 bytes (16 for full-width stores).
+ * Asynchronous on `stream`; the caller's inter-rank barrier after it makes the table complete everywhere. */
+int g2p_peer_push(const void* local_base, void* const* peer_bases /* host */, int n_peers, int64_t row_bytes,
+                  int64_t col_off, int64_t seg_bytes, int n_rows, void* stream);
+
 /* K5  weights from raw (idx, dist).  Same arithmetic as the fused epilogue of g2p_knn; kept as
  * its own entry point so the stage can be checked in isolation.  In place on idx / coef. */
 int g2p_weights(int mode, int k, int64_t m, int64_t n_src, double mub, int dtype,
@@ -191,6 +207,16 @@ int g2p_table_unpack_rec(const void* rec, int64_t m, int k, int coeff_dtype, int
  *   touched_out: int32, capacity min(n, m*k); cidx_out: int32 [k][m] (sentinel = nc); nc_out: host.  Synchronises. */
 int g2p_table_compact(const int32_t* idx, int64_t m, int k, int64_t n, int32_t* touched_out, int32_t* cidx_out,
                       int64_t* nc_out /* host */, void* stream);
+
+/* Host-side staging helper of the ingest path - the one entry point that takes HOST pointers for data and does no
+ * device work: out[c] = src[touched[c]] for the nc source points a table reads (g2p_table_compact's list, copied to
+ * the host), straight out of the pageable array a GRIB decoder returned (readers/grib.py:191-201) into a small
+ * page-locked buffer - 2.2 MB instead of staging the 52.8 MB field.  mask (nullable): one byte per source value,
+ * nonzero = missing; out_mask (nullable): the mask bytes of the picked points; fold_marker != 0: masked points get
+ * G2P_MASK_MARKER as their value (input of G2P_MASK_MARKED).  The caller runs it on a decoder-side thread (ctypes
+ * releases the GIL) while the device works on the previous message. */
+int g2p_host_pick(const double* src /* host */, const uint8_t* mask /* host */, const int32_t* touched /* host */,
+                  int64_t nc, double* out /* host */, uint8_t* out_mask /* host */, int fold_marker);
 
 /* K7  batched intertable apply.  Replaces Interpolator._interpolate_scipy_append_mv
  * (interpolation/__init__.py:142-162) for `b` messages in one launch.

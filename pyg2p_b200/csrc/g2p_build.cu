@@ -637,6 +637,7 @@ struct KnnArgs {
   const void* tlat;
   const double* txyz;
   int64_t m;
+  int64_t os, oo;            // idx_out / coef_out: row stride and column offset (a block of a larger table)
   Rot rot;
   double xyz_radius;  // radius used by to_3d for the targets (= grid_details['radius'])
   int k, mode;
@@ -965,11 +966,11 @@ __global__ void __launch_bounds__(256, KK <= 2 ? 5 : (KK <= 4 ? 4 : (KK < 11 ? 3
         inside = false;
       }
       const int32_t nsrc2 = (int32_t)a.ix.n;
-      const int64_t sa = (int64_t)(2 * lane) * a.m + q;
+      const int64_t sa = (int64_t)(2 * lane) * a.os + a.oo + q;
       a.idx_out[sa] = (inside && ida != INT_MAX) ? ida : nsrc2;
       a.coef_out[sa] = wa;
-      a.idx_out[sa + a.m] = (inside && idb != INT_MAX) ? idb : nsrc2;
-      a.coef_out[sa + a.m] = wb;
+      a.idx_out[sa + a.os] = (inside && idb != INT_MAX) ? idb : nsrc2;
+      a.coef_out[sa + a.os] = wb;
       if (lane == 0) {
         if (a.xyz_out) {
           a.xyz_out[3 * q] = qx; a.xyz_out[3 * q + 1] = qy; a.xyz_out[3 * q + 2] = qz;
@@ -1017,13 +1018,13 @@ __global__ void __launch_bounds__(256, KK <= 2 ? 5 : (KK <= 4 ? 4 : (KK < 11 ? 3
 #pragma unroll
       for (int s = 0; s < KK; ++s)
         if (s < k) {
-          a.idx_out[(int64_t)s * a.m + q] = (top.id[s] == INT_MAX) ? nsrc : top.id[s];
-          a.coef_out[(int64_t)s * a.m + q] = dist[s];
+          a.idx_out[(int64_t)s * a.os + a.oo + q] = (top.id[s] == INT_MAX) ? nsrc : top.id[s];
+          a.coef_out[(int64_t)s * a.os + a.oo + q] = dist[s];
         }
     } else if (a.mode == G2P_MODE_NEAREST) {
       // _build_nn: idx = ix if dist <= mub else N ; coeffs = distance for every row
-      a.idx_out[q] = (dist[0] <= a.mub && top.id[0] != INT_MAX) ? top.id[0] : nsrc;
-      a.coef_out[q] = dist[0];
+      a.idx_out[a.oo + q] = (dist[0] <= a.mub && top.id[0] != INT_MAX) ? top.id[0] : nsrc;
+      a.coef_out[a.oo + q] = dist[0];
     } else {
       double w[KK];
       bool inside;
@@ -1031,8 +1032,8 @@ __global__ void __launch_bounds__(256, KK <= 2 ? 5 : (KK <= 4 ? 4 : (KK < 11 ? 3
 #pragma unroll
       for (int s = 0; s < KK; ++s)
         if (s < k) {
-          a.idx_out[(int64_t)s * a.m + q] = (inside && top.id[s] != INT_MAX) ? top.id[s] : nsrc;
-          a.coef_out[(int64_t)s * a.m + q] = w[s];
+          a.idx_out[(int64_t)s * a.os + a.oo + q] = (inside && top.id[s] != INT_MAX) ? top.id[s] : nsrc;
+          a.coef_out[(int64_t)s * a.os + a.oo + q] = w[s];
         }
     }
   }
@@ -1283,6 +1284,16 @@ int g2p_index_max_nn_dist_part(g2p_index* ix, int64_t first, int64_t last, doubl
 int g2p_knn(const g2p_index* ix, const void* tlon, const void* tlat, const double* txyz, int64_t m, int dtype,
             double radius, const g2p_rotation* rot, int k, int mode, double mub, int32_t* idx_out, double* coef_out,
             uint8_t* flags_out, double* xyz_out, void* stream) {
+  return g2p_knn_block(ix, tlon, tlat, txyz, m, dtype, radius, rot, k, mode, mub, idx_out, coef_out, m, 0, flags_out,
+                       xyz_out, stream);
+}
+
+int g2p_knn_block(const g2p_index* ix, const void* tlon, const void* tlat, const double* txyz, int64_t m, int dtype,
+                  double radius, const g2p_rotation* rot, int k, int mode, double mub, int32_t* idx_out, double* coef_out,
+                  int64_t out_stride, int64_t out_offset, uint8_t* flags_out, double* xyz_out, void* stream) {
+  if (out_stride < m || out_offset < 0 || out_offset + m > out_stride)
+    return set_error(G2P_ERR_INVALID, "g2p_knn_block: the block [%lld, %lld) does not fit rows of %lld", (long long)out_offset,
+                     (long long)(out_offset + m), (long long)out_stride);
   if (!ix || !idx_out || !coef_out) return set_error(G2P_ERR_INVALID, "g2p_knn: null index/outputs");
   if (!txyz && (!tlon || !tlat)) return set_error(G2P_ERR_INVALID, "g2p_knn: give tlon+tlat or txyz");
   if (k < 1 || k > 16) return set_error(G2P_ERR_INVALID, "g2p_knn: k=%d out of range 1..16", k);
@@ -1299,6 +1310,8 @@ int g2p_knn(const g2p_index* ix, const void* tlon, const void* tlat, const doubl
   a.tlat = tlat;
   a.txyz = txyz;
   a.m = m;
+  a.os = out_stride;
+  a.oo = out_offset;
   a.rot = make_rot(rot);
   a.xyz_radius = radius > 0.0 ? radius : (ix->user_radius > 0.0 ? ix->user_radius : ix->radius);
   a.k = k;

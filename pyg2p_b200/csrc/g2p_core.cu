@@ -1,6 +1,7 @@
 // Error handling, device queries and launch accounting for libg2pgpu.so.
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 
 #include "g2p_common.cuh"
 
@@ -58,5 +59,31 @@ int g2p_set_device(int device) {
 }
 
 int64_t g2p_launch_count(void) { return g2p::g_launches.load(); }
+
+// Host-side staging helper of the ingest path (no device work): out[c] = src[touched[c]] for the nc source points a
+// table reads, straight from the pageable array the GRIB decoder returned into a (pinned) compact buffer; optionally
+// the mask bytes of those points (out_mask) and / or the marker NaN folded into the values of masked points.
+int g2p_host_pick(const double* src, const uint8_t* mask, const int32_t* touched, int64_t nc, double* out,
+                  uint8_t* out_mask, int fold_marker) {
+  if (!src || !touched || !out || nc < 0) return g2p::set_error(G2P_ERR_INVALID, "g2p_host_pick: null pointer");
+  const double marker = [] {
+    const unsigned long long u = G2P_MASK_MARKER;
+    double d;
+    memcpy(&d, &u, sizeof d);
+    return d;
+  }();
+  if (!mask) {
+    for (int64_t c = 0; c < nc; ++c) out[c] = src[touched[c]];
+    if (out_mask) memset(out_mask, 0, (size_t)nc);
+    return G2P_OK;
+  }
+  for (int64_t c = 0; c < nc; ++c) {
+    const int32_t j = touched[c];
+    const uint8_t mk = mask[j] ? 1 : 0;
+    out[c] = (mk && fold_marker) ? marker : src[j];
+    if (out_mask) out_mask[c] = mk;
+  }
+  return G2P_OK;
+}
 
 }  // extern "C"

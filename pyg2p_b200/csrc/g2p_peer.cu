@@ -1,0 +1,67 @@
+// Multi-GPU assembly of intertable shards over NVLink peer memory (north_star: "all-gather ... only to
+// assemble table shards").  Every rank owns the table rows of a contiguous block of targets; the full table lives in a
+// buffer that is mapped into every process of the node (torch symmetric memory / CUDA IPC), at the same layout on every
+// GPU.  A rank writes its block into its own copy (g2p_knn_block) and this kernel stores the same bytes into the peers'
+// copies - plain 16-byte stores through the NVLink mapping, one launch for all peers and all table rows, running on a
+// second stream while the k-NN of the rank's next target block computes.  No staging buffer, no library collective: the
+// only other exchange is the barrier that tells every rank the table is complete.
+#include "g2p_common.cuh"
+
+namespace g2p {
+
+constexpr int kMaxPeers = 15;
+struct PeerList {
+  char* base[kMaxPeers];
+};
+
+// rows of `row_bytes` bytes; the segment [col_off, col_off + seg_bytes) of every row goes to all peers.
+// grid.y = row, grid.z = peer, grid.x strides over the segment.  VEC = bytes per access (16 or 4).
+template <int VEC>
+__global__ void __launch_bounds__(256) peer_push_kernel(const char* __restrict__ local, PeerList peers, int64_t row_bytes,
+                                                        int64_t col_off, int64_t seg_bytes) {
+  const int64_t at = (int64_t)blockIdx.y * row_bytes + col_off;
+  const char* src = local + at;
+  char* dst = peers.base[blockIdx.z] + at;
+  const int64_t nvec = seg_bytes / VEC;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    if (VEC == 16) {
+      const int4 v = __ldg(reinterpret_cast<const int4*>(src) + i);
+      reinterpret_cast<int4*>(dst)[i] = v;
+    } else {
+      reinterpret_cast<int32_t*>(dst)[i] = __ldg(reinterpret_cast<const int32_t*>(src) + i);
+    }
+  }
+}
+
+}  // namespace g2p
+
+using namespace g2p;
+
+extern "C" int g2p_peer_push(const void* local_base, void* const* peer_bases, int n_peers, int64_t row_bytes,
+                             int64_t col_off, int64_t seg_bytes, int n_rows, void* stream) {
+  if (!local_base || (n_peers > 0 && !peer_bases)) return set_error(G2P_ERR_INVALID, "g2p_peer_push: null pointer");
+  if (n_peers < 0 || n_peers > kMaxPeers) return set_error(G2P_ERR_INVALID, "g2p_peer_push: 0..%d peers", kMaxPeers);
+  if (row_bytes < 0 || col_off < 0 || seg_bytes < 0 || col_off + seg_bytes > row_bytes || n_rows < 0)
+    return set_error(G2P_ERR_INVALID, "g2p_peer_push: bad sizes");
+  if ((row_bytes | col_off | seg_bytes) & 3) return set_error(G2P_ERR_INVALID, "g2p_peer_push: sizes must be multiples of 4 bytes");
+  if (n_peers == 0 || n_rows == 0 || seg_bytes == 0) return G2P_OK;
+  PeerList pl{};
+  bool v16 = (((uintptr_t)local_base | (uintptr_t)row_bytes | (uintptr_t)col_off | (uintptr_t)seg_bytes) & 15) == 0;
+  for (int p = 0; p < n_peers; ++p) {
+    if (!peer_bases[p]) return set_error(G2P_ERR_INVALID, "g2p_peer_push: peer %d has no mapping", p);
+    pl.base[p] = static_cast<char*>(peer_bases[p]);
+    v16 = v16 && (((uintptr_t)peer_bases[p]) & 15) == 0;
+  }
+  const int vec = v16 ? 16 : 4;
+  const int64_t nvec = seg_bytes / vec;
+  // enough CTAs in flight to cover the NVLink latency, spread over rows and peers
+  int gx = (int)std::min<int64_t>(ceil_div(nvec, 256 * 4), std::max(1, num_sms() * 4 / std::max(1, n_rows * n_peers)));
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)n_rows, (unsigned)n_peers);
+  if (v16)
+    peer_push_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const char*>(local_base), pl, row_bytes, col_off, seg_bytes);
+  else
+    peer_push_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const char*>(local_base), pl, row_bytes, col_off, seg_bytes);
+  G2P_LAUNCHED();
+  return G2P_OK;
+}

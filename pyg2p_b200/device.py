@@ -124,8 +124,10 @@ class SourceIndex:
         return dmax + dmax * 4 / nj
 
     def knn(self, tlon=None, tlat=None, k=1, mode=L.MODE_RAW, mub=0.0, radius=None, rotation=None, txyz=None,
-            want_flags=True, want_xyz=False):
+            want_flags=True, want_xyz=False, into=None):
         """k nearest sources of every target; returns dict(idx int32 [k,m], coef f64 [k,m], flags u8 [m], xyz).
+        `into` = (idx_full [k, M], coef_full [k, M], offset): write the result as columns [offset, offset + m) of a larger
+        table (g2p_knn_block) - the returned idx / coef are views of that block.
 
         tlon/tlat: numpy arrays or device tensors, float64 or float32 (PCRaster REAL4 maps keep
         float32: the reference then rounds xyz and distances to float32, :627-628, :691-694)."""
@@ -147,15 +149,25 @@ class SourceIndex:
                 m = lo.numel()
                 code = L.F32 if lo.dtype == torch.float32 else L.F64
                 tx = None
-            idx = torch.empty((k, m), dtype=torch.int32, device=self.device)
-            coef = torch.empty((k, m), dtype=torch.float64, device=self.device)
+            if into is None:
+                idx = torch.empty((k, m), dtype=torch.int32, device=self.device)
+                coef = torch.empty((k, m), dtype=torch.float64, device=self.device)
+                base_i, base_c, stride, off = idx, coef, m, 0
+            else:
+                base_i, base_c, off = into
+                stride = base_i.shape[1]
+                if (base_i.shape != base_c.shape or base_i.shape[0] != k or base_i.dtype != torch.int32
+                        or base_c.dtype != torch.float64 or not base_i.is_contiguous() or not base_c.is_contiguous()
+                        or off < 0 or off + m > stride):
+                    raise ValueError('knn(into=): idx int32 / coef float64 [k, M] contiguous tables and a block inside them')
+                idx, coef = base_i[:, off:off + m], base_c[:, off:off + m]
             flags = torch.empty((m,), dtype=torch.uint8, device=self.device) if want_flags else None
             xyz = torch.empty((m, 3), dtype=torch.float64, device=self.device) if want_xyz else None
             r = float(radius) if radius is not None else (float(self.radius) if self.radius else 0.0)
             if m > 0:
-                L.check(self._lib.g2p_knn(self._h, _ptr(lo), _ptr(la), _ptr(tx), m, code, r, L.rotation_arg(rotation),
-                                          int(k), int(mode), float(mub), _ptr(idx), _ptr(coef), _ptr(flags), _ptr(xyz),
-                                          _stream()))
+                L.check(self._lib.g2p_knn_block(self._h, _ptr(lo), _ptr(la), _ptr(tx), m, code, r, L.rotation_arg(rotation),
+                                                int(k), int(mode), float(mub), _ptr(base_i), _ptr(base_c), int(stride),
+                                                int(off), _ptr(flags), _ptr(xyz), _stream()))
         return {'idx': idx, 'coef': coef, 'flags': flags, 'xyz': xyz, 'coef_dtype': code}
 
 
@@ -686,7 +698,10 @@ class HostApplyPipeline:
             self._stage[key] = [pinned_empty((self.c, host.shape[1]), tdt) for _ in range(2)]
         slot = self._stage[key][(lo // self.c) % 2]
         view = slot[:hi - lo]
-        view.numpy()[...] = host[lo:hi]
+        if hasattr(host, 'copy_rows'):
+            host.copy_rows(lo, hi, view.numpy())      # a list of separate pageable arrays (Interpolator._RowStack)
+        else:
+            view.numpy()[...] = host[lo:hi]
         return view
 
     def run(self, src, mv_out, src_mask=None, mask_policy=L.MASK_AS_REFERENCE, out=None, out_mask=None,
@@ -866,10 +881,25 @@ class CompactHostPipeline:
         return out, (out_mask if want_omask else None)
 
     def touched_host(self):
-        """the touched source indexes as a host index array (for `numpy.take` on pageable fields)."""
+        """the touched source indexes as a host int32 array (for `pick` on pageable fields)."""
         if getattr(self, '_touched_host', None) is None:
-            self._touched_host = self.touched.cpu().numpy().astype(np.intp)
+            self._touched_host = np.ascontiguousarray(self.touched.cpu().numpy().astype(np.int32))
         return self._touched_host
+
+    def pick(self, field, out_values, out_mask=None):
+        """g2p_host_pick: the touched values of one pageable message (ndarray / MaskedArray, n values) -> out_values
+        [>= nc] (a numpy view of a pinned buffer), their mask bytes -> out_mask (zeros for an unmasked message).  Pure
+        host staging; releases the GIL."""
+        th = self.touched_host()
+        data = np.ascontiguousarray(np.ma.getdata(field), dtype=np.float64).reshape(-1)
+        if data.size != self.t.n_src:
+            raise ValueError(f'source field has {data.size} values, intertable was built for {self.t.n_src}')
+        mask = None
+        if out_mask is not None and isinstance(field, np.ma.MaskedArray) and field.mask is not np.ma.nomask:
+            mask = np.ascontiguousarray(np.broadcast_to(np.ma.getmaskarray(field).reshape(-1), data.shape)).view(np.uint8)
+        L.check(L.lib().g2p_host_pick(data.ctypes.data, mask.ctypes.data if mask is not None else None, th.ctypes.data,
+                                      th.size, out_values.ctypes.data, out_mask.ctypes.data if out_mask is not None else None,
+                                      0))
 
     def run_compact(self, h_c, mv_out, h_cm=None, mask_policy=L.MASK_AS_REFERENCE, out=None, out_mask=None,
                     correction=None, post=None):

@@ -117,6 +117,22 @@ def _normalize_filename(name):
     return name.replace('.', '_') if len(stem) < 3 else stem[:10]
 
 
+class _RowStack:
+    """a batch of pageable 1-D arrays presented as [b, n] rows to HostApplyPipeline._staged (which copies rows lo:hi into
+    a page-locked slot through `copy_rows`); a None row is all zeros (an unmasked message)"""
+
+    def __init__(self, rows, dtype, n=None):
+        self.rows, self.dtype = rows, np.dtype(dtype)
+        self.shape = (len(rows), n if n is not None else rows[0].size)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def copy_rows(self, lo, hi, dst):
+        for i, r in enumerate(self.rows[lo:hi]):
+            dst[i] = 0 if r is None else r
+
+
 class Interpolator:
     _LOADED_INTERTABLES = {}      # path -> numpy record array (as the reference, :21)
     _DEVICE_TABLES = {}           # (path, device index) -> DeviceTable
@@ -241,33 +257,145 @@ class Interpolator:
             if isinstance(pipe, device.CompactHostPipeline):
                 # pageable fields and a regional table: pick the touched values of every message straight into a
                 # small pinned buffer (2.2 MB of a 52.8 MB O1280 field for EFAS) instead of staging whole fields
-                th = pipe.touched_host()
-                nc = th.size
+                nc = pipe.touched_host().size
                 h_c = device.pinned_empty((b, nc))
                 h_cm = device.pinned_empty((b, nc), torch.uint8) if propagate else None
                 for i, x in enumerate(values):
-                    np.take(np.asarray(ma.getdata(x), dtype=np.float64).reshape(-1), th, out=h_c.numpy()[i])
-                    if propagate:
-                        if masked_in[i]:
-                            np.take(np.broadcast_to(ma.getmaskarray(x).reshape(-1), (n,)).view(np.uint8), th,
-                                    out=h_cm.numpy()[i])
-                        else:
-                            h_cm.numpy()[i] = 0
+                    pipe.pick(x, h_c.numpy()[i], h_cm.numpy()[i] if propagate else None)
                 out, omask = pipe.run_compact(h_c, float(self.mv_output), h_cm=h_cm,
                                               mask_policy=L.MASK_PROPAGATE if propagate else L.MASK_AS_REFERENCE, out=out,
                                               out_mask=out_mask, correction=corrector, post=writer_post)
                 return self._batch_result(table, out, omask, b, shape, propagate, pinned, values, writer_post)
-            h_src = device.pinned_empty((b, n))
-            h_np = h_src.numpy()
-            h_msk = device.pinned_empty((b, n), torch.uint8) if propagate else None
-            for i, x in enumerate(values):
-                h_np[i] = np.asarray(ma.getdata(x), dtype=np.float64).ravel()
-                if propagate:
-                    h_msk.numpy()[i] = np.broadcast_to(ma.getmaskarray(x).ravel(), (n,)) if masked_in[i] else 0
+            # pageable fields and a table that reads most of the source grid: HostApplyPipeline stages them chunk by chunk
+            # through two page-locked slots of ~256 MB (never the whole batch: a run of 383 O1280 messages is 20 GB)
+            h_src = _RowStack([np.asarray(ma.getdata(x), dtype=np.float64).reshape(-1) for x in values], np.float64)
+            h_msk = _RowStack([np.broadcast_to(ma.getmaskarray(x).reshape(-1), (n,)) if masked_in[i] else None
+                               for i, x in enumerate(values)], np.uint8, n) if propagate else None
         out, omask = pipe.run(h_src, float(self.mv_output), src_mask=h_msk,
                               mask_policy=L.MASK_PROPAGATE if propagate else L.MASK_AS_REFERENCE, out=out,
                               out_mask=out_mask, correction=corrector, post=writer_post)
         return self._batch_result(table, out, omask, b, shape, propagate, pinned, values, writer_post)
+
+    def interpolate_stream(self, latgrib, longrib, values_iter, grid_id, grid_details=None, depth=4, corrector=None,
+                           writer_post=None):
+        """The per-step loop of the writers (writers/__init__.py:55-70, 96-109) as a generator: takes an iterator of
+        source fields as the GRIB reader yields them - pageable numpy arrays / MaskedArrays, one per message
+        (readers/grib.py:191-201) - and yields the interpolated fields in the same order.
+
+        A host thread picks the touched values of the NEXT messages out of the pageable arrays into a ring of `depth`
+        small pinned buffers (2.2 MB of a 52.8 MB O1280 field for the EFAS table) while the device copies, applies and
+        returns the previous ones; every result lands in its own page-locked array (recycled by torch's pinned
+        allocator once the caller drops it), so nothing is copied on the host after the D2H.  Tables that read most of
+        the source grid fall back to one `interpolate_batch` call per message."""
+        import collections
+        import itertools
+        import queue
+        import threading
+        it = iter(values_iter)
+        try:
+            first = next(it)
+        except StopIteration:
+            return
+        table = self._table_for(latgrib, longrib, first, grid_id, grid_details)
+        shape = self._target_coords.lons.shape
+        want_mask = self.mask_policy == 'propagate'
+        pipe = self._pipeline(table, want_mask)
+        if not isinstance(pipe, device.CompactHostPipeline):
+            for x in itertools.chain([first], it):
+                yield self.interpolate_batch(latgrib, longrib, [x], grid_id, grid_details, corrector=corrector,
+                                             writer_post=writer_post)[0]
+            return
+        n, m = table.n_src, table.m
+        th = pipe.touched_host()
+        nc = th.size
+        nc_pad = -(-nc // 16) * 16
+        dev = table.device
+        ring_v = device.pinned_empty((depth, nc_pad))
+        ring_m = device.pinned_empty((depth, nc_pad), torch.uint8) if want_mask else None
+        ring_v.numpy()[:, nc:] = 0.0
+        if want_mask:
+            ring_m.numpy()[:, nc:] = 0
+        free = [threading.Event() for _ in range(depth)]    # slot may be overwritten (its H2D has completed)
+        for f in free:
+            f.set()
+        h2d_done = [None] * depth
+        ready = queue.Queue(maxsize=depth)
+        stop = threading.Event()
+
+        def producer():
+            try:
+                for i, x in enumerate(itertools.chain([first], it)):
+                    s = i % depth
+                    while not free[s].wait(0.05):
+                        if stop.is_set():
+                            return
+                    free[s].clear()
+                    if h2d_done[s] is not None:
+                        h2d_done[s].synchronize()
+                    pipe.pick(x, ring_v.numpy()[s, :nc], ring_m.numpy()[s, :nc] if want_mask else None)
+                    ready.put((s, isinstance(x, ma.MaskedArray)))
+                ready.put(None)
+            except BaseException as e:      # noqa: BLE001 - handed to the consumer
+                ready.put(e)
+
+        worker = threading.Thread(target=producer, daemon=True)
+        worker.start()
+        side = torch.cuda.Stream(device=dev)
+        policy = L.MASK_PROPAGATE if want_mask else L.MASK_AS_REFERENCE
+        d_v = [torch.zeros((1, nc_pad), dtype=torch.float64, device=dev) for _ in range(2)]
+        d_m = [torch.zeros((1, nc_pad), dtype=torch.uint8, device=dev) for _ in range(2)] if want_mask else None
+        d_o = [torch.empty((1, m), dtype=torch.float64, device=dev) for _ in range(2)]
+        d_om = [torch.empty((1, m), dtype=torch.uint8, device=dev) for _ in range(2)] if want_mask else None
+        pending = collections.deque()
+
+        def finish(entry):
+            h_o, h_om, ev, was_ma = entry
+            ev.synchronize()
+            res = h_o.numpy().reshape(shape)
+            if writer_post is not None:
+                return res
+            if want_mask:
+                return ma.masked_array(res, mask=h_om.numpy().view(np.bool_).reshape(shape), fill_value=self.mv_output,
+                                       copy=False)
+            return ma.masked_array(res) if (table.k == 1 and was_ma) else res
+
+        try:
+            i = 0
+            with torch.cuda.device(dev), torch.cuda.stream(side):
+                while True:
+                    item = ready.get()
+                    if item is None:
+                        break
+                    if isinstance(item, BaseException):
+                        raise item
+                    s, was_ma = item
+                    b = i % 2
+                    d_v[b].copy_(ring_v[s:s + 1], non_blocking=True)
+                    if want_mask:
+                        d_m[b].copy_(ring_m[s:s + 1], non_blocking=True)
+                    ev_in = torch.cuda.Event()
+                    ev_in.record(side)
+                    h2d_done[s] = ev_in
+                    free[s].set()
+                    pipe.ct.apply(d_v[b][:, :nc], float(self.mv_output), src_mask=d_m[b][:, :nc] if want_mask else None,
+                                  mask_policy=policy, out=d_o[b], out_mask=d_om[b] if want_mask else None,
+                                  correction=corrector, post=writer_post)
+                    h_o = device.pinned_empty((m,))
+                    h_o.copy_(d_o[b][0], non_blocking=True)
+                    h_om = None
+                    if want_mask and writer_post is None:
+                        h_om = device.pinned_empty((m,), torch.uint8)
+                        h_om.copy_(d_om[b][0], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    pending.append((h_o, h_om, ev, was_ma))
+                    i += 1
+                    if len(pending) >= 2:                  # the device buffers of message i-2 are free again after this
+                        yield finish(pending.popleft())
+                while pending:
+                    yield finish(pending.popleft())
+        finally:
+            stop.set()
 
     def _batch_result(self, table, out, omask, b, shape, propagate, pinned, values, writer_post):
         torch.cuda.current_stream(table.device).synchronize()

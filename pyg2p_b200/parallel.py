@@ -10,6 +10,9 @@
 Nothing here computes on the CPU: the functions take and return tensors on whatever device the
 process group works on.
 """
+import ctypes as C
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -93,3 +96,116 @@ def gather_pairs(pair, device):
     dist.all_gather_into_tensor(full, mine)
     h = full.cpu().tolist()
     return [(h[2 * r], h[2 * r + 1]) for r in range(ws)]
+
+
+class TableAssembler:
+    """Build + assembly of a sharded intertable on every GPU of the node, the exchange fused with the build.
+
+    The full SoA table (idx int32 [k, M], coef float64 [k, M]) is allocated ONCE in symmetric memory
+    (torch.distributed._symmetric_memory: the same buffer of every rank is mapped into every process over NVLink).
+    `build` runs the rank's k-NN in `blocks` target blocks; each block is written straight into the rank's own copy
+    (g2p_knn_block) and then pushed into the 7 peers' copies by g2p_peer_push (plain 16-byte stores through the peer
+    mapping, our own kernel) on a second stream, so the NVLink transfer of block i overlaps the k-NN of block i+1.  One
+    barrier at the end tells every rank that all pushes have landed.
+    Where symmetric memory cannot be set up (no peer access, gloo / CPU groups), the same blocks are exchanged with ONE
+    `all_gather_into_tensor` per block of the packed {idx, coef} bytes (NCCL over NVLink), still overlapped with the
+    k-NN of the next block.  `how` says which of the two ran."""
+
+    def __init__(self, m_total, k, align, device, blocks=4, force_nccl=None):
+        self.m, self.k, self.align, self.device = int(m_total), int(k), int(align), device
+        self.rank, self.ws = world()
+        self.bounds = [shard_bounds(self.m, r, self.ws, align) for r in range(self.ws)]
+        self.lo, self.hi = self.bounds[self.rank]
+        self.blocks = max(1, int(blocks))
+        self.side = torch.cuda.Stream(device=device) if device.type == 'cuda' else None
+        self.p2p = False
+        self.why_not = None
+        if force_nccl is None:
+            force_nccl = os.environ.get('G2P_ASSEMBLE', '') == 'nccl'
+        nbytes_i, nbytes_c = self.k * self.m * 4, self.k * self.m * 8
+        self._off_c = -(-nbytes_i // 256) * 256
+        if self.ws > 1 and device.type == 'cuda' and not force_nccl:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                buf = symm.empty(self._off_c + nbytes_c, dtype=torch.uint8, device=device)
+                hdl = symm.rendezvous(buf, dist.group.WORLD)
+                self._buf, self._hdl = buf, hdl
+                self._peer_ptrs = [int(p) for p in hdl.buffer_ptrs]
+                self.p2p = True
+            except Exception as e:           # noqa: BLE001 - any failure of the optional fast path selects the NCCL path
+                self.why_not = f'{type(e).__name__}: {e}'
+        if not self.p2p:
+            self._buf = torch.empty(self._off_c + nbytes_c, dtype=torch.uint8, device=device)
+        self.idx = self._buf[:nbytes_i].view(torch.int32).view(self.k, self.m)
+        self.coef = self._buf[self._off_c:self._off_c + nbytes_c].view(torch.float64).view(self.k, self.m)
+        self.how = ('peer stores over NVLink into symmetric memory (g2p_peer_push), overlapped with the k-NN in '
+                    f'{self.blocks} target blocks, one barrier' if self.p2p else
+                    f'one NCCL all_gather_into_tensor of the packed {{idx, coef}} bytes per target block ({self.blocks} blocks), '
+                    f'overlapped with the k-NN' + (f' [symmetric memory unavailable: {self.why_not}]' if self.why_not else ''))
+
+    def _block_bounds(self):
+        units = -(-(self.hi - self.lo) // self.align)
+        out = []
+        for b in range(self.blocks):
+            lo_u, hi_u = shard_bounds(units, b, self.blocks)
+            lo, hi = self.lo + lo_u * self.align, min(self.hi, self.lo + hi_u * self.align)
+            if hi > lo:
+                out.append((lo, hi))
+        return out
+
+    def build(self, index, tlon, tlat, mode, mub, radius=None, rotation=None):
+        """tlon / tlat: this rank's targets (device tensors, columns [lo, hi) of the table).  Returns (flags of the rank's
+        targets, idx [k, M], coef [k, M]) - the assembled table, valid on the current stream when this returns."""
+        from . import _lib as L
+        from . import device as D
+        lib = D.require_cuda()
+        cur = torch.cuda.current_stream(self.device)
+        flags = []
+        if self.p2p:
+            peers = [p for r, p in enumerate(self._peer_ptrs) if r != self.rank]
+            arr_i = (C.c_void_p * len(peers))(*peers)
+            arr_c = (C.c_void_p * len(peers))(*[p + self._off_c for p in peers])
+            self._hdl.barrier()                         # nobody still reads the previous table
+            for lo, hi in self._block_bounds():
+                o = index.knn(tlon[lo - self.lo:hi - self.lo], tlat[lo - self.lo:hi - self.lo], k=self.k, mode=mode, mub=mub,
+                              radius=radius, rotation=rotation, want_flags=True, into=(self.idx, self.coef, lo))
+                flags.append(o['flags'])
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                self.side.wait_event(ev)
+                st = C.c_void_p(self.side.cuda_stream)
+                L.check(lib.g2p_peer_push(C.c_void_p(self.idx.data_ptr()), arr_i, len(peers), self.m * 4, lo * 4, (hi - lo) * 4,
+                                          self.k, st))
+                L.check(lib.g2p_peer_push(C.c_void_p(self.coef.data_ptr()), arr_c, len(peers), self.m * 8, lo * 8, (hi - lo) * 8,
+                                          self.k, st))
+            cur.wait_stream(self.side)
+            self._hdl.barrier()                         # every rank's pushes have landed
+        else:
+            # packed per-block exchange: [ws][k * mb * 12 bytes]; blocks of equal size on every rank are required for the
+            # one-call form, ragged tails go through all_gather_table
+            works = []
+            sizes = {hi - lo for lo, hi in self.bounds}
+            if len(sizes) != 1:
+                o = index.knn(tlon, tlat, k=self.k, mode=mode, mub=mub, radius=radius, rotation=rotation, want_flags=True)
+                idx_f, coef_f = all_gather_table(o['idx'], o['coef'], self.m, align=self.align)
+                self.idx.copy_(idx_f)
+                self.coef.copy_(coef_f)
+                return o['flags'], self.idx, self.coef
+            for lo, hi in self._block_bounds():
+                mb = hi - lo
+                o = index.knn(tlon[lo - self.lo:hi - self.lo], tlat[lo - self.lo:hi - self.lo], k=self.k, mode=mode, mub=mub,
+                              radius=radius, rotation=rotation, want_flags=True)
+                flags.append(o['flags'])
+                pack = torch.empty(self.k * mb * 12, dtype=torch.uint8, device=self.device)
+                pack[:self.k * mb * 4].view(torch.int32).view(self.k, mb).copy_(o['idx'])
+                pack[self.k * mb * 4:].view(torch.float64).view(self.k, mb).copy_(o['coef'])
+                full = torch.empty(self.ws * pack.numel(), dtype=torch.uint8, device=self.device)
+                works.append((dist.all_gather_into_tensor(full, pack, async_op=True), full, lo - self.lo, mb))
+            for w, full, rel, mb in works:
+                w.wait()
+                parts = full.view(self.ws, -1)
+                for r in range(self.ws):
+                    at = self.bounds[r][0] + rel
+                    self.idx[:, at:at + mb].copy_(parts[r, :self.k * mb * 4].view(torch.int32).view(self.k, mb))
+                    self.coef[:, at:at + mb].copy_(parts[r, self.k * mb * 4:].view(torch.float64).view(self.k, mb))
+        return torch.cat(flags) if len(flags) > 1 else flags[0], self.idx, self.coef

@@ -191,7 +191,7 @@ def test_scipy_interpolation_signature_and_outputs(api):
         ok = same & ((idx.reshape(3500, -1)[:, 0] < z.size) if k > 1 else np.ones(3500, bool))
         np.testing.assert_allclose(np.asarray(ma.getdata(res))[ok], np.asarray(ma.filled(r_ref))[ok], rtol=1e-12)
     with pytest.raises(ApplicationException):
-        ScipyInterpolation(lon, lat, det, z, 11, 0.0, 0.0, mode='adw')
+        ScipyInterpolation(lon, lat, det, z, 11, 0.0, 0.0, mode='cdd')
 
 
 def test_compact_zero_copy_pipeline_equals_full_copy(api):
@@ -225,6 +225,48 @@ def test_compact_zero_copy_pipeline_equals_full_copy(api):
     torch.cuda.synchronize()
     assert torch.equal(ref.view(torch.int64), o3.view(torch.int64))
     assert comp.h2d_bytes < full.h2d_bytes / 4
+
+
+@pytest.mark.parametrize('source', ['global', 'regional'])
+def test_stream_of_pageable_messages_equals_batch(api, tmp_path, source):
+    """`interpolate_stream` (the writers' per-step loop as a generator over pageable per-message arrays, the touched
+    values picked by a host thread while the device works) gives the results of `interpolate_batch`, in order, under both
+    mask policies and with the writers' post-processing; a global source takes the compact pinned-ring path, a regional
+    one (the table reads most of the grid) the per-message fallback."""
+    from pyg2p_b200 import device
+    Interpolator, _ = api
+    Interpolator._LOADED_INTERTABLES.clear()
+    Interpolator._DEVICE_TABLES.clear()
+    lat, lon, det = synth.octahedral_grid(96) if source == 'global' else _source()
+    rng = np.random.default_rng(2)
+    n_msg = 11
+    fields = [synth.field_2t(lat, lon, member=i) for i in range(n_msg)]
+    masks = [rng.random(lat.size) < 0.02 * (i % 3) for i in range(n_msg)]
+    msgs = [ma.masked_where(mk, np.where(mk, synth.GRIB_MV, f)) if i % 4 else f for i, (f, mk) in enumerate(zip(fields, masks))]
+    it = Interpolator(_ctx(tmp_path, 'invdist'), synth.GRIB_MV)
+    if source == 'regional':        # force the whole-field pipeline, as for a table that reads most of the source grid
+        pipes = {}
+        it._pipeline = lambda table, with_mask: pipes.setdefault(
+            with_mask, device.HostApplyPipeline(table, chunk_messages=4, with_mask=with_mask))
+    for policy in ('as_reference', 'propagate'):
+        it.mask_policy = policy
+        want = it.interpolate_batch(lat, lon, msgs, 'g$5', det)
+        got = list(it.interpolate_stream(lat, lon, iter(msgs), 'g$5', det, depth=3))
+        assert len(got) == n_msg
+        table = it._table_for(lat, lon, fields[0], 'g$5', det)
+        assert isinstance(it._pipeline(table, policy == 'propagate'), device.CompactHostPipeline) == (source == 'global')
+        for i in range(n_msg):
+            np.testing.assert_array_equal(ma.getdata(got[i]), ma.getdata(want[i]))
+            if policy == 'propagate':
+                np.testing.assert_array_equal(ma.getmaskarray(got[i]), ma.getmaskarray(want[i]))
+    clone = rng.random(want.shape[1:]) < 0.2
+    post = it.writer_post(clone, 1e20, netcdf=True)
+    want = it.interpolate_batch(lat, lon, msgs, 'g$5', det, writer_post=post)
+    got = list(it.interpolate_stream(lat, lon, iter(msgs), 'g$5', det, writer_post=post))
+    np.testing.assert_array_equal(np.stack(got), want)
+    assert list(it.interpolate_stream(lat, lon, iter([]), 'g$5', det)) == []
+    with pytest.raises(ValueError):
+        list(it.interpolate_stream(lat, lon, iter([fields[0], fields[1][:-3]]), 'g$5', det))
 
 
 @pytest.mark.parametrize('mode', ['grib_nearest', 'grib_invdist'])
