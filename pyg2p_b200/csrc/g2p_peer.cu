@@ -5,6 +5,8 @@
 // copies - plain 16-byte stores through the NVLink mapping, one launch for all peers and all table rows, running on a
 // second stream while the k-NN of the rank's next target block computes.  No staging buffer, no library collective: the
 // only other exchange is the barrier that tells every rank the table is complete.
+#include <cstdlib>
+
 #include "g2p_common.cuh"
 
 namespace g2p {
@@ -23,13 +25,24 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const char* __restrict__
   const char* src = local + at;
   char* dst = peers.base[blockIdx.z] + at;
   const int64_t nvec = seg_bytes / VEC;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    if (VEC == 16) {
-      const int4 v = __ldg(reinterpret_cast<const int4*>(src) + i);
-      reinterpret_cast<int4*>(dst)[i] = v;
-    } else {
-      reinterpret_cast<int32_t*>(dst)[i] = __ldg(reinterpret_cast<const int32_t*>(src) + i);
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (VEC == 16) {
+    // four independent 16-byte loads in flight per thread: the few CTAs this kernel is given (it shares the SMs with
+    // the k-NN of the next target block) must cover the HBM latency on their own
+    for (; i + 3 * step < nvec; i += 4 * step) {
+      const int4 v0 = __ldg(reinterpret_cast<const int4*>(src) + i);
+      const int4 v1 = __ldg(reinterpret_cast<const int4*>(src) + i + step);
+      const int4 v2 = __ldg(reinterpret_cast<const int4*>(src) + i + 2 * step);
+      const int4 v3 = __ldg(reinterpret_cast<const int4*>(src) + i + 3 * step);
+      reinterpret_cast<int4*>(dst)[i] = v0;
+      reinterpret_cast<int4*>(dst)[i + step] = v1;
+      reinterpret_cast<int4*>(dst)[i + 2 * step] = v2;
+      reinterpret_cast<int4*>(dst)[i + 3 * step] = v3;
     }
+    for (; i < nvec; i += step) reinterpret_cast<int4*>(dst)[i] = __ldg(reinterpret_cast<const int4*>(src) + i);
+  } else {
+    for (; i < nvec; i += step) reinterpret_cast<int32_t*>(dst)[i] = __ldg(reinterpret_cast<const int32_t*>(src) + i);
   }
 }
 
@@ -45,6 +58,18 @@ extern "C" int g2p_peer_push(const void* local_base, void* const* peer_bases, in
     return set_error(G2P_ERR_INVALID, "g2p_peer_push: bad sizes");
   if ((row_bytes | col_off | seg_bytes) & 3) return set_error(G2P_ERR_INVALID, "g2p_peer_push: sizes must be multiples of 4 bytes");
   if (n_peers == 0 || n_rows == 0 || seg_bytes == 0) return G2P_OK;
+  // G2P_PUSH_MODE=ce: the copy engines instead of SMs (one strided DMA per peer); the default is the store kernel
+  static const bool use_ce = [] {
+    const char* e = getenv("G2P_PUSH_MODE");
+    return e && e[0] == 'c';
+  }();
+  if (use_ce) {
+    for (int p = 0; p < n_peers; ++p)
+      G2P_CUDA(cudaMemcpy2DAsync(static_cast<char*>(peer_bases[p]) + col_off, (size_t)row_bytes,
+                                 static_cast<const char*>(local_base) + col_off, (size_t)row_bytes, (size_t)seg_bytes,
+                                 (size_t)n_rows, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return G2P_OK;
+  }
   PeerList pl{};
   bool v16 = (((uintptr_t)local_base | (uintptr_t)row_bytes | (uintptr_t)col_off | (uintptr_t)seg_bytes) & 15) == 0;
   for (int p = 0; p < n_peers; ++p) {
@@ -54,8 +79,15 @@ extern "C" int g2p_peer_push(const void* local_base, void* const* peer_bases, in
   }
   const int vec = v16 ? 16 : 4;
   const int64_t nvec = seg_bytes / vec;
-  // enough CTAs in flight to cover the NVLink latency, spread over rows and peers
-  int gx = (int)std::min<int64_t>(ceil_div(nvec, 256 * 4), std::max(1, num_sms() * 4 / std::max(1, n_rows * n_peers)));
+  // a small grid over all rows and peers (G2P_PUSH_CTAS; default 32 CTAs, 56 for >= 4 peers): enough to fill the
+  // NVLink ports (measured 800 GB/s per GPU at 8 GPUs), few enough to leave the SMs to the k-NN kernel this push
+  // overlaps with (with 148+ CTAs the overlap is lost: 3.18 against 2.83 ms per 2-GPU table assembly)
+  static const int env_ctas = [] {
+    const char* e = getenv("G2P_PUSH_CTAS");
+    return e ? atoi(e) : 0;
+  }();
+  const int want_ctas = env_ctas > 0 ? env_ctas : (n_peers >= 4 ? 56 : 32);
+  int gx = (int)std::min<int64_t>(ceil_div(nvec, 256 * 4), std::max(1, want_ctas / std::max(1, n_rows * n_peers)));
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)n_rows, (unsigned)n_peers);
   if (v16)

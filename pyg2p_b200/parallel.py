@@ -117,7 +117,8 @@ class TableAssembler:
         self.bounds = [shard_bounds(self.m, r, self.ws, align) for r in range(self.ws)]
         self.lo, self.hi = self.bounds[self.rank]
         self.blocks = max(1, int(blocks))
-        self.side = torch.cuda.Stream(device=device) if device.type == 'cuda' else None
+        # high priority: the push kernel needs only a few SMs, and it gets them as soon as CTAs of the running k-NN retire
+        self.side = torch.cuda.Stream(device=device, priority=-1) if device.type == 'cuda' else None
         self.p2p = False
         self.why_not = None
         if force_nccl is None:
