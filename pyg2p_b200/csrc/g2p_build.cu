@@ -650,6 +650,7 @@ struct KnnArgs {
   int64_t q0;                // SELF mode: first source record of this call (sharded self query)
   unsigned long long* stats; // [0] extra passes, [1] candidates examined (debug counters; nullable)
   double r0_scale;           // scales the initial search radius (experiments: G2P_KNN_R0)
+  double stop2;              // INVDIST: (min_upper_bound * (1 + 1e-6))^2, rows whose nearest point is farther end early; else +inf
 };
 
 __device__ __forceinline__ bool lex_lt(double da, int ia, double db, int ib) {
@@ -826,7 +827,7 @@ __device__ __forceinline__ double initial_radius_factor(int k) {
 template <int KK, int LANES>
 __device__ __forceinline__ void knn_search(const IndexView& ix, int k, double qx, double qy, double qz, int lane,
                                            unsigned gmask, TopK<KK>& top, unsigned& passes, unsigned& examined,
-                                           double r0_scale) {
+                                           double r0_scale, double stop2) {
   const double qnorm = sqrt(qx * qx + qy * qy + qz * qz);
   double D = ix.h * initial_radius_factor(k) * r0_scale;
   const double Dmax = 2.0 * (ix.radius + qnorm) + ix.radius;
@@ -840,6 +841,11 @@ __device__ __forceinline__ void knn_search(const IndexView& ix, int k, double qx
     ++passes;
     const double dk2 = top.d[k - 1];
     if (whole || dk2 <= D * D) return;
+    // invdist only (stop2 = min_upper_bound^2 with a safety margin, else +inf): the row is "outside" as soon as the nearest
+    // source point is known to lie beyond min_upper_bound - either it was found inside the cap (then it IS the
+    // nearest) or the cap is empty and already wider than the bound.  Far targets of a regional source end here
+    // instead of widening the cap up to the exhaustive scan; the epilogue only looks at d0 for such rows.
+    if (top.d[0] <= D * D ? top.d[0] > stop2 : D * D > stop2) return;
     if (dk2 < __longlong_as_double(0x7ff0000000000000LL)) {
       D = sqrt(dk2) * (1.0 + 1e-9);  // k candidates known: the cap through the k-th one is final
     } else {
@@ -917,7 +923,7 @@ __global__ void __launch_bounds__(256, KK <= 2 ? 5 : (KK <= 4 ? 4 : (KK < 11 ? 3
     }
     TopK<KK> top;
     unsigned passes, examined;
-    knn_search<KK, LANES>(a.ix, k, qx, qy, qz, lane, gmask, top, passes, examined, a.r0_scale);
+    knn_search<KK, LANES>(a.ix, k, qx, qy, qz, lane, gmask, top, passes, examined, a.r0_scale, a.stop2);
     extra_passes += passes - 1;
     cand += examined;
     if (QSRC == QUERY_SELF) {
@@ -1267,6 +1273,7 @@ int g2p_index_max_nn_dist_part(g2p_index* ix, int64_t first, int64_t last, doubl
   a.q0 = first;
   a.k = 2;
   a.mode = G2P_MODE_RAW;
+  a.stop2 = __builtin_huge_val();
   a.dmax2_out = d_max;
   int rc = launch_knn(a, QUERY_SELF, st);
   double d2 = 0.0;
@@ -1317,6 +1324,8 @@ int g2p_knn_block(const g2p_index* ix, const void* tlon, const void* tlat, const
   a.k = k;
   a.mode = mode;
   a.mub = mub;
+  a.stop2 = (mode == G2P_MODE_INVDIST && mub > 0.0 && mub < 1e300) ? (mub * (1.0 + 1e-6)) * (mub * (1.0 + 1e-6))
+                                                                    : __builtin_huge_val();
   a.idx_out = idx_out;
   a.coef_out = coef_out;
   a.flags_out = flags_out;

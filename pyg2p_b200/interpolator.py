@@ -510,11 +510,21 @@ class Interpolator:
             table = si.build_table(self._target_coords.lons, self._target_coords.lats)
             self.tie_rows = si.tie_rows()
             rec = table.to_record()
-            if path.endswith('.gz'):
-                save_npy_gz_parallel(path, rec, level=self.gzip_level)
-            else:
-                np.save(path, rec)
-            self.update_intertable_conf(rec, intertable_id, path, np.asarray(v).shape)
+            # under torch.distributed every rank holds the whole table: rank 0 alone writes the file (to a temporary
+            # name, then an atomic rename) and dumps the configuration; the others wait for it
+            from . import parallel
+            rank, ws = parallel.world()
+            if rank == 0:
+                tmp = f'{path}.tmp{os.getpid()}'
+                if path.endswith('.gz'):
+                    save_npy_gz_parallel(tmp, rec, level=self.gzip_level)
+                else:
+                    with open(tmp, 'wb') as f:
+                        np.save(f, rec)
+                os.replace(tmp, path)
+            self.update_intertable_conf(rec, intertable_id, path, np.asarray(v).shape, dump=rank == 0)
+            if ws > 1:
+                torch.distributed.barrier()
         else:
             raise ApplicationException.get_exc(NO_INTERTABLE_CREATED, details=path)
         assert (table.k == 1 and nnear == 1) or table.k == nnear, f'table has k={table.k}, mode {self._mode} needs {nnear}'
@@ -533,11 +543,12 @@ class Interpolator:
                 pipes[with_mask] = device.HostApplyPipeline(table, chunk_messages=chunk, with_mask=with_mask)
         return pipes[with_mask]
 
-    def update_intertable_conf(self, intertable, intertable_id, intertable_name, source_shape):
+    def update_intertable_conf(self, intertable, intertable_id, intertable_name, source_shape, dump=True):
         """:373-384 - remember the new table in the (user) intertables configuration."""
         self._LOADED_INTERTABLES[intertable_name] = intertable
         item = {'filename': os.path.basename(intertable_name), 'method': self._mode, 'source_shape': source_shape,
                 'target_shape': self._target_coords.lons.shape}
         self.intertables_config.vars[intertable_id] = item
         self.intertables_config.user_vars[intertable_id] = item
-        self.intertables_config.dump()
+        if dump:
+            self.intertables_config.dump()

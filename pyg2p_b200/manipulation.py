@@ -559,6 +559,10 @@ class FusedPipeline:
         else:
             if plan.synth:
                 raise ApplicationException.get_exc(NOT_IMPLEMENTED, 'synthesised steps with members > 1')
+            if src_mask is not None and any(it.mask_all == 1 for _, it in plan.outputs):
+                # mask_all = 1 ORs the masks of ALL input rows of the launch: with the members stacked in one launch one
+                # member's mask would leak into the others
+                raise ApplicationException.get_exc(NOT_IMPLEMENTED, 'mask_all averages with members > 1 (run the members one by one)')
             per = len(plan.slots)
             items = [ManipItem(it.kind, [i + mb * per if i >= 0 else i for i in it.inputs], it.unit_time, it.divisor,
                                it.mask_all, it.w_edge, it.edge_mask) for mb in range(members) for _, it in plan.outputs]
