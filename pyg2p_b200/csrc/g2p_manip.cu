@@ -16,6 +16,8 @@
 // fields: out[o][c] = manip(V[..][touched[c]]), so only the 4 % of an O1280 field that the EFAS table
 // reads is ever converted, aggregated and handed to the apply kernel (whose table is remapped to the
 // compact numbering).  Without it the kernel is the plain elementwise stage on the whole grid.
+#include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "g2p_common.cuh"
@@ -28,6 +30,8 @@ struct ManipItem {       // device copy of g2p_manip_item
   int kind, n_in, mask_all, edge_mask;
   int in[kManipMaxIn];
   double unit_time, divisor, w_edge;
+  double rcp;            // RN(1 / divisor), computed on the host
+  int fast_div, pad;     // divisor is a normal number of moderate size: div_by may use rcp
 };
 
 struct ManipArgs {
@@ -52,6 +56,28 @@ __device__ __forceinline__ double conv_op(int op, double c, double x) {
   }
 }
 
+// x / d for a divisor that is the same for a whole message (the aggregation step, the count of an average), bit for
+// bit the IEEE quotient.  __ddiv_rn is a long subroutine on this path - and a zero numerator (dry cells of an accumulated
+// precipitation field: most of them) sends it through its slow branch.  Here: q = fma(r, y, q0) with y = RN(1/d),
+// q0 = RN(x*y), r = x - q0*d (exact in an FMA) is the correctly rounded quotient in all but rare cases (Markstein), and
+// instead of relying on that the candidate is CHECKED: its exact residual r1 = x - q*d must be strictly smaller than half
+// an ulp of q times |d| (then q is the unique nearest double; powers of two, whose lower neighbour is closer, and
+// results outside a safe exponent range are left to __ddiv_rn, like NaN and infinity, which fail the comparison).
+__device__ __forceinline__ double div_by(double x, double d, double y, int fast) {
+  if (!fast) return __ddiv_rn(x, d);
+  const double q0 = __dmul_rn(x, y);
+  if (x == 0.0) return q0;                       // +-0 / d: the sign is the product's
+  const double r0 = __fma_rn(-q0, d, x);
+  const double q = __fma_rn(r0, y, q0);
+  const double r1 = __fma_rn(-q, d, x);
+  const int hi = __double2hiint(q);
+  const int ex = (hi >> 20) & 0x7ff;
+  const bool pow2 = ((hi & 0xfffff) | __double2loint(q)) == 0;
+  const double half_ulp = __hiloint2double((ex - 53) << 20, 0);      // 2^(e - 53) for ex in the range tested below
+  if (ex >= 200 && ex <= 1800 && !pow2 && fabs(r1) < __dmul_rn(fabs(d), half_ulp)) return q;
+  return __ddiv_rn(x, d);
+}
+
 // where(x != mv, f(x), mv)  (conversion.py:21)
 __device__ __forceinline__ double convert(const ManipArgs& a, double x) {
   if (a.op1 == G2P_OP_NONE) return x;  // 'x=x' is the identity: no guard either (conversion.py:34-35)
@@ -60,20 +86,23 @@ __device__ __forceinline__ double convert(const ManipArgs& a, double x) {
 }
 
 
-// value and mask of one output message at source point i
+// value and mask of one output message at source point i.  KIND: the item kind when the whole launch has one kind
+// (compile-time: the other branches disappear), -1 = read it from the item
+template <int KIND>
 __device__ __forceinline__ double manip_point(const ManipArgs& a, const ManipItem& it, int64_t i, uint8_t& mk) {
   double res;
-  if (it.kind == G2P_AGG_ACCUM) {
+  const int kind = KIND >= 0 ? KIND : it.kind;
+  if (kind == G2P_AGG_ACCUM) {
     // v_iter = 0.0 + V[t]; ((v_iter - V[t-D]) * unit_time) / D   (aggregator.py:142-147)
     const double cur = __dadd_rn(0.0, convert(a, __ldg(a.src + (int64_t)it.in[0] * a.src_stride + i)));
     const double prev = it.in[1] >= 0 ? convert(a, __ldg(a.src + (int64_t)it.in[1] * a.src_stride + i)) : 0.0;
-    res = __ddiv_rn(__dmul_rn(__dsub_rn(cur, prev), it.unit_time), it.divisor);
-  } else if (it.kind == G2P_AGG_AVERAGE) {
+    res = div_by(__dmul_rn(__dsub_rn(cur, prev), it.unit_time), it.divisor, it.rcp, it.fast_div);
+  } else if (kind == G2P_AGG_AVERAGE) {
     // temp_sum = 0.0; temp_sum += V[next available step >= hour] per hourly iterator; / count (:209-230)
     double s = 0.0;
     for (int q = 0; q < it.n_in; ++q) s = __dadd_rn(s, convert(a, __ldg(a.src + (int64_t)it.in[q] * a.src_stride + i)));
-    res = __ddiv_rn(s, it.divisor);
-  } else if (it.kind == G2P_AGG_WAVERAGE) {
+    res = div_by(s, it.divisor, it.rcp, it.fast_div);
+  } else if (kind == G2P_AGG_WAVERAGE) {
     // `@halfweights`: v_ma = V[h] * dt (dt/2 for the first and last hour of the window); temp_sum += v_ma;
     // / sum of the weights (:186-207, :230).  V[h] * dt on a MaskedArray leaves the masked elements unmultiplied.
     double s = 0.0;
@@ -84,8 +113,8 @@ __device__ __forceinline__ double manip_point(const ManipArgs& a, const ManipIte
       const bool masked = a.src_mask && __ldg(a.src_mask + at) != 0;
       s = __dadd_rn(s, masked ? x : __dmul_rn(x, edge ? it.w_edge : it.unit_time));
     }
-    res = __ddiv_rn(s, it.divisor);
-  } else if (it.kind == G2P_AGG_COPY) {
+    res = div_by(s, it.divisor, it.rcp, it.fast_div);
+  } else if (kind == G2P_AGG_COPY) {
     res = convert(a, a.src[(int64_t)it.in[0] * a.src_stride + i]);
   } else {
     // res = zeros; res += V[t]   (:264-276); in[0] < 0: step 0 absent -> zeros
@@ -99,44 +128,47 @@ __device__ __forceinline__ double manip_point(const ManipArgs& a, const ManipIte
       // argument, the dict view, which is no MaskedArray - the mask is None and the averages come out unmasked
     } else if (it.mask_all == 1) {  // the OR of ALL inputs of the run (what the comment at aggregator.py:231 intends)
       for (int q = 0; q < a.b_in; ++q) mk |= __ldg(a.src_mask + (int64_t)q * a.src_stride + i);
-    } else if (it.kind == G2P_AGG_ACCUM) {
+    } else if (kind == G2P_AGG_ACCUM) {
       // the current step is copied into a fresh ndarray (`v_iter_ma += V[t]`, :142-143) and loses its
       // mask there: only the mask of V[t-D] survives (:148)
       if (it.in[1] >= 0) mk = __ldg(a.src_mask + (int64_t)it.in[1] * a.src_stride + i);
-    } else if (it.kind == G2P_AGG_AVERAGE || it.kind == G2P_AGG_WAVERAGE) {
+    } else if (kind == G2P_AGG_AVERAGE || kind == G2P_AGG_WAVERAGE) {
       for (int q = 0; q < it.n_in; ++q) mk |= __ldg(a.src_mask + (int64_t)it.in[q] * a.src_stride + i);
-    } else if (it.kind == G2P_AGG_COPY) {
+    } else if (kind == G2P_AGG_COPY) {
       mk = a.src_mask[(int64_t)it.in[0] * a.src_stride + i];
     }                          // PICK: `res_inst += V[t]` on a plain ndarray drops the mask (:264-276)
   }
   return res;
 }
 
-// PT consecutive points per thread: four independent gather chains in flight for the aggregations from device
-// memory (+7 %); one point per thread for the plain compaction, whose reads go over PCIe when the messages lie in
-// pinned host memory and want as many requests in flight as possible (4 per thread: -6 % end to end)
-template <int kManipPerThread>
-__device__ __forceinline__ void manip_body(const ManipArgs& a, const ManipItem& it, int o) {
-  for (int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kManipPerThread; c0 < a.nc;
-       c0 += (int64_t)gridDim.x * blockDim.x * kManipPerThread) {
-    int64_t idx[kManipPerThread];
-    double res[kManipPerThread];
-    uint8_t mk[kManipPerThread];
+// PT points per thread: four independent gather chains in flight for the aggregations from device memory (+7 %); one
+// point per thread for the plain compaction, whose reads go over PCIe when the messages lie in pinned host memory and
+// want as many requests in flight as possible (4 per thread: -6 % end to end)
+template <int kManipPerThread, int KIND>
+__device__ __forceinline__ void manip_chunk(const ManipArgs& a, const ManipItem& it, int o, int64_t chunk) {
+  // a warp owns 32 * PT consecutive points; lane l takes points l, l + 32, ...: every load and store instruction of the
+  // warp covers 32 consecutive values (the touched source indexes of neighbouring points are consecutive too)
+  const int lane = threadIdx.x & 31;
+  const int64_t c0 = (chunk * blockDim.x + (threadIdx.x - lane)) * kManipPerThread + lane;
+  if (c0 - lane >= a.nc) return;
+  int64_t idx[kManipPerThread];
+  double res[kManipPerThread];
+  uint8_t mk[kManipPerThread];
 #pragma unroll
-    for (int u = 0; u < kManipPerThread; ++u) {
-      const int64_t c = c0 + u < a.nc ? c0 + u : a.nc - 1;
-      idx[u] = a.touched ? (int64_t)__ldg(a.touched + c) : c;
-    }
+  for (int u = 0; u < kManipPerThread; ++u) {
+    const int64_t c = c0 + 32 * u < a.nc ? c0 + 32 * u : a.nc - 1;
+    idx[u] = a.touched ? (int64_t)__ldg(a.touched + c) : c;
+  }
 #pragma unroll
-    for (int u = 0; u < kManipPerThread; ++u) res[u] = manip_point(a, it, idx[u], mk[u]);
+  for (int u = 0; u < kManipPerThread; ++u) res[u] = manip_point<KIND>(a, it, idx[u], mk[u]);
 #pragma unroll
-    for (int u = 0; u < kManipPerThread; ++u) {
-      if (c0 + u >= a.nc) break;
-      // no out_mask: a masked output carries the marker NaN instead (the MARKED input form of the apply kernels)
-      if (a.src_mask && !a.out_mask && mk[u]) res[u] = __longlong_as_double((long long)G2P_MASK_MARKER);
-      a.out[(int64_t)o * a.out_stride + c0 + u] = res[u];
-      if (a.out_mask) a.out_mask[(int64_t)o * a.out_stride + c0 + u] = mk[u] ? 1 : 0;
-    }
+  for (int u = 0; u < kManipPerThread; ++u) {
+    const int64_t c = c0 + 32 * u;
+    if (c >= a.nc) break;
+    // no out_mask: a masked output carries the marker NaN instead (the MARKED input form of the apply kernels)
+    if (a.src_mask && !a.out_mask && mk[u]) res[u] = __longlong_as_double((long long)G2P_MASK_MARKER);
+    a.out[(int64_t)o * a.out_stride + c] = res[u];
+    if (a.out_mask) a.out_mask[(int64_t)o * a.out_stride + c] = mk[u] ? 1 : 0;
   }
 }
 
@@ -146,9 +178,15 @@ struct ManipInline {
   ManipItem items[kManipInline];
 };
 
-template <int PT>
-__global__ void __launch_bounds__(256) manip_kernel(const ManipArgs a, const __grid_constant__ ManipInline in, int o_base) {
-  manip_body<PT>(a, in.items[blockIdx.y], o_base + blockIdx.y);
+// work units = (output message, chunk of 256 * PT points), a CTA strides over them: the grid is a few CTAs per SM whatever
+// the number of outputs (tens of thousands of 1-microsecond CTAs cost more in launch rate than the work they do)
+template <int PT, int KIND>
+__global__ void __launch_bounds__(256) manip_kernel(const ManipArgs a, const __grid_constant__ ManipInline in, int o_base,
+                                                    int cnt, int64_t n_chunks) {
+  for (int64_t u = blockIdx.x; u < n_chunks * cnt; u += gridDim.x) {
+    const int o = (int)(u / n_chunks);
+    manip_chunk<PT, KIND>(a, in.items[o], o_base + o, u - (int64_t)o * n_chunks);
+  }
 }
 
 // V[a] + (V[b] - V[a]) * frac : linear-in-time synthesis of a missing step (aggregator.py:105,128)
@@ -236,6 +274,9 @@ int g2p_manip(const g2p_manip_desc* desc, const double* src, const uint8_t* src_
     }
     d.unit_time = s.unit_time;
     d.divisor = s.divisor;
+    d.rcp = 1.0 / s.divisor;
+    const double ad = fabs(s.divisor);
+    d.fast_div = (std::isfinite(s.divisor) && ad >= 0x1p-100 && ad <= 0x1p100) ? 1 : 0;
   }
   cudaStream_t st = as_stream(stream);
   ManipArgs a{};
@@ -256,21 +297,36 @@ int g2p_manip(const g2p_manip_desc* desc, const double* src, const uint8_t* src_
   a.c2 = desc->conv_c2;
   a.mv_grib = desc->mv_grib;
   a.cut_off = desc->cut_off_negative;
-  bool all_copy = true;
-  for (const ManipItem& it : items) all_copy = all_copy && it.kind == G2P_AGG_COPY;
-  const int per_thread = all_copy ? 1 : 4;
-  int64_t bx = std::min<int64_t>(ceil_div(nc, 256 * (int64_t)per_thread), 0x7fffffffLL);
-  // the compaction reads over PCIe when the messages are in pinned host memory: a modest grid that strides
-  // through the points measured best (5 100 messages/s end to end against 4 880 with one point per thread)
-  if (all_copy) bx = std::min<int64_t>(bx, std::max<int64_t>(1, (int64_t)num_sms() * 16 / std::min(desc->n_out, kManipInline)));
+  bool all_copy = true, all_accum = true, all_pick = true;
+  for (const ManipItem& it : items) {
+    all_copy = all_copy && it.kind == G2P_AGG_COPY;
+    all_accum = all_accum && it.kind == G2P_AGG_ACCUM;
+    all_pick = all_pick && it.kind == G2P_AGG_PICK;
+  }
+  // points per thread: two independent gather chains for the aggregations (measured on the 90-output pipeline pass: 2:
+  // 0.218 ms, 4: 0.233, 8: 0.275); one for the plain compaction, whose reads go over PCIe when the messages lie in pinned
+  // host memory and want as many requests in flight as possible
+  const int per_thread = all_copy ? 1 : 2;
+  const int64_t n_chunks = ceil_div(nc, 256 * (int64_t)per_thread);
   for (int o0 = 0; o0 < desc->n_out; o0 += kManipInline) {
     const int cnt = std::min(kManipInline, desc->n_out - o0);
     ManipInline in{};
     for (int o = 0; o < cnt; ++o) in.items[o] = items[o0 + o];
+    const int64_t units = n_chunks * cnt;
+    // the compaction over PCIe: a modest grid that strides through the points measured best (5 100 messages/s end to
+    // end against 4 880 with one CTA per chunk)
+    // (the aggregations: one CTA per unit - a grid capped at 16 CTAs per SM that strides over the units measured 0.265
+    // against 0.232 ms for the 90-output pass)
+    const int64_t cap = all_copy ? (int64_t)num_sms() * 16 : 0x7fffffffLL;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(units, cap));
     if (all_copy)
-      manip_kernel<1><<<dim3((unsigned)bx, (unsigned)cnt), 256, 0, st>>>(a, in, o0);
+      manip_kernel<1, G2P_AGG_COPY><<<grid, 256, 0, st>>>(a, in, o0, cnt, n_chunks);
+    else if (all_accum)
+      manip_kernel<2, G2P_AGG_ACCUM><<<grid, 256, 0, st>>>(a, in, o0, cnt, n_chunks);
+    else if (all_pick)
+      manip_kernel<2, G2P_AGG_PICK><<<grid, 256, 0, st>>>(a, in, o0, cnt, n_chunks);
     else
-      manip_kernel<4><<<dim3((unsigned)bx, (unsigned)cnt), 256, 0, st>>>(a, in, o0);
+      manip_kernel<2, -1><<<grid, 256, 0, st>>>(a, in, o0, cnt, n_chunks);
     G2P_LAUNCHED();
   }
   return G2P_OK;

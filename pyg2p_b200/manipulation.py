@@ -49,6 +49,71 @@ class Step:
                 f'level:{self.level}')
 
 
+class Messages:
+    """The decoded messages of one GRIB parameter as the reference's readers hand them to the Controller:
+    `pyg2p.Messages` (src/pyg2p/__init__.py:146-209) - `{Step: values}` for the first (or single) resolution and
+    optionally the second, with their missing value, unit, step type and grid details.  `apply_conversion` is the
+    Controller-side seam of the unit conversion (controller.py:106-110): here all messages go through one kernel
+    launch per resolution instead of one numexpr call each."""
+
+    def __init__(self, values, mv, unit, type_of_level, type_of_step, step_units, grid_details, val_2nd=None,
+                 data_date=None, data_time='0'):
+        from datetime import datetime
+        self.values_first_or_single_res = values
+        self.values_second_res = val_2nd or {}
+        self.step_type = type_of_step
+        self.step_units = step_units
+        self.type_of_level = type_of_level
+        self.unit = unit
+        self.missing_value = mv
+        self.data_date = datetime.strptime(f'{data_date}{data_time}', '%Y%m%d%H') if data_date is not None else None
+        self.grid_details = grid_details
+        # order key list to get first step
+        self.first_step_range = sorted(self.values_first_or_single_res.keys(), key=lambda k: (int(k.end_step)))[0]
+
+    def append_2nd_res_messages(self, messages):
+        self.grid_details.set_2nd_resolution(messages.grid_details, messages.first_step_range)
+        self.values_second_res = messages.first_resolution_values()
+
+    def first_resolution_values(self):
+        return self.values_first_or_single_res
+
+    def second_resolution_values(self):
+        return self.values_second_res
+
+    @property
+    def grid_id(self):
+        return self.grid_details.grid_id
+
+    @property
+    def grid2_id(self):
+        return self.grid_details.get_2nd_resolution().grid_id
+
+    @property
+    def latlons(self):
+        return self.grid_details.latlons
+
+    @property
+    def latlons_2nd(self):
+        second = self.grid_details.get_2nd_resolution()
+        return second.latlons if second else (None, None)
+
+    def have_resolution_change(self):
+        return self.grid_details.get_2nd_resolution() is not None
+
+    def change_resolution_step(self):
+        return self.grid_details.get_change_res_step()
+
+    def apply_conversion(self, converter):
+        converter.set_unit_to_convert(self.unit)
+        converter.set_missing_value(self.missing_value)
+        self.values_first_or_single_res = converter.convert_messages(self.values_first_or_single_res)
+        self.values_second_res = converter.convert_messages(self.values_second_res)
+
+    def __len__(self):
+        return len(self.values_first_or_single_res) + len(self.values_second_res)
+
+
 # --------------------------------------------------------------------------- conversion functions
 def parse_function(function_str, var='x'):
     """'x=x*1000' / 'x=x-273.15' / 'x=-x*1000' / '(z/9.81)*0.0065' ... -> [(op, constant), ...] (<= 2 steps).
@@ -109,10 +174,14 @@ class Converter:
 
     def __init__(self, func=None, cut_off=False):
         self._mv = -1
+        self._initial_unit = None
         self._function_str = func
         self._do_cut_off = cut_off
         self.ops = [] if func in (None, 'x=x') else parse_function(func)
         self.identity = func in (None, 'x=x')
+
+    def set_unit_to_convert(self, unit):
+        self._initial_unit = unit
 
     def set_missing_value(self, mv):
         self._mv = mv
@@ -120,6 +189,20 @@ class Converter:
     @property
     def must_cut_off(self):
         return self._do_cut_off
+
+    def __str__(self):
+        return ('\nConverting values from units {}. \nFunction: {}\nMissing value: {:.2f}'
+                .format(getattr(self, '_initial_unit', None), self._function_str, self._mv))
+
+    def convert_messages(self, values):
+        """`{key: converter.convert(v)}` for all messages of a dict in ONE launch (what Messages.apply_conversion
+        loops over, src/pyg2p/__init__.py:205-206); masks preserved per message."""
+        if self.identity or not values:
+            return dict(values)
+        keys = list(values)
+        outs = run_manip([values[k] for k in keys], [ManipItem.pick(i) for i in range(len(keys))], converter=self)
+        return {k: (ma.masked_where(values[k].mask, o, copy=False) if isinstance(values[k], ma.MaskedArray) else o)
+                for k, o in zip(keys, outs)}
 
     def desc_fields(self):
         ops = self.ops + [(L.OP_NONE, 0.0)] * (2 - len(self.ops))
@@ -356,11 +439,23 @@ def _upload(fields):
     return src, msk
 
 
-def manip_device(src, src_mask, items, converter=None, cut_off=False, touched=None, marked=False, src_ptrs=None):
+class ItemArray(list):
+    """a list of ManipItems with its ctypes array built once (a pass over 90 outputs rebuilds nothing per call)"""
+
+    def c_array(self):
+        if getattr(self, '_c', None) is None or self._c_len != len(self):
+            self._c = (L.ManipItem * max(len(self), 1))(*[it.to_c() for it in self])
+            self._c_len = len(self)
+        return self._c
+
+
+def manip_device(src, src_mask, items, converter=None, cut_off=False, touched=None, marked=False, src_ptrs=None,
+                 scratch=None):
     """g2p_manip on device tensors: src [b, n] -> out [n_out, nc] (+ mask).  `touched`: int32 device tensor.
     `marked`: no mask array comes out, masked outputs hold G2P_MASK_MARKER instead (the input form of the apply
     kernels' MARKED policy).  `src_ptrs` = (values address, mask address or 0, b_in, n, row stride, device): raw
-    addresses instead of tensors - PINNED HOST memory works, the kernel then reads the touched values over PCIe."""
+    addresses instead of tensors - PINNED HOST memory works, the kernel then reads the touched values over PCIe.
+    `scratch`: a dict the caller keeps between calls - the output buffers (padding zeroed once) are then reused."""
     lib = device.require_cuda()
     if src_ptrs is not None:
         v_ptr, m_ptr, b_in, n, stride, dev = src_ptrs
@@ -370,7 +465,7 @@ def manip_device(src, src_mask, items, converter=None, cut_off=False, touched=No
     has_mask = bool(m_ptr)
     nc = n if touched is None else touched.numel()
     n_out = len(items)
-    carr = (L.ManipItem * max(n_out, 1))(*[it.to_c() for it in items])
+    carr = items.c_array() if isinstance(items, ItemArray) else (L.ManipItem * max(n_out, 1))(*[it.to_c() for it in items])
     desc = L.ManipDesc()
     fields = converter.desc_fields() if converter is not None and not converter.identity else dict(
         conv_op1=L.OP_NONE, conv_c1=0.0, conv_op2=L.OP_NONE, conv_c2=0.0, mv_grib=0.0)
@@ -380,12 +475,20 @@ def manip_device(src, src_mask, items, converter=None, cut_off=False, touched=No
     desc.n_out = n_out
     desc.items = C.cast(carr, C.POINTER(L.ManipItem))
     nc_pad = -(-nc // 16) * 16                       # rows padded to 16 values: what the windowed apply needs
-    out = torch.empty((n_out, nc_pad), dtype=torch.float64, device=dev)
-    omask = torch.empty((n_out, nc_pad), dtype=torch.uint8, device=dev) if has_mask and not marked else None
-    if nc_pad != nc:
-        out[:, nc:] = 0.0
-        if omask is not None:
-            omask[:, nc:] = 0
+    want_omask = has_mask and not marked
+    key = (n_out, nc_pad, want_omask, str(dev))
+    if scratch is not None and key in scratch:
+        out, omask = scratch[key]
+    else:
+        out = torch.empty((n_out, nc_pad), dtype=torch.float64, device=dev)
+        omask = torch.empty((n_out, nc_pad), dtype=torch.uint8, device=dev) if want_omask else None
+        if nc_pad != nc:
+            out[:, nc:] = 0.0
+            if omask is not None:
+                omask[:, nc:] = 0
+        if scratch is not None:
+            scratch.clear()              # one shape at a time: a pass over other outputs replaces the buffers
+            scratch[key] = (out, omask)
     L.check(lib.g2p_set_device(dev.index))
     L.check(lib.g2p_manip(C.byref(desc), C.c_void_p(v_ptr), C.c_void_p(m_ptr) if has_mask else None, n, b_in, stride,
                           C.c_void_p(touched.data_ptr()) if touched is not None else None, nc, out.stride(0),
@@ -538,6 +641,7 @@ class FusedPipeline:
     def __init__(self, table):
         self.table = table
         self.compact, self.touched = table.compact()
+        self._scratch = {}         # compact fields between the two kernels, reused from pass to pass
 
     def run(self, src, src_mask, plan, converter=None, cut_off=False, mv_out=NC_FILL_F64,
             mask_policy=L.MASK_AS_REFERENCE, corrector=None, members=1, fused=None):
@@ -553,9 +657,10 @@ class FusedPipeline:
         single launch is the slower one (measured 1.22 ms against 0.57 ms for 90 accumulation outputs of O1280 ->
         EFAS: inside the kernel every source value is aggregated once per tile window that contains it - 2.4x on
         average - with a float64 division each, and the two staged inputs halve the occupancy)."""
+        cache = plan.__dict__.setdefault('_item_arrays', {})
         if members == 1:
             src, src_mask = synthesise_steps(plan, src, src_mask)
-            items = [it for _, it in plan.outputs]
+            items = cache.get(1) or cache.setdefault(1, ItemArray(it for _, it in plan.outputs))
         else:
             if plan.synth:
                 raise ApplicationException.get_exc(NOT_IMPLEMENTED, 'synthesised steps with members > 1')
@@ -564,8 +669,9 @@ class FusedPipeline:
                 # member's mask would leak into the others
                 raise ApplicationException.get_exc(NOT_IMPLEMENTED, 'mask_all averages with members > 1 (run the members one by one)')
             per = len(plan.slots)
-            items = [ManipItem(it.kind, [i + mb * per if i >= 0 else i for i in it.inputs], it.unit_time, it.divisor,
-                               it.mask_all, it.w_edge, it.edge_mask) for mb in range(members) for _, it in plan.outputs]
+            items = cache.get(members) or cache.setdefault(members, ItemArray(
+                ManipItem(it.kind, [i + mb * per if i >= 0 else i for i in it.inputs], it.unit_time, it.divisor,
+                          it.mask_all, it.w_edge, it.edge_mask) for mb in range(members) for _, it in plan.outputs))
         use_mask = src_mask is not None and mask_policy != L.MASK_AS_REFERENCE
         policy = mask_policy if use_mask else L.MASK_AS_REFERENCE
         can_fuse = self._can_fuse(src, src_mask if use_mask else None, items, use_mask)
@@ -578,10 +684,10 @@ class FusedPipeline:
         if policy == L.MASK_MARKED:
             # masks in (bytes), markers between the two kernels, bit-packed mask out: the apply kernel stages no mask
             vals, _ = manip_device(src, src_mask, items, converter=converter, cut_off=cut_off, touched=self.touched,
-                                   marked=True)
+                                   marked=True, scratch=self._scratch)
             return self.compact.apply(vals, float(mv_out), mask_policy=L.MASK_MARKED, correction=corrector)
         vals, vmask = manip_device(src, src_mask if use_mask else None, items,
-                                   converter=converter, cut_off=cut_off, touched=self.touched)
+                                   converter=converter, cut_off=cut_off, touched=self.touched, scratch=self._scratch)
         return self.compact.apply(vals, float(mv_out), src_mask=vmask, mask_policy=policy, correction=corrector)
 
     def run_host(self, h_src, h_mask, plan, converter=None, cut_off=False, mv_out=NC_FILL_F64, corrector=None,
@@ -601,7 +707,8 @@ class FusedPipeline:
             raise ValueError('h_src must be a pinned float64 tensor [members * steps, n]')
         if h_mask is not None and (not h_mask.is_pinned() or h_mask.stride(0) != h_src.stride(0)):
             raise ValueError('h_mask must be a pinned uint8 tensor with the row stride of h_src')
-        items = [it for _, it in plan.outputs]
+        cache = plan.__dict__.setdefault('_item_arrays', {})
+        items = cache.get(1) or cache.setdefault(1, ItemArray(it for _, it in plan.outputs))
         want_mask = h_mask is not None and post is None
         if out is None:
             out = device.pinned_empty((members * n_out, t.m))
@@ -630,7 +737,7 @@ class FusedPipeline:
                         (h_mask.data_ptr() + mb * per * h_src.stride(0)) if h_mask is not None else 0,
                         per, t.n_src, h_src.stride(0), dev)
                 vals, _ = manip_device(None, None, items, converter=converter, cut_off=cut_off, touched=self.touched,
-                                       marked=True, src_ptrs=ptrs)
+                                       marked=True, src_ptrs=ptrs, scratch=self._scratch)
                 # every output reads its inputs' touched values (an accumulation: two steps), masks as bytes
                 self.h2d_bytes += sum(len([i for i in it.inputs if i >= 0]) for it in items) * nc * (9 if h_mask is not None else 8)
                 if h_mask is not None:
@@ -672,7 +779,7 @@ class FusedPipeline:
         lib = device.require_cuda()
         t = self.table
         n_out = len(items)
-        carr = (L.ManipItem * max(n_out, 1))(*[it.to_c() for it in items])
+        carr = items.c_array() if isinstance(items, ItemArray) else (L.ManipItem * max(n_out, 1))(*[it.to_c() for it in items])
         desc = L.ManipDesc()
         fields = converter.desc_fields() if converter is not None and not converter.identity else dict(
             conv_op1=L.OP_NONE, conv_c1=0.0, conv_op2=L.OP_NONE, conv_c2=0.0, mv_grib=0.0)

@@ -375,3 +375,37 @@ def test_edge_cases_of_the_boundary(dev):
         ix.knn(np.array([10.0]), np.array([50.0]), k=17)
     with pytest.raises(Exception):
         dev.SourceIndex(np.array([np.nan, 1.0]), np.array([0.0, 1.0]), 6371229.0)
+
+
+@pytest.mark.parametrize('mode,k', [('nearest', 1), ('invdist', 4)])
+def test_rotated_target_build_end_to_end(dev, mode, k):
+    """`ScipyInterpolation(..., target_is_rotated=True)` (scipy_interpolation_lib.py:624, :673-678): the target maps go
+    through `to_regular` with the GRIB's south pole and land on the UNIT sphere while the sources keep the radius of the
+    default branch - the reference's literal behaviour: every target is ~r metres from every source, so `nearest` stores
+    those distances with the sentinel index and `invdist` rows are all outside.  Against the oracle with the same rotation."""
+    from pyg2p_b200.scipy_interpolation import ScipyInterpolation
+    lat, lon, det = synth.regular_ll_grid(12.0, -12.0, 49, -15.0, 15.0, 61)
+    det = synth.GridDetails(det, gridType='rotated_ll', latitudeOfSouthernPoleInDegrees=-40.0,
+                            longitudeOfSouthernPoleInDegrees=10.0)
+    rng = np.random.default_rng(6)
+    tlat = rng.uniform(-10.0, 10.0, (30, 40))
+    tlon = rng.uniform(-12.0, 12.0, (30, 40))
+    z = synth.field_2t(lat, lon)
+    si = ScipyInterpolation(lon, lat, det, z, k, synth.NC_FILL_F64, synth.GRIB_MV, target_is_rotated=True, mode=mode)
+    assert si.source_grid_is_rotated and si.target_grid_is_rotated
+    res, w, idx = si.interpolate(tlon, tlat)
+    o = R.BuildOracle(lon, lat, det, z, k, synth.NC_FILL_F64, synth.GRIB_MV, mode=mode, target_rotation=(-40.0, 10.0))
+    assert si.min_upper_bound == o.min_upper_bound
+    r_ref, w_ref, i_ref = o.interpolate(tlon, tlat)
+    np.testing.assert_array_equal(idx, i_ref)
+    assert (idx == z.size).all()                                 # nothing is within min_upper_bound of a unit-sphere point
+    if mode == 'nearest':
+        # the stored distances (~ r - 1 m): the same points to 2 ulp of the rotated coordinates
+        np.testing.assert_allclose(w, w_ref, rtol=1e-15)
+        assert abs(w.mean() - det['radius']) < 10.0
+    else:
+        assert np.isnan(w).all() and np.isnan(w_ref).all()
+    # the same target coordinates with a rotated target AND the to_3d rotation on the xyz level agree with the oracle
+    got = dev.latlon_to_xyz(tlon.ravel(), tlat.ravel(), det['radius'], rotation=(-40.0, 10.0)).cpu().numpy()
+    want = R.stack_xyz(*R.to_3d(tlon.ravel(), tlat.ravel(), det['radius'], rotation=(-40.0, 10.0)))
+    np.testing.assert_allclose(got, want, rtol=0, atol=4e-16)

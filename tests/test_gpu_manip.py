@@ -328,3 +328,32 @@ def test_pipeline_marked_and_host_buffers(M):
     h_out3, _ = pipe.run_host(h_src, None, plan, converter=conv, cut_off=True, mv_out=mv_out, corrector=corr, members=members)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(h_out3.numpy(), plain.cpu().numpy())
+
+
+def test_division_by_message_constants_is_the_ieee_quotient(M):
+    """the aggregation divisions (`/ aggr_step`, `/ count`) use a reciprocal + FMA candidate that is verified against its
+    exact residual and falls back to the division routine: every quotient must be the correctly rounded IEEE one -
+    zeros, signed zeros, subnormals, huge values, powers of two, NaN and infinities included (numpy as the oracle)."""
+    rng = np.random.default_rng(123)
+    n = 1 << 20
+    bits = rng.integers(0, 1 << 63, size=n, dtype=np.int64) | (rng.integers(0, 2, size=n, dtype=np.int64) << 63)
+    x = bits.view(np.float64).copy()                           # every exponent, both signs, NaNs and infinities
+    x[:4096] = rng.standard_normal(4096) * 10.0 ** rng.integers(-12, 12, 4096)
+    x[4096:8192] = np.ldexp(1.0, rng.integers(-1070, 1020, 4096)) * rng.choice([1.0, 3.0, 24.0, 6.0], 4096)
+    x[8192:8200] = [0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, -5e-324, 1.7976931348623157e308]
+    x[8200:12296] = np.arange(4096) * 24.0                     # exact quotients
+    x[12296:16392] = np.nextafter(np.arange(1, 4097) * 24.0, np.inf)
+    src = torch.from_numpy(x.reshape(1, n)).cuda()
+    for d in (24.0, 6.0, 3.0, 7.0, 4.0, 0.1, 1e-3, 12.0, 1.0, -24.0, 1e120, 5e-324, np.inf):
+        item = M.ManipItem(L.AGG_AVERAGE, [0], divisor=d, mask_all=-1)
+        got, _ = M.manip_device(src, None, [item])
+        with np.errstate(all='ignore'):
+            want = (0.0 + x) / np.float64(d)
+        np.testing.assert_array_equal(got.cpu().numpy()[0].view(np.int64), want.view(np.int64), err_msg=f'divisor {d}')
+    # the accumulation form ((cur - prev) * unit) / step on a field with many dry cells
+    cur = np.maximum(0.0, rng.standard_normal(n)) * 2e-3
+    prev = np.where(rng.random(n) < 0.5, cur, cur * rng.random(n))
+    both = torch.from_numpy(np.stack([cur, prev])).cuda()
+    item = M.ManipItem(L.AGG_ACCUM, [0, 1], unit_time=24.0, divisor=24.0)
+    got, _ = M.manip_device(both, None, [item])
+    np.testing.assert_array_equal(got.cpu().numpy()[0], (((0.0 + cur) - prev) * 24.0) / 24.0)

@@ -219,3 +219,30 @@ class TestConversion:
         res = converter.cut_off_negative(res)
         assert res[res < 0].size == 0
         assert np.allclose(res[res > 0], data[data > 0])
+
+    def test_messages_apply_conversion(self):
+        """the Controller-side seam (controller.py:106-110 -> Messages.apply_conversion, src/pyg2p/__init__.py:199-207): all
+        messages of both resolutions converted in one launch each, `where(x != mv, f(x), mv)` with the masks preserved."""
+        import numpy.ma as ma
+
+        from oracle import manip_ref as MR
+        from pyg2p_b200 import synth
+        from pyg2p_b200.manipulation import Converter, Messages, Step
+        rng = np.random.default_rng(4)
+        mv = 9999.0
+        first = {Step(s, s, 415, 6, 2): np.where(rng.random((100, 100)) < 0.05, mv, self.data + s) for s in (0, 6, 12)}
+        mask = rng.random((100, 100)) < 0.1
+        second = {Step(s, s, 200, 12, 2): ma.masked_where(mask, self.data * 2 + s) for s in (24, 36)}
+        msgs = Messages(dict(first), mv, 'K', 'surface', 'instant', 'h', synth.GridDetails(gridType='regular_ll'),
+                        val_2nd=dict(second), data_date='20240101', data_time='00')
+        assert len(msgs) == 5 and msgs.first_step_range == Step(0, 0, 415, 6, 2)
+        conv = Converter('x=x-273.15')
+        msgs.apply_conversion(conv)
+        assert conv._mv == mv and conv._initial_unit == 'K' and 'x=x-273.15' in str(conv)
+        for k, v in first.items():
+            np.testing.assert_array_equal(msgs.first_resolution_values()[k], MR.convert(v.copy(), 'x=x-273.15', mv))
+        for k, v in second.items():
+            got = msgs.second_resolution_values()[k]
+            assert isinstance(got, ma.MaskedArray)
+            np.testing.assert_array_equal(ma.getmaskarray(got), mask)
+            np.testing.assert_array_equal(ma.getdata(got), MR.convert(np.asarray(ma.getdata(v)).copy(), 'x=x-273.15', mv))
