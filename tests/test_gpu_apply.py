@@ -422,3 +422,47 @@ def test_apply_with_writer_post_epilogue(dev, monkeypatch):
                     np.testing.assert_array_equal(two.cpu().numpy().reshape(want.shape), want)
         assert np.isnan(ref.cpu().numpy()).any() or (ref == mv_out).any()
 
+
+
+def test_windowed_kernel_repeats_bit_identically(dev, monkeypatch):
+    """Stand-in for a racecheck run (compute-sanitizer is closed on the GPU pool, profiles/r02_sanitizer_closed.log): the
+    4-stage cp.async ring + fold pass of the windowed kernel is the race-prone code of the tree.  A race between the
+    staging copies, the fold pass and the gathers shows up as run-to-run differences: the same launch is repeated 40 times
+    for every mask form on a ragged table with several chunks per tile (b > stages, odd sizes), each result compared bit
+    for bit with the first and with the generic gather kernel, which has no shared-memory staging at all."""
+    rng = np.random.default_rng(99)
+    rows, cols, k, b, n = 61, 1003, 4, 37, 30011
+    m = rows * cols
+    centre = (np.arange(m) * (n / m)).astype(np.int64)
+    idx = np.clip(centre[:, None] + rng.integers(-60, 61, size=(m, k)), 0, n)
+    idx[rng.random(m) < 0.02] = n
+    w = rng.random((m, k))
+    w /= w.sum(axis=1, keepdims=True)
+    tbl = dev.DeviceTable.from_record(R.to_record(idx, w), n, grid_shape=(rows, cols))
+    v = rng.standard_normal((b, n)) * 100
+    mask = rng.random((b, n)) < 0.05
+    src, msk = _padded(v), _padded(mask.view(np.uint8))
+    bits = torch.from_numpy(dev.pack_mask_bits(mask, src.stride(0))).cuda()
+    marked = src.clone()
+    dev.mark_masked(marked, msk)
+    forms = {'plain': lambda: (tbl.apply(src, 1e20),),
+             'propagate': lambda: tbl.apply(src, 1e20, src_mask=msk, mask_policy=L.MASK_PROPAGATE),
+             'bits': lambda: tbl.apply(src, 1e20, src_mask=bits, mask_policy=L.MASK_PROPAGATE_BITS),
+             'marked': lambda: tbl.apply(marked, 1e20, mask_policy=L.MASK_MARKED)}
+    monkeypatch.setenv('G2P_APPLY_PATH', 'generic')
+    ref_plain = tbl.apply(src, 1e20).clone()
+    ref_o, ref_m = [t.clone() for t in tbl.apply(src, 1e20, src_mask=msk, mask_policy=L.MASK_PROPAGATE)]
+    monkeypatch.setenv('G2P_APPLY_PATH', 'window')
+    for name, fn in forms.items():
+        first = [t.clone() for t in fn()]
+        assert tbl.last_path == 'window', tbl.plan_error
+        want = ref_plain if name == 'plain' else ref_o
+        assert torch.equal(first[0].view(torch.int64), want.view(torch.int64)), name
+        if name == 'propagate':
+            assert torch.equal(first[1], ref_m)
+        if name in ('bits', 'marked'):
+            assert np.array_equal(dev.unpack_mask_bits(first[1], m), ref_m.cpu().numpy().astype(bool)), name
+        for _ in range(40):
+            again = fn()
+            for a_, f_ in zip(again, first):
+                assert torch.equal(a_.view(torch.uint8), f_.view(torch.uint8)), f'{name}: a repeated launch differs'
