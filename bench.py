@@ -619,7 +619,11 @@ def run_b200(args):
     from pyg2p_b200.interpolator import Interpolator
     from pyg2p_b200.maps import LatLong
 
-    tmpdir = tempfile.mkdtemp(prefix=f'g2p_bench_{rank}_')
+    # one intertable directory for all ranks, as in a real run (rank 0 writes the table, the others wait and load it)
+    box = [tempfile.mkdtemp(prefix='g2p_bench_') if rank == 0 else None]
+    if ws > 1:
+        dist.broadcast_object_list(box, src=0)
+    tmpdir = box[0]
     ctx = _Ctx({'interpolation.mode': 'invdist', 'interpolation.create': True, 'interpolation.parallel': True,
                 'interpolation.dirs': {'user': tmpdir, 'global': tmpdir}, 'input.file': 'ens_o1280.grib',
                 'interpolation.latMap': LatLong(tl, tlo, mv=synth.NC_FILL_F64, identifier='efas5km_laea_1000x950'),
@@ -740,7 +744,9 @@ def run_b200(args):
                                           'applies and returns the previous ones'}
     del pm_fields, one
     import shutil
-    shutil.rmtree(tmpdir, ignore_errors=True)
+    barrier()
+    if rank == 0:
+        shutil.rmtree(tmpdir, ignore_errors=True)
     del interp, first
     del h_src, h_msk, h_out, h_om, pipe, src, src_mask, marked, out_t, out_m, out_b
     torch.cuda.empty_cache()

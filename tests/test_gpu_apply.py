@@ -443,7 +443,7 @@ def test_windowed_kernel_repeats_bit_identically(dev, monkeypatch):
     mask = rng.random((b, n)) < 0.05
     src, msk = _padded(v), _padded(mask.view(np.uint8))
     bits = torch.from_numpy(dev.pack_mask_bits(mask, src.stride(0))).cuda()
-    marked = src.clone()
+    marked = _padded(v)
     dev.mark_masked(marked, msk)
     forms = {'plain': lambda: (tbl.apply(src, 1e20),),
              'propagate': lambda: tbl.apply(src, 1e20, src_mask=msk, mask_policy=L.MASK_PROPAGATE),
