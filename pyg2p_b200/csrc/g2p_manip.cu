@@ -63,8 +63,10 @@ __device__ __forceinline__ double conv_op(int op, double c, double x) {
 // instead of relying on that the candidate is CHECKED: its exact residual r1 = x - q*d must be strictly smaller than half
 // an ulp of q times |d| (then q is the unique nearest double; powers of two, whose lower neighbour is closer, and
 // results outside a safe exponent range are left to __ddiv_rn, like NaN and infinity, which fail the comparison).
+__device__ __noinline__ double div_slow(double x, double d) { return __ddiv_rn(x, d); }   // rare: kept out of line
+
 __device__ __forceinline__ double div_by(double x, double d, double y, int fast) {
-  if (!fast) return __ddiv_rn(x, d);
+  if (!fast) return div_slow(x, d);
   const double q0 = __dmul_rn(x, y);
   if (x == 0.0) return q0;                       // +-0 / d: the sign is the product's
   const double r0 = __fma_rn(-q0, d, x);
@@ -75,11 +77,16 @@ __device__ __forceinline__ double div_by(double x, double d, double y, int fast)
   const bool pow2 = ((hi & 0xfffff) | __double2loint(q)) == 0;
   const double half_ulp = __hiloint2double((ex - 53) << 20, 0);      // 2^(e - 53) for ex in the range tested below
   if (ex >= 200 && ex <= 1800 && !pow2 && fabs(r1) < __dmul_rn(fabs(d), half_ulp)) return q;
-  return __ddiv_rn(x, d);
+  return div_slow(x, d);
 }
 
-// where(x != mv, f(x), mv)  (conversion.py:21)
+// where(x != mv, f(x), mv)  (conversion.py:21).  CONV: the conversion known at compile time - 0 identity, 1 `x*c`,
+// 2 `x+c` (the one-step functions of parameters.json: `x*1000`, `x-273.15`, ...) - or 3: read the ops from the arguments
+template <int CONV>
 __device__ __forceinline__ double convert(const ManipArgs& a, double x) {
+  if (CONV == 0) return x;
+  if (CONV == 1) return x == a.mv_grib ? a.mv_grib : __dmul_rn(x, a.c1);
+  if (CONV == 2) return x == a.mv_grib ? a.mv_grib : __dadd_rn(x, a.c1);
   if (a.op1 == G2P_OP_NONE) return x;  // 'x=x' is the identity: no guard either (conversion.py:34-35)
   if (x == a.mv_grib) return a.mv_grib;
   return conv_op(a.op2, a.c2, conv_op(a.op1, a.c1, x));
@@ -88,19 +95,19 @@ __device__ __forceinline__ double convert(const ManipArgs& a, double x) {
 
 // value and mask of one output message at source point i.  KIND: the item kind when the whole launch has one kind
 // (compile-time: the other branches disappear), -1 = read it from the item
-template <int KIND>
+template <int KIND, int CONV>
 __device__ __forceinline__ double manip_point(const ManipArgs& a, const ManipItem& it, int64_t i, uint8_t& mk) {
   double res;
   const int kind = KIND >= 0 ? KIND : it.kind;
   if (kind == G2P_AGG_ACCUM) {
     // v_iter = 0.0 + V[t]; ((v_iter - V[t-D]) * unit_time) / D   (aggregator.py:142-147)
-    const double cur = __dadd_rn(0.0, convert(a, __ldg(a.src + (int64_t)it.in[0] * a.src_stride + i)));
-    const double prev = it.in[1] >= 0 ? convert(a, __ldg(a.src + (int64_t)it.in[1] * a.src_stride + i)) : 0.0;
+    const double cur = __dadd_rn(0.0, convert<CONV>(a, __ldg(a.src + (int64_t)it.in[0] * a.src_stride + i)));
+    const double prev = it.in[1] >= 0 ? convert<CONV>(a, __ldg(a.src + (int64_t)it.in[1] * a.src_stride + i)) : 0.0;
     res = div_by(__dmul_rn(__dsub_rn(cur, prev), it.unit_time), it.divisor, it.rcp, it.fast_div);
   } else if (kind == G2P_AGG_AVERAGE) {
     // temp_sum = 0.0; temp_sum += V[next available step >= hour] per hourly iterator; / count (:209-230)
     double s = 0.0;
-    for (int q = 0; q < it.n_in; ++q) s = __dadd_rn(s, convert(a, __ldg(a.src + (int64_t)it.in[q] * a.src_stride + i)));
+    for (int q = 0; q < it.n_in; ++q) s = __dadd_rn(s, convert<CONV>(a, __ldg(a.src + (int64_t)it.in[q] * a.src_stride + i)));
     res = div_by(s, it.divisor, it.rcp, it.fast_div);
   } else if (kind == G2P_AGG_WAVERAGE) {
     // `@halfweights`: v_ma = V[h] * dt (dt/2 for the first and last hour of the window); temp_sum += v_ma;
@@ -108,17 +115,17 @@ __device__ __forceinline__ double manip_point(const ManipArgs& a, const ManipIte
     double s = 0.0;
     for (int q = 0; q < it.n_in; ++q) {
       const int64_t at = (int64_t)it.in[q] * a.src_stride + i;
-      const double x = convert(a, __ldg(a.src + at));
+      const double x = convert<CONV>(a, __ldg(a.src + at));
       const bool edge = (q == 0 && (it.edge_mask & 1)) || (q == it.n_in - 1 && (it.edge_mask & 2));
       const bool masked = a.src_mask && __ldg(a.src_mask + at) != 0;
       s = __dadd_rn(s, masked ? x : __dmul_rn(x, edge ? it.w_edge : it.unit_time));
     }
     res = div_by(s, it.divisor, it.rcp, it.fast_div);
   } else if (kind == G2P_AGG_COPY) {
-    res = convert(a, a.src[(int64_t)it.in[0] * a.src_stride + i]);
+    res = convert<CONV>(a, a.src[(int64_t)it.in[0] * a.src_stride + i]);
   } else {
     // res = zeros; res += V[t]   (:264-276); in[0] < 0: step 0 absent -> zeros
-    res = it.in[0] >= 0 ? __dadd_rn(0.0, convert(a, __ldg(a.src + (int64_t)it.in[0] * a.src_stride + i))) : 0.0;
+    res = it.in[0] >= 0 ? __dadd_rn(0.0, convert<CONV>(a, __ldg(a.src + (int64_t)it.in[0] * a.src_stride + i))) : 0.0;
   }
   if (a.cut_off && res < 0.0) res = 0.0;  // where(v < 0, 0, v): NaN stays NaN
   mk = 0;
@@ -144,12 +151,12 @@ __device__ __forceinline__ double manip_point(const ManipArgs& a, const ManipIte
 // PT points per thread: four independent gather chains in flight for the aggregations from device memory (+7 %); one
 // point per thread for the plain compaction, whose reads go over PCIe when the messages lie in pinned host memory and
 // want as many requests in flight as possible (4 per thread: -6 % end to end)
-template <int kManipPerThread, int KIND>
-__device__ __forceinline__ void manip_chunk(const ManipArgs& a, const ManipItem& it, int o, int64_t chunk) {
+template <int kManipPerThread, int KIND, int CONV>
+__device__ __forceinline__ void manip_chunk(const ManipArgs& a, const ManipItem& it, int o, int chunk) {
   // a warp owns 32 * PT consecutive points; lane l takes points l, l + 32, ...: every load and store instruction of the
   // warp covers 32 consecutive values (the touched source indexes of neighbouring points are consecutive too)
   const int lane = threadIdx.x & 31;
-  const int64_t c0 = (chunk * blockDim.x + (threadIdx.x - lane)) * kManipPerThread + lane;
+  const int64_t c0 = ((int64_t)chunk * blockDim.x + (threadIdx.x - lane)) * kManipPerThread + lane;
   if (c0 - lane >= a.nc) return;
   int64_t idx[kManipPerThread];
   double res[kManipPerThread];
@@ -160,7 +167,7 @@ __device__ __forceinline__ void manip_chunk(const ManipArgs& a, const ManipItem&
     idx[u] = a.touched ? (int64_t)__ldg(a.touched + c) : c;
   }
 #pragma unroll
-  for (int u = 0; u < kManipPerThread; ++u) res[u] = manip_point<KIND>(a, it, idx[u], mk[u]);
+  for (int u = 0; u < kManipPerThread; ++u) res[u] = manip_point<KIND, CONV>(a, it, idx[u], mk[u]);
 #pragma unroll
   for (int u = 0; u < kManipPerThread; ++u) {
     const int64_t c = c0 + 32 * u;
@@ -178,15 +185,14 @@ struct ManipInline {
   ManipItem items[kManipInline];
 };
 
-// work units = (output message, chunk of 256 * PT points), a CTA strides over them: the grid is a few CTAs per SM whatever
-// the number of outputs (tens of thousands of 1-microsecond CTAs cost more in launch rate than the work they do)
-template <int PT, int KIND>
+// grid.y = output message of the launch; grid.x strides over the chunks of 256 * PT points (one CTA per chunk for the
+// aggregations; the compaction over PCIe caps grid.x and loops)
+template <int PT, int KIND, int CONV>
 __global__ void __launch_bounds__(256) manip_kernel(const ManipArgs a, const __grid_constant__ ManipInline in, int o_base,
-                                                    int cnt, int64_t n_chunks) {
-  for (int64_t u = blockIdx.x; u < n_chunks * cnt; u += gridDim.x) {
-    const int o = (int)(u / n_chunks);
-    manip_chunk<PT, KIND>(a, in.items[o], o_base + o, u - (int64_t)o * n_chunks);
-  }
+                                                    int n_chunks) {
+  const int o = blockIdx.y;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x)
+    manip_chunk<PT, KIND, CONV>(a, in.items[o], o_base + o, chunk);
 }
 
 // V[a] + (V[b] - V[a]) * frac : linear-in-time synthesis of a missing step (aggregator.py:105,128)
@@ -303,8 +309,8 @@ int g2p_manip(const g2p_manip_desc* desc, const double* src, const uint8_t* src_
     all_accum = all_accum && it.kind == G2P_AGG_ACCUM;
     all_pick = all_pick && it.kind == G2P_AGG_PICK;
   }
-  // points per thread: two independent gather chains for the aggregations (measured on the 90-output pipeline pass: 2:
-  // 0.218 ms, 4: 0.233, 8: 0.275); one for the plain compaction, whose reads go over PCIe when the messages lie in pinned
+  // points per thread: two independent gather chains for the aggregations (measured on the 90-output pipeline pass: 1:
+  // 0.161 ms, 2: 0.140, 4: 0.179); one for the plain compaction, whose reads go over PCIe when the messages lie in pinned
   // host memory and want as many requests in flight as possible
   const int per_thread = all_copy ? 1 : 2;
   const int64_t n_chunks = ceil_div(nc, 256 * (int64_t)per_thread);
@@ -312,21 +318,31 @@ int g2p_manip(const g2p_manip_desc* desc, const double* src, const uint8_t* src_
     const int cnt = std::min(kManipInline, desc->n_out - o0);
     ManipInline in{};
     for (int o = 0; o < cnt; ++o) in.items[o] = items[o0 + o];
-    const int64_t units = n_chunks * cnt;
     // the compaction over PCIe: a modest grid that strides through the points measured best (5 100 messages/s end to
-    // end against 4 880 with one CTA per chunk)
-    // (the aggregations: one CTA per unit - a grid capped at 16 CTAs per SM that strides over the units measured 0.265
-    // against 0.232 ms for the 90-output pass)
-    const int64_t cap = all_copy ? (int64_t)num_sms() * 16 : 0x7fffffffLL;
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(units, cap));
-    if (all_copy)
-      manip_kernel<1, G2P_AGG_COPY><<<grid, 256, 0, st>>>(a, in, o0, cnt, n_chunks);
-    else if (all_accum)
-      manip_kernel<2, G2P_AGG_ACCUM><<<grid, 256, 0, st>>>(a, in, o0, cnt, n_chunks);
-    else if (all_pick)
-      manip_kernel<2, G2P_AGG_PICK><<<grid, 256, 0, st>>>(a, in, o0, cnt, n_chunks);
-    else
-      manip_kernel<2, -1><<<grid, 256, 0, st>>>(a, in, o0, cnt, n_chunks);
+    // end against 4 880 with one CTA per chunk); the aggregations: one CTA per chunk (a grid capped at 16 CTAs per SM
+    // measured 0.265 against 0.232 ms for the 90-output pass)
+    const int64_t cap = all_copy ? std::max<int64_t>(1, (int64_t)num_sms() * 16 / cnt) : 0x7fffffffLL;
+    const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(n_chunks, cap)), (unsigned)cnt);
+    // kernel variant: item kind x conversion known at launch (the branches and the unused division code disappear)
+    const int conv = a.op1 == G2P_OP_NONE ? 0 : (a.op2 == G2P_OP_NONE && a.op1 == G2P_OP_MUL) ? 1
+                     : (a.op2 == G2P_OP_NONE && a.op1 == G2P_OP_ADD) ? 2 : 3;
+#define G2P_MANIP_LAUNCH(PT, KIND)                                                                  \
+  switch (conv) {                                                                                   \
+    case 0: manip_kernel<PT, KIND, 0><<<grid, 256, 0, st>>>(a, in, o0, (int)n_chunks); break;       \
+    case 1: manip_kernel<PT, KIND, 1><<<grid, 256, 0, st>>>(a, in, o0, (int)n_chunks); break;       \
+    case 2: manip_kernel<PT, KIND, 2><<<grid, 256, 0, st>>>(a, in, o0, (int)n_chunks); break;       \
+    default: manip_kernel<PT, KIND, 3><<<grid, 256, 0, st>>>(a, in, o0, (int)n_chunks); break;      \
+  }
+    if (all_copy) {
+      G2P_MANIP_LAUNCH(1, G2P_AGG_COPY)
+    } else if (all_accum) {
+      G2P_MANIP_LAUNCH(2, G2P_AGG_ACCUM)
+    } else if (all_pick) {
+      G2P_MANIP_LAUNCH(2, G2P_AGG_PICK)
+    } else {
+      manip_kernel<2, -1, 3><<<grid, 256, 0, st>>>(a, in, o0, (int)n_chunks);
+    }
+#undef G2P_MANIP_LAUNCH
     G2P_LAUNCHED();
   }
   return G2P_OK;
