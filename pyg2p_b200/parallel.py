@@ -157,12 +157,12 @@ class TableAssembler:
     def build(self, index, tlon, tlat, mode, mub, radius=None, rotation=None):
         """tlon / tlat: this rank's targets (device tensors, columns [lo, hi) of the table).  Returns (flags of the rank's
         targets, idx [k, M], coef [k, M]) - the assembled table, valid on the current stream when this returns."""
-        from . import _lib as L
-        from . import device as D
-        lib = D.require_cuda()
-        cur = torch.cuda.current_stream(self.device)
         flags = []
         if self.p2p:
+            from . import _lib as L
+            from . import device as D
+            lib = D.require_cuda()
+            cur = torch.cuda.current_stream(self.device)
             peers = [p for r, p in enumerate(self._peer_ptrs) if r != self.rank]
             arr_i = (C.c_void_p * len(peers))(*peers)
             arr_c = (C.c_void_p * len(peers))(*[p + self._off_c for p in peers])

@@ -32,6 +32,28 @@ def _worker(rank, ws, port, rows, cols, k, q):
         ok = torch.equal(idx, full_idx) and torch.equal(w, full_w)
         t = parallel.max_over_ranks(1.0 + rank, torch.device('cpu'))
         s = parallel.sum_over_ranks(1.0 + rank, torch.device('cpu'))
+        # the partial double-double sums of the ADW reference radius, in rank order on every rank
+        pairs = parallel.gather_pairs((10.0 + rank, 1e-20 * (rank + 1)), torch.device('cpu'))
+        ok = ok and pairs == [(10.0, 1e-20), (11.0, 2e-20)]
+        # build + assembly in target blocks (the exchange used without peer memory): a stand-in index whose "k-NN" of
+        # target j is a function of j alone, so the assembled table is known
+        asm = parallel.TableAssembler(m, k, cols, torch.device('cpu'), blocks=3)
+        assert not asm.p2p and asm.bounds[rank] == (lo, hi)
+        bb = asm._block_bounds()
+        assert bb[0][0] == lo and bb[-1][1] == hi and all(a[1] == b[0] for a, b in zip(bb, bb[1:]))
+        assert all((b0 - lo) % cols == 0 for b0, _ in bb)
+
+        class FakeIndex:
+            def knn(self, tlon, tlat, k, mode, mub, radius=None, rotation=None, want_flags=True):
+                j = tlon.to(torch.int64)                       # the targets carry their own number
+                idx_b = (j[None, :] * k + torch.arange(k)[:, None]).to(torch.int32)
+                return {'idx': idx_b, 'coef': idx_b.double() / 7.0, 'flags': (j % 3).to(torch.uint8)}
+
+        tl = torch.arange(lo, hi, dtype=torch.float64)
+        flags, idx_a, w_a = asm.build(FakeIndex(), tl, tl, 2, 1.0)
+        want_idx = (torch.arange(m)[None, :] * k + torch.arange(k)[:, None]).to(torch.int32)
+        ok = ok and torch.equal(idx_a, want_idx) and torch.equal(w_a, want_idx.double() / 7.0)
+        ok = ok and torch.equal(flags, (torch.arange(lo, hi) % 3).to(torch.uint8))
         q.put((rank, ok, lo, hi, t, s))
     except Exception as e:  # noqa: BLE001 - report instead of letting the parent wait for the queue
         q.put((rank, False, -1, -1, repr(e), 0.0))
