@@ -704,7 +704,26 @@ def run_b200(args):
                                    'd2h_bytes_per_step': pipe.d2h_bytes // args.steps,
                                    'what': 'interpolate_batch(..., writer_post=...): clone mask / value mask / NaN / '
                                            'mv_output -> fill value in the apply epilogue, no mask array copied back'}
-    del ready, want, post
+    # ... and handed over as float32, what a PCRaster REAL4 band / netCDF f4 variable stores: half the D2H bytes
+    post32 = interp.writer_post(clone, 9.969209968386869e36, netcdf=True, out_dtype=np.float32)
+    h_out32 = interp.pinned_output_buffer(Be, torch.float32)
+    interp.interpolate_batch(lat, lon, h_src, grid_id, det, masks=h_msk, out=h_out32, writer_post=post32)
+    torch.cuda.synchronize()
+    pipe.h2d_bytes = pipe.d2h_bytes = 0
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    q0.record()
+    for _ in range(args.steps):
+        ready32 = interp.interpolate_batch(lat, lon, h_src, grid_id, det, masks=h_msk, out=h_out32, writer_post=post32)
+    q1.record()
+    barrier()
+    post32_ms = parallel.max_over_ranks(q0.elapsed_time(q1), dev)
+    assert ready32.dtype == np.float32 and torch.equal(torch.from_numpy(ready32.reshape(Be, -1)).to(dev), want.to(torch.float32))
+    e2e['writer_ready_float32_variant'] = {
+        'messages_per_s': Be * args.steps * ws / (post32_ms * 1e-3), 'd2h_bytes_per_step': pipe.d2h_bytes // args.steps,
+        'what': 'writer_post(..., out_dtype=float32): the same fields cast to float32 in the epilogue (round to nearest) - '
+                'the precision of the PCRaster REAL4 / netCDF f4 file they are written to - half the D2H bytes'}
+    del ready, want, post, ready32, post32, h_out32
     # the reference's own call pattern: one `interpolate_scipy(lat, lon, v, grid_id, details)` per message, v a
     # pageable numpy MaskedArray as ecCodes hands it over
     pm_fields = [np.ma.masked_array(src[i].cpu().numpy(), mask=src_mask[i].cpu().numpy().astype(bool)) for i in range(4)]

@@ -374,6 +374,9 @@ typedef struct g2p_writer_post {
   double mv_match;
   int32_t use_match;
   double mv_write;
+  int32_t out_f32;            /* g2p_apply_planned_post only: `out` is float32 [b][out_stride] - what a PCRaster REAL4 band
+                                 (writers/pcr.py:38: GDAL WriteArray into the Float32 clone) or a netCDF `f4` variable
+                                 stores anyway; values are rounded to nearest like a C / numpy cast, half the D2H bytes */
 } g2p_writer_post;
 
 int g2p_writer_post_apply(double* values, const uint8_t* mask, int64_t m, int b, int64_t stride,

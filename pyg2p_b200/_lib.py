@@ -64,7 +64,8 @@ class Correction(C.Structure):
 
 
 class WriterPost(C.Structure):
-    _fields_ = [('clone_mask', C.c_void_p), ('mv_match', C.c_double), ('use_match', C.c_int32), ('mv_write', C.c_double)]
+    _fields_ = [('clone_mask', C.c_void_p), ('mv_match', C.c_double), ('use_match', C.c_int32), ('mv_write', C.c_double),
+                ('out_f32', C.c_int32)]
 
 
 _vp, _i64, _i32, _f64 = C.c_void_p, C.c_int64, C.c_int, C.c_double

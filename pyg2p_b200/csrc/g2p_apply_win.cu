@@ -389,6 +389,7 @@ struct WinArgs {
   int corr_mode;  // g2p_correction.mode
   // writers' post-processing (g2p_writer_post), after the correction
   int post_on, post_use_match;
+  int post_f32;           // CORR: the fields leave as float32 rows of out_stride values (g2p_writer_post.out_f32)
   const uint8_t* post_clone;
   double post_mv_match, post_mv_write;
   // AGG: the source-grid stages fused into the staging step (see apply_window_kernel)
@@ -725,7 +726,9 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
         pclone[t] = (ok[t] && a.post_clone) ? __ldg(a.post_clone + j) != 0 : false;
       }
     }
-    char* o = reinterpret_cast<char*>(a.out) + (int64_t)msg_begin * a.out_stride * 8;       // block-uniform
+    // bytes per output value: 8, or 4 when the writers' epilogue hands over float32 fields (CORR variants only)
+    const int out_vbytes = (CORR && a.post_f32) ? 4 : 8;
+    char* o = reinterpret_cast<char*>(a.out) + (int64_t)msg_begin * a.out_stride * out_vbytes;       // block-uniform
     char* om = (MP == 1) ? reinterpret_cast<char*>(a.out_mask) + (int64_t)msg_begin * a.out_stride : nullptr;
     uint32_t* ob_row = (OBITS && a.out_mask) ? reinterpret_cast<uint32_t*>(a.out_mask) + (int64_t)msg_begin * a.obits_stride : nullptr;
     // Bit-packed output mask from ballots: per target slot a warp owns whole bytes of the mask rows (8 neighbouring
@@ -811,7 +814,10 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
           if (a.post_on && (pclone[t] || mk || res != res || (a.post_use_match && res == a.post_mv_match))) res = a.post_mv_write;
         }
         if (ok[t]) {
-          __stcs(reinterpret_cast<double*>(o + ob[t]), res);
+          if (CORR && a.post_f32)
+            __stcs(reinterpret_cast<float*>(o + (ob[t] >> 1)), (float)res);   // round to nearest, as a C / numpy cast
+          else
+            __stcs(reinterpret_cast<double*>(o + ob[t]), res);
           if (MP == 1) *reinterpret_cast<uint8_t*>(om + (ob[t] >> 3)) = (uint8_t)mk;
         }
       }
@@ -829,7 +835,7 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
       }
       gv_s += stage_vbytes;
       if (gv_s == val_end) gv_s = val_base;
-      o += a.out_stride * 8;
+      o += a.out_stride * out_vbytes;
       if (MP == 1) om += a.out_stride;
       if (OBITS && ob_row) ob_row += a.obits_stride;
     }
@@ -1260,6 +1266,7 @@ static int apply_planned(const g2p_plan* p, const double* coef, const double* sr
     a.post_use_match = post->use_match;
     a.post_mv_match = post->mv_match;
     a.post_mv_write = post->mv_write;
+    a.post_f32 = post->out_f32 ? 1 : 0;
   }
   cudaStream_t st = as_stream(stream);
   int rc;

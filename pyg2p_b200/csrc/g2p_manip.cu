@@ -385,6 +385,7 @@ int g2p_correct(double* values, const uint8_t* mask, int64_t m, int b, int64_t s
 int g2p_writer_post_apply(double* values, const uint8_t* mask, int64_t m, int b, int64_t stride, const g2p_writer_post* post,
                           void* stream) {
   if (!values || !post || m < 0 || b < 0 || stride < m) return set_error(G2P_ERR_INVALID, "g2p_writer_post_apply: bad arguments");
+  if (post->out_f32) return set_error(G2P_ERR_UNSUPPORTED, "g2p_writer_post_apply: the in-place pass keeps float64 (out_f32 is an epilogue of g2p_apply_planned_post)");
   if (m == 0 || b == 0) return G2P_OK;
   int64_t blocks = std::min<int64_t>(ceil_div(m, 256), (int64_t)num_sms() * 16);
   writer_post_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(values, mask, m, b, stride, post->clone_mask,

@@ -450,9 +450,12 @@ class DeviceTable:
         propagate = mask_policy in (L.MASK_PROPAGATE, L.MASK_FILL)        # byte masks in
         bits = mask_policy == L.MASK_PROPAGATE_BITS                       # bit-packed masks in and out
         marked = mask_policy == L.MASK_MARKED                             # no mask in; bit-packed mask out (optional)
+        out_f32 = post is not None and post.out_f32
         with torch.cuda.device(self.device):
             if out is None:
-                out = torch.empty((b, self.m), dtype=torch.float64, device=self.device)
+                out = torch.empty((b, self.m), dtype=torch.float32 if out_f32 else torch.float64, device=self.device)
+            elif out.dtype != (torch.float32 if out_f32 else torch.float64):
+                raise ValueError('out must be float32 with a float32 WriterPost, float64 otherwise')
             if propagate:
                 if src_mask is None:
                     raise ValueError('PROPAGATE / FILL need src_mask')
@@ -502,6 +505,9 @@ class DeviceTable:
                     L.check(rc)
                     self.last_path = 'window'
                     done = True
+            if not done and out_f32:
+                raise NotImplementedError('float32 writer output is an epilogue of the windowed apply kernel; this table has '
+                                          'no window plan: ' + str(self.plan_error))
             if not done and b > 0 and self.m > 0:
                 self.last_path = 'generic'
                 # no plan for this table: the Corrector and the writers' post-processing run as their own passes.
@@ -587,8 +593,14 @@ class WriterPost:
     match: the Interpolator's mv_output on the netCDF path (`out_v[out_v == mv_output] = nan`), None on the
     PCRaster path."""
 
-    def __init__(self, clone_mask, mv_write, match=None, device='cuda'):
+    def __init__(self, clone_mask, mv_write, match=None, device='cuda', out_dtype=None):
+        """out_dtype=np.float32: the fields leave the device as float32 (windowed apply only) - what a PCRaster REAL4 band
+        or a netCDF `f4` variable stores anyway (GDAL / netCDF4 cast the float64 array they are handed), rounded to
+        nearest like `values.astype(np.float32)`; half the bytes over PCIe."""
         require_cuda()
+        self.out_f32 = out_dtype is not None and np.dtype(out_dtype) == np.float32
+        if out_dtype is not None and not self.out_f32 and np.dtype(out_dtype) != np.float64:
+            raise ValueError('WriterPost out_dtype: float64 (default) or float32')
         self.clone = None
         if clone_mask is not None:
             cm = np.ascontiguousarray(np.asarray(clone_mask)).astype(np.uint8).ravel()
@@ -596,7 +608,8 @@ class WriterPost:
         self.mv_write = float(mv_write)
         self.match = None if match is None else float(match)
         self._c = L.WriterPost(self.clone.data_ptr() if self.clone is not None else None,
-                               self.match if self.match is not None else 0.0, 0 if self.match is None else 1, self.mv_write)
+                               self.match if self.match is not None else 0.0, 0 if self.match is None else 1, self.mv_write,
+                               1 if self.out_f32 else 0)
 
     def c_struct(self):
         return self._c
@@ -663,6 +676,16 @@ def pinned_empty(shape, dtype=torch.float64):
     return torch.empty(shape, dtype=dtype, pin_memory=True)
 
 
+def _out_buffers(pipe, post):
+    """(device result slots, host dtype, bytes per value) of a host pipeline for this call: the float64 slots, or -
+    allocated on first use - float32 ones when the writers' epilogue hands over float32 fields"""
+    if post is not None and post.out_f32:
+        if getattr(pipe, 'd_out32', None) is None:
+            pipe.d_out32 = [torch.empty(o.shape, dtype=torch.float32, device=o.device) for o in pipe.d_out]
+        return pipe.d_out32, torch.float32, 4
+    return pipe.d_out, torch.float64, 8
+
+
 class HostApplyPipeline:
     """Host-buffer front end of K7: messages in (pinned) host memory -> interpolated fields in pinned
     host memory, chunked and double-buffered so that H2D, the apply kernel and D2H overlap.
@@ -723,8 +746,9 @@ class HostApplyPipeline:
             src_mask = src_mask.view(np.uint8)
         if isinstance(src_mask, torch.Tensor) and src_mask.dtype == torch.bool:
             src_mask = src_mask.view(torch.uint8)
+        d_out, out_dtype, vbytes = _out_buffers(self, post)
         if out is None:
-            out = pinned_empty((b, t.m))
+            out = pinned_empty((b, t.m), out_dtype)
         if want_omask and out_mask is None:
             out_mask = pinned_empty((b, t.m), torch.uint8)
         cur = torch.cuda.current_stream(t.device)
@@ -758,16 +782,16 @@ class HostApplyPipeline:
                 cur.wait_event(ev_out[s])                  # slot's previous output has left the device
             if propagate:
                 t.apply(self.d_src[s][:nb], mv_out, src_mask=self.d_msk[s][:nb], mask_policy=mask_policy,
-                        out=self.d_out[s][:nb], out_mask=self.d_omk[s][:nb] if dev_omask else None,
+                        out=d_out[s][:nb], out_mask=self.d_omk[s][:nb] if dev_omask else None,
                         correction=correction, post=post)
             else:
-                t.apply(self.d_src[s][:nb], mv_out, out=self.d_out[s][:nb], correction=correction, post=post)
+                t.apply(self.d_src[s][:nb], mv_out, out=d_out[s][:nb], correction=correction, post=post)
             ev_k[s] = torch.cuda.Event()
             ev_k[s].record(cur)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ev_k[s])
-                out[lo:hi].copy_(self.d_out[s][:nb], non_blocking=True)
-                self.d2h_bytes += nb * t.m * 8
+                out[lo:hi].copy_(d_out[s][:nb], non_blocking=True)
+                self.d2h_bytes += nb * t.m * vbytes
                 if want_omask:
                     out_mask[lo:hi].copy_(self.d_omk[s][:nb], non_blocking=True)
                     self.d2h_bytes += nb * t.m
@@ -838,8 +862,9 @@ class CompactHostPipeline:
         b, n = src.shape
         if n != t.n_src:
             raise ValueError(f'source field has {n} values, intertable was built for {t.n_src}')
+        d_out, out_dtype, vbytes = _out_buffers(self, post)
         if out is None:
-            out = pinned_empty((b, t.m))
+            out = pinned_empty((b, t.m), out_dtype)
         if want_omask and out_mask is None:
             out_mask = pinned_empty((b, t.m), torch.uint8)
         _bind_device(t.device)
@@ -862,14 +887,14 @@ class CompactHostPipeline:
                                self.touched, self.d_c[s][:nb], self.d_cm[s][:nb] if masks_in else None)
                 self.h2d_bytes += nb * nc * (9 if masks_in else 8)     # what the gather pulls over PCIe (touched values)
                 self.ct.apply(self.d_c[s][:nb, :nc], mv_out, src_mask=self.d_cm[s][:nb, :nc] if masks_in else None,
-                              mask_policy=mask_policy, out=self.d_out[s][:nb],
+                              mask_policy=mask_policy, out=d_out[s][:nb],
                               out_mask=self.d_omk[s][:nb] if dev_omask else None, correction=correction, post=post)
                 ev_k = torch.cuda.Event()
                 ev_k.record(cur)
                 with torch.cuda.stream(self.s_out):
                     self.s_out.wait_event(ev_k)
-                    out[lo:hi].copy_(self.d_out[s][:nb], non_blocking=True)
-                    self.d2h_bytes += nb * t.m * 8
+                    out[lo:hi].copy_(d_out[s][:nb], non_blocking=True)
+                    self.d2h_bytes += nb * t.m * vbytes
                     if want_omask:
                         out_mask[lo:hi].copy_(self.d_omk[s][:nb], non_blocking=True)
                         self.d2h_bytes += nb * t.m
@@ -915,8 +940,9 @@ class CompactHostPipeline:
             raise ValueError('pipeline was created without mask buffers')
         b = h_c.shape[0]
         nc = self.ct.n_src
+        d_out, out_dtype, vbytes = _out_buffers(self, post)
         if out is None:
-            out = pinned_empty((b, t.m))
+            out = pinned_empty((b, t.m), out_dtype)
         if want_omask and out_mask is None:
             out_mask = pinned_empty((b, t.m), torch.uint8)
         _bind_device(t.device)
@@ -934,14 +960,14 @@ class CompactHostPipeline:
                     self.d_cm[s][:nb, :nc].copy_(h_cm[lo:hi, :nc], non_blocking=True)
                     self.h2d_bytes += nb * nc
                 self.ct.apply(self.d_c[s][:nb, :nc], mv_out, src_mask=self.d_cm[s][:nb, :nc] if masks_in else None,
-                              mask_policy=mask_policy, out=self.d_out[s][:nb],
+                              mask_policy=mask_policy, out=d_out[s][:nb],
                               out_mask=self.d_omk[s][:nb] if dev_omask else None, correction=correction, post=post)
                 ev_k = torch.cuda.Event()
                 ev_k.record(cur)
                 with torch.cuda.stream(self.s_out):
                     self.s_out.wait_event(ev_k)
-                    out[lo:hi].copy_(self.d_out[s][:nb], non_blocking=True)
-                    self.d2h_bytes += nb * t.m * 8
+                    out[lo:hi].copy_(d_out[s][:nb], non_blocking=True)
+                    self.d2h_bytes += nb * t.m * vbytes
                     if want_omask:
                         out_mask[lo:hi].copy_(self.d_omk[s][:nb], non_blocking=True)
                         self.d2h_bytes += nb * t.m

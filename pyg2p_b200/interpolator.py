@@ -344,7 +344,8 @@ class Interpolator:
         policy = L.MASK_PROPAGATE if want_mask else L.MASK_AS_REFERENCE
         d_v = [torch.zeros((1, nc_pad), dtype=torch.float64, device=dev) for _ in range(2)]
         d_m = [torch.zeros((1, nc_pad), dtype=torch.uint8, device=dev) for _ in range(2)] if want_mask else None
-        d_o = [torch.empty((1, m), dtype=torch.float64, device=dev) for _ in range(2)]
+        o_dtype = torch.float32 if (writer_post is not None and writer_post.out_f32) else torch.float64
+        d_o = [torch.empty((1, m), dtype=o_dtype, device=dev) for _ in range(2)]
         d_om = [torch.empty((1, m), dtype=torch.uint8, device=dev) for _ in range(2)] if want_mask else None
         pending = collections.deque()
 
@@ -380,7 +381,7 @@ class Interpolator:
                     pipe.ct.apply(d_v[b][:, :nc], float(self.mv_output), src_mask=d_m[b][:, :nc] if want_mask else None,
                                   mask_policy=policy, out=d_o[b], out_mask=d_om[b] if want_mask else None,
                                   correction=corrector, post=writer_post)
-                    h_o = device.pinned_empty((m,))
+                    h_o = device.pinned_empty((m,), o_dtype)
                     h_o.copy_(d_o[b][0], non_blocking=True)
                     h_om = None
                     if want_mask and writer_post is None:
@@ -409,12 +410,14 @@ class Interpolator:
             return ma.masked_array(res)          # `v[indexes]` of a MaskedArray stays one, with no mask (:153)
         return res
 
-    def writer_post(self, clone_mask, mv_write, netcdf=True):
+    def writer_post(self, clone_mask, mv_write, netcdf=True, out_dtype=None):
         """the writers' post-processing as an epilogue for `interpolate_batch`: `clone_mask` = missing cells of
         the clone map (`Writer._mask`), `mv_write` = the file's missing value (netCDF: `default_fillvals[fmt] *
         scale_factor + offset`, writers/netcdf.py:149; PCRaster: nodata of the clone map, writers/pcr.py:29);
-        `netcdf` adds the `out_v[out_v == mv_output] = nan` of writers/__init__.py:66."""
-        return device.WriterPost(clone_mask, mv_write, match=self.mv_output if netcdf else None)
+        `netcdf` adds the `out_v[out_v == mv_output] = nan` of writers/__init__.py:66.  `out_dtype=np.float32`: the fields
+        come back as float32 - what a PCRaster REAL4 band (writers/pcr.py:38) or a netCDF `f4` variable stores anyway -
+        with half the bytes over PCIe (tables with a window plan)."""
+        return device.WriterPost(clone_mask, mv_write, match=self.mv_output if netcdf else None, out_dtype=out_dtype)
 
     @staticmethod
     def pinned_source_buffer(b, n):

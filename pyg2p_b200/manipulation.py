@@ -710,8 +710,9 @@ class FusedPipeline:
         cache = plan.__dict__.setdefault('_item_arrays', {})
         items = cache.get(1) or cache.setdefault(1, ItemArray(it for _, it in plan.outputs))
         want_mask = h_mask is not None and post is None
+        o_dtype = torch.float32 if (post is not None and post.out_f32) else torch.float64
         if out is None:
-            out = device.pinned_empty((members * n_out, t.m))
+            out = device.pinned_empty((members * n_out, t.m), o_dtype)
         brow = device.bits_row_bytes(t.m)
         if want_mask and out_mask is None:
             out_mask = device.pinned_empty((members * n_out, brow), torch.uint8)
@@ -719,10 +720,9 @@ class FusedPipeline:
         cur = torch.cuda.current_stream(dev)
         if getattr(self, '_s_out', None) is None:
             self._s_out = torch.cuda.Stream(device=dev)
-            self._slots = [(torch.empty((n_out, t.m), dtype=torch.float64, device=dev),
-                            torch.empty((n_out, brow), dtype=torch.uint8, device=dev)) for _ in range(2)]
-        if self._slots[0][0].shape[0] != n_out:
-            self._slots = [(torch.empty((n_out, t.m), dtype=torch.float64, device=dev),
+            self._slots = None
+        if self._slots is None or self._slots[0][0].shape[0] != n_out or self._slots[0][0].dtype != o_dtype:
+            self._slots = [(torch.empty((n_out, t.m), dtype=o_dtype, device=dev),
                             torch.empty((n_out, brow), dtype=torch.uint8, device=dev)) for _ in range(2)]
         ev_out = [None, None]
         self.h2d_bytes = self.d2h_bytes = 0
@@ -750,7 +750,7 @@ class FusedPipeline:
                 with torch.cuda.stream(self._s_out):
                     self._s_out.wait_event(ev_k)
                     out[mb * n_out:(mb + 1) * n_out].copy_(d_out, non_blocking=True)
-                    self.d2h_bytes += n_out * t.m * 8
+                    self.d2h_bytes += n_out * t.m * (4 if o_dtype == torch.float32 else 8)
                     if want_mask:
                         out_mask[mb * n_out:(mb + 1) * n_out].copy_(d_bits, non_blocking=True)
                         self.d2h_bytes += n_out * brow

@@ -165,6 +165,15 @@ def test_batch_equals_per_message_and_mask_policies(api, tmp_path):
     assert isinstance(ready, np.ndarray) and not isinstance(ready, ma.MaskedArray)
     np.testing.assert_array_equal(ready, R.writer_post(ma.getdata(prop), clone, mv_nc, mv_output=it.mv_output,
                                                        value_mask=ma.getmaskarray(prop)))
+    # ... and as float32, the way a PCRaster REAL4 band / a netCDF f4 variable stores them: the float64 result cast
+    # (round to nearest) element by element, half the bytes over PCIe
+    post32 = it.writer_post(clone, -3.4028234663852886e38, netcdf=True, out_dtype=np.float32)
+    ready32 = it.interpolate_batch(lat, lon, masked, 'g$3', det, writer_post=post32)
+    assert ready32.dtype == np.float32
+    want64 = R.writer_post(ma.getdata(prop), clone, -3.4028234663852886e38, mv_output=it.mv_output, value_mask=ma.getmaskarray(prop))
+    np.testing.assert_array_equal(ready32, want64.astype(np.float32))
+    got32 = list(it.interpolate_stream(lat, lon, iter(masked), 'g$3', det, writer_post=post32))
+    np.testing.assert_array_equal(np.stack(got32), ready32)
     it.mask_policy = 'as_reference'
     ready = it.interpolate_batch(lat, lon, masked, 'g$3', det, writer_post=it.writer_post(clone, it.mv_output, netcdf=False))
     np.testing.assert_array_equal(ready, R.writer_post(ref, clone, it.mv_output))
