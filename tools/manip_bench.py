@@ -57,3 +57,8 @@ for name, fn in (('no masks', lambda: MP.manip_device(src, None, items, converte
 vals, _ = MP.manip_device(src, None, items, converter=conv, cut_off=True, touched=touched)
 ms = timed(lambda: ct.apply(vals, synth.NC_FILL_F64))
 print(f'apply of the 90 compact fields {ms:7.4f} ms')
+dem = synth.field_dem(tl, tlo, synth.PCR_MV_F32).astype(np.float32)
+corr = MP.Corrector.from_geopotential(table, synth.field_geopotential(lat, lon), synth.GRIB_MV, synth.NC_FILL_F64, dem,
+                                      float(synth.PCR_MV_F32))
+ms = timed(lambda: ct.apply(vals, synth.NC_FILL_F64, correction=corr))
+print(f'... with the Corrector epilogue   {ms:7.4f} ms')
