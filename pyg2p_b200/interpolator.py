@@ -179,6 +179,9 @@ class Interpolator:
     def interpolate_grib(self, v, gid, grid_id, is_second_res=False):
         """`grib_nearest` / `grib_invdist` (reference :268-371): existing intertables of both layouts are APPLIED
         on the GPU; creating one is an ecCodes-internal nearest-point search and stays with the reference."""
+        return self.interpolate_grib_batch([v], gid, grid_id, is_second_res=is_second_res)[0]
+
+    def _grib_table(self, v, grid_id):
         if self._mode not in ('grib_nearest', 'grib_invdist'):
             raise ApplicationException.get_exc(NOT_IMPLEMENTED, f'mode {self._mode} with GRIB interpolation')
         intertable_id, path = self._intertable_filename(grid_id)
@@ -199,15 +202,45 @@ class Interpolator:
             table = (device.DeviceTable.from_grib_nearest(raw, n_src, shape) if self._mode == 'grib_nearest'
                      else device.DeviceTable.from_grib_invdist(raw, n_src, shape))
             self._DEVICE_TABLES[key] = table
-        src = torch.from_numpy(np.ascontiguousarray(ma.getdata(v), dtype=np.float64).reshape(1, -1)).to(table.device)
-        if isinstance(v, ma.MaskedArray) and v.mask is not ma.nomask:
-            # `result_masked` fills masked results with mv_out (util/numeric.py:21-27) = MASK_FILL
-            msk = torch.from_numpy(np.array(np.broadcast_to(ma.getmaskarray(v).ravel(), (src.shape[1],))).view(np.uint8))
-            out = table.apply(src, float(self.mv_output), src_mask=msk.reshape(1, -1).to(table.device),
-                              mask_policy=L.MASK_FILL)
-        else:
-            out = table.apply(src, float(self.mv_output))
-        return out[0].cpu().numpy().reshape(self._target_coords.lons.shape)
+        return table
+
+    def interpolate_grib_batch(self, values, gid, grid_id, is_second_res=False):
+        """all messages of a run through a `grib_nearest` / `grib_invdist` intertable on the batched host pipelines
+        (pinned staging, H2D / kernel / D2H overlapped) -> [b, rows, cols].  A masked input gives `mv_output` where a
+        contributing point is masked (`result_masked` fills, util/numeric.py:21-27 = MASK_FILL)."""
+        values = list(values)
+        if not values:
+            return np.empty((0,) + self._target_coords.lons.shape)
+        table = self._grib_table(values[0], grid_id)
+        any_mask = any(isinstance(x, ma.MaskedArray) and x.mask is not ma.nomask for x in values)
+        out, _ = self._run_pageable(table, values, L.MASK_FILL if any_mask else L.MASK_AS_REFERENCE)
+        torch.cuda.current_stream(table.device).synchronize()
+        return out.numpy().reshape((len(values),) + self._target_coords.lons.shape)
+
+    def _run_pageable(self, table, values, policy, out=None, out_mask=None, corrector=None, writer_post=None):
+        """pageable per-message arrays through the table's host pipeline: the touched values picked into a small pinned
+        buffer (compact tables), or whole fields staged chunk by chunk through two page-locked slots"""
+        masks_in = policy in (L.MASK_PROPAGATE, L.MASK_FILL)
+        pipe = self._pipeline(table, masks_in)
+        b, n = len(values), table.n_src
+        masked_in = [isinstance(x, ma.MaskedArray) and x.mask is not ma.nomask for x in values]
+        if isinstance(pipe, device.CompactHostPipeline):
+            # a regional table: pick the touched values of every message straight into a small pinned buffer (2.2 MB of a
+            # 52.8 MB O1280 field for EFAS) instead of staging whole fields
+            nc = pipe.touched_host().size
+            h_c = device.pinned_empty((b, nc))
+            h_cm = device.pinned_empty((b, nc), torch.uint8) if masks_in else None
+            for i, x in enumerate(values):
+                pipe.pick(x, h_c.numpy()[i], h_cm.numpy()[i] if masks_in else None)
+            return pipe.run_compact(h_c, float(self.mv_output), h_cm=h_cm, mask_policy=policy, out=out, out_mask=out_mask,
+                                    correction=corrector, post=writer_post)
+        # a table that reads most of the source grid: HostApplyPipeline stages the fields chunk by chunk through two
+        # page-locked slots of ~256 MB (never the whole batch: a run of 383 O1280 messages is 20 GB)
+        h_src = _RowStack([np.asarray(ma.getdata(x), dtype=np.float64).reshape(-1) for x in values], np.float64)
+        h_msk = _RowStack([np.broadcast_to(ma.getmaskarray(x).reshape(-1), (n,)) if masked_in[i] else None
+                           for i, x in enumerate(values)], np.uint8, n) if masks_in else None
+        return pipe.run(h_src, float(self.mv_output), src_mask=h_msk, mask_policy=policy, out=out, out_mask=out_mask,
+                        correction=corrector, post=writer_post)
 
     def _read_intertable_raw(self, tbl_fullpath):
         if tbl_fullpath not in self._LOADED_INTERTABLES:
@@ -253,24 +286,9 @@ class Interpolator:
         else:
             masked_in = [isinstance(x, ma.MaskedArray) and x.mask is not ma.nomask for x in values]
             propagate = self.mask_policy == 'propagate' and any(masked_in)
-            pipe = self._pipeline(table, propagate)
-            if isinstance(pipe, device.CompactHostPipeline):
-                # pageable fields and a regional table: pick the touched values of every message straight into a
-                # small pinned buffer (2.2 MB of a 52.8 MB O1280 field for EFAS) instead of staging whole fields
-                nc = pipe.touched_host().size
-                h_c = device.pinned_empty((b, nc))
-                h_cm = device.pinned_empty((b, nc), torch.uint8) if propagate else None
-                for i, x in enumerate(values):
-                    pipe.pick(x, h_c.numpy()[i], h_cm.numpy()[i] if propagate else None)
-                out, omask = pipe.run_compact(h_c, float(self.mv_output), h_cm=h_cm,
-                                              mask_policy=L.MASK_PROPAGATE if propagate else L.MASK_AS_REFERENCE, out=out,
-                                              out_mask=out_mask, correction=corrector, post=writer_post)
-                return self._batch_result(table, out, omask, b, shape, propagate, pinned, values, writer_post)
-            # pageable fields and a table that reads most of the source grid: HostApplyPipeline stages them chunk by chunk
-            # through two page-locked slots of ~256 MB (never the whole batch: a run of 383 O1280 messages is 20 GB)
-            h_src = _RowStack([np.asarray(ma.getdata(x), dtype=np.float64).reshape(-1) for x in values], np.float64)
-            h_msk = _RowStack([np.broadcast_to(ma.getmaskarray(x).reshape(-1), (n,)) if masked_in[i] else None
-                               for i, x in enumerate(values)], np.uint8, n) if propagate else None
+            out, omask = self._run_pageable(table, values, L.MASK_PROPAGATE if propagate else L.MASK_AS_REFERENCE, out=out,
+                                            out_mask=out_mask, corrector=corrector, writer_post=writer_post)
+            return self._batch_result(table, out, omask, b, shape, propagate, pinned, values, writer_post)
         out, omask = pipe.run(h_src, float(self.mv_output), src_mask=h_msk,
                               mask_policy=L.MASK_PROPAGATE if propagate else L.MASK_AS_REFERENCE, out=out,
                               out_mask=out_mask, correction=corrector, post=writer_post)

@@ -316,3 +316,12 @@ def test_grib_layout_tables_apply(api, tmp_path, mode):
     wantm = (R.apply_grib_nearest(vm, xs, ys, tbl[2], (rows, cols), it.mv_output) if mode == 'grib_nearest'
              else R.apply_grib_invdist(vm, tbl, (rows, cols), it.mv_output))
     np.testing.assert_array_equal(outm, wantm)
+    # all messages of a run at once, through the batched host pipeline (masked and plain ones mixed)
+    batch = it.interpolate_grib_batch([v, vm, v * 2.0, vm + 1.0], -1, 'g$1')
+    assert batch.shape == (4, rows, cols)
+    np.testing.assert_array_equal(batch[0], want)
+    np.testing.assert_array_equal(batch[1], wantm)
+    want3 = (R.apply_grib_nearest(vm + 1.0, xs, ys, tbl[2], (rows, cols), it.mv_output) if mode == 'grib_nearest'
+             else R.apply_grib_invdist(vm + 1.0, tbl, (rows, cols), it.mv_output))
+    np.testing.assert_array_equal(batch[3], want3)
+    assert it.interpolate_grib_batch([], -1, 'g$1').shape == (0, rows, cols)
