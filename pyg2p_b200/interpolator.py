@@ -358,7 +358,8 @@ class Interpolator:
 
         worker = threading.Thread(target=producer, daemon=True)
         worker.start()
-        side = torch.cuda.Stream(device=dev)
+        side = torch.cuda.Stream(device=dev)       # H2D + apply of message i ...
+        s_out = torch.cuda.Stream(device=dev)      # ... while the results of message i-1 leave (D2H is the long leg)
         policy = L.MASK_PROPAGATE if want_mask else L.MASK_AS_REFERENCE
         d_v = [torch.zeros((1, nc_pad), dtype=torch.float64, device=dev) for _ in range(2)]
         d_m = [torch.zeros((1, nc_pad), dtype=torch.uint8, device=dev) for _ in range(2)] if want_mask else None
@@ -399,14 +400,18 @@ class Interpolator:
                     pipe.ct.apply(d_v[b][:, :nc], float(self.mv_output), src_mask=d_m[b][:, :nc] if want_mask else None,
                                   mask_policy=policy, out=d_o[b], out_mask=d_om[b] if want_mask else None,
                                   correction=corrector, post=writer_post)
+                    ev_k = torch.cuda.Event()
+                    ev_k.record(side)
                     h_o = device.pinned_empty((m,), o_dtype)
-                    h_o.copy_(d_o[b][0], non_blocking=True)
                     h_om = None
-                    if want_mask and writer_post is None:
-                        h_om = device.pinned_empty((m,), torch.uint8)
-                        h_om.copy_(d_om[b][0], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(side)
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(ev_k)
+                        h_o.copy_(d_o[b][0], non_blocking=True)
+                        if want_mask and writer_post is None:
+                            h_om = device.pinned_empty((m,), torch.uint8)
+                            h_om.copy_(d_om[b][0], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(s_out)
                     pending.append((h_o, h_om, ev, was_ma))
                     i += 1
                     if len(pending) >= 2:                  # the device buffers of message i-2 are free again after this
