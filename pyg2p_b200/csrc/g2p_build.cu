@@ -44,6 +44,15 @@ struct __align__(32) Pt {
 };
 
 // one candidate record = one 32-byte sector = one 256-bit read-only load (LDG.E.256 on sm_100a)
+// a block of kFarB x kFarB cells of one face that holds source points, with the cap (unit centre, angular radius) that
+// bounds it: the coarse level of the search for queries far from every source point
+constexpr int kFarB = 16;
+struct __align__(32) FarBlock {
+  float cx, cy, cz;     // unit vector to the middle of the block
+  float cos_r, sin_r;   // of the angular radius (a little enlarged)
+  int32_t f, ib0, ia0;  // face, first cell row / column
+};
+
 __device__ __forceinline__ void load_pt(const Pt* p, double& x, double& y, double& z, int& id) {
   long long w;
   asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=l"(w) : "l"(p));
@@ -440,6 +449,52 @@ __global__ void scatter_kernel(const double* __restrict__ xyz, const uint32_t* _
 
 }  // namespace g2p
 
+namespace g2p {
+// one thread per block of kFarB x kFarB cells: occupied blocks are appended (in any order) with their bounding cap
+__global__ void far_blocks_kernel(const uint32_t* __restrict__ cell_start, int G, int Gb, FarBlock* __restrict__ out,
+                                  int* __restrict__ count) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 6 * Gb * Gb) return;
+  const int f = t / (Gb * Gb), bb = (t / Gb) % Gb, ba = t % Gb;
+  const int ia0 = ba * kFarB, ib0 = bb * kFarB;
+  const int ia1 = min(ia0 + kFarB, G), ib1 = min(ib0 + kFarB, G);
+  bool occupied = false;
+  for (int r = ib0; r < ib1 && !occupied; ++r) {
+    const int64_t row = ((int64_t)f * G + r) * G;
+    occupied = cell_start[row + ia0] != cell_start[row + ia1];
+  }
+  if (!occupied) return;
+  const double step = (kPi / 2.0) / (double)G;
+  auto dir = [&](double al, double be, double& x, double& y, double& z) {
+    // inverse of face_local for the point (tan alpha, tan beta, 1) of the face
+    const double a = tan(al), b = tan(be), inv = 1.0 / sqrt(a * a + b * b + 1.0);
+    const double la = a * inv, lb = b * inv, lc = inv;
+    const int ax = f >> 1;
+    const double sg = (f & 1) ? -1.0 : 1.0;
+    if (ax == 0) { x = sg * lc; y = la; z = lb; }
+    else if (ax == 1) { y = sg * lc; z = la; x = lb; }
+    else { z = sg * lc; x = la; y = lb; }
+  };
+  const double a0 = -kQuarterPi + ia0 * step, a1 = -kQuarterPi + ia1 * step;
+  const double b0 = -kQuarterPi + ib0 * step, b1 = -kQuarterPi + ib1 * step;
+  double cx, cy, cz;
+  dir(0.5 * (a0 + a1), 0.5 * (b0 + b1), cx, cy, cz);
+  double min_dot = 1.0;
+  for (int q = 0; q < 4; ++q) {   // the farthest point of a gnomonic rectangle from an inner point is a corner
+    double x, y, z;
+    dir((q & 1) ? a1 : a0, (q & 2) ? b1 : b0, x, y, z);
+    min_dot = fmin(min_dot, x * cx + y * cy + z * cz);
+  }
+  const double rad = acos(fmax(-1.0, fmin(1.0, min_dot))) + 2e-4;   // slack >> float rounding of the stored cap
+  FarBlock fb;
+  fb.cx = (float)cx; fb.cy = (float)cy; fb.cz = (float)cz;
+  fb.cos_r = (float)cos(rad); fb.sin_r = (float)sin(rad);
+  fb.f = f; fb.ib0 = ib0; fb.ia0 = ia0;
+  out[atomicAdd(count, 1)] = fb;
+}
+
+}  // namespace g2p
+
 struct g2p_index {
   int device;
   int64_t n;
@@ -451,6 +506,9 @@ struct g2p_index {
   double* xyz;          // (n,3) original order
   g2p::Pt* pts;         // counting-sorted by cell key
   uint32_t* cell_start; // n_cells + 1
+  g2p::FarBlock* blocks; // occupied blocks of 16 x 16 cells with their bounding caps (the far search)
+  int n_blocks;
+  size_t blocks_bytes;
   int64_t bytes;
 };
 
@@ -523,6 +581,7 @@ static void free_index(g2p_index* ix) {
   pool_free(ix->xyz, (size_t)ix->n * 24);
   pool_free(ix->pts, (size_t)ix->n * sizeof(g2p::Pt));
   pool_free(ix->cell_start, (size_t)(ix->n_cells + 1) * 4);
+  if (ix->blocks) pool_free(ix->blocks, ix->blocks_bytes);
   delete ix;
 }
 
@@ -610,7 +669,19 @@ static int build_cells(g2p_index* ix, cudaStream_t st) {
   G2P_LAUNCHED();
   scatter_kernel<<<grid_for(n, 256), 256, 0, st>>>(ix->xyz, d_keys, n, d_cursor, ix->pts);
   G2P_LAUNCHED();
+  // 4. occupied blocks of 16 x 16 cells with their bounding caps: the coarse level of the far search
+  const int Gb = (G + kFarB - 1) / kFarB;
+  const int max_blocks = 6 * Gb * Gb;
+  int* d_nblocks = nullptr;
+  G2P_CUDA(pool_alloc(&d_nblocks, sizeof(int), st));
+  G2P_CUDA(pool_alloc(&ix->blocks, (size_t)max_blocks * sizeof(FarBlock), st));
+  G2P_CUDA(cudaMemsetAsync(d_nblocks, 0, sizeof(int), st));
+  far_blocks_kernel<<<(max_blocks + 127) / 128, 128, 0, st>>>(ix->cell_start, G, Gb, ix->blocks, d_nblocks);
+  G2P_LAUNCHED();
+  G2P_CUDA(cudaMemcpyAsync(&ix->n_blocks, d_nblocks, sizeof(int), cudaMemcpyDeviceToHost, st));
   G2P_CUDA(cudaStreamSynchronize(st));
+  pool_free(d_nblocks, sizeof(int));
+  ix->blocks_bytes = (size_t)max_blocks * sizeof(FarBlock);
   if (timing)
     fprintf(stderr, "[g2p] index n=%lld: wait-for-xyz %.2f ms, stats+readback %.2f ms, allocations %.2f ms, sort kernels %.2f ms\n",
             (long long)n, t_enter - t0, t_stats - t_enter, t_alloc - t_stats, now_ms() - t_alloc);
@@ -629,6 +700,8 @@ struct IndexView {
   int G;
   int64_t n;
   double radius, h;
+  const FarBlock* blocks;   // occupied 16 x 16 cell blocks with bounding caps
+  int n_blocks;
 };
 
 struct KnnArgs {
@@ -651,6 +724,8 @@ struct KnnArgs {
   unsigned long long* stats; // [0] extra passes, [1] candidates examined (debug counters; nullable)
   double r0_scale;           // scales the initial search radius (experiments: G2P_KNN_R0)
   double stop2;              // INVDIST: (min_upper_bound * (1 + 1e-6))^2, rows whose nearest point is farther end early; else +inf
+  uint32_t* far_rows;        // queries whose cap outgrew the cell search (targets far from a regional source): listed here
+  unsigned int* far_count;   // ... and answered by knn_far_kernel; null: exhaustive scan in place
 };
 
 __device__ __forceinline__ bool lex_lt(double da, int ia, double db, int ib) {
@@ -759,12 +834,17 @@ __device__ __forceinline__ bool axis_range(float a, float c, float s, int G, int
 // Examine every source point within Euclidean distance D of q (and possibly more).
 template <int KK, int LANES, bool LEX>
 __device__ __forceinline__ void scan_cap(const IndexView& ix, double qx, double qy, double qz, double qnorm, double D,
-                                         int lane, TopK<KK>& top, unsigned& examined, bool& whole) {
+                                         int lane, TopK<KK>& top, unsigned& examined, bool& whole, bool far_ok, bool& far) {
   // |p-q|^2 = R^2 + rho^2 - 2 R rho cos(g)  =>  cos(g) >= c
   const double R = ix.radius, rho = qnorm;
   const double c = (R * R + rho * rho - D * D) / (2.0 * R * rho);
   if (c > 1.0 + 1e-9) return;  // the sphere is farther than D from q
   if (!(c > 0.82) || !(rho > 0.0)) {
+    if (far_ok) {   // the coarse-to-fine pass takes this query (knn_far_kernel)
+      far = true;
+      whole = true;
+      return;
+    }
     // cap wider than ~35 degrees (or a degenerate query): exhaustive scan
     scan_range<KK, LANES, LEX>(ix.pts, 0u, (uint32_t)ix.n, lane, qx, qy, qz, top, examined);
     whole = true;
@@ -849,7 +929,7 @@ __device__ __forceinline__ double initial_radius_factor(int k) {
 template <int KK, int LANES, bool LEX>
 __device__ __forceinline__ void knn_search(const IndexView& ix, int k, double qx, double qy, double qz, int lane,
                                            unsigned gmask, TopK<KK>& top, unsigned& passes, unsigned& examined,
-                                           double r0_scale, double stop2) {
+                                           double r0_scale, double stop2, bool far_ok, bool& far) {
   const double qnorm = sqrt(qx * qx + qy * qy + qz * qz);
   double D = ix.h * initial_radius_factor(k) * r0_scale;
   const double Dmax = 2.0 * (ix.radius + qnorm) + ix.radius;
@@ -858,7 +938,8 @@ __device__ __forceinline__ void knn_search(const IndexView& ix, int k, double qx
   for (;;) {
     top.reset();
     bool whole = false;
-    scan_cap<KK, LANES, LEX>(ix, qx, qy, qz, qnorm, D, lane, top, examined, whole);
+    scan_cap<KK, LANES, LEX>(ix, qx, qy, qz, qnorm, D, lane, top, examined, whole, far_ok, far);
+    if (far) return;
     merge_group<KK, LANES>(top, gmask);
     ++passes;
     const double dk2 = top.d[k - 1];
@@ -871,6 +952,13 @@ __device__ __forceinline__ void knn_search(const IndexView& ix, int k, double qx
     if (dk2 < __longlong_as_double(0x7ff0000000000000LL)) {
       D = sqrt(dk2) * (1.0 + 1e-9);  // k candidates known: the cap through the k-th one is final
     } else {
+      // fewer than k points within eight times the initial radius: the query lies outside the source domain (or in a
+      // hole of it).  Wider caps walk thousands of empty cell rows - the coarse-to-fine far pass answers such a query
+      // at a fixed, small cost whatever its distance
+      if (far_ok && passes >= 4) {
+        far = true;
+        return;
+      }
       D *= 2.0;
       if (D > Dmax) D = Dmax * 4.0;  // forces the exhaustive branch
     }
@@ -922,6 +1010,60 @@ __device__ __forceinline__ void invdist_weights(const double* d, int k, double m
 
 enum { QUERY_LATLON_F64 = 0, QUERY_LATLON_F32 = 1, QUERY_XYZ = 2, QUERY_SELF = 3 };
 
+// one row of the output from a finished (merged) list: flags, distances, the mode's indexes / coefficients.  Called by one
+// lane per query.
+template <int KK, bool F32>
+__device__ __forceinline__ void emit_row(const KnnArgs& a, int64_t q, int k, const TopK<KK>& top, double qx, double qy,
+                                         double qz) {
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    if (a.xyz_out) {
+    a.xyz_out[3 * q] = qx; a.xyz_out[3 * q + 1] = qy; a.xyz_out[3 * q + 2] = qz;
+  }
+  uint8_t flag = 0;
+  double dist[KK];
+#pragma unroll
+  for (int s = 0; s < KK; ++s) {
+    if (s < k) {
+      double d = __dsqrt_rn(top.d[s]);
+      if (F32) d = (double)(float)d;
+      dist[s] = d;
+      if (top.id[s] == INT_MAX) flag |= G2P_FLAG_SHORT;
+      // the next-best squared distance after slot s: the following slot, or `nxt` behind the last one
+      const double after = (s + 1 < KK) ? top.d[(s + 1 < KK) ? s + 1 : s] : top.nxt;
+      if (after < inf) {
+        if (top.d[s] == after) flag |= G2P_FLAG_TIE;
+        else if (after - top.d[s] <= after * 5.7e-14) flag |= G2P_FLAG_NEAR_TIE;
+      }
+    }
+  }
+  if (a.flags_out) a.flags_out[q] = flag;
+  const int32_t nsrc = (int32_t)a.ix.n;
+  if (a.mode == G2P_MODE_RAW) {
+#pragma unroll
+    for (int s = 0; s < KK; ++s)
+      if (s < k) {
+        a.idx_out[(int64_t)s * a.os + a.oo + q] = (top.id[s] == INT_MAX) ? nsrc : top.id[s];
+        a.coef_out[(int64_t)s * a.os + a.oo + q] = dist[s];
+      }
+  } else if (a.mode == G2P_MODE_NEAREST) {
+    // _build_nn: idx = ix if dist <= mub else N ; coeffs = distance for every row
+    a.idx_out[a.oo + q] = (dist[0] <= a.mub && top.id[0] != INT_MAX) ? top.id[0] : nsrc;
+    a.coef_out[a.oo + q] = dist[0];
+  } else {
+    double w[KK];
+    bool inside;
+    invdist_weights<F32>(dist, k, a.mub, w, inside);
+#pragma unroll
+    for (int s = 0; s < KK; ++s)
+      if (s < k) {
+        a.idx_out[(int64_t)s * a.os + a.oo + q] = (inside && top.id[s] != INT_MAX) ? top.id[s] : nsrc;
+        a.coef_out[(int64_t)s * a.os + a.oo + q] = w[s];
+      }
+  }
+  }
+
+
+
 template <int KK, int LANES, int QSRC>
 __global__ void __launch_bounds__(256, KK <= 2 ? 5 : (KK <= 4 ? 4 : (KK < 11 ? 3 : 1))) knn_kernel(const KnnArgs a) {
   constexpr bool F32 = (QSRC == QUERY_LATLON_F32);
@@ -945,11 +1087,17 @@ __global__ void __launch_bounds__(256, KK <= 2 ? 5 : (KK <= 4 ? 4 : (KK < 11 ? 3
     }
     TopK<KK> top;
     unsigned passes, examined;
-    knn_search<KK, LANES, false>(a.ix, k, qx, qy, qz, lane, gmask, top, passes, examined, a.r0_scale, a.stop2);
+    bool far = false;
+    const bool far_ok = QSRC != QUERY_SELF && a.far_rows != nullptr;
+    knn_search<KK, LANES, false>(a.ix, k, qx, qy, qz, lane, gmask, top, passes, examined, a.r0_scale, a.stop2, far_ok, far);
+    if (far) {   // every lane of the query takes this branch
+      if (lane == 0) a.far_rows[atomicAdd(a.far_count, 1u)] = (uint32_t)q;
+      continue;
+    }
     if (QSRC != QUERY_SELF && top.has_tie()) {
       // exact float64 ties (54 of 21.6 M rows on O1280 -> 0.05 deg): once more with the (distance, id) order, which
       // decides the order inside the list and who stays at its end.  All lanes of a query see the same merged list.
-      knn_search<KK, LANES, true>(a.ix, k, qx, qy, qz, lane, gmask, top, passes, examined, a.r0_scale, a.stop2);
+      knn_search<KK, LANES, true>(a.ix, k, qx, qy, qz, lane, gmask, top, passes, examined, a.r0_scale, a.stop2, false, far);
     }
     extra_passes += passes - 1;
     cand += examined;
@@ -1025,50 +1173,7 @@ __global__ void __launch_bounds__(256, KK <= 2 ? 5 : (KK <= 4 ? 4 : (KK < 11 ? 3
       continue;
     }
     if (lane != 0) continue;
-    if (a.xyz_out) {
-      a.xyz_out[3 * q] = qx; a.xyz_out[3 * q + 1] = qy; a.xyz_out[3 * q + 2] = qz;
-    }
-    uint8_t flag = 0;
-    double dist[KK];
-#pragma unroll
-    for (int s = 0; s < KK; ++s) {
-      if (s < k) {
-        double d = __dsqrt_rn(top.d[s]);
-        if (F32) d = (double)(float)d;
-        dist[s] = d;
-        if (top.id[s] == INT_MAX) flag |= G2P_FLAG_SHORT;
-        // the next-best squared distance after slot s: the following slot, or `nxt` behind the last one
-        const double after = (s + 1 < KK) ? top.d[(s + 1 < KK) ? s + 1 : s] : top.nxt;
-        if (after < inf) {
-          if (top.d[s] == after) flag |= G2P_FLAG_TIE;
-          else if (after - top.d[s] <= after * 5.7e-14) flag |= G2P_FLAG_NEAR_TIE;
-        }
-      }
-    }
-    if (a.flags_out) a.flags_out[q] = flag;
-    const int32_t nsrc = (int32_t)a.ix.n;
-    if (a.mode == G2P_MODE_RAW) {
-#pragma unroll
-      for (int s = 0; s < KK; ++s)
-        if (s < k) {
-          a.idx_out[(int64_t)s * a.os + a.oo + q] = (top.id[s] == INT_MAX) ? nsrc : top.id[s];
-          a.coef_out[(int64_t)s * a.os + a.oo + q] = dist[s];
-        }
-    } else if (a.mode == G2P_MODE_NEAREST) {
-      // _build_nn: idx = ix if dist <= mub else N ; coeffs = distance for every row
-      a.idx_out[a.oo + q] = (dist[0] <= a.mub && top.id[0] != INT_MAX) ? top.id[0] : nsrc;
-      a.coef_out[a.oo + q] = dist[0];
-    } else {
-      double w[KK];
-      bool inside;
-      invdist_weights<F32>(dist, k, a.mub, w, inside);
-#pragma unroll
-      for (int s = 0; s < KK; ++s)
-        if (s < k) {
-          a.idx_out[(int64_t)s * a.os + a.oo + q] = (inside && top.id[s] != INT_MAX) ? top.id[s] : nsrc;
-          a.coef_out[(int64_t)s * a.os + a.oo + q] = w[s];
-        }
-    }
+    emit_row<KK, F32>(a, q, k, top, qx, qy, qz);
   }
   if (QSRC == QUERY_SELF) {
     for (int o = 16; o > 0; o >>= 1) self_max = fmax(self_max, __shfl_xor_sync(0xffffffffu, self_max, o));
@@ -1077,6 +1182,134 @@ __global__ void __launch_bounds__(256, KK <= 2 ? 5 : (KK <= 4 ? 4 : (KK < 11 ? 3
   if (a.stats && lane == 0) {
     atomicAdd(&a.stats[0], extra_passes);
     atomicAdd(&a.stats[1], cand);
+  }
+}
+
+// ---- the far pass: queries whose cap outgrew the cell search (targets far from a regional source: `nearest` stores the
+// true distance of every row, App. C.4, and RAW / ADW need the neighbours).  One warp per listed query, coarse to fine:
+// the occupied 16 x 16 cell blocks carry a bounding cap, so |q - p|^2 >= R^2 + rho^2 - 2 R rho cos(max(0, theta - r))
+// for every point p of a block at angle theta from q.  The block with the smallest upper bound is scanned first; then
+// every block whose lower bound does not exceed the current k-th best (the smallest k-th best of any lane bounds the
+// warp's) is scanned by all 32 lanes.  Distances and ordering are the main kernel's (float64, no FMA, (d2, id) order), so
+// the rows are the ones the exhaustive scan produced - at ~1e3 instead of n distance evaluations per query.
+template <int KK>
+__device__ __forceinline__ void far_scan_block(const IndexView& ix, const FarBlock& fb, int lane, double qx, double qy,
+                                               double qz, TopK<KK>& top) {
+  const int G = ix.G;
+  const int ia1 = min(fb.ia0 + kFarB, G), ib1 = min(fb.ib0 + kFarB, G);
+  // lane r < kFarB holds the record range of cell row ib0 + r; a prefix sum over those lanes numbers the block's points
+  // 0 .. total-1, and the 32 lanes walk that numbering together (one round of dependent loads instead of one per row)
+  uint32_t p0 = 0, p1 = 0;
+  if (lane < kFarB && fb.ib0 + lane < ib1) {
+    const int64_t row = ((int64_t)fb.f * G + fb.ib0 + lane) * G;
+    p0 = __ldg(ix.cell_start + row + fb.ia0);
+    p1 = __ldg(ix.cell_start + row + ia1);
+  }
+  const int cnt = (int)(p1 - p0);
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < kFarB; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, kFarB - 1);
+  const int excl = incl - cnt;
+  for (int base = 0; base < total; base += 32) {
+    const int t = base + lane;
+    int j = 0;   // the last row whose first point number is <= t
+#pragma unroll
+    for (int step = kFarB / 2; step >= 1; step >>= 1) {
+      const int e = __shfl_sync(0xffffffffu, excl, j + step);
+      if (t >= e) j += step;
+    }
+    const uint32_t first = __shfl_sync(0xffffffffu, p0, j);
+    const int e0 = __shfl_sync(0xffffffffu, excl, j);
+    if (t < total) {
+      double px, py, pz;
+      int id;
+      load_pt(ix.pts + first + (uint32_t)(t - e0), px, py, pz, id);
+      const double dx = __dsub_rn(qx, px), dy = __dsub_rn(qy, py), dz = __dsub_rn(qz, pz);
+      const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+      top.template insert<true>(d2, id);
+    }
+  }
+}
+
+template <int KK, int QSRC>
+__global__ void __launch_bounds__(256) knn_far_kernel(const KnnArgs a) {
+  constexpr bool F32 = (QSRC == QUERY_LATLON_F32);
+  const int lane = threadIdx.x & 31;
+  const unsigned n_far = *a.far_count;
+  const int warps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  const int k = a.k;
+  for (unsigned w = (unsigned)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < n_far; w += warps) {
+    const int64_t q = a.far_rows[w];
+    double qx, qy, qz;
+    if (QSRC == QUERY_XYZ) {
+      qx = a.txyz[3 * q]; qy = a.txyz[3 * q + 1]; qz = a.txyz[3 * q + 2];
+    } else {
+      latlon_to_xyz<F32>(a.tlon, a.tlat, q, a.xyz_radius, a.rot, qx, qy, qz, 0u);   // the main kernel's bits
+    }
+    const double rho = sqrt(qx * qx + qy * qy + qz * qz), R = a.ix.radius;
+    const double inv = rho > 0.0 ? 1.0 / rho : 0.0;
+    const float ux = (float)(qx * inv), uy = (float)(qy * inv), uz = (float)(qz * inv);
+    const double base = R * R + rho * rho, two = 2.0 * R * rho;
+    // bounds of a block: cos of (theta -+ r), clamped; 1e-5 absorbs the float32 rounding of the dot product
+    auto bounds = [&](const FarBlock& fb, double& lb2, double& ub2) {
+      float ct = fminf(1.0f, fmaxf(-1.0f, ux * fb.cx + uy * fb.cy + uz * fb.cz));
+      const float st = sqrtf(fmaxf(0.0f, 1.0f - ct * ct));
+      const float c_near = (ct >= fb.cos_r) ? 1.0f : fminf(1.0f, ct * fb.cos_r + st * fb.sin_r + 1e-5f);   // cos(theta - r)
+      const float c_far = (ct <= -fb.cos_r) ? -1.0f : fmaxf(-1.0f, ct * fb.cos_r - st * fb.sin_r - 1e-5f);  // cos(theta + r)
+      lb2 = fmax(0.0, base - two * (double)c_near) * (1.0 - 1e-6);
+      ub2 = (base - two * (double)c_far) * (1.0 + 1e-6);
+    };
+    TopK<KK> top;
+    top.reset();
+    // seed: the block with the smallest upper bound
+    double best_ub = inf;
+    int best_b = -1;
+    for (int b = lane; b < a.ix.n_blocks; b += 32) {
+      double lb2, ub2;
+      bounds(a.ix.blocks[b], lb2, ub2);
+      if (ub2 < best_ub) {
+        best_ub = ub2;
+        best_b = b;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ou = __shfl_xor_sync(0xffffffffu, best_ub, o);
+      const int ob = __shfl_xor_sync(0xffffffffu, best_b, o);
+      if (ou < best_ub || (ou == best_ub && ob >= 0 && (best_b < 0 || ob < best_b))) {
+        best_ub = ou;
+        best_b = ob;
+      }
+    }
+    if (best_b >= 0) far_scan_block<KK>(a.ix, a.ix.blocks[best_b], lane, qx, qy, qz, top);
+    auto kth_bound = [&]() {   // an upper bound of the warp's k-th best: the smallest k-th best of any lane
+      double v = top.d[k - 1];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+      return v;
+    };
+    double B = kth_bound();
+    for (int b0 = 0; b0 < a.ix.n_blocks; b0 += 32) {
+      const int b = b0 + lane;
+      double lb2 = inf, ub2;
+      bool need = b < a.ix.n_blocks && b != best_b;      // (B is +inf while fewer than k points are known)
+      if (need) bounds(a.ix.blocks[b], lb2, ub2);
+      for (;;) {
+        const unsigned mask = __ballot_sync(0xffffffffu, need && lb2 <= B);
+        if (!mask) break;
+        const int src = __ffs(mask) - 1;
+        far_scan_block<KK>(a.ix, a.ix.blocks[b0 + src], lane, qx, qy, qz, top);
+        if (lane == src) need = false;
+        B = kth_bound();
+      }
+    }
+    merge_group<KK, 32>(top, 0xffffffffu);
+    if (lane == 0) emit_row<KK, F32>(a, q, k, top, qx, qy, qz);
   }
 }
 
@@ -1155,6 +1388,24 @@ static int launch_knn(const KnnArgs& a, int qsrc, cudaStream_t st) {
   return launch_knn_l<16>(a, qsrc, st);
 }
 
+template <int KK>
+static int launch_far_k(const KnnArgs& a, int qsrc, cudaStream_t st) {
+  const int grid = num_sms() * 4;   // reads the number of listed queries on the device: no host round trip
+  switch (qsrc) {
+    case QUERY_LATLON_F64: knn_far_kernel<KK, QUERY_LATLON_F64><<<grid, 256, 0, st>>>(a); break;
+    case QUERY_LATLON_F32: knn_far_kernel<KK, QUERY_LATLON_F32><<<grid, 256, 0, st>>>(a); break;
+    default: knn_far_kernel<KK, QUERY_XYZ><<<grid, 256, 0, st>>>(a); break;
+  }
+  G2P_LAUNCHED();
+  return G2P_OK;
+}
+
+static int launch_far(const KnnArgs& a, int qsrc, cudaStream_t st) {
+  if (a.k <= 1) return launch_far_k<1>(a, qsrc, st);
+  if (a.k <= 4) return launch_far_k<4>(a, qsrc, st);
+  return launch_far_k<16>(a, qsrc, st);
+}
+
 static IndexView view_of(const g2p_index* ix) {
   IndexView v;
   v.pts = ix->pts;
@@ -1163,6 +1414,8 @@ static IndexView view_of(const g2p_index* ix) {
   v.n = ix->n;
   v.radius = ix->radius;
   v.h = ix->mean_spacing;
+  v.blocks = ix->blocks;
+  v.n_blocks = ix->n_blocks;
   return v;
 }
 
@@ -1358,12 +1611,34 @@ int g2p_knn_block(const g2p_index* ix, const void* tlon, const void* tlat, const
   a.flags_out = flags_out;
   a.xyz_out = xyz_out;
   int qsrc = txyz ? QUERY_XYZ : (dtype == G2P_F32 ? QUERY_LATLON_F32 : QUERY_LATLON_F64);
+  // queries far from every source point (a regional source, a larger target) are listed by the main kernel and answered
+  // by the coarse-to-fine far pass; G2P_KNN_FAR=0 keeps the exhaustive scan in place (experiments)
+  static const bool far_pass = env_double("G2P_KNN_FAR", 1.0) != 0.0;
+  uint32_t* d_far = nullptr;
+  unsigned int* d_far_n = nullptr;
+  const bool use_far = far_pass && ix->blocks && ix->n_blocks > 0 && m < 0xffffffffLL;
+  if (use_far) {
+    G2P_CUDA(pool_alloc(&d_far, (size_t)m * 4, as_stream(stream)));
+    G2P_CUDA(pool_alloc(&d_far_n, sizeof(unsigned int), as_stream(stream)));
+    G2P_CUDA(cudaMemsetAsync(d_far_n, 0, sizeof(unsigned int), as_stream(stream)));
+    a.far_rows = d_far;
+    a.far_count = d_far_n;
+  }
+  auto run = [&]() {
+    int rc = launch_knn(a, qsrc, as_stream(stream));
+    if (rc == G2P_OK && use_far) rc = launch_far(a, qsrc, as_stream(stream));
+    if (use_far) {   // stream order protects the reuse of pooled buffers
+      pool_free(d_far, (size_t)m * 4);
+      pool_free(d_far_n, sizeof(unsigned int));
+    }
+    return rc;
+  };
   if (getenv("G2P_KNN_STATS")) {  // diagnostics: search passes and candidates per query, on stderr (synchronises)
     unsigned long long* d_stats = nullptr;
     G2P_CUDA(cudaMalloc(&d_stats, 16));
     G2P_CUDA(cudaMemsetAsync(d_stats, 0, 16, as_stream(stream)));
     a.stats = d_stats;
-    const int rc = launch_knn(a, qsrc, as_stream(stream));
+    const int rc = run();
     unsigned long long h[2] = {0, 0};
     cudaMemcpyAsync(h, d_stats, 16, cudaMemcpyDeviceToHost, as_stream(stream));
     cudaStreamSynchronize(as_stream(stream));
@@ -1372,7 +1647,7 @@ int g2p_knn_block(const g2p_index* ix, const void* tlon, const void* tlat, const
             (double)h[0] / (double)m, (double)h[1] / (double)m);
     return rc;
   }
-  return launch_knn(a, qsrc, as_stream(stream));
+  return run();
 }
 
 int g2p_weights(int mode, int k, int64_t m, int64_t n_src, double mub, int dtype, int32_t* idx, double* coef,

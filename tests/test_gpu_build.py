@@ -409,3 +409,31 @@ def test_rotated_target_build_end_to_end(dev, mode, k):
     got = dev.latlon_to_xyz(tlon.ravel(), tlat.ravel(), det['radius'], rotation=(-40.0, 10.0)).cpu().numpy()
     want = R.stack_xyz(*R.to_3d(tlon.ravel(), tlat.ravel(), det['radius'], rotation=(-40.0, 10.0)))
     np.testing.assert_allclose(got, want, rtol=0, atol=4e-16)
+
+
+@pytest.mark.parametrize('k', [1, 4, 11])
+def test_far_targets_of_a_regional_source_match_ckdtree(dev, k):
+    """A limited-area source and a global target: most targets are far from every source point, the cap search hands them
+    to the coarse-to-fine far pass (occupied 16 x 16 cell blocks with bounding caps).  Ids, order and distances against
+    cKDTree on the same xyz for every row - the far rows included (`nearest` stores their true distance, reference quirk
+    C.4; RAW / adw need their neighbours)."""
+    lat, lon, det = synth.regular_ll_grid(70.0, 30.0, 161, -20.0, 40.0, 241)
+    tl, tlo = synth.latlon_target(1.0, lat_max=90.0, lat_min=-90.0)
+    ix = dev.SourceIndex(lon, lat, det['radius'])
+    out = ix.knn(tlo.ravel(), tl.ravel(), k=k, mode=L.MODE_RAW, want_xyz=True)
+    src_xyz = ix.xyz().cpu().numpy()
+    txyz = out['xyz'].cpu().numpy()
+    idx = out['idx'].cpu().numpy().T.astype(np.int64)
+    dist = out['coef'].cpu().numpy().T
+    flags = out['flags'].cpu().numpy()
+    n_tie = _check_raw_vs_tree(src_xyz, txyz, k, idx, dist, flags, False)
+    assert n_tie < 0.2 * len(idx)           # a regular target over a regular source: many exactly equal distances
+    far = dist[:, 0] > 50 * ix.info()['mean_spacing']
+    assert far.mean() > 0.8                                   # the far pass answered most of the rows
+    # nearest mode on the same rows: sentinel index beyond min_upper_bound, the true distance stored everywhere
+    if k == 1:
+        mub = ix.min_upper_bound(det['Nj'])
+        nn = ix.knn(tlo.ravel(), tl.ravel(), k=1, mode=L.MODE_NEAREST, mub=mub)
+        np.testing.assert_array_equal(nn['coef'].cpu().numpy()[0], dist[:, 0])
+        want_idx = np.where(dist[:, 0] <= mub, idx[:, 0], lat.size)
+        np.testing.assert_array_equal(nn['idx'].cpu().numpy()[0].astype(np.int64), want_idx)
