@@ -58,8 +58,10 @@ enum {
  * Default: ((w0*v0 + w1*v1) + w2*v2) + w3*v3 - what numpy's einsum does on the strided float64 field views of a table
  * loaded from file (reference interpolation/__init__.py:156).  G2P_SUM_PAIRWISE:
  * (w0*v0 + w2*v2) + (w1*v1 + w3*v3) - what the same einsum does when it buffers its operands: tables with float32
- * coefficients (PCRaster REAL4 target maps) and freshly built contiguous tables.  Separate multiplies and adds in
- * both; other k are not affected. */
+ * coefficients (PCRaster REAL4 target maps) and freshly built contiguous tables.  For other k (g2p_apply only) the flag
+ * selects the same routine's order: two lanes taking the even / odd products, eight products per trip in the order
+ * 6,7 | 4,5 | 2,3 | 0,1, then pairs, lane 0 + lane 1 (numpy `sum_of_products_contig_two`, SSE2).  Separate multiplies
+ * and adds throughout. */
 #define G2P_SUM_PAIRWISE 0x100
 
 /* Bit-packed masks (G2P_MASK_PROPAGATE_BITS / G2P_MASK_MARKED): bit j of a row is bit (j & 7) of byte (j >> 3),

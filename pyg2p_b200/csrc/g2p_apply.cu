@@ -176,14 +176,45 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel_anyk(const ApplyAr
     const double* __restrict__ s = a.src + (int64_t)msg * a.src_stride;
     double acc = 0.0;
     uint32_t mk = 0;
-    for (int kk = 0; kk < a.k; ++kk) {
-      const int32_t i = __ldg(a.idx + (int64_t)kk * a.m + j);
-      const double w = __ldg(a.coef + (int64_t)kk * a.m + j);
-      const bool in = (uint32_t)i < n;
-      const double v = in ? __ldg(s + i) : a.mv_out;
-      const double p = __dmul_rn(w, v);
-      acc = (kk == 0) ? p : __dadd_rn(acc, p);
-      if (MP != 0 && in) mk |= src_masked<MP>(a, msg, i, v);
+    if (!a.pairwise) {
+      for (int kk = 0; kk < a.k; ++kk) {
+        const int32_t i = __ldg(a.idx + (int64_t)kk * a.m + j);
+        const double w = __ldg(a.coef + (int64_t)kk * a.m + j);
+        const bool in = (uint32_t)i < n;
+        const double v = in ? __ldg(s + i) : a.mv_out;
+        const double p = __dmul_rn(w, v);
+        acc = (kk == 0) ? p : __dadd_rn(acc, p);
+        if (MP != 0 && in) mk |= src_masked<MP>(a, msg, i, v);
+      }
+    } else {
+      // G2P_SUM_PAIRWISE for any k: the order of numpy's buffered einsum (`sum_of_products_contig_two`, two SSE2 lanes
+      // that take the even / odd products; eight products per trip in the order 6,7 | 4,5 | 2,3 | 0,1, then pairs, a
+      // zero-filled last lane, lane 0 + lane 1) - what tables with float32 coefficients are summed with.  For k = 4
+      // this is (p0 + p2) + (p1 + p3).
+      double p[16];
+      for (int kk = 0; kk < 16; ++kk) {
+        p[kk] = 0.0;
+        if (kk < a.k) {
+          const int32_t i = __ldg(a.idx + (int64_t)kk * a.m + j);
+          const double w = __ldg(a.coef + (int64_t)kk * a.m + j);
+          const bool in = (uint32_t)i < n;
+          const double v = in ? __ldg(s + i) : a.mv_out;
+          p[kk] = __dmul_rn(w, v);
+          if (MP != 0 && in) mk |= src_masked<MP>(a, msg, i, v);
+        }
+      }
+      double l0 = 0.0, l1 = 0.0;
+      int at = 0, left = a.k;
+      for (; left >= 8; left -= 8, at += 8)
+        for (int vv = 3; vv >= 0; --vv) {
+          l0 = __dadd_rn(l0, p[at + 2 * vv]);
+          l1 = __dadd_rn(l1, p[at + 2 * vv + 1]);
+        }
+      for (; left > 0; left -= 2, at += 2) {
+        l0 = __dadd_rn(l0, p[at]);
+        l1 = __dadd_rn(l1, left > 1 ? p[at + 1] : 0.0);
+      }
+      acc = __dadd_rn(l0, l1);
     }
     if (MP != 0 && mk) acc = a.mv_out;
     __stcs(a.out + (int64_t)msg * a.out_stride + j, acc);

@@ -134,6 +134,27 @@ def test_apply_f32_coeff_table(dev):
     assert tbl.coef_f32 and tbl.to_record().tobytes() == np.ascontiguousarray(rec).tobytes()
 
 
+@pytest.mark.parametrize('k', [2, 3, 5, 8, 11, 16])
+def test_apply_f32_coeff_any_k_matches_einsum_order(dev, k):
+    """float32-coefficient tables of any k (mode adw on PCRaster REAL4 maps: k = 11): numpy's einsum buffers the operands
+    and sums with two SSE2 lanes (even / odd products, eight per trip in the order 6,7 | 4,5 | 2,3 | 0,1, then pairs, lane 0
+    + lane 1); the float64 record views of a loaded table are summed left to right.  The generic kernel follows the
+    table's dtype: bit for bit `_interpolate_scipy_append_mv`'s own einsum on the record's field views."""
+    rng = np.random.default_rng(31 + k)
+    m, n, b = 4099, 2000, 3
+    idx = rng.integers(0, n + 1, size=(m, k))                  # n = the appended slot
+    w = rng.random((m, k))
+    w /= w.sum(axis=1, keepdims=True)
+    v = 280.0 + 20 * rng.standard_normal((b, n))
+    for dt in (np.float32, np.float64):
+        rec = R.to_record(idx, w.astype(dt))
+        tbl = dev.DeviceTable.from_record(rec, n)
+        assert tbl.sum_pairwise == (dt == np.float32)
+        out = tbl.apply(torch.from_numpy(v).cuda(), 1e20).cpu().numpy()
+        for i in range(b):
+            _eq(out[i], R.apply_as_reference(v[i], rec['coeffs'], rec['indexes'], k, 1e20))
+
+
 @pytest.mark.parametrize('path', ['generic', 'window'])
 def test_apply_f32_coeff_k4_matches_einsum_order(dev, path, monkeypatch):
     """float32 coefficients (tables built for PCRaster REAL4 maps): numpy's einsum buffers the operands and adds

@@ -48,7 +48,7 @@ def _source():
     return lat, lon, det
 
 
-@pytest.mark.parametrize('mode,k', [('nearest', 1), ('invdist', 4)])
+@pytest.mark.parametrize('mode,k', [('nearest', 1), ('invdist', 4), ('adw', 11)])
 def test_interpolation_create_and_reuse(api, tmp_path, mode, k):
     """build on first use (-B), file + configuration written in the reference's layout, reused afterwards."""
     Interpolator, _ = api
@@ -66,8 +66,9 @@ def test_interpolation_create_and_reuse(api, tmp_path, mode, k):
     assert item == {'filename': path.name, 'method': mode, 'source_shape': v.shape, 'target_shape': (60, 45)}
     with gzip.GzipFile(path) as f:
         rec = np.load(f)
-    want_dt = [('indexes', '<i8'), ('coeffs', '<f4' if k == 1 else '<f8')]   # float32 maps -> float32 distances
-    assert rec.dtype == np.dtype(want_dt) and rec.shape == ((2700,) if k == 1 else (2700, 4))
+    # float32 maps -> float32 distances (nearest) and float32 adw weights; invdist stores its weights into float64
+    want_dt = [('indexes', '<i8'), ('coeffs', '<f8' if mode == 'invdist' else '<f4')]
+    assert rec.dtype == np.dtype(want_dt) and rec.shape == ((2700,) if k == 1 else (2700, k))
     # numbers: the oracle's apply of the table that was written == what the call returned
     with np.errstate(all='ignore'):
         want = R.apply_as_reference(v, rec['coeffs'], rec['indexes'], k, it.mv_output).reshape(60, 45)
