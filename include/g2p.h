@@ -171,6 +171,12 @@ int g2p_knn_block(const g2p_index* index, const void* tlon, const void* tlat, co
 int g2p_peer_push(const void* local_base, void* const* peer_bases /* host */, int n_peers, int64_t row_bytes,
                   int64_t col_off, int64_t seg_bytes, int n_rows, void* stream);
 
+/* The same through the NVSwitch: `multicast_base` is the multicast (NVLS) address of the symmetric buffer; every 16-byte
+ * store is replicated by the switch into all GPUs of the group (this one included), so a rank sends its block once
+ * instead of once per peer (`multimem.st`).  16-byte aligned bases, rows and segments. */
+int g2p_multicast_push(const void* local_base, void* multicast_base, int64_t row_bytes, int64_t col_off,
+                       int64_t seg_bytes, int n_rows, void* stream);
+
 /* K5  weights from raw (idx, dist).  Same arithmetic as the fused epilogue of g2p_knn; kept as
  * its own entry point so the stage can be checked in isolation.  In place on idx / coef. */
 int g2p_weights(int mode, int k, int64_t m, int64_t n_src, double mub, int dtype,

@@ -90,6 +90,7 @@ PROTOTYPES = {
     'g2p_knn_block': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f64, _rotp, _i32, _i32, _f64, _vp, _vp, _i64, _i64, _vp, _vp,
                                 _vp]),
     'g2p_peer_push': (C.c_int, [_vp, C.POINTER(_vp), _i32, _i64, _i64, _i64, _i32, _vp]),
+    'g2p_multicast_push': (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     'g2p_weights': (C.c_int, [_i32, _i32, _i64, _i64, _f64, _i32, _vp, _vp, _vp]),
     'g2p_adw_distance_sum': (C.c_int, [_vp, _i64, _i32, _i32, _i32, C.POINTER(C.c_double), _vp]),
     'g2p_weights_adw': (C.c_int, [_i64, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),

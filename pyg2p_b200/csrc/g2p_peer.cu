@@ -46,9 +46,55 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const char* __restrict__
   }
 }
 
+// the same rows stored ONCE to the multicast address of the buffer: the NVSwitch replicates every 16-byte store into all
+// GPUs of the group (NVLS; this GPU's own copy included), so a rank sends its block once instead of once per peer
+__global__ void __launch_bounds__(256) multicast_push_kernel(const char* __restrict__ local, char* __restrict__ mc,
+                                                             int64_t row_bytes, int64_t col_off, int64_t seg_bytes) {
+  const int64_t at = (int64_t)blockIdx.y * row_bytes + col_off;
+  const int4* src = reinterpret_cast<const int4*>(local + at);
+  char* dst = mc + at;
+  const int64_t nvec = seg_bytes / 16;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  auto mc_store = [&](int64_t i, const int4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 16 * i), "f"(__int_as_float(v.x)),
+                 "f"(__int_as_float(v.y)), "f"(__int_as_float(v.z)), "f"(__int_as_float(v.w))
+                 : "memory");
+  };
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * step < nvec; i += 4 * step) {
+    const int4 v0 = __ldg(src + i), v1 = __ldg(src + i + step), v2 = __ldg(src + i + 2 * step), v3 = __ldg(src + i + 3 * step);
+    mc_store(i, v0);
+    mc_store(i + step, v1);
+    mc_store(i + 2 * step, v2);
+    mc_store(i + 3 * step, v3);
+  }
+  for (; i < nvec; i += step) mc_store(i, __ldg(src + i));
+}
+
 }  // namespace g2p
 
 using namespace g2p;
+
+extern "C" int g2p_multicast_push(const void* local_base, void* multicast_base, int64_t row_bytes, int64_t col_off,
+                                  int64_t seg_bytes, int n_rows, void* stream) {
+  if (!local_base || !multicast_base) return set_error(G2P_ERR_INVALID, "g2p_multicast_push: null pointer");
+  if (row_bytes < 0 || col_off < 0 || seg_bytes < 0 || col_off + seg_bytes > row_bytes || n_rows < 0)
+    return set_error(G2P_ERR_INVALID, "g2p_multicast_push: bad sizes");
+  if ((((uintptr_t)local_base | (uintptr_t)multicast_base | (uintptr_t)row_bytes | (uintptr_t)col_off | (uintptr_t)seg_bytes) & 15) != 0)
+    return set_error(G2P_ERR_UNSUPPORTED, "g2p_multicast_push: 16-byte aligned buffers, rows and segments only (use g2p_peer_push)");
+  if (n_rows == 0 || seg_bytes == 0) return G2P_OK;
+  static const int env_ctas = [] {
+    const char* e = getenv("G2P_PUSH_CTAS");
+    return e ? atoi(e) : 0;
+  }();
+  const int want_ctas = env_ctas > 0 ? env_ctas : 32;
+  int gx = (int)std::min<int64_t>(ceil_div(seg_bytes / 16, 256 * 4), std::max(1, want_ctas / std::max(1, n_rows)));
+  if (gx < 1) gx = 1;
+  multicast_push_kernel<<<dim3((unsigned)gx, (unsigned)n_rows), 256, 0, as_stream(stream)>>>(
+      static_cast<const char*>(local_base), static_cast<char*>(multicast_base), row_bytes, col_off, seg_bytes);
+  G2P_LAUNCHED();
+  return G2P_OK;
+}
 
 extern "C" int g2p_peer_push(const void* local_base, void* const* peer_bases, int n_peers, int64_t row_bytes,
                              int64_t col_off, int64_t seg_bytes, int n_rows, void* stream) {

@@ -132,6 +132,13 @@ class TableAssembler:
                 hdl = symm.rendezvous(buf, dist.group.WORLD)
                 self._buf, self._hdl = buf, hdl
                 self._peer_ptrs = [int(p) for p in hdl.buffer_ptrs]
+                # NVLS: one store to the multicast address lands in every GPU's copy (G2P_ASSEMBLE=p2p keeps the per-peer stores)
+                # (default from 4 GPUs up: with one peer the per-peer stores are faster - 2.66 against 2.82 ms per 2-GPU
+                # assembly - with seven the block leaves the GPU once instead of seven times; G2P_ASSEMBLE=mc|p2p forces one)
+                mc = int(getattr(hdl, 'multicast_ptr', 0) or 0)
+                mode = os.environ.get('G2P_ASSEMBLE', '')
+                want_mc = mode == 'mc' or (mode != 'p2p' and self.ws >= 4)
+                self._mc_ptr = mc if (mc and want_mc and self._off_c % 16 == 0 and (self.m * 4) % 16 == 0) else 0
                 self.p2p = True
             except Exception as e:           # noqa: BLE001 - any failure of the optional fast path selects the NCCL path
                 self.why_not = f'{type(e).__name__}: {e}'
@@ -139,8 +146,9 @@ class TableAssembler:
             self._buf = torch.empty(self._off_c + nbytes_c, dtype=torch.uint8, device=device)
         self.idx = self._buf[:nbytes_i].view(torch.int32).view(self.k, self.m)
         self.coef = self._buf[self._off_c:self._off_c + nbytes_c].view(torch.float64).view(self.k, self.m)
-        self.how = ('peer stores over NVLink into symmetric memory (g2p_peer_push), overlapped with the k-NN in '
-                    f'{self.blocks} target blocks, one barrier' if self.p2p else
+        self.how = (('multicast stores through the NVSwitch into symmetric memory (g2p_multicast_push, NVLS), '
+                     if getattr(self, '_mc_ptr', 0) else 'peer stores over NVLink into symmetric memory (g2p_peer_push), ') +
+                    f'overlapped with the k-NN in {self.blocks} target blocks, one barrier' if self.p2p else
                     f'one NCCL all_gather_into_tensor of the packed {{idx, coef}} bytes per target block ({self.blocks} blocks), '
                     f'overlapped with the k-NN' + (f' [symmetric memory unavailable: {self.why_not}]' if self.why_not else ''))
 
@@ -175,6 +183,12 @@ class TableAssembler:
                 ev.record(cur)
                 self.side.wait_event(ev)
                 st = C.c_void_p(self.side.cuda_stream)
+                if self._mc_ptr and (lo * 4) % 16 == 0 and ((hi - lo) * 4) % 16 == 0:
+                    L.check(lib.g2p_multicast_push(C.c_void_p(self.idx.data_ptr()), C.c_void_p(self._mc_ptr), self.m * 4,
+                                                   lo * 4, (hi - lo) * 4, self.k, st))
+                    L.check(lib.g2p_multicast_push(C.c_void_p(self.coef.data_ptr()), C.c_void_p(self._mc_ptr + self._off_c),
+                                                   self.m * 8, lo * 8, (hi - lo) * 8, self.k, st))
+                    continue
                 L.check(lib.g2p_peer_push(C.c_void_p(self.idx.data_ptr()), arr_i, len(peers), self.m * 4, lo * 4, (hi - lo) * 4,
                                           self.k, st))
                 L.check(lib.g2p_peer_push(C.c_void_p(self.coef.data_ptr()), arr_c, len(peers), self.m * 8, lo * 8, (hi - lo) * 8,
