@@ -111,12 +111,13 @@ class TableAssembler:
     `all_gather_into_tensor` per block of the packed {idx, coef} bytes (NCCL over NVLink), still overlapped with the
     k-NN of the next block.  `how` says which of the two ran."""
 
-    def __init__(self, m_total, k, align, device, blocks=4, force_nccl=None):
+    def __init__(self, m_total, k, align, device, blocks=None, force_nccl=None):
         self.m, self.k, self.align, self.device = int(m_total), int(k), int(align), device
         self.rank, self.ws = world()
         self.bounds = [shard_bounds(self.m, r, self.ws, align) for r in range(self.ws)]
         self.lo, self.hi = self.bounds[self.rank]
-        self.blocks = max(1, int(blocks))
+        # target blocks per rank: 4 at 2 GPUs, 8 from 4 GPUs up (8-GPU build: 1 block 3.10 ms, 2: 2.87, 4: 2.75, 8: 2.69)
+        self.blocks = max(1, int(blocks)) if blocks else (8 if self.ws >= 4 else 4)
         # high priority: the push kernel needs only a few SMs, and it gets them as soon as CTAs of the running k-NN retire
         self.side = torch.cuda.Stream(device=device, priority=-1) if device.type == 'cuda' else None
         self.p2p = False
