@@ -222,9 +222,10 @@ int g2p_table_compact(const int32_t* idx, int64_t m, int k, int64_t n, int32_t* 
  * page-locked buffer - 2.2 MB instead of staging the 52.8 MB field.  mask (nullable): one byte per source value,
  * nonzero = missing; out_mask (nullable): the mask bytes of the picked points; fold_marker != 0: masked points get
  * G2P_MASK_MARKER as their value (input of G2P_MASK_MARKED).  The caller runs it on a decoder-side thread (ctypes
- * releases the GIL) while the device works on the previous message. */
+ * releases the GIL) while the device works on the previous message.  threads: the pick is split over that many threads
+ * (the caller + persistent helpers; <= 0: the default, 2). */
 int g2p_host_pick(const double* src /* host */, const uint8_t* mask /* host */, const int32_t* touched /* host */,
-                  int64_t nc, double* out /* host */, uint8_t* out_mask /* host */, int fold_marker);
+                  int64_t nc, double* out /* host */, uint8_t* out_mask /* host */, int fold_marker, int threads);
 
 /* K7  batched intertable apply.  Replaces Interpolator._interpolate_scipy_append_mv
  * (interpolation/__init__.py:142-162) for `b` messages in one launch.

@@ -97,7 +97,7 @@ PROTOTYPES = {
     'g2p_table_pack_rec': (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     'g2p_table_unpack_rec': (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     'g2p_table_compact': (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp, C.POINTER(C.c_int64), _vp]),
-    'g2p_host_pick': (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i32]),
+    'g2p_host_pick': (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32]),
     'g2p_apply': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _i32, _i64, _i64, _f64, _i32, _vp, _vp, _vp]),
     'g2p_mark_masked': (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i64, _vp]),
     'g2p_plan_create': (C.c_int, [_vp, _i64, _i32, _i64, _i64, _i64, C.POINTER(_vp), _vp]),

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <functional>
 
 #include "../../include/g2p.h"
 
@@ -13,6 +14,8 @@ int set_error(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 extern std::atomic<int64_t> g_launches;
 int num_sms();
+// f(lo, hi) over [0, n) in a few slices on persistent helper threads (host-side staging loops)
+void host_parallel_for(int64_t n, int64_t min_slice, int threads, const std::function<void(int64_t, int64_t)>& f);
 
 #define G2P_CUDA(expr)                                                     \
   do {                                                                     \

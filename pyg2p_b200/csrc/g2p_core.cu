@@ -2,6 +2,12 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <cstdlib>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 #include "g2p_common.cuh"
 
@@ -37,6 +43,90 @@ int num_sms() {
   return cached[dev];
 }
 
+// ---- a few persistent helper threads for host-side staging loops (g2p_host_pick).  One job at a time per process
+// (callers serialise on the job mutex); the calling thread takes the first slice itself.
+namespace {
+struct HostPool {
+  std::mutex job_mutex;                 // one parallel_for at a time
+  std::mutex m;
+  std::condition_variable cv_work, cv_done;
+  std::vector<std::thread> workers;
+  const std::function<void(int64_t, int64_t)>* fn = nullptr;
+  int64_t n = 0, slice = 0;
+  int n_slices = 0, next = 0, pending = 0;
+  uint64_t generation = 0;
+  bool stop = false;
+
+  explicit HostPool(int helpers) {
+    for (int i = 0; i < helpers; ++i) workers.emplace_back([this] { loop(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> g(m);
+      stop = true;
+    }
+    cv_work.notify_all();
+    for (auto& t : workers) t.join();
+  }
+  void run_slices(std::unique_lock<std::mutex>& lk) {
+    while (next < n_slices) {
+      const int s = next++;
+      lk.unlock();
+      const int64_t lo = (int64_t)s * slice, hi = std::min(n, lo + slice);
+      (*fn)(lo, hi);
+      lk.lock();
+      if (--pending == 0) cv_done.notify_all();
+    }
+  }
+  void loop() {
+    std::unique_lock<std::mutex> lk(m);
+    uint64_t seen = 0;
+    for (;;) {
+      cv_work.wait(lk, [&] { return stop || (generation != seen && next < n_slices); });
+      if (stop) return;
+      seen = generation;
+      run_slices(lk);
+    }
+  }
+  void parallel_for(int64_t total, int64_t step, const std::function<void(int64_t, int64_t)>& f) {
+    std::lock_guard<std::mutex> job(job_mutex);
+    std::unique_lock<std::mutex> lk(m);
+    fn = &f;
+    n = total;
+    slice = step;
+    n_slices = (int)((total + step - 1) / step);
+    next = 0;
+    pending = n_slices;
+    ++generation;
+    // one helper per extra slice: waking sleepers that find no slice left costs more than their help is worth (a
+    // 7-helper pool woken as a whole: 0.45 ms per streamed message, 3 helpers: 0.29)
+    for (int i = 1; i < n_slices && i <= (int)workers.size(); ++i) cv_work.notify_one();
+    run_slices(lk);
+    cv_done.wait(lk, [&] { return pending == 0; });
+    fn = nullptr;
+  }
+};
+}  // namespace
+
+void host_parallel_for(int64_t n, int64_t min_slice, int threads, const std::function<void(int64_t, int64_t)>& f) {
+  constexpr int kMaxThreads = 4;
+  static const int dflt = [] {
+    const char* e = getenv("G2P_HOST_PICK_THREADS");
+    const int v = e ? atoi(e) : 2;
+    return v < 1 ? 1 : (v > kMaxThreads ? kMaxThreads : v);
+  }();
+  if (threads <= 0) threads = dflt;
+  if (threads > kMaxThreads) threads = kMaxThreads;
+  if (n <= 0) return;
+  if (threads == 1 || n < 2 * min_slice) {
+    f(0, n);
+    return;
+  }
+  static HostPool pool(kMaxThreads - 1);          // the helpers sleep until a job has slices for them
+  const int64_t parts = std::min<int64_t>(threads, n / min_slice);
+  pool.parallel_for(n, (n + parts - 1) / parts, f);
+}
+
 }  // namespace g2p
 
 extern "C" {
@@ -63,8 +153,12 @@ int64_t g2p_launch_count(void) { return g2p::g_launches.load(); }
 // Host-side staging helper of the ingest path (no device work): out[c] = src[touched[c]] for the nc source points a
 // table reads, straight from the pageable array the GRIB decoder returned into a (pinned) compact buffer; optionally
 // the mask bytes of those points (out_mask) and / or the marker NaN folded into the values of masked points.
+// The gather is bound by the latency of the host memory (276 589 picks out of a 52.8 MB field: 0.28 ms on one core), so
+// large picks are split over a few persistent helper threads: `threads` <= 0 = the default (G2P_HOST_PICK_THREADS, else 2:
+// a blocking per-message call gains nothing from more - waking sleeping helpers costs what they save - while a stream of
+// messages, whose helpers never go to sleep, is fastest with 4: 0.44 -> 0.24 ms per message), 1 = the caller alone.
 int g2p_host_pick(const double* src, const uint8_t* mask, const int32_t* touched, int64_t nc, double* out,
-                  uint8_t* out_mask, int fold_marker) {
+                  uint8_t* out_mask, int fold_marker, int threads) {
   if (!src || !touched || !out || nc < 0) return g2p::set_error(G2P_ERR_INVALID, "g2p_host_pick: null pointer");
   const double marker = [] {
     const unsigned long long u = G2P_MASK_MARKER;
@@ -72,18 +166,20 @@ int g2p_host_pick(const double* src, const uint8_t* mask, const int32_t* touched
     memcpy(&d, &u, sizeof d);
     return d;
   }();
-  if (!mask) {
-    for (int64_t c = 0; c < nc; ++c) out[c] = src[touched[c]];
-    if (out_mask) memset(out_mask, 0, (size_t)nc);
-    return G2P_OK;
-  }
-  for (int64_t c = 0; c < nc; ++c) {
-    const int32_t j = touched[c];
-    const uint8_t mk = mask[j] ? 1 : 0;
-    out[c] = (mk && fold_marker) ? marker : src[j];
-    if (out_mask) out_mask[c] = mk;
-  }
+  auto part = [=](int64_t lo, int64_t hi) {
+    if (!mask) {
+      for (int64_t c = lo; c < hi; ++c) out[c] = src[touched[c]];
+      if (out_mask) memset(out_mask + lo, 0, (size_t)(hi - lo));
+      return;
+    }
+    for (int64_t c = lo; c < hi; ++c) {
+      const int32_t j = touched[c];
+      const uint8_t mk = mask[j] ? 1 : 0;
+      out[c] = (mk && fold_marker) ? marker : src[j];
+      if (out_mask) out_mask[c] = mk;
+    }
+  };
+  g2p::host_parallel_for(nc, 32768, threads, part);
   return G2P_OK;
 }
-
 }  // extern "C"

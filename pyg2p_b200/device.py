@@ -911,7 +911,7 @@ class CompactHostPipeline:
             self._touched_host = np.ascontiguousarray(self.touched.cpu().numpy().astype(np.int32))
         return self._touched_host
 
-    def pick(self, field, out_values, out_mask=None):
+    def pick(self, field, out_values, out_mask=None, threads=0):
         """g2p_host_pick: the touched values of one pageable message (ndarray / MaskedArray, n values) -> out_values
         [>= nc] (a numpy view of a pinned buffer), their mask bytes -> out_mask (zeros for an unmasked message).  Pure
         host staging; releases the GIL."""
@@ -924,7 +924,7 @@ class CompactHostPipeline:
             mask = np.ascontiguousarray(np.broadcast_to(np.ma.getmaskarray(field).reshape(-1), data.shape)).view(np.uint8)
         L.check(L.lib().g2p_host_pick(data.ctypes.data, mask.ctypes.data if mask is not None else None, th.ctypes.data,
                                       th.size, out_values.ctypes.data, out_mask.ctypes.data if out_mask is not None else None,
-                                      0))
+                                      0, int(threads)))
 
     def run_compact(self, h_c, mv_out, h_cm=None, mask_policy=L.MASK_AS_REFERENCE, out=None, out_mask=None,
                     correction=None, post=None):

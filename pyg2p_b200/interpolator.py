@@ -350,7 +350,8 @@ class Interpolator:
                     free[s].clear()
                     if h2d_done[s] is not None:
                         h2d_done[s].synchronize()
-                    pipe.pick(x, ring_v.numpy()[s, :nc], ring_m.numpy()[s, :nc] if want_mask else None)
+                    # (four threads: the helpers of a continuous stream never go to sleep)
+                    pipe.pick(x, ring_v.numpy()[s, :nc], ring_m.numpy()[s, :nc] if want_mask else None, threads=4)
                     ready.put((s, isinstance(x, ma.MaskedArray)))
                 ready.put(None)
             except BaseException as e:      # noqa: BLE001 - handed to the consumer
