@@ -223,7 +223,7 @@ int g2p_table_compact(const int32_t* idx, int64_t m, int k, int64_t n, int32_t* 
  * nonzero = missing; out_mask (nullable): the mask bytes of the picked points; fold_marker != 0: masked points get
  * G2P_MASK_MARKER as their value (input of G2P_MASK_MARKED).  The caller runs it on a decoder-side thread (ctypes
  * releases the GIL) while the device works on the previous message.  threads: the pick is split over that many threads
- * (the caller + persistent helpers; <= 0: the default, 2). */
+ * (the caller + persistent helpers, at most 4; <= 0: the default, the caller alone). */
 int g2p_host_pick(const double* src /* host */, const uint8_t* mask /* host */, const int32_t* touched /* host */,
                   int64_t nc, double* out /* host */, uint8_t* out_mask /* host */, int fold_marker, int threads);
 

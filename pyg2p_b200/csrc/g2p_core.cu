@@ -112,7 +112,7 @@ void host_parallel_for(int64_t n, int64_t min_slice, int threads, const std::fun
   constexpr int kMaxThreads = 4;
   static const int dflt = [] {
     const char* e = getenv("G2P_HOST_PICK_THREADS");
-    const int v = e ? atoi(e) : 2;
+    const int v = e ? atoi(e) : 1;
     return v < 1 ? 1 : (v > kMaxThreads ? kMaxThreads : v);
   }();
   if (threads <= 0) threads = dflt;
@@ -154,9 +154,10 @@ int64_t g2p_launch_count(void) { return g2p::g_launches.load(); }
 // table reads, straight from the pageable array the GRIB decoder returned into a (pinned) compact buffer; optionally
 // the mask bytes of those points (out_mask) and / or the marker NaN folded into the values of masked points.
 // The gather is bound by the latency of the host memory (276 589 picks out of a 52.8 MB field: 0.28 ms on one core), so
-// large picks are split over a few persistent helper threads: `threads` <= 0 = the default (G2P_HOST_PICK_THREADS, else 2:
-// a blocking per-message call gains nothing from more - waking sleeping helpers costs what they save - while a stream of
-// messages, whose helpers never go to sleep, is fastest with 4: 0.44 -> 0.24 ms per message), 1 = the caller alone.
+// large picks can be split over a few persistent helper threads: `threads` <= 0 = the default (G2P_HOST_PICK_THREADS,
+// else 1, the caller alone: a blocking per-message call loses with helpers - 0.79 / 0.86 / 0.88 ms with 1 / 2 / 4 threads,
+// waking sleepers costs more than they save), while a stream of messages, whose helpers stay warm, is fastest with 4
+// (0.44 -> 0.23 ms per message).
 int g2p_host_pick(const double* src, const uint8_t* mask, const int32_t* touched, int64_t nc, double* out,
                   uint8_t* out_mask, int fold_marker, int threads) {
   if (!src || !touched || !out || nc < 0) return g2p::set_error(G2P_ERR_INVALID, "g2p_host_pick: null pointer");
