@@ -532,7 +532,7 @@ struct CachedBuf {
 };
 static std::vector<CachedBuf> g_free_bufs[64];
 static std::mutex g_free_mutex;
-constexpr size_t kCacheMaxEntries = 24;
+constexpr size_t kCacheMaxEntries = 40;
 constexpr size_t kCacheMaxBytes = (size_t)2 << 30;   // at most 2 GiB parked per device
 
 template <typename T>
@@ -565,8 +565,18 @@ static void pool_free(void* p, size_t bytes) {
     auto& fl = g_free_bufs[dev];
     size_t held = 0;
     for (const CachedBuf& b : fl) held += b.bytes;
-    if (fl.size() < kCacheMaxEntries && held + bytes <= kCacheMaxBytes) {
+    if (bytes <= kCacheMaxBytes) {
+      // the newest buffer stays, the oldest ones go: after a change of problem size (another grid) the list turns over
+      // once and the new sizes are served from it again (without this, a full list of stale sizes made every later
+      // build pay cudaMalloc + cudaFree per buffer: 1.16 instead of 0.47 ms for an O320 -> EFAS build)
+      std::vector<void*> evict;
+      while (!fl.empty() && (fl.size() >= kCacheMaxEntries || held + bytes > kCacheMaxBytes)) {
+        held -= fl.front().bytes;
+        evict.push_back(fl.front().p);
+        fl.erase(fl.begin());
+      }
       fl.push_back({p, bytes ? bytes : 1});
+      for (void* e : evict) cudaFree(e);
       return;
     }
   }
