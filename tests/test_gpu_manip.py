@@ -323,6 +323,13 @@ def test_pipeline_marked_and_host_buffers(M):
     ready[want_mask | np.isnan(want) | (want == mv_out) | clone.ravel()[None, :]] = 1e20
     assert none is None
     np.testing.assert_array_equal(h_out2.numpy(), ready)
+    # ... and as float32, what a PCRaster REAL4 band stores: the same fields cast element by element
+    post32 = device.WriterPost(clone, 1e20, match=mv_out, out_dtype=np.float32)
+    h_out32, _ = pipe.run_host(h_src, h_msk, plan, converter=conv, cut_off=True, mv_out=mv_out, corrector=corr,
+                               members=members, post=post32)
+    torch.cuda.synchronize()
+    assert h_out32.dtype == torch.float32 and pipe.d2h_bytes == ready.size * 4
+    np.testing.assert_array_equal(h_out32.numpy(), ready.astype(np.float32))
     # without masks
     plain = pipe.run(src, None, plan, converter=conv, cut_off=True, mv_out=mv_out, corrector=corr, members=members)
     h_out3, _ = pipe.run_host(h_src, None, plan, converter=conv, cut_off=True, mv_out=mv_out, corrector=corr, members=members)
