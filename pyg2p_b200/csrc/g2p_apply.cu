@@ -42,6 +42,26 @@ __device__ __forceinline__ double weighted(const double (&w)[K], const double (&
   if (K == 4 && pairwise)   // G2P_SUM_PAIRWISE
     return __dadd_rn(__dadd_rn(__dmul_rn(w[0], v[0]), __dmul_rn(w[K > 2 ? 2 : 0], v[K > 2 ? 2 : 0])),
                      __dadd_rn(__dmul_rn(w[1], v[1]), __dmul_rn(w[K > 3 ? 3 : 0], v[K > 3 ? 3 : 0])));
+  if (K > 4 && pairwise) {
+    // the order of numpy's buffered einsum for any k (see apply_kernel_anyk): two lanes, even / odd products, eight per
+    // trip in the order 6,7 | 4,5 | 2,3 | 0,1, then pairs, lane 0 + lane 1
+    double l0 = 0.0, l1 = 0.0;
+    constexpr int full = (K / 8) * 8;
+#pragma unroll
+    for (int c = 0; c < full; c += 8) {
+#pragma unroll
+      for (int vv = 3; vv >= 0; --vv) {
+        l0 = __dadd_rn(l0, __dmul_rn(w[c + 2 * vv], v[c + 2 * vv]));
+        l1 = __dadd_rn(l1, __dmul_rn(w[c + 2 * vv + 1], v[c + 2 * vv + 1]));
+      }
+    }
+#pragma unroll
+    for (int c = full; c < K; c += 2) {
+      l0 = __dadd_rn(l0, __dmul_rn(w[c], v[c]));
+      l1 = __dadd_rn(l1, (c + 1 < K) ? __dmul_rn(w[c + 1 < K ? c + 1 : c], v[c + 1 < K ? c + 1 : c]) : 0.0);
+    }
+    return __dadd_rn(l0, l1);
+  }
   double acc = __dmul_rn(w[0], v[0]);
 #pragma unroll
   for (int kk = 1; kk < K; ++kk) acc = __dadd_rn(acc, __dmul_rn(w[kk], v[kk]));
@@ -159,8 +179,9 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const ApplyArgs a)
     const int msg_begin = mc * a.msgs_per_chunk;
     const int msg_end = min(a.b, msg_begin + a.msgs_per_chunk);
     int msg = msg_begin;
-    for (; msg + kMsgUnroll <= msg_end; msg += kMsgUnroll)
-      apply_messages<K, MP, kMsgUnroll>(a, msg, j0, has1, i0, i1, w0, w1);
+    constexpr int MU = K > 4 ? 1 : kMsgUnroll;   // k = 11: the table of two targets already fills the registers
+    for (; msg + MU <= msg_end; msg += MU)
+      apply_messages<K, MP, MU>(a, msg, j0, has1, i0, i1, w0, w1);
     for (; msg < msg_end; ++msg) apply_messages<K, MP, 1>(a, msg, j0, has1, i0, i1, w0, w1);
   }
 }
@@ -378,7 +399,7 @@ int g2p_apply(const int32_t* idx, const double* coef, int64_t m, int k, const do
     // k = 1 / 4: whole mask bytes come from warp ballots, only the padding bytes of the rows are cleared here;
     // other k: only masked outputs touch the rows (atomicOr) and everything else is this memset
     const size_t row_bytes = (size_t)a.obits_stride * 4, used = (size_t)((m + 7) / 8);
-    if (k != 1 && k != 4) G2P_CUDA(cudaMemsetAsync(out_mask, 0, (size_t)b * row_bytes, st));
+    if (k != 1 && k != 4 && k != 11) G2P_CUDA(cudaMemsetAsync(out_mask, 0, (size_t)b * row_bytes, st));
     else if (row_bytes > used) G2P_CUDA(cudaMemset2DAsync(out_mask + used, row_bytes, 0, row_bytes - used, (size_t)b, st));
   }
   const int mp = bits ? 3 : marked ? 4 : mask ? 1 : 0;
@@ -386,6 +407,11 @@ int g2p_apply(const int32_t* idx, const double* coef, int64_t m, int k, const do
     return mp == 3 ? launch_apply<1, 3>(a, st) : mp == 4 ? launch_apply<1, 4>(a, st) : mp == 1 ? launch_apply<1, 1>(a, st) : launch_apply<1, 0>(a, st);
   if (k == 4)
     return mp == 3 ? launch_apply<4, 3>(a, st) : mp == 4 ? launch_apply<4, 4>(a, st) : mp == 1 ? launch_apply<4, 1>(a, st) : launch_apply<4, 0>(a, st);
+  // k = 11 (mode adw / cdd tables): the batched kernel keeps the 11 indexes and weights of its targets in registers and
+  // reads them once per chunk of messages (the per-message kernel below re-reads 132 B of table per output value)
+  static const bool anyk_only = getenv("G2P_APPLY_ANYK") != nullptr;
+  if (k == 11 && !anyk_only)
+    return mp == 3 ? launch_apply<11, 3>(a, st) : mp == 4 ? launch_apply<11, 4>(a, st) : mp == 1 ? launch_apply<11, 1>(a, st) : launch_apply<11, 0>(a, st);
   return mp == 3 ? launch_apply_anyk<3>(a, st) : mp == 4 ? launch_apply_anyk<4>(a, st) : mp == 1 ? launch_apply_anyk<1>(a, st) : launch_apply_anyk<0>(a, st);
 }
 
