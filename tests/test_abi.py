@@ -53,3 +53,29 @@ def test_product_never_touches_the_oracle():
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
                 # ... nor reach for a CPU implementation of the path (scipy's cKDTree, numexpr)
                 assert not re.search(r'^\s*(from|import)\s+(scipy|numexpr)\b', text, flags=re.M), f
+
+
+@pytest.mark.parametrize('threads', [0, 1, 2, 4])
+def test_host_pick_is_pure_host_staging(threads):
+    """g2p_host_pick is the one entry point that works on HOST memory and needs no device: the touched values of a decoded
+    message into a compact buffer - with their mask bytes, or with the marker NaN folded in - on 1..4 threads."""
+    import numpy as np
+    lib = L.lib()
+    rng = np.random.default_rng(5 + threads)
+    n, nc = 300_000, 131_075                      # large enough to be split over the helper threads
+    touched = np.sort(rng.choice(n, nc, replace=False)).astype(np.int32)
+    x = rng.standard_normal(n)
+    mask = (rng.random(n) < 0.03).view(np.uint8)
+    out, om = np.empty(nc), np.full(nc, 7, np.uint8)
+    assert lib.g2p_host_pick(x.ctypes.data, mask.ctypes.data, touched.ctypes.data, nc, out.ctypes.data, om.ctypes.data, 0,
+                             threads) == 0
+    np.testing.assert_array_equal(out, x[touched])
+    np.testing.assert_array_equal(om, mask[touched])
+    assert lib.g2p_host_pick(x.ctypes.data, None, touched.ctypes.data, nc, out.ctypes.data, om.ctypes.data, 0, threads) == 0
+    np.testing.assert_array_equal(out, x[touched])
+    assert not om.any()
+    assert lib.g2p_host_pick(x.ctypes.data, mask.ctypes.data, touched.ctypes.data, nc, out.ctypes.data, None, 1, threads) == 0
+    marked = mask[touched] != 0
+    assert (out[marked].view(np.uint64) == L.MASK_MARKER).all()
+    np.testing.assert_array_equal(out[~marked], x[touched][~marked])
+    assert lib.g2p_host_pick(None, None, touched.ctypes.data, nc, out.ctypes.data, None, 0, threads) == -1
