@@ -676,6 +676,17 @@ def pinned_empty(shape, dtype=torch.float64):
     return torch.empty(shape, dtype=dtype, pin_memory=True)
 
 
+_PINNED_OUT_LIMIT = 16 << 30
+
+
+def _check_implicit_out(b, m, vbytes):
+    """a batch whose results do not fit a reasonable page-locked allocation must bring its own `out=` (or come in
+    smaller batches): 383 O1280 messages to the 0.05 deg grid are 66 GB"""
+    if b * m * vbytes > _PINNED_OUT_LIMIT:
+        raise ValueError(f'{b} messages x {m} targets need {b * m * vbytes / 2**30:.0f} GiB of page-locked memory for the '
+                         f'results: pass out= (e.g. Interpolator.pinned_output_buffer of a smaller batch) or split the batch')
+
+
 def _out_buffers(pipe, post):
     """(device result slots, host dtype, bytes per value) of a host pipeline for this call: the float64 slots, or -
     allocated on first use - float32 ones when the writers' epilogue hands over float32 fields"""
@@ -748,6 +759,7 @@ class HostApplyPipeline:
             src_mask = src_mask.view(torch.uint8)
         d_out, out_dtype, vbytes = _out_buffers(self, post)
         if out is None:
+            _check_implicit_out(b, t.m, vbytes)
             out = pinned_empty((b, t.m), out_dtype)
         if want_omask and out_mask is None:
             out_mask = pinned_empty((b, t.m), torch.uint8)
@@ -864,6 +876,7 @@ class CompactHostPipeline:
             raise ValueError(f'source field has {n} values, intertable was built for {t.n_src}')
         d_out, out_dtype, vbytes = _out_buffers(self, post)
         if out is None:
+            _check_implicit_out(b, t.m, vbytes)
             out = pinned_empty((b, t.m), out_dtype)
         if want_omask and out_mask is None:
             out_mask = pinned_empty((b, t.m), torch.uint8)
@@ -942,6 +955,7 @@ class CompactHostPipeline:
         nc = self.ct.n_src
         d_out, out_dtype, vbytes = _out_buffers(self, post)
         if out is None:
+            _check_implicit_out(b, t.m, vbytes)
             out = pinned_empty((b, t.m), out_dtype)
         if want_omask and out_mask is None:
             out_mask = pinned_empty((b, t.m), torch.uint8)

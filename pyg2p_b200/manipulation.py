@@ -554,22 +554,24 @@ class Corrector:
     _PRESSURE = re.compile(r'^p/gem\*\(10\*\*\(' + _NUM + r'\*dem/' + _NUM + r'\)\)$')
     _GEM_PRESSURE = re.compile(r'^\(?10\*\*\(' + _NUM + r'\*\(z/' + _NUM + r'\)/' + _NUM + r'\)\)?$')
 
-    def __init__(self, dem_values, dem_mv, gem_values, gem_mv, formula='p+gem-dem*0.0065'):
+    def __init__(self, dem_values, dem_mv, gem_values, gem_mv, formula='p+gem-dem*0.0065', dev=None):
         compact = formula.replace(' ', '')
         lib = device.require_cuda()
+        dev = torch.device('cuda', torch.cuda.current_device()) if dev is None else torch.device(dev)   # the table's GPU
         dem = np.ascontiguousarray(dem_values)
         if dem.dtype not in (np.float32, np.float64):
             dem = dem.astype(np.float64)
         self.shape = dem.shape
         m = dem.size
-        self.gem = device.to_device(np.asarray(ma.getdata(gem_values), dtype=np.float64).ravel(), torch.float64, 'cuda')
-        self.dem_term = torch.empty(m, dtype=torch.float64, device='cuda')
-        self.valid = torch.empty(m, dtype=torch.uint8, device='cuda')
+        self.gem = device.to_device(np.asarray(ma.getdata(gem_values), dtype=np.float64).ravel(), torch.float64, dev)
+        self.dem_term = torch.empty(m, dtype=torch.float64, device=dev)
+        self.valid = torch.empty(m, dtype=torch.uint8, device=dev)
         lin, prs = self._LINEAR.match(compact), self._PRESSURE.match(compact)
         if lin:
             # `p+gem-dem*c`: dem_term = dem*c and the guards, per target, on the device
             self.mode, self.coeff = 0, float(lin.group(1))
-            d_dem = torch.from_numpy(dem.ravel()).cuda()
+            d_dem = torch.from_numpy(dem.ravel()).to(dev)
+            L.check(lib.g2p_set_device(dev.index))
             L.check(lib.g2p_correction_prepare(C.c_void_p(d_dem.data_ptr()), L.F32 if dem.dtype == np.float32 else L.F64,
                                                float(dem_mv), C.c_void_p(self.gem.data_ptr()), float(gem_mv), self.coeff, m,
                                                C.c_void_p(self.dem_term.data_ptr()), C.c_void_p(self.valid.data_ptr()),
@@ -616,7 +618,7 @@ class Corrector:
         buf = torch.zeros((1, n_pad), dtype=torch.float64, device='cuda')
         buf[0, :table.n_src] = g_src[0]
         gem = table.apply(buf[:, :table.n_src], float(mv_out))[0]
-        return cls(dem_values, dem_mv, gem.cpu().numpy(), z_mv, formula)
+        return cls(dem_values, dem_mv, gem.cpu().numpy(), z_mv, formula, dev=table.device)
 
     def c_struct(self):
         return self._c
