@@ -60,17 +60,71 @@ def algorithmic_bytes_apply(b, n_touched, m, k, masks):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  The timed region
+    of the apply step is ~20 ms, shorter than one `nvidia-smi -lms` period, so the samples come from NVML directly
+    (the library nvidia-smi itself reads), polled by a thread every ~2 ms between `start()` and `stop()`; `nvidia-smi`
+    is the fall-back when NVML cannot be loaded."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []          # nvidia-smi fall-back: csv rows
+        self.samples = []       # NVML: (sm_mhz, power_w, reasons bit mask)
         self.proc = None
+        self.nvml = None
+        self.handle = None
+        self.sm_max = None
+        self._stop = threading.Event()
+        self.thread = None
+
+    def _open_nvml(self):
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            handle = None
+            try:    # the CUDA device behind `gpu_index` (CUDA_VISIBLE_DEVICES may renumber): look it up by UUID
+                uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith('GPU-') else 'GPU-' + uuid)
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.handle = pynvml, handle
+            return True
+        except Exception:
+            self.nvml = None
+            return False
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = float('nan')
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def prepare(self):
+        """load NVML ahead of the timed region (nvmlInit takes tens of ms)"""
+        self._open_nvml()
 
     def start(self):
+        if self.nvml is not None or self._open_nvml():
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.gpu}', f'--query-gpu={self.Q}',
                                           '--format=csv,noheader,nounits', '-lms', '100'],
@@ -85,6 +139,21 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(',')])
 
     def stop(self):
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            nv = self.nvml
+            bits = {'hw_slowdown': nv.nvmlClocksThrottleReasonHwSlowdown,
+                    'hw_thermal_slowdown': nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    'sw_thermal_slowdown': nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    'sw_power_cap': nv.nvmlClocksThrottleReasonSwPowerCap}
+            sm = [s[0] for s in self.samples]
+            pw = [s[1] for s in self.samples if s[1] == s[1]]
+            reasons = sorted(nm for nm, bit in bits.items() if any(s[2] & bit for s in self.samples))
+            return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': self.sm_max,
+                    'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': reasons,
+                    'source': 'NVML polled every ~2 ms over the timed region'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
@@ -95,7 +164,6 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw = [], [], []
         reasons = set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for r in self.rows:
             if len(r) < 9:
                 continue
@@ -109,7 +177,8 @@ class ClockSampler:
                 if v.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+                'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons),
+                'source': 'nvidia-smi -lms 100'}
 
 
 # =============================================================================== reference arm (CPU)
@@ -532,15 +601,17 @@ def run_b200(args):
     def step():
         table.apply(marked, synth.NC_FILL_F64, mask_policy=L.MASK_MARKED, out=out_t, out_mask=out_b)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.prepare()
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = device.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    if rank == 0:
+        sampler.start()
     t_wall0 = time.perf_counter()
     torch.cuda.nvtx.range_push('timed_apply')       # ncu --nvtx --nvtx-include "timed_apply/" lists exactly these launches
     for a, b_ in ev:
@@ -1025,7 +1096,7 @@ def run_b200(args):
             'config': workload_config(B),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
                          'frac': achieved / hbm_peak, 'traffic': traffic,
-                         'kernel': 'g2p::apply_window_kernel<4, 4, CV, 4, false, false> (marked fields in, bit-packed mask out)',
+                         'kernel': 'g2p::apply_window_kernel<4, 4, CV, 5, false, false, 1> (marked fields in, bit-packed mask out; five stages handed over through mbarrier rings)',
                          'plan': table.plan_info() or table.plan_error,
                          'algorithmic_bytes_per_launch': bytes_launch, 'avg_launch_ms': avg_kernel_ms,
                          'launch_ms_min_median_max': [float(np.min(kern_ms)), float(np.median(kern_ms)), float(np.max(kern_ms))],

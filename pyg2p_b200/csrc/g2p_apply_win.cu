@@ -334,6 +334,28 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// mbarrier (shared-memory barrier objects) for the lagged message loop of the FAST marked-field kernels
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+// the arrival is triggered when every cp.async this thread has issued so far has landed (counts as one expected arrival)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t addr) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "G2P_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra G2P_MBAR_DONE;\n"
+      "bra G2P_MBAR_WAIT;\n"
+      "G2P_MBAR_DONE:\n"
+      "}" ::"r"(addr), "r"(parity) : "memory");
+}
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -474,7 +496,11 @@ __device__ __forceinline__ double agg_convert(const WinArgs& a, double x) {
 //       anyway - evaluates conversion, aggregation (PICK / ACCUM / AVERAGE of <= 2 / COPY, g2p_manip's arithmetic)
 //       and the cut-off on every staged source value before the targets gather it.  convert -> aggregate ->
 //       cut-off -> interpolate -> correct is then ONE launch that reads every needed source value once.
-template <int K, int MP, int CV, int S, bool CORR, bool AGG>
+// FAST: the block-uniform run-time switches of the message loop resolved at compile time for the resident-field paths
+//       (MP >= 3, no epilogue): 1 = sequential sum, bit mask rows from ballots; 2 = sequential sum, no mask rows;
+//       0 = everything read from WinArgs (pairwise sums, atomicOr mask rows, and every other variant).  The loop of
+//       the headline launch drops from 210 to ~165 instructions per thread and message (profiles/r02_apply.md).
+template <int K, int MP, int CV, int S, bool CORR, bool AGG, int FAST = 0>
 __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_window_kernel(const WinArgs a) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ Range s_ranges[kMaxRanges];
@@ -485,6 +511,27 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
   constexpr bool OBITS = MP >= 3;            // bit-packed output mask
   constexpr bool FOLD = MASK || BITS || AGG;
   constexpr int NIN = AGG ? 2 : 1;  // staged input windows per message
+  static_assert(FAST == 0 || (MP >= 3 && !CORR && !AGG), "FAST variants exist for the resident-field paths only");
+  const int pairwise = FAST ? 0 : a.pairwise;
+  // LAG: the per-message __syncthreads replaced by two rings of mbarriers with one message of slack.  full[s]: the
+  // copies of the message in stage s have landed (every thread's cp.async arrival); empty[s]: every warp is done
+  // gathering from stage s.  A warp that is ahead runs into the next message instead of waiting at a CTA barrier for
+  // the slowest one.  Copies run S-2 = 3 messages ahead and land in the stage of message it-2.  Measured on
+  // O1280 -> EFAS (profiles/r02_apply_lag.md): 3 messages ahead is the optimum in both schemes (2 and 4 lose 3-8 %),
+  // rings longer than look-ahead + 2 and stages cut to each tile's own window gain nothing.
+  constexpr bool LAG = FAST != 0 && MP == 4 && S == 5;
+  __shared__ __align__(8) unsigned long long s_mbar[LAG ? 2 * S : 2];
+  const uint32_t mb_full = smem_u32(s_mbar), mb_empty = mb_full + 8u * S;
+  // stage cursors and phase parities of the copies (p) and the gathers (g), kept across items: every item leaves the
+  // barriers quiescent (as many messages gathered as copied)
+  uint32_t lag_ps = 0, lag_pp = 0, lag_gs = 0, lag_gp = 0;
+  if (LAG && threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      mbar_init(mb_full + 8u * i, kWinThreads);
+      mbar_init(mb_empty + 8u * i, kWinThreads / 32);
+    }
+  }
   constexpr int CM = (CV + 7) / 8;  // 16-byte mask chunks per thread; also 4-element fold groups per thread / 4
   constexpr int CF = (CV + 1) / 2;  // fold groups (4 mask bytes) per thread
   constexpr int CB = (CV + 3) / 4;  // 8-element groups (one byte of mask bits) per thread
@@ -685,10 +732,32 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
         mk = msk_base;
       }
     };
+    // LAG: next message of the chunk -> stage lag_ps, once every warp has left the message that used it
+    auto prefetch_lag = [&]() {
+      if (n_left > 0) {
+        mbar_wait(mb_empty + 8u * lag_ps, lag_pp ^ 1u);
+        const uint32_t sv = val_base + lag_ps * stage_vbytes;
 #pragma unroll
-    for (int s = 0; s < S - 1; ++s) {
-      prefetch(pv, pm);
-      advance(pv, pm);
+        for (int i = 0; i < CV; ++i)
+          if (vsrc[i] >= 0) cp_async16(sv + 16u * tid + 16u * kWinThreads * i, grow_v + vsrc[i]);
+        cp_async_mbar_arrive(mb_full + 8u * lag_ps);
+        grow_v += vrow;
+        --n_left;
+        if (++lag_ps == S) {
+          lag_ps = 0;
+          lag_pp ^= 1u;
+        }
+      }
+    };
+    if (LAG) {
+#pragma unroll
+      for (int s = 0; s < S - 2; ++s) prefetch_lag();
+    } else {
+#pragma unroll
+      for (int s = 0; s < S - 1; ++s) {
+        prefetch(pv, pm);
+        advance(pv, pm);
+      }
     }
 
     // ---- this thread's targets: window offsets and weights stay in registers for the whole chunk
@@ -730,19 +799,21 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
     const int out_vbytes = (CORR && a.post_f32) ? 4 : 8;
     char* o = reinterpret_cast<char*>(a.out) + (int64_t)msg_begin * a.out_stride * out_vbytes;       // block-uniform
     char* om = (MP == 1) ? reinterpret_cast<char*>(a.out_mask) + (int64_t)msg_begin * a.out_stride : nullptr;
-    uint32_t* ob_row = (OBITS && a.out_mask) ? reinterpret_cast<uint32_t*>(a.out_mask) + (int64_t)msg_begin * a.obits_stride : nullptr;
+    uint32_t* ob_row = (OBITS && FAST != 2 && (FAST == 1 || a.out_mask)) ? reinterpret_cast<uint32_t*>(a.out_mask) + (int64_t)msg_begin * a.obits_stride : nullptr;
+    const bool use_ballot = FAST == 1 ? true : FAST == 2 ? false : (OBITS && ob_row != nullptr && a.obits_ballot);
+    const bool use_atomic = FAST != 0 ? false : (OBITS && ob_row != nullptr && !a.obits_ballot);
     // Bit-packed output mask from ballots: per target slot a warp owns whole bytes of the mask rows (8 neighbouring
     // columns of one row sit in 8 neighbouring lanes - two nibbles for 4x4 blocks), 4 bytes per slot, 16 per
     // message.  Lane q < 16 writes byte (slot q >> 2, byte q & 3): its row offset and the position of its bits in
     // the slot's ballot are fixed for the whole chunk.
-    if (OBITS && ob_row && a.obits_ballot && tile == a.n_tiles - 1) {   // the padding bytes of the chunk's mask rows
+    if (use_ballot && tile == a.n_tiles - 1) {   // the padding bytes of the chunk's mask rows
       const int used = (int)((a.m + 7) >> 3), tail = (int)(a.obits_stride * 4) - used;
       for (int i = tid; i < tail * n_msg; i += kWinThreads)
         reinterpret_cast<uint8_t*>(ob_row)[(int64_t)(i / tail) * a.obits_stride * 4 + used + (i % tail)] = 0;
     }
     int ob_byte = -1;        // byte offset in a mask row (-1: nothing to write)
     uint32_t ob_shift = 0;   // lane of the byte's first bit
-    if (OBITS && ob_row && a.obits_ballot) {
+    if (use_ballot) {
       const int lane = tid & 31;
       const int bc_small = a.g.block_cols_log2 == 2;
 #pragma unroll
@@ -760,7 +831,7 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
       }
     }
 
-    uint32_t gv_s = val_base;                   // stage of the message being gathered
+    uint32_t gv_s = LAG ? val_base + lag_gs * stage_vbytes : val_base;   // stage of the message being gathered
     uint32_t fv_s = val_base, fm_s = msk_base;  // stage of the message being folded (one ahead)
     if (FOLD) {  // message 0 must be folded before the first gather
       cp_async_wait<S - 2>();
@@ -776,10 +847,15 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
     // ---- messages
     for (int it = 0; it < n_msg; ++it) {
       // masked: message it+1 has landed (it is folded below, one message ahead of the gathers); else message it
-      cp_async_wait<FOLD ? S - 3 : S - 2>();
-      __syncthreads();        // copies / folds of the others are visible; everyone is done with message it-1
-      prefetch(pv, pm);       // message it+S-1, into the stage message it-1 used
-      advance(pv, pm);
+      if (LAG) {
+        prefetch_lag();       // message it+S-2, into the stage message it-2 used
+        mbar_wait(mb_full + 8u * lag_gs, lag_gp);   // everyone's copies of message it have landed
+      } else {
+        cp_async_wait<FOLD ? S - 3 : S - 2>();
+        __syncthreads();        // copies / folds of the others are visible; everyone is done with message it-1
+        prefetch(pv, pm);       // message it+S-1, into the stage message it-1 used
+        advance(pv, pm);
+      }
       if (FOLD) {
         if (it + 1 < n_msg) fold(fv_s, fm_s);
         advance(fv_s, fm_s);
@@ -797,16 +873,16 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
 #pragma unroll
         for (int kk = 0; kk < K; ++kk)
           v[kk] = K == 1 ? lds_f64(gv_s + li[t][0]) : (kk & 1) ? lds_f64_hi16(gv_s, li[t][kk >> 1]) : lds_f64_lo16(gv_s, li[t][kk >> 1]);
-        double res = weighted_sum<K>(w[t], v, a.pairwise);
+        double res = weighted_sum<K>(w[t], v, pairwise);
         uint32_t mk = 0;
         if (ANYMASK) {
           // branch-free: with scattered missing points nearly every warp holds a masked target
 #pragma unroll
           for (int kk = 0; kk < K; ++kk) mk |= (uint32_t)((uint32_t)__double2hiint(v[kk]) == kMarkerHi);
           if (mk) res = a.mv_out;
-          if (OBITS && ob_row && !a.obits_ballot && mk && ok[t]) atomicOr(ob_row + (ob[t] >> 8), 1u << ((ob[t] >> 3) & 31u));
+          if (use_atomic && mk && ok[t]) atomicOr(ob_row + (ob[t] >> 8), 1u << ((ob[t] >> 3) & 31u));
         }
-        if (OBITS) mkbits |= (mk != 0 && ok[t]) ? (1u << t) : 0u;
+        if (OBITS && FAST != 2) mkbits |= (mk != 0 && ok[t]) ? (1u << t) : 0u;
         if (CORR) {
           if (a.corr_gem && !mk)  // a masked output stays the missing value; p = NaN passes the guards and stays NaN
             res = !(cvalid[t] && res != a.corr_mv) ? a.corr_mv
@@ -821,7 +897,7 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
           if (MP == 1) *reinterpret_cast<uint8_t*>(om + (ob[t] >> 3)) = (uint8_t)mk;
         }
       }
-      if (OBITS && ob_row && a.obits_ballot) {   // block-uniform; the votes come after the four slots' arithmetic
+      if (use_ballot) {   // block-uniform; the votes come after the four slots' arithmetic
         const int slot = (tid & 31) >> 2;
         uint32_t bt = 0;
 #pragma unroll
@@ -833,11 +909,19 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
                                                        : ((bt >> ob_shift) & 0xffu);
         if (ob_byte >= 0) reinterpret_cast<uint8_t*>(ob_row)[ob_byte] = (uint8_t)byte;
       }
+      if (LAG) {   // this warp is done with the stage
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(mb_empty + 8u * lag_gs);
+        if (++lag_gs == S) {
+          lag_gs = 0;
+          lag_gp ^= 1u;
+        }
+      }
       gv_s += stage_vbytes;
       if (gv_s == val_end) gv_s = val_base;
       o += a.out_stride * out_vbytes;
       if (MP == 1) om += a.out_stride;
-      if (OBITS && ob_row) ob_row += a.obits_stride;
+      if (OBITS && FAST != 2 && (FAST == 1 || ob_row)) ob_row += a.obits_stride;
     }
     cp_async_wait<0>();
   }
@@ -847,11 +931,11 @@ static size_t win_smem_bytes(int stages, int stage_elems, int stage_melems, bool
   return (size_t)stages * nin * ((size_t)stage_elems * 8 + (mask ? stage_melems : 0));
 }
 
-template <int K, int MP, int CV, int S, bool CORR, bool AGG>
+template <int K, int MP, int CV, int S, bool CORR, bool AGG, int FAST = 0>
 static int launch_window_c(const g2p_plan* p, WinArgs a, cudaStream_t st) {
   constexpr bool MASK = MP == 1 || MP == 2;  // byte masks are the only ones staged
   const size_t smem = win_smem_bytes(S, a.stage_elems, a.stage_melems, MASK, AGG ? 2 : 1);
-  auto kern = apply_window_kernel<K, MP, CV, S, CORR, AGG>;
+  auto kern = apply_window_kernel<K, MP, CV, S, CORR, AGG, FAST>;
   G2P_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   G2P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWinThreads, smem));
@@ -886,8 +970,16 @@ static int launch_window_s(const g2p_plan* p, WinArgs a, cudaStream_t st) {
       return (a.corr_gem || a.post_on) ? launch_window_c<K, MP, CV, S, true, true>(p, a, st)
                                        : launch_window_c<K, MP, CV, S, false, true>(p, a, st);
   }
-  return (a.corr_gem || a.post_on) ? launch_window_c<K, MP, CV, S, true, false>(p, a, st)
-                                   : launch_window_c<K, MP, CV, S, false, false>(p, a, st);
+  if (a.corr_gem || a.post_on) return launch_window_c<K, MP, CV, S, true, false>(p, a, st);
+  if constexpr (MP >= 3) {   // resident fields (marked / bit masks), no epilogue: the switches of the loop at compile time
+    const char* ev = getenv("G2P_WIN_NO_FAST");   // experiments / tests: the run-time-switch kernel
+    const bool no_fast = ev && atoi(ev);
+    if (!a.pairwise && !no_fast) {
+      if (!a.out_mask) return launch_window_c<K, MP, CV, S, false, false, 2>(p, a, st);
+      if (a.obits_ballot) return launch_window_c<K, MP, CV, S, false, false, 1>(p, a, st);
+    }
+  }
+  return launch_window_c<K, MP, CV, S, false, false>(p, a, st);
 }
 
 template <int K, int MP, int CV>
@@ -898,6 +990,17 @@ static int launch_window_cv(const g2p_plan* p, WinArgs a, cudaStream_t st) {
   // shared memory per CTA leaves less L1 for the table and output traffic)
   const int nin = a.agg_items ? 2 : 1;
   constexpr bool staged_mask = MP == 1 || MP == 2;
+  if constexpr (MP == 4) {
+    // marked resident fields, no epilogue: the lagged message loop (mbarrier rings, five stages) when its ring fits
+    // next to three CTAs per SM.  G2P_WIN_NO_LAG=1 / G2P_WIN_NO_FAST=1: the __syncthreads loop (experiments, tests).
+    const char* e1 = getenv("G2P_WIN_NO_FAST");
+    const char* e2 = getenv("G2P_WIN_NO_LAG");
+    const bool off = (e1 && atoi(e1)) || (e2 && atoi(e2));
+    if (!off && !a.agg_items && !a.corr_gem && !a.post_on && !a.pairwise && (!a.out_mask || a.obits_ballot) &&
+        win_smem_bytes(5, a.stage_elems, a.stage_melems, false, 1) <= (size_t)72 * 1024)
+      return a.out_mask ? launch_window_c<K, MP, CV, 5, false, false, 1>(p, a, st)
+                        : launch_window_c<K, MP, CV, 5, false, false, 2>(p, a, st);
+  }
   if (win_smem_bytes(4, a.stage_elems, a.stage_melems, staged_mask, nin) <= (size_t)(nin == 2 ? 100 : 72) * 1024)
     return launch_window_s<K, MP, CV, 4>(p, a, st);
   if (win_smem_bytes(3, a.stage_elems, a.stage_melems, staged_mask, nin) > 220 * 1024)

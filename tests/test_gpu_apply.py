@@ -298,6 +298,15 @@ def test_window_path_random_tables(dev, k, shape, b, monkeypatch):
             _eq(m2[i].cpu().numpy().astype(bool), mk)
             _eq(o3[i].cpu().numpy(), data)
         _check_bits_and_marked(dev, tbl, v, mask, mv, rec, k, 'window')
+        # the same launches through the kernel that reads its switches (summation order, ballot / atomicOr mask
+        # rows) at run time instead of the compile-time FAST variants
+        monkeypatch.setenv('G2P_WIN_NO_FAST', '1')
+        _check_bits_and_marked(dev, tbl, v, mask, mv, rec, k, 'window')
+        monkeypatch.delenv('G2P_WIN_NO_FAST')
+        # ... and the FAST variants on the __syncthreads loop instead of the lagged mbarrier rings
+        monkeypatch.setenv('G2P_WIN_NO_LAG', '1')
+        _check_bits_and_marked(dev, tbl, v, mask, mv, rec, k, 'window')
+        monkeypatch.delenv('G2P_WIN_NO_LAG')
 
 
 def test_scattered_table_falls_back_to_generic_gpu_kernel(dev):
@@ -445,14 +454,17 @@ def test_apply_with_writer_post_epilogue(dev, monkeypatch):
 
 
 
-def test_windowed_kernel_repeats_bit_identically(dev, monkeypatch):
+@pytest.mark.parametrize('cols', [1003, 1000])
+def test_windowed_kernel_repeats_bit_identically(dev, monkeypatch, cols):
     """Stand-in for a racecheck run (compute-sanitizer is closed on the GPU pool, profiles/r02_sanitizer_closed.log): the
     4-stage cp.async ring + fold pass of the windowed kernel is the race-prone code of the tree.  A race between the
     staging copies, the fold pass and the gathers shows up as run-to-run differences: the same launch is repeated 40 times
     for every mask form on a ragged table with several chunks per tile (b > stages, odd sizes), each result compared bit
-    for bit with the first and with the generic gather kernel, which has no shared-memory staging at all."""
+    for bit with the first and with the generic gather kernel, which has no shared-memory staging at all.  cols = 1000
+    (rows of whole mask bytes) puts the marked forms on the lagged loop - five stages handed over through mbarrier rings
+    instead of __syncthreads - with ballot-assembled mask rows; cols = 1003 on the atomicOr rows."""
     rng = np.random.default_rng(99)
-    rows, cols, k, b, n = 61, 1003, 4, 37, 30011
+    rows, k, b, n = 61, 4, 37, 30011
     m = rows * cols
     centre = (np.arange(m) * (n / m)).astype(np.int64)
     idx = np.clip(centre[:, None] + rng.integers(-60, 61, size=(m, k)), 0, n)
@@ -469,7 +481,8 @@ def test_windowed_kernel_repeats_bit_identically(dev, monkeypatch):
     forms = {'plain': lambda: (tbl.apply(src, 1e20),),
              'propagate': lambda: tbl.apply(src, 1e20, src_mask=msk, mask_policy=L.MASK_PROPAGATE),
              'bits': lambda: tbl.apply(src, 1e20, src_mask=bits, mask_policy=L.MASK_PROPAGATE_BITS),
-             'marked': lambda: tbl.apply(marked, 1e20, mask_policy=L.MASK_MARKED)}
+             'marked': lambda: tbl.apply(marked, 1e20, mask_policy=L.MASK_MARKED),
+             'marked, no mask rows': lambda: (tbl.apply(marked, 1e20, mask_policy=L.MASK_MARKED, out_mask=False),)}
     monkeypatch.setenv('G2P_APPLY_PATH', 'generic')
     ref_plain = tbl.apply(src, 1e20).clone()
     ref_o, ref_m = [t.clone() for t in tbl.apply(src, 1e20, src_mask=msk, mask_policy=L.MASK_PROPAGATE)]
