@@ -112,9 +112,80 @@ struct PlanArgs {
   int32_t* status;  // [0] = first failing reason (0 ok), [1] = max value window, [2] = max ranges, [3] = max mask window
   unsigned long long* total_window;
   unsigned long long* total_wavefronts;  // shared-memory wavefronts of all half-warp gathers of one message
+  int swap01;       // 1: targets load neighbours 0 / 1 in either order, 2: and 2 / 3 (k = 4); 0: distance order
+  int swap_sweeps;  // refinement passes of pick_pair_order
   int dry;          // only measure (no lidx / ranges written): used to choose the tile shape
   int skew_mod, skew_step;  // range i goes to bank group skew_step * (i % skew_mod)
 };
+
+// wavefronts of one 64-bit shared-memory load of a half-warp: distinct words on the busiest of the 16 8-byte banks
+__device__ __forceinline__ int half_warp_wavefronts(unsigned word, int hw_base, int hl) {
+  const unsigned half = 0xffffu << hw_base;
+  const unsigned same = __match_any_sync(0xffffffffu, word) & half;
+  const bool first = (__ffs(same) - 1) == hw_base + hl;           // no lower lane of the half-warp loads this word
+  const unsigned firsts = __ballot_sync(0xffffffffu, first);
+  const unsigned bank = __match_any_sync(0xffffffffu, word & 15u) & half;
+  int cnt = __popc(bank & firsts);
+  for (int o = 8; o > 0; o >>= 1) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, o));
+  return cnt;
+}
+
+// Every lane of a half-warp loads word A with one instruction and word B with another, and may exchange the two.
+// Greedy over the 16 lanes (lane q takes the orientation that adds fewer wavefronts to the two loads given the
+// choices of lanes 0..q-1), then `sweeps` passes that flip single lanes while the two loads get cheaper.  Returns
+// whether this lane exchanges its pair; A and B come back in the chosen order.  Called by whole warps.
+__device__ __forceinline__ bool pick_pair_order(unsigned& A, unsigned& B, bool can, int hw_base, int hl, int sweeps) {
+  bool first_a = false, first_b = false, swapped = false;
+  int cur_a = 0, cur_b = 0;
+  auto hb = [&](bool pred) { return (__ballot_sync(0xffffffffu, pred) >> hw_base) & 0xffffu; };
+  for (int q = 0; q < 16; ++q) {
+    const unsigned x = __shfl_sync(0xffffffffu, A, hw_base + q), y = __shfl_sync(0xffffffffu, B, hw_base + q);
+    const int cq = __shfl_sync(0xffffffffu, (int)can, hw_base + q);
+    const bool dec = hl < q;   // this lane has chosen
+    // distinct words already on the candidate's bank (+1 for the candidate unless some lane loads the same word)
+    const int n_ax = __popc(hb(dec && first_a && ((A ^ x) & 15u) == 0)), n_ay = __popc(hb(dec && first_a && ((A ^ y) & 15u) == 0));
+    const int n_bx = __popc(hb(dec && first_b && ((B ^ x) & 15u) == 0)), n_by = __popc(hb(dec && first_b && ((B ^ y) & 15u) == 0));
+    const bool p_ax = hb(dec && A == x) != 0, p_ay = hb(dec && A == y) != 0;
+    const bool p_bx = hb(dec && B == x) != 0, p_by = hb(dec && B == y) != 0;
+    const int c_ax = p_ax ? 0 : n_ax + 1, c_ay = p_ay ? 0 : n_ay + 1, c_bx = p_bx ? 0 : n_bx + 1, c_by = p_by ? 0 : n_by + 1;
+    const int keep = max(cur_a, c_ax) + max(cur_b, c_by), swap = max(cur_a, c_ay) + max(cur_b, c_bx);
+    const bool sw = cq && swap < keep;   // the same in all lanes of the half-warp
+    if (hl == q) {
+      if (sw) {
+        const unsigned tmp = A;
+        A = B;
+        B = tmp;
+        swapped = true;
+      }
+      first_a = !(sw ? p_ay : p_ax);
+      first_b = !(sw ? p_bx : p_by);
+    }
+    cur_a = max(cur_a, sw ? c_ay : c_ax);
+    cur_b = max(cur_b, sw ? c_bx : c_by);
+  }
+  if (sweeps > 0) {
+    int best = half_warp_wavefronts(A, hw_base, hl) + half_warp_wavefronts(B, hw_base, hl);
+    for (int sweep = 0; sweep < sweeps; ++sweep) {
+      bool improved = false;   // the same in all lanes of the half-warp
+      for (int q = 0; q < 16; ++q) {
+        const bool me = hl == q;
+        const int cq = __shfl_sync(0xffffffffu, (int)can, hw_base + q);
+        const unsigned a2 = me ? B : A, b2 = me ? A : B;
+        const int c = half_warp_wavefronts(a2, hw_base, hl) + half_warp_wavefronts(b2, hw_base, hl);
+        if (cq && c < best) {
+          best = c;
+          improved = true;
+          if (me) swapped = !swapped;
+          A = a2;
+          B = b2;
+        }
+      }
+      // the two half-warps of a warp run the collectives together: no early exit unless both are done
+      if (!__any_sync(0xffffffffu, improved)) break;
+    }
+  }
+  return swapped;
+}
 
 __global__ void __launch_bounds__(kWinThreads) plan_kernel(const PlanArgs a) {
   extern __shared__ uint32_t s_bits[];  // kPlanSpanBlocks / 32 words
@@ -299,9 +370,31 @@ __global__ void __launch_bounds__(kWinThreads) plan_kernel(const PlanArgs a) {
   for (int t = 0; t < kWinTPT; ++t) {
     const bool ok = r < a.g.rows && c[t] < a.g.cols;
     const int64_t j = r * a.g.cols + c[t];
+    uint16_t lo[16];
     for (int kk = 0; kk < a.k; ++kk) {
       uint16_t l = kLocalSentinel;   // the sentinel slot is the last element of a stage: bank 15, like 0xffff
       if (rr[t][kk] >= 0) l = (uint16_t)(8 * (s_ranges[rr[t][kk]].smem_off + (my[t][kk] - s_ranges[rr[t][kk]].src_start)));
+      lo[kk] = l;
+    }
+    // ---- the order in which a target loads neighbours 0 / 1 and 2 / 3 is free: the sequential sum starts with
+    // w0*v0 + w1*v1 and IEEE addition commutes, so the kernel may exchange the two (weights with them) without
+    // changing a bit of the result; for 2 / 3 the kernel loads them exchanged and puts the two products back in
+    // distance order with a select before they are added.  pick_pair_order() chooses per half-warp.  Bit 0 of the
+    // pair's first offset (byte offsets are multiples of 8) tells the kernel that the pair is exchanged.
+    // O1280 -> EFAS, 2x8 blocks, wavefronts of the four gathers: 1.11 1.38 1.47 1.78 (mean 1.43) -> 1.01 1.06 1.07 1.12.
+    if (a.k >= 2 && a.swap01) {
+      for (int pr = 0; pr < ((a.k == 4 && a.swap01 >= 2) ? 2 : 1); ++pr) {
+        unsigned A = lo[2 * pr] >> 3, B = lo[2 * pr + 1] >> 3;
+        const bool can = lo[2 * pr] != kLocalSentinel && lo[2 * pr + 1] != kLocalSentinel;
+        if (pick_pair_order(A, B, can, hw_base, hl, a.swap_sweeps)) {
+          const uint16_t tmp = lo[2 * pr];
+          lo[2 * pr] = lo[2 * pr + 1] | 1u;
+          lo[2 * pr + 1] = tmp;
+        }
+      }
+    }
+    for (int kk = 0; kk < a.k; ++kk) {
+      const uint16_t l = lo[kk];
       if (ok && !a.dry) a.lidx[(int64_t)kk * a.m + j] = l;
       const unsigned mine = l >> 3;  // the 8-byte word
       bool first = true;  // no lower lane of the half-warp reads the same word
@@ -421,12 +514,19 @@ struct WinArgs {
 };
 
 // pairwise (block-uniform, K = 4): (w0*v0 + w2*v2) + (w1*v1 + w3*v3), see G2P_SUM_PAIRWISE
+// x23 (K = 4, sequential order): neighbours 2 and 3 were loaded exchanged (weights too): their products go back in
+// distance order before they are added
 template <int K>
-__device__ __forceinline__ double weighted_sum(const double (&w)[K], const double (&v)[K], int pairwise) {
+__device__ __forceinline__ double weighted_sum(const double (&w)[K], const double (&v)[K], int pairwise, bool x23) {
   if (K == 1) return v[0];
   if (K == 4 && pairwise)
     return __dadd_rn(__dadd_rn(__dmul_rn(w[0], v[0]), __dmul_rn(w[K > 2 ? 2 : 0], v[K > 2 ? 2 : 0])),
                      __dadd_rn(__dmul_rn(w[1], v[1]), __dmul_rn(w[K > 3 ? 3 : 0], v[K > 3 ? 3 : 0])));
+  if (K == 4) {
+    const double q2 = __dmul_rn(w[K > 2 ? 2 : 0], v[K > 2 ? 2 : 0]), q3 = __dmul_rn(w[K > 3 ? 3 : 0], v[K > 3 ? 3 : 0]);
+    const double acc = __dadd_rn(__dmul_rn(w[0], v[0]), __dmul_rn(w[1], v[1]));
+    return __dadd_rn(__dadd_rn(acc, x23 ? q3 : q2), x23 ? q2 : q3);
+  }
   double acc = __dmul_rn(w[0], v[0]);
 #pragma unroll
   for (int kk = 1; kk < K; ++kk) acc = __dadd_rn(acc, __dmul_rn(w[kk], v[kk]));
@@ -764,6 +864,7 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
     int64_t r, c[kWinTPT];
     thread_targets(a.g, tile, tid, r, c);
     bool ok[kWinTPT];
+    uint32_t x23 = 0;   // bit t: slot t loads neighbours 2 and 3 exchanged
     // window byte offsets of the neighbours, two uint16 per register (K = 4): the kernel lives at the 80-register
     // line of three CTAs per SM, and eight registers saved here are what the bit-mask paths need
     constexpr int KP = K > 1 ? K / 2 : 1;
@@ -778,14 +879,48 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
       ok[t] = r < a.g.rows && c[t] < a.g.cols;
       const int64_t j = j0 + (int64_t)t * a.g.threads_per_row;
       ob[t] = 8u * (uint32_t)j;
+      uint16_t lr[K];
 #pragma unroll
       for (int kk = 0; kk < K; ++kk) {
-        const uint16_t l = ok[t] ? __ldg(a.lidx + (int64_t)kk * a.m + j) : kLocalSentinel;
-        const uint32_t lb = (l == kLocalSentinel) ? 8u * (uint32_t)sent : (uint32_t)l;  // byte offsets as the plan stores them
+        lr[kk] = ok[t] ? __ldg(a.lidx + (int64_t)kk * a.m + j) : kLocalSentinel;
+        w[t][kk] = (K > 1 && ok[t]) ? __ldg(a.coef + (int64_t)kk * a.m + j) : 1.0;
+      }
+      if (K == 4 && lr[K > 2 ? 2 : 0] != kLocalSentinel && (lr[K > 2 ? 2 : 0] & 1u)) {
+        // ... and neighbours 2 / 3 (bit 0 of the third offset): loaded exchanged, with the weights; weighted_sum puts the
+        // two products back in distance order
+        constexpr int i2 = K > 2 ? 2 : 0, i3 = K > 3 ? 3 : 0;
+        lr[i2] &= (uint16_t)~1u;
+        if (pairwise) {
+          const uint16_t tmp = lr[i2];
+          lr[i2] = lr[i3];
+          lr[i3] = tmp;
+        } else {
+          const double tmp = w[t][i2];
+          w[t][i2] = w[t][i3];
+          w[t][i3] = tmp;
+          x23 |= 1u << t;
+        }
+      }
+      if (K >= 2 && lr[0] != kLocalSentinel && (lr[0] & 1u)) {
+        // the plan exchanged the two nearest neighbours (bit 0 of the first offset): w0*v0 + w1*v1 commutes, so the
+        // sequential sum takes the weights exchanged too; the pairwise order puts the offsets back
+        lr[0] &= (uint16_t)~1u;
+        if (pairwise) {
+          const uint16_t tmp = lr[0];
+          lr[0] = lr[K > 1 ? 1 : 0];
+          lr[K > 1 ? 1 : 0] = tmp;
+        } else {
+          const double tmp = w[t][0];
+          w[t][0] = w[t][K > 1 ? 1 : 0];
+          w[t][K > 1 ? 1 : 0] = tmp;
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk) {
+        const uint32_t lb = (lr[kk] == kLocalSentinel) ? 8u * (uint32_t)sent : (uint32_t)lr[kk];  // byte offsets as the plan stores them
         if (K == 1) li[t][0] = lb;
         else if ((kk & 1) == 0) li[t][kk >> 1] = lb;
         else li[t][kk >> 1] |= lb << 16;
-        w[t][kk] = (K > 1 && ok[t]) ? __ldg(a.coef + (int64_t)kk * a.m + j) : 1.0;
       }
       if (CORR) {
         const bool cr = ok[t] && a.corr_gem != nullptr;
@@ -873,7 +1008,7 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
 #pragma unroll
         for (int kk = 0; kk < K; ++kk)
           v[kk] = K == 1 ? lds_f64(gv_s + li[t][0]) : (kk & 1) ? lds_f64_hi16(gv_s, li[t][kk >> 1]) : lds_f64_lo16(gv_s, li[t][kk >> 1]);
-        double res = weighted_sum<K>(w[t], v, pairwise);
+        double res = weighted_sum<K>(w[t], v, pairwise, (x23 >> t) & 1u);
         uint32_t mk = 0;
         if (ANYMASK) {
           // branch-free: with scattered missing points nearly every warp holds a masked target
@@ -1140,6 +1275,10 @@ int g2p_plan_create(const int32_t* idx, int64_t m, int k, int64_t n, int64_t row
     a.total_window = d_total;
     a.total_wavefronts = d_total + 1;
     a.dry = dry;
+    a.swap01 = 2;
+    a.swap_sweeps = 2;
+    if (const char* ev = getenv("G2P_WIN_SWAP")) a.swap01 = std::max(0, std::min(2, atoi(ev)));   // experiments: 0 = distance order
+    if (const char* ev = getenv("G2P_WIN_SWAP_SWEEPS")) a.swap_sweeps = std::max(0, std::min(4, atoi(ev)));
     plan_kernel<<<p->n_tiles, kWinThreads, kPlanSpanBlocks / 8, st>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     err = cudaGetLastError();
