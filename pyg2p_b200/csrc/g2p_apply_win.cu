@@ -422,6 +422,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src_gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
 }
+// ... with an L2 eviction-priority hint: the staged source values are read again by the neighbouring tiles (windows
+// overlap 2.4x on O1280 -> EFAS) while the outputs stream through the same L2
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void cp_async16_hint(uint32_t dst_smem, const void* src_gmem, unsigned long long pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src_gmem), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -625,6 +635,7 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
   // stage cursors and phase parities of the copies (p) and the gathers (g), kept across items: every item leaves the
   // barriers quiescent (as many messages gathered as copied)
   uint32_t lag_ps = 0, lag_pp = 0, lag_gs = 0, lag_gp = 0;
+  const unsigned long long l2_keep = LAG ? l2_policy_evict_last() : 0ull;
   if (LAG && threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < S; ++i) {
@@ -839,7 +850,7 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
         const uint32_t sv = val_base + lag_ps * stage_vbytes;
 #pragma unroll
         for (int i = 0; i < CV; ++i)
-          if (vsrc[i] >= 0) cp_async16(sv + 16u * tid + 16u * kWinThreads * i, grow_v + vsrc[i]);
+          if (vsrc[i] >= 0) cp_async16_hint(sv + 16u * tid + 16u * kWinThreads * i, grow_v + vsrc[i], l2_keep);
         cp_async_mbar_arrive(mb_full + 8u * lag_ps);
         grow_v += vrow;
         --n_left;
