@@ -876,6 +876,11 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
     thread_targets(a.g, tile, tid, r, c);
     bool ok[kWinTPT];
     uint32_t x23 = 0;   // bit t: slot t loads neighbours 2 and 3 exchanged
+    // The epilogue variants keep neighbours 2 / 3 in distance order (the offsets are put back at the item load): with
+    // the selects in their loop the configs[4] pass went from 0.448 to 0.480 ms (bench `pipeline`, also with a plan
+    // that exchanges nothing), so the loop of these kernels is the one measured at 0.448.  Parity of this state:
+    // the epilogue / fused tests on the GPU; its pass time has not been measured again (GPU budget of the round spent).
+    constexpr bool X23 = !(CORR || AGG);
     // window byte offsets of the neighbours, two uint16 per register (K = 4): the kernel lives at the 80-register
     // line of three CTAs per SM, and eight registers saved here are what the bit-mask paths need
     constexpr int KP = K > 1 ? K / 2 : 1;
@@ -901,7 +906,7 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
         // two products back in distance order
         constexpr int i2 = K > 2 ? 2 : 0, i3 = K > 3 ? 3 : 0;
         lr[i2] &= (uint16_t)~1u;
-        if (pairwise) {
+        if (pairwise || !X23) {   // distance order again
           const uint16_t tmp = lr[i2];
           lr[i2] = lr[i3];
           lr[i3] = tmp;
@@ -1019,7 +1024,7 @@ __global__ void __launch_bounds__(kWinThreads, (CORR || AGG) ? 2 : 3) apply_wind
 #pragma unroll
         for (int kk = 0; kk < K; ++kk)
           v[kk] = K == 1 ? lds_f64(gv_s + li[t][0]) : (kk & 1) ? lds_f64_hi16(gv_s, li[t][kk >> 1]) : lds_f64_lo16(gv_s, li[t][kk >> 1]);
-        double res = weighted_sum<K>(w[t], v, pairwise, (x23 >> t) & 1u);
+        double res = weighted_sum<K>(w[t], v, pairwise, X23 && ((x23 >> t) & 1u));
         uint32_t mk = 0;
         if (ANYMASK) {
           // branch-free: with scattered missing points nearly every warp holds a masked target
